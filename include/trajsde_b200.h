@@ -1,0 +1,172 @@
+/*
+ * trajsde_b200.h — C ABI of the B200-native fused Euler–Maruyama solve that replaces TrajSDE's two solver call sites.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference repo daeheepark/TrajSDE):
+ *   trajsde_euler_fwd   : torchsde.sdeint(sde, y0, ts, dt=.., method='euler')      models/decoders/dec_hivt_nusargo_sde.py:88
+ *                         sdeint_dual(sde, y0, ts, nus_mask, dt=..)                models/utils/sdeint.py:110-197,
+ *                           called at models/encoders/enc_hivt_nusargo_sde_sep2.py:149 and :274
+ *                         (solver loop models/utils/sdeint.py:326-384, Euler step :467-485, f/g glue :537-566,
+ *                          nets dec…sde.py:107-127,141-158,180-195 / enc…sep2.py:372-398,412-440,462-482)
+ *   trajsde_euler_bwd   : torch.autograd through that solver (config `adjoint: false`, yml:41): discretise-then-optimise
+ *   trajsde_enc_fwd/bwd : the encoder recurrence 21 x [sdeint_dual one step + GRU_Unit jump]
+ *                           enc_hivt_nusargo_sde_sep2.py:128-182 + models/utils/ode_utils.py:136-152
+ *   trajsde_philox_dw   : BrownianInterval increments W(t1)-W(t0) ~ N(0,(t1-t0) I)  models/utils/sdeint.py:983-984
+ *
+ * Conventions
+ *   - Every pointer named *device* is a CUDA device pointer owned by the caller; the library never allocates or frees
+ *     device memory and keeps no reference after the call returns.  Scratch comes from `workspace` (size queried with
+ *     trajsde_*_workspace_bytes).  All calls only ENQUEUE work on `cuda_stream` (a cudaStream_t / CUstream passed as void*;
+ *     NULL = legacy default stream) and never synchronise the device.
+ *   - All tensors are fp32, dim (channels) == 64, rows are independent (one row = one agent latent, or agent x mode).
+ *   - Return value: 0 on success, negative TrajsdeStatus otherwise; trajsde_last_error_string() gives a thread-local
+ *     message.  The library never calls abort()/exit() and never throws across the ABI.
+ *   - Re-entrant; safe from several host threads on different streams.
+ */
+#ifndef TRAJSDE_B200_H_
+#define TRAJSDE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRAJSDE_ABI_VERSION 1
+#define TRAJSDE_DIM 64
+
+typedef enum {
+  TRAJSDE_OK = 0,
+  TRAJSDE_ERR_INVALID_ARGUMENT = -1, /* null pointer, bad size, struct_bytes mismatch */
+  TRAJSDE_ERR_UNSUPPORTED = -2,      /* dim != 64, unknown mode, misaligned pointer */
+  TRAJSDE_ERR_WORKSPACE = -3,        /* workspace too small */
+  TRAJSDE_ERR_CUDA = -4,             /* CUDA runtime / launch error */
+  TRAJSDE_ERR_NO_DEVICE = -5         /* no sm_100 device / kernel image unavailable */
+} TrajsdeStatus;
+
+/* Arithmetic mode of the MLP contractions (state, h, dW, accumulation and the Euler update are fp32 in every mode). */
+typedef enum {
+  TRAJSDE_MODE_EXACT_F32 = 0, /* fp32 FFMA on CUDA cores, libm-accurate tanh/sigmoid: the validation path            */
+  TRAJSDE_MODE_TC_F16 = 1,    /* tcgen05 tensor cores, fp16 operands (10-bit mantissa = TF32 precision), fp32 accum,
+                                 MUFU tanh; the throughput path                                                     */
+  TRAJSDE_MODE_TC_BF16 = 2    /* tcgen05 tensor cores, bf16 operands (reserved)                                      */
+} TrajsdeMode;
+
+/* One 3-layer MLP exactly as stored by nn.Linear (row-major [out,in]); device pointers.
+ * drift:     w1[64,66] b1[64] w2[64,64] b2[64] w3[64,64] b3[64]     (FFunc.net[0],[2],[4])
+ * diffusion: w1[64,66] b1[64] w2[64,64] b2[64] w3[1,64]  b3[1]      (GFunc.net[0],[2],[4]; sigmoid applied on top)
+ * Columns 64 and 65 of w1 multiply sin(t0) and cos(t0) (time features, dec…sde.py:124-126). */
+typedef struct {
+  const float* w1;
+  const float* b1;
+  const float* w2;
+  const float* b2;
+  const float* w3;
+  const float* b3;
+} TrajsdeMlp;
+
+/* Same layout for gradients (device, written — not accumulated — by the backward call). */
+typedef struct {
+  float* w1;
+  float* b1;
+  float* w2;
+  float* b2;
+  float* w3;
+  float* b3;
+} TrajsdeMlpGrad;
+
+/* Step schedule, computed on the host by replaying the reference's float32 time loop (models/utils/sdeint.py:340-384)
+ * and uploaded once per (ts, dt); device pointers.
+ *   step_tab[4*k + {0,1,2,3}] = t0_k, h_k = t1_k - t0_k, sin(t0_k), cos(t0_k)          k = 0..n_steps-1
+ *   out_begin[k] .. out_begin[k+1]-1 = the outputs j (0-based, ys index j+1) whose interpolation interval ends with
+ *                  step k; n_steps+1 entries, non-decreasing, out_begin[n_steps] == n_outputs
+ *   out_w[2*j + {0,1}] = w0_j, w1_j  with  ys[j+1] = w0_j * Y[k] + w1_j * Y[k+1]  (torchsde linear_interp)            */
+typedef struct {
+  int32_t n_steps;
+  int32_t n_outputs;
+  const float* step_tab;
+  const int32_t* out_begin;
+  const float* out_w;
+} TrajsdeSchedule;
+
+/* Brownian increments: either caller-supplied (validation / parity) or generated in-kernel.
+ *   dw != NULL : dw[n_steps, rows, 64] contiguous, slab k consumed by schedule step k (Var = h_k).
+ *   dw == NULL : Philox4x32-10, key = (seed lo, seed hi), counter = (global_row lo, global_row hi, step_offset + k,
+ *                channel/4); Box–Muller; scaled by sqrt(h_k).  global_row = row + row_offset so results do not depend
+ *                on how rows are sharded over GPUs. */
+typedef struct {
+  const float* dw;
+  uint64_t seed;
+  uint64_t row_offset;
+  uint32_t step_offset;
+  uint32_t reserved;
+} TrajsdeNoise;
+
+typedef struct {
+  uint32_t struct_bytes; /* = sizeof(TrajsdeEulerFwdArgs): ABI check */
+  int32_t mode;          /* TrajsdeMode */
+  int64_t rows;
+  int32_t dim;           /* must be 64 */
+  int32_t flags;         /* reserved, 0 */
+  TrajsdeSchedule sched;
+  TrajsdeMlp drift;
+  TrajsdeMlp diffusion;     /* rows with alt_mask[row] != 0, or all rows when alt_mask == NULL  (decoder g / encoder g_nus) */
+  TrajsdeMlp diffusion_alt; /* rows with alt_mask[row] == 0 (encoder g_argo); ignored when alt_mask == NULL              */
+  const uint8_t* alt_mask;  /* device [rows] (torch.bool storage) or NULL                                               */
+  TrajsdeNoise noise;
+  const float* y0;       /* [rows,64], row stride y0_row_stride elements, unit channel stride */
+  int64_t y0_row_stride;
+  float* ys;             /* n_outputs+1 slabs: ys[0] = y0; element (t,row,c) at t*ys_t_stride + row*ys_row_stride + c */
+  int64_t ys_t_stride;
+  int64_t ys_row_stride;
+  float* g_last;         /* [rows] diffusion evaluated at the start of the LAST step (sdeint_dual's 2nd result), or NULL */
+  float* states;         /* [n_steps, rows, 64] state at the START of every step (saved for backward), or NULL           */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeEulerFwdArgs;
+
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;
+  int64_t rows;
+  int32_t dim;
+  int32_t flags;
+  TrajsdeSchedule sched;
+  TrajsdeMlp drift;
+  TrajsdeMlp diffusion;
+  TrajsdeMlp diffusion_alt;
+  const uint8_t* alt_mask;
+  TrajsdeNoise noise;
+  const float* states;       /* [n_steps, rows, 64] from the forward call */
+  const float* grad_ys;      /* dL/d ys, same indexing as ys (incl. slab 0), or NULL */
+  int64_t grad_ys_t_stride;
+  int64_t grad_ys_row_stride;
+  const float* grad_g_last;  /* [rows] dL/d g_last or NULL */
+  float* grad_y0;            /* [rows,64] contiguous */
+  TrajsdeMlpGrad grad_drift;
+  TrajsdeMlpGrad grad_diffusion;
+  TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeEulerBwdArgs;
+
+int trajsde_abi_version(void);
+const char* trajsde_last_error_string(void);
+
+/* Number of resident CTAs the persistent kernels use on the current device (148 SMs on B200 x CTAs/SM); <0 on error. */
+int trajsde_device_sm_count(void);
+
+int64_t trajsde_euler_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
+int trajsde_euler_fwd(const TrajsdeEulerFwdArgs* args, void* cuda_stream);
+
+int64_t trajsde_euler_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
+int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* args, void* cuda_stream);
+
+/* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
+ * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */
+int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out,
+                      void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJSDE_B200_H_ */

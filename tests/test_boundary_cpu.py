@@ -1,0 +1,81 @@
+"""Host-side contract of the drop-in boundary (no GPU): argument validation mirrors the reference's check_contract
+(models/utils/sdeint.py:827-995); unsupported configurations raise instead of falling back."""
+import types
+
+import pytest
+import torch
+
+import trajsde_b200 as tb
+from helpers import DecoderSDE, EncoderSDE
+from trajsde_b200 import patch
+
+
+class _FakeCuda(torch.Tensor):
+    pass
+
+
+def test_sdeint_contract_errors_cpu():
+    sde = DecoderSDE()
+    ts = torch.linspace(0, 1, 11)
+    with pytest.raises(ValueError, match="must be a torch.Tensor"):
+        tb.sdeint(sde, [[0.0] * 64], ts, dt=0.1, method='euler')
+    with pytest.raises(ValueError, match="2-dimensional"):
+        tb.sdeint(sde, torch.zeros(64), ts, dt=0.1, method='euler')
+    with pytest.raises(NotImplementedError):
+        tb.sdeint(sde, torch.zeros(2, 64), ts, dt=0.1, method='euler', adaptive=True)
+    with pytest.raises(NotImplementedError):
+        tb.sdeint(sde, torch.zeros(2, 64), ts, dt=0.1, method='euler', logqp=True)
+    bad = DecoderSDE()
+    bad.noise_type = 'general'
+    with pytest.raises(NotImplementedError):
+        tb.sdeint(bad, torch.zeros(2, 64), ts, dt=0.1, method='euler')
+    del bad.noise_type
+    type(bad).noise_type  # class attr still there; emulate missing attribute with a bare object
+    with pytest.raises(ValueError, match="noise_type"):
+        tb.sdeint(types.SimpleNamespace(sde_type='ito'), torch.zeros(2, 64), ts, dt=0.1, method='euler')
+
+
+def test_default_mode_and_seed_api():
+    assert tb.get_default_mode() in ('tc_f16', 'exact')
+    old = tb.get_default_mode()
+    tb.set_default_mode('exact')
+    assert tb.get_default_mode() == 'exact'
+    with pytest.raises(ValueError):
+        tb.set_default_mode('fp8')
+    tb.set_default_mode(old)
+    tb.manual_seed(123)
+    from trajsde_b200 import solver as mod
+    a, b = mod._next_call_seed(), mod._next_call_seed()
+    tb.manual_seed(123)
+    assert (a, b) == (mod._next_call_seed(), mod._next_call_seed()) and a != b
+
+
+def test_install_rebinds_reference_module_globals():
+    """patch.install swaps the two module globals the reference stages call (dec…sde.py:11,88; enc…sep2.py:23,149)."""
+    def make(name, glob_name):
+        g = {glob_name: 'ORIGINAL', '__name__': name}
+        src = f"class Stage:\n    def forward(self):\n        return {glob_name}\n"
+        exec(src, g)
+        return g['Stage'](), g
+
+    dec, gd = make('SDEDecoder', 'sdeint')
+    enc, ge = make('LocalEncoderSDESepPara2', 'sdeint_dual')
+    model = types.SimpleNamespace(decoder=dec, encoder=enc)
+    saved = patch.install(model)
+    assert dec.forward() is tb.sdeint and enc.forward() is tb.sdeint_dual
+    patch.uninstall(saved)
+    assert dec.forward() == 'ORIGINAL' and enc.forward() == 'ORIGINAL'
+    with pytest.raises(KeyError):
+        patch.install(decoder=enc)
+
+
+def test_unsupported_net_layout_raises():
+    from trajsde_b200.solver import _mlp_params
+    import torch.nn as nn
+    n = types.SimpleNamespace(net=nn.Sequential(nn.Linear(66, 64), nn.ReLU(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, 64)))
+    with pytest.raises(NotImplementedError):
+        _mlp_params(n, 64, 'f')
+    n = types.SimpleNamespace(net=nn.Sequential(nn.Linear(34, 32), nn.Tanh(), nn.Linear(32, 32), nn.Tanh(), nn.Linear(32, 32)))
+    with pytest.raises(NotImplementedError):
+        _mlp_params(n, 32, 'f')
+    assert len(_mlp_params(EncoderSDE().g_argo, 1, 'g')) == 6

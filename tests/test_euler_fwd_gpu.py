@@ -1,0 +1,200 @@
+"""GPU parity of the fused forward solve against the oracle and the committed reference fixtures, through the
+reference-facing API (sdeint / sdeint_dual -> torch op -> C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+import trajsde_b200 as tb
+from conftest import sub
+from helpers import DecoderSDE, EncoderSDE, init_like_reference, load_net, make_dw, net_params
+from oracle import sde_oracle as so
+from trajsde_b200 import ops
+from trajsde_b200.schedule import euler_schedule
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+# Tolerances (max-abs over all steps/rows/channels; latents are O(1..20)):
+#   exact : fp32 FFMA with a different summation order than MKL sgemm, libm-accurate tanh -> rounding-level only
+#   tc_f16: fp16 operands (2^-11 relative, = TF32 operand precision) + MUFU tanh.approx, compounded over 61 steps
+TOL = {'exact': dict(atol=2e-4, rtol=2e-5), 'tc_f16': dict(atol=6e-2, rtol=2e-2)}
+
+
+def modes():
+    return ['exact', 'tc_f16']
+
+
+def decoder_from_golden(d):
+    sde = DecoderSDE()
+    load_net(sde.f_func, sub(d, 'f'))
+    load_net(sde.g_func, sub(d, 'g'))
+    return sde.to(DEV)
+
+
+@pytest.mark.parametrize('mode', modes())
+def test_decoder_golden_fixture(mode, golden_decoder):
+    """Reference fixture: SDEDecoder's own nets + torchsde.sdeint call, 48 rows x 61 steps, caller-supplied dW."""
+    d = golden_decoder
+    sde = decoder_from_golden(d)
+    y0 = torch.from_numpy(d['y0']).to(DEV)
+    ys = tb.sdeint(sde, y0, torch.from_numpy(d['ts']), bm=torch.from_numpy(d['dW']).to(DEV), dt=float(d['dt']),
+                   dt_min=0.1, rtol=1e-3, atol=1e-3, method='euler', mode=mode)
+    ref = torch.from_numpy(d['ys']).to(DEV)
+    assert ys.shape == ref.shape == (61, 48, 64)
+    assert torch.equal(ys[0], y0)
+    err = (ys - ref).abs().max().item()
+    rel = ((ys - ref).abs() / (ref.abs() + 1.0)).max().item()
+    print(f"[{mode}] decoder golden: max-abs {err:.3e}  max-rel {rel:.3e}")
+    assert torch.allclose(ys, ref, **TOL[mode])
+    assert sde.fnfe == 61 and sde.gnfe == 61
+    if mode == 'exact':
+        # ADE/FDE agreement through the unchanged heads
+        loc = so.decoder_loc_head_ref(sub(d, 'head', DEV), ys[1:].permute(1, 0, 2))
+        assert (loc - torch.from_numpy(d['loc']).to(DEV)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize('mode', modes())
+@pytest.mark.parametrize('rows', [1, 63, 64, 65, 200, 1000])
+def test_decoder_ragged_rows_vs_oracle(mode, rows):
+    sde = init_like_reference(DecoderSDE(), seed=rows).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    sched = euler_schedule(ts, 0.1)
+    g = torch.Generator().manual_seed(rows)
+    y0 = torch.relu(torch.randn(rows, 64, generator=g))
+    dW = make_dw(sched.h, rows, seed=rows + 1)
+    ref, _ = so.euler_solve_ref(net_params(sde.f_func), net_params(sde.g_func), y0, ts, 0.1, dW)
+    ys = tb.sdeint(sde, y0.to(DEV), ts, bm=dW.to(DEV), dt=0.1, method='euler', mode=mode)
+    assert torch.allclose(ys.cpu(), ref, **TOL[mode])
+
+
+def test_empty_batch():
+    sde = init_like_reference(DecoderSDE(), seed=0).to(DEV)
+    ys = tb.sdeint(sde, torch.zeros(0, 64, device=DEV), torch.linspace(0, 1, 11), dt=0.1, method='euler', mode='exact')
+    assert ys.shape == (11, 0, 64)
+
+
+@pytest.mark.parametrize('mode', modes())
+@pytest.mark.parametrize('F', [10, 30, 100, 200])
+def test_other_grids_incl_zero_step_intervals(mode, F):
+    """F=100/200: one output interval takes 0 steps, another 2 — several outputs per step."""
+    sde = init_like_reference(DecoderSDE(), seed=F).to(DEV)
+    ts = torch.linspace(0, 0.1 * F, F + 1)
+    sched = euler_schedule(ts, 0.1)
+    y0 = torch.relu(torch.randn(70, 64, generator=torch.Generator().manual_seed(F)))
+    dW = make_dw(sched.h, 70, seed=F) * 0.5
+    ref, _ = so.euler_solve_ref(net_params(sde.f_func), net_params(sde.g_func), y0, ts, 0.1, dW)
+    ys = tb.sdeint(sde, y0.to(DEV), ts, bm=dW.to(DEV), dt=0.1, method='euler', mode=mode)
+    tol = dict(TOL[mode])
+    if mode != 'exact':
+        tol['atol'] *= max(1.0, F / 60)
+    assert torch.allclose(ys.cpu(), ref, **tol)
+
+
+@pytest.mark.parametrize('mode', modes())
+def test_sdeint_dual_one_step_vs_golden_and_oracle(mode, golden_encoder):
+    """Encoder call site: one Euler step, dual g routed by nus_mask, returns (ys[2,rows,64], g[rows,64])."""
+    e = golden_encoder
+    sde = EncoderSDE()
+    load_net(sde.f_func, sub(e, 'f')); load_net(sde.g_nus, sub(e, 'g_nus')); load_net(sde.g_argo, sub(e, 'g_argo'))
+    sde = sde.to(DEV)
+    h0 = torch.from_numpy(e['h0']).to(DEV)
+    nus = torch.from_numpy(e['nus_mask']).to(DEV)
+    q = e['queries']
+    ts0 = torch.tensor([q[0, 0], q[0, 1]])
+    ys, g = tb.sdeint_dual(sde, h0, ts0, nus, bm=torch.from_numpy(e['dW'][0:1]).to(DEV), dt=0.1, rtol=1e-3, atol=1e-3,
+                           method='euler', mode=mode)
+    assert ys.shape == (2, 40, 64) and g.shape == (40, 64)
+    assert torch.equal(ys[0], h0)
+    ref_ys, ref_g = so.euler_solve_ref(sub(e, 'f'), sub(e, 'g_nus'), torch.from_numpy(e['h0']), ts0, 0.1,
+                                       torch.from_numpy(e['dW'][0:1]), torch.from_numpy(e['nus_mask']), sub(e, 'g_argo'))
+    assert torch.allclose(ys.cpu(), ref_ys, **TOL[mode])
+    gt = dict(atol=1e-6, rtol=1e-5) if mode == 'exact' else dict(atol=2e-3, rtol=0)
+    assert torch.allclose(g.cpu(), ref_g.expand(-1, 64), **gt)
+    assert torch.allclose(g.cpu(), torch.from_numpy(e['g'][0]), **gt)       # reference's own g of iteration 0
+
+
+@pytest.mark.parametrize('mode', modes())
+def test_encoder_loop_through_sdeint_dual_vs_golden(mode, golden_encoder):
+    """21 x [fused sdeint_dual + GRU jump in plain torch (stays on the reference path)] vs the reference loop fixture."""
+    e = golden_encoder
+    sde = EncoderSDE()
+    load_net(sde.f_func, sub(e, 'f')); load_net(sde.g_nus, sub(e, 'g_nus')); load_net(sde.g_argo, sub(e, 'g_argo'))
+    sde = sde.to(DEV)
+    pgru = sub(e, 'gru', DEV)
+    h = torch.from_numpy(e['h0']).to(DEV)
+    nus = torch.from_numpy(e['nus_mask']).to(DEV)
+    aa = torch.from_numpy(e['aa_out']).to(DEV)
+    am = torch.from_numpy(e['actors_mask']).to(DEV)
+    dW = torch.from_numpy(e['dW']).to(DEV)
+    lat, gs = [], []
+    for idx, (prev_t, t_i, t) in enumerate(tb.encoder_time_pairs()):
+        ys, g = tb.sdeint_dual(sde, h, torch.tensor([prev_t, t_i]), nus, bm=dW[idx:idx + 1], dt=0.1, method='euler', mode=mode)
+        h = so.gru_ref(pgru, ys[-1], aa[t], am[:, t])
+        lat.append(h); gs.append(g)
+    lat, gs = torch.stack(lat).cpu(), torch.stack(gs).cpu()
+    tol = dict(atol=2e-5, rtol=1e-5) if mode == 'exact' else dict(atol=2e-2, rtol=1e-2)
+    assert torch.allclose(lat, torch.from_numpy(e['latent_ys']), **tol)
+    assert torch.allclose(gs, torch.from_numpy(e['g']), atol=(1e-6 if mode == 'exact' else 3e-3), rtol=0)
+
+
+@pytest.mark.parametrize('mode', modes())
+def test_philox_mode_replays_through_oracle(mode):
+    """bm=None: in-kernel Philox.  The increments the kernel drew are dumped with trajsde_philox_dw and replayed
+    (a) through the supplied-dW path (must agree bit-for-bit in exact mode) and (b) through the oracle."""
+    sde = init_like_reference(DecoderSDE(), seed=9).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    sched = euler_schedule(ts, 0.1)
+    y0 = torch.relu(torch.randn(150, 64, generator=torch.Generator().manual_seed(9))).to(DEV)
+    ys = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode=mode, seed=77)
+    ys_again = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode=mode, seed=77)
+    assert torch.equal(ys, ys_again)                                     # deterministic
+    assert not torch.equal(ys, tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode=mode, seed=78))
+    dW = ops.philox_dw(ops.DeviceSchedule.get(sched, torch.device(DEV)), 150, 77, torch.device(DEV))
+    ys_sup = tb.sdeint(sde, y0, ts, bm=dW, dt=0.1, method='euler', mode=mode)
+    if mode == 'exact':
+        assert torch.equal(ys, ys_sup)
+    else:
+        assert torch.allclose(ys, ys_sup, atol=1e-4, rtol=1e-4)
+    ref, _ = so.euler_solve_ref(net_params(sde.f_func), net_params(sde.g_func), y0.cpu(), ts, 0.1, dW.cpu())
+    assert torch.allclose(ys.cpu(), ref, **TOL[mode])
+    # increments are N(0, h_k): check moments per step
+    z = dW / torch.sqrt(torch.from_numpy(sched.h)).view(-1, 1, 1).to(DEV)
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
+    assert abs((z ** 4).mean().item() - 3.0) < 0.05
+    # sharding invariance: rows [50:150] with row_offset=50 draw the same noise as in the full batch
+    part = tb.sdeint(sde, y0[50:], ts, dt=0.1, method='euler', mode=mode, seed=77, row_offset=50)
+    assert torch.allclose(part, ys[:, 50:], atol=0 if mode == 'exact' else 1e-4, rtol=0)
+
+
+def test_noncontiguous_y0_and_callable_bm():
+    sde = init_like_reference(DecoderSDE(), seed=4).to(DEV)
+    ts = torch.linspace(0, 1, 11)
+    sched = euler_schedule(ts, 0.1)
+    big = torch.randn(40, 130, generator=torch.Generator().manual_seed(4)).to(DEV)
+    y0 = big[:, 1:65]                                  # misaligned, strided view
+    dW = make_dw(sched.h, 40, seed=5).to(DEV)
+
+    class BM:
+        shape = (40, 64)
+        def __init__(self): self.k = 0
+        def __call__(self, ta, tb_):
+            self.k += 1
+            return dW[self.k - 1]
+    bm = BM()
+    ys = tb.sdeint(sde, y0, ts, bm=bm, dt=0.1, method='euler', mode='exact')
+    assert bm.k == sched.n_steps
+    ref, _ = so.euler_solve_ref(net_params(sde.f_func), net_params(sde.g_func), y0.cpu(), ts, 0.1, dW.cpu())
+    assert torch.allclose(ys.cpu(), ref, **TOL['exact'])
+
+
+def test_linearity_property_full_size_exact_vs_tc():
+    """Size-independent property at BASELINE config-2 scale is covered in bench.py; here: zero diffusion weight => the
+    solve is deterministic and independent of dW (g multiplies dW; sigmoid(-inf) -> 0)."""
+    sde = init_like_reference(DecoderSDE(), seed=2).to(DEV)
+    with torch.no_grad():
+        sde.g_func.net[4].weight.zero_(); sde.g_func.net[4].bias.fill_(-200.0)
+    ts = torch.linspace(0, 6, 61)
+    y0 = torch.relu(torch.randn(256, 64, generator=torch.Generator().manual_seed(2))).to(DEV)
+    a = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode='exact', seed=1)
+    b = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode='exact', seed=2)
+    assert torch.equal(a, b)

@@ -1,0 +1,114 @@
+"""ctypes binding of include/trajsde_b200.h.  There is NO fallback: a missing library raises at first use."""
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')
+
+ABI_VERSION = 1
+MODE_EXACT_F32 = 0
+MODE_TC_F16 = 1
+MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
+
+EXPORTED_SYMBOLS = (
+    'trajsde_abi_version', 'trajsde_last_error_string', 'trajsde_device_sm_count',
+    'trajsde_euler_fwd_workspace_bytes', 'trajsde_euler_fwd',
+    'trajsde_euler_bwd_workspace_bytes', 'trajsde_euler_bwd',
+    'trajsde_philox_dw',
+)
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class Mlp(C.Structure):
+    _fields_ = [(n, _fp) for n in ('w1', 'b1', 'w2', 'b2', 'w3', 'b3')]
+
+
+class Schedule(C.Structure):
+    _fields_ = [('n_steps', C.c_int32), ('n_outputs', C.c_int32), ('step_tab', _fp), ('out_begin', _fp), ('out_w', _fp)]
+
+
+class Noise(C.Structure):
+    _fields_ = [('dw', _fp), ('seed', C.c_uint64), ('row_offset', C.c_uint64), ('step_offset', C.c_uint32),
+                ('reserved', C.c_uint32)]
+
+
+class EulerFwdArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
+                ('alt_mask', _fp), ('noise', Noise), ('y0', _fp), ('y0_row_stride', C.c_int64), ('ys', _fp),
+                ('ys_t_stride', C.c_int64), ('ys_row_stride', C.c_int64), ('g_last', _fp), ('states', _fp),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class EulerBwdArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
+                ('alt_mask', _fp), ('noise', Noise), ('states', _fp), ('grad_ys', _fp), ('grad_ys_t_stride', C.c_int64),
+                ('grad_ys_row_stride', C.c_int64), ('grad_g_last', _fp), ('grad_y0', _fp), ('grad_drift', Mlp),
+                ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class Gru(C.Structure):
+    """GRU_Unit parameters (models/utils/ode_utils.py:111-134): three 2-layer nets, nn.Linear layout."""
+    _fields_ = [(n, _fp) for n in ('u1', 'ub1', 'u2', 'ub2', 'r1', 'rb1', 'r2', 'rb2', 'n1', 'nb1', 'n2', 'nb2')]
+
+
+class EncFwdArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
+                ('alt_mask', _fp), ('gru', Gru), ('noise', Noise), ('h0', _fp), ('h0_row_stride', C.c_int64),
+                ('aa_out', _fp), ('slot', _fp), ('obs_mask', _fp), ('obs_mask_row_stride', C.c_int64),
+                ('latent', _fp), ('g_out', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+class TrajsdeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libtrajsde_b200.so (built by `python -m trajsde_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise TrajsdeError(f"{LIB_PATH} is missing: build it with `python -m trajsde_b200.build`. "
+                               "trajsde_b200 has no CPU / PyTorch fallback by design.")
+        L = C.CDLL(LIB_PATH)
+        L.trajsde_abi_version.restype = C.c_int
+        L.trajsde_last_error_string.restype = C.c_char_p
+        L.trajsde_device_sm_count.restype = C.c_int
+        for name in ('trajsde_euler_fwd_workspace_bytes', 'trajsde_euler_bwd_workspace_bytes',
+                     'trajsde_enc_fwd_workspace_bytes'):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_int64
+                getattr(L, name).argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+        L.trajsde_euler_fwd.restype = C.c_int
+        L.trajsde_euler_fwd.argtypes = [C.POINTER(EulerFwdArgs), C.c_void_p]
+        L.trajsde_euler_bwd.restype = C.c_int
+        L.trajsde_euler_bwd.argtypes = [C.POINTER(EulerBwdArgs), C.c_void_p]
+        L.trajsde_philox_dw.restype = C.c_int
+        L.trajsde_philox_dw.argtypes = [C.POINTER(Schedule), C.POINTER(Noise), C.c_int64, C.c_void_p, C.c_void_p]
+        if hasattr(L, 'trajsde_enc_fwd'):
+            L.trajsde_enc_fwd.restype = C.c_int
+            L.trajsde_enc_fwd.argtypes = [C.POINTER(EncFwdArgs), C.c_void_p]
+        v = L.trajsde_abi_version()
+        if v != ABI_VERSION:
+            raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc < 0:
+        msg = lib().trajsde_last_error_string()
+        raise TrajsdeError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")
+    return rc

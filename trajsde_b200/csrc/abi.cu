@@ -1,0 +1,151 @@
+// C-ABI entry points (include/trajsde_b200.h): argument validation + dispatch.  No device allocation, no sync.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace trajsde {
+
+char* last_error_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int check_mlp(const TrajsdeMlp& m, const char* name) {
+  if (!m.w1 || !m.b1 || !m.w2 || !m.b2 || !m.w3 || !m.b3)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "%s: null weight pointer", name);
+  return TRAJSDE_OK;
+}
+
+static int check_sched(const TrajsdeSchedule& s) {
+  if (s.n_steps <= 0 || s.n_outputs < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "schedule: n_steps=%d n_outputs=%d", s.n_steps, s.n_outputs);
+  if (!s.step_tab || !s.out_begin || (s.n_outputs > 0 && !s.out_w))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "schedule: null table pointer");
+  if (!aligned16(s.step_tab)) return set_error(TRAJSDE_ERR_UNSUPPORTED, "schedule: step_tab must be 16-byte aligned");
+  return TRAJSDE_OK;
+}
+
+static int check_device() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(TRAJSDE_ERR_NO_DEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return set_error(TRAJSDE_ERR_NO_DEVICE, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+  if (major != 10) return set_error(TRAJSDE_ERR_NO_DEVICE, "device compute capability %d.x: this library is sm_100a only", major);
+  return TRAJSDE_OK;
+}
+
+}  // namespace trajsde
+
+using namespace trajsde;
+
+extern "C" {
+
+int trajsde_abi_version(void) { return TRAJSDE_ABI_VERSION; }
+
+const char* trajsde_last_error_string(void) { return last_error_buf(); }
+
+int trajsde_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error(TRAJSDE_ERR_NO_DEVICE, "no CUDA device");
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return set_error(TRAJSDE_ERR_CUDA, "cudaDeviceGetAttribute failed");
+  return sms;
+}
+
+int64_t trajsde_euler_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {
+  if (mode == TRAJSDE_MODE_EXACT_F32) return 0;
+  if (mode == TRAJSDE_MODE_TC_F16) return euler_fwd_tc_workspace_bytes(rows, n_steps, dual);
+  return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", mode);
+}
+
+int trajsde_euler_fwd(const TrajsdeEulerFwdArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeEulerFwdArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeEulerFwdArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows %lld < 0", (long long)a->rows);
+  int rc;
+  if ((rc = check_sched(a->sched)) != 0) return rc;
+  if ((rc = check_mlp(a->drift, "drift")) != 0) return rc;
+  if ((rc = check_mlp(a->diffusion, "diffusion")) != 0) return rc;
+  if (a->alt_mask && (rc = check_mlp(a->diffusion_alt, "diffusion_alt")) != 0) return rc;
+  if (a->rows == 0) return TRAJSDE_OK;
+  if (!a->y0 || !a->ys) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "y0/ys null");
+  if (!aligned16(a->y0) || !aligned16(a->ys) || (a->y0_row_stride & 3) || (a->ys_row_stride & 3) || (a->ys_t_stride & 3) ||
+      (a->noise.dw && !aligned16(a->noise.dw)) || (a->states && !aligned16(a->states)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "y0/ys/dw/states must be 16-byte aligned with strides multiple of 4 elements");
+  if (a->y0_row_stride < 64 || a->ys_row_stride < 64)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "row strides must be >= 64");
+  if ((rc = check_device()) != 0) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  switch (a->mode) {
+    case TRAJSDE_MODE_EXACT_F32:
+      return launch_euler_fwd_exact(*a, s);
+    case TRAJSDE_MODE_TC_F16: {
+      int64_t need = euler_fwd_tc_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
+      if (need < 0) return (int)need;
+      if (a->workspace_bytes < need || (need > 0 && !a->workspace))
+        return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+      return launch_euler_fwd_tc(*a, s);
+    }
+    default:
+      return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", a->mode);
+  }
+}
+
+int64_t trajsde_euler_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {
+  if (mode == TRAJSDE_MODE_EXACT_F32 || mode == TRAJSDE_MODE_TC_F16) return euler_bwd_exact_workspace_bytes(rows, n_steps, dual);
+  return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", mode);
+}
+
+int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeEulerBwdArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeEulerBwdArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  int rc;
+  if ((rc = check_sched(a->sched)) != 0) return rc;
+  if ((rc = check_mlp(a->drift, "drift")) != 0) return rc;
+  if ((rc = check_mlp(a->diffusion, "diffusion")) != 0) return rc;
+  if (a->alt_mask && (rc = check_mlp(a->diffusion_alt, "diffusion_alt")) != 0) return rc;
+  if (!a->grad_drift.w1 || !a->grad_drift.b1 || !a->grad_drift.w2 || !a->grad_drift.b2 || !a->grad_drift.w3 || !a->grad_drift.b3 ||
+      !a->grad_diffusion.w1 || !a->grad_diffusion.b1 || !a->grad_diffusion.w2 || !a->grad_diffusion.b2 || !a->grad_diffusion.w3 ||
+      !a->grad_diffusion.b3)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null gradient pointer");
+  if (a->alt_mask && (!a->grad_diffusion_alt.w1 || !a->grad_diffusion_alt.b1 || !a->grad_diffusion_alt.w2 ||
+                      !a->grad_diffusion_alt.b2 || !a->grad_diffusion_alt.w3 || !a->grad_diffusion_alt.b3))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null grad_diffusion_alt pointer with alt_mask set");
+  if (a->rows > 0 && (!a->states || !a->grad_y0)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "states/grad_y0 null");
+  if (a->grad_ys && ((a->grad_ys_row_stride & 3) || (a->grad_ys_t_stride & 3) || !aligned16(a->grad_ys)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_ys must be 16-byte aligned with strides multiple of 4 elements");
+  int64_t need = euler_bwd_exact_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
+  if (a->workspace_bytes < need || (need > 0 && !a->workspace))
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  if ((rc = check_device()) != 0) return rc;
+  return launch_euler_bwd_exact(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
+  if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
+  int rc;
+  if ((rc = check_sched(*sched)) != 0) return rc;
+  if (rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  if (rows == 0) return TRAJSDE_OK;
+  if (!dw_out || !aligned16(dw_out)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "dw_out null or misaligned");
+  if ((rc = check_device()) != 0) return rc;
+  return launch_philox_dw(*sched, *noise, rows, dw_out, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared device/host helpers for the trajsde_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/trajsde_b200.h"
+
+#define TS_DIM 64
+#define TS_IN1 66  // y (64) + sin t + cos t: row length of net[0].weight
+
+namespace trajsde {
+
+// ---- thread-local error string (C-ABI: trajsde_last_error_string) -------------------------------------------------
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define TS_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return ::trajsde::set_error(TRAJSDE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+// ---- Philox4x32-10 + Box–Muller ----------------------------------------------------------------------------------
+// Stream definition: key = (seed_lo, seed_hi); counter = (grow_lo, grow_hi, step, chunk) where
+// grow = global row id, step = step_offset + k, chunk = channel/4.  One call -> 4 uint32 -> 4 standard normals for
+// channels 4*chunk .. 4*chunk+3 via two Box–Muller pairs.
+__host__ __device__ __forceinline__ uint32_t ts_mulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r > 0) {
+      k.x += W0;
+      k.y += W1;
+    }
+    uint32_t hi0 = ts_mulhi(M0, c.x), lo0 = M0 * c.x;
+    uint32_t hi1 = ts_mulhi(M1, c.z), lo1 = M1 * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+  }
+  return c;
+}
+
+// uniform in (0,1]: (x + 0.5) * 2^-32 evaluated in fp32 (never 0).
+__device__ __forceinline__ float ts_u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+// 4 standard normals for (global row, step, chunk).
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t grow, uint32_t step, uint32_t chunk) {
+  uint4 r = philox4x32_10(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), step, chunk),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float u0 = ts_u01(r.x), u1 = ts_u01(r.y), u2 = ts_u01(r.z), u3 = ts_u01(r.w);
+  float r0 = sqrtf(-2.0f * __logf(u0));
+  float r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// ---- small math helpers -------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ts_sigmoid_exact(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float ts_tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float4 ld_nc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- launchers implemented in the kernel translation units --------------------------------------------------------
+int launch_euler_fwd_exact(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
+int launch_euler_bwd_exact(const TrajsdeEulerBwdArgs& a, cudaStream_t s);
+int64_t euler_bwd_exact_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
+int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
+int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
+int launch_philox_dw(const TrajsdeSchedule& sched, const TrajsdeNoise& noise, int64_t rows, float* out, cudaStream_t s);
+
+}  // namespace trajsde

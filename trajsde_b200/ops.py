@@ -1,0 +1,226 @@
+"""torch custom ops over the C ABI (include/trajsde_b200.h).  CUDA only, no CPU / eager fallback.
+
+    trajsde::euler_fwd   fused Euler–Maruyama solve (all steps, one launch)        -> ys, g_last, states
+    trajsde::euler_bwd   discretise-then-optimise backward (recompute from states)   -> grad_y0, grad_params...
+
+The ops do not own parameters: they read the caller's ``nn.Linear`` tensors on every call (reference checkpoints load
+unchanged) and return gradients for them through ``register_autograd``.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .schedule import EulerSchedule
+
+_N_MLP = 6  # w1 b1 w2 b2 w3 b3
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device-resident schedule tables
+# ---------------------------------------------------------------------------------------------------------------------
+class DeviceSchedule:
+    """TrajsdeSchedule tables uploaded once per (schedule, device)."""
+    _cache = {}
+
+    def __init__(self, sched: EulerSchedule, device: torch.device):
+        self.n_steps, self.n_outputs = sched.n_steps, sched.n_outputs
+        self.step_tab = torch.from_numpy(sched.step_tab()).to(device)
+        self.out_begin = torch.from_numpy(sched.out_begin()).to(device)
+        ow = sched.out_w() if sched.n_outputs else np.zeros((1, 2), np.float32)
+        self.out_w = torch.from_numpy(ow).to(device)
+
+    @classmethod
+    def get(cls, sched: EulerSchedule, device: torch.device) -> "DeviceSchedule":
+        key = (id(sched), str(device))
+        hit = cls._cache.get(key)
+        if hit is None or hit[0] is not sched:
+            if len(cls._cache) > 256:
+                cls._cache.clear()
+            hit = (sched, cls(sched, device))
+            cls._cache[key] = hit
+        return hit[1]
+
+
+def _mlp_struct(ts: Sequence[torch.Tensor]) -> _lib.Mlp:
+    m = _lib.Mlp()
+    m.w1, m.b1, m.w2, m.b2, m.w3, m.b3 = (t.data_ptr() for t in ts)
+    return m
+
+
+def _check_params(params: Sequence[torch.Tensor], dual: bool, device):
+    n = _N_MLP * (3 if dual else 2)
+    if len(params) != n:
+        raise ValueError(f"expected {n} parameter tensors, got {len(params)}")
+    shapes = [(64, 66), (64,), (64, 64), (64,), (64, 64), (64,)] + [(64, 66), (64,), (64, 64), (64,), (1, 64), (1,)] * (2 if dual else 1)
+    out = []
+    for t, shp in zip(params, shapes):
+        if tuple(t.shape) != shp:
+            raise ValueError(f"parameter shape {tuple(t.shape)} != expected {shp} (only the reference's 66-64-64-64/1 nets are supported)")
+        if t.dtype != torch.float32 or t.device != device:
+            raise ValueError("parameters must be float32 on the same CUDA device as y0")
+        out.append(t.detach().contiguous())
+    return out
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# forward
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("trajsde::euler_fwd", mutates_args=(), device_types="cuda")
+def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor,
+              out_w: torch.Tensor, n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor],
+              seed: int, row_offset: int, step_offset: int, mode: int, save_states: bool,
+              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """ys[T,rows,64] (T = n_outputs+1, ys[0] = y0), g_last[rows], states[S,rows,64] (empty unless save_states)."""
+    if y0.dim() != 2 or y0.shape[1] != 64 or y0.dtype != torch.float32:
+        raise ValueError("`y0` must be float32 of shape (rows, 64)")
+    dev = y0.device
+    rows = y0.shape[0]
+    S = step_tab.shape[0]
+    dual = alt_mask is not None
+    ps = _check_params(params, dual, dev)
+    y0c = y0.detach()
+    if y0c.stride(1) != 1 or y0c.stride(0) % 4 != 0 or y0c.data_ptr() % 16 != 0:
+        y0c = y0c.contiguous()
+    ys = torch.empty((n_outputs + 1, rows, 64), dtype=torch.float32, device=dev)
+    g_last = torch.empty((rows,), dtype=torch.float32, device=dev)
+    states = torch.empty((S if save_states else 0, rows, 64), dtype=torch.float32, device=dev)
+    a = _lib.EulerFwdArgs()
+    a.struct_bytes = C.sizeof(_lib.EulerFwdArgs)
+    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, 0
+    a.sched.n_steps, a.sched.n_outputs = S, n_outputs
+    a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
+    a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
+    mask_u8 = None
+    if dual:
+        if alt_mask.shape != (rows,) or alt_mask.dtype not in (torch.bool, torch.uint8):
+            raise ValueError("`nus_mask` must be a bool tensor of shape (rows,)")
+        mask_u8 = alt_mask.contiguous().view(torch.uint8)
+        a.diffusion_alt = _mlp_struct(ps[12:18])
+        a.alt_mask = mask_u8.data_ptr()
+    if dw is not None:
+        if tuple(dw.shape) != (S, rows, 64) or dw.dtype != torch.float32:
+            raise ValueError(f"`dW` must be float32 of shape ({S}, {rows}, 64): one slab per schedule step")
+        dw = dw.contiguous()
+        a.noise.dw = dw.data_ptr()
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    a.y0, a.y0_row_stride = y0c.data_ptr(), y0c.stride(0)
+    a.ys, a.ys_t_stride, a.ys_row_stride = ys.data_ptr(), ys.stride(0), ys.stride(1)
+    a.g_last = g_last.data_ptr()
+    a.states = states.data_ptr() if save_states and rows > 0 else None
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_euler_fwd_workspace_bytes(mode, rows, S, int(dual)), "trajsde_euler_fwd_workspace_bytes")
+    ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_euler_fwd(C.byref(a), _stream_ptr(dev)), "trajsde_euler_fwd")
+    return ys, g_last, states
+
+
+@euler_fwd.register_fake
+def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, save_states):
+    rows, S = y0.shape[0], step_tab.shape[0]
+    return (y0.new_empty((n_outputs + 1, rows, 64)), y0.new_empty((rows,)),
+            y0.new_empty((S if save_states else 0, rows, 64)))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("trajsde::euler_bwd", mutates_args=(), device_types="cuda")
+def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], states: torch.Tensor,
+              params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor, out_w: torch.Tensor,
+              n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor], seed: int, row_offset: int,
+              step_offset: int, mode: int) -> List[torch.Tensor]:
+    """[grad_y0] + gradients of every tensor in ``params`` (same order/shapes)."""
+    dev = states.device
+    S, rows = states.shape[0], states.shape[1]
+    dual = alt_mask is not None
+    ps = _check_params(params, dual, dev)
+    grad_y0 = torch.empty((rows, 64), dtype=torch.float32, device=dev)
+    gparams = [torch.zeros_like(p) for p in ps]
+    a = _lib.EulerBwdArgs()
+    a.struct_bytes = C.sizeof(_lib.EulerBwdArgs)
+    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, 0
+    a.sched.n_steps, a.sched.n_outputs = S, n_outputs
+    a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
+    a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
+    a.grad_drift, a.grad_diffusion = _mlp_struct(gparams[0:6]), _mlp_struct(gparams[6:12])
+    mask_u8 = None
+    if dual:
+        mask_u8 = alt_mask.contiguous().view(torch.uint8)
+        a.diffusion_alt, a.grad_diffusion_alt = _mlp_struct(ps[12:18]), _mlp_struct(gparams[12:18])
+        a.alt_mask = mask_u8.data_ptr()
+    if dw is not None:
+        dw = dw.contiguous()
+        a.noise.dw = dw.data_ptr()
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    states = states.contiguous()
+    a.states = states.data_ptr()
+    if grad_ys is not None:
+        if grad_ys.stride(2) != 1 or grad_ys.stride(0) % 4 or grad_ys.stride(1) % 4 or grad_ys.data_ptr() % 16:
+            grad_ys = grad_ys.contiguous()
+        a.grad_ys, a.grad_ys_t_stride, a.grad_ys_row_stride = grad_ys.data_ptr(), grad_ys.stride(0), grad_ys.stride(1)
+    if grad_g is not None:
+        grad_g = grad_g.contiguous()
+        a.grad_g_last = grad_g.data_ptr()
+    a.grad_y0 = grad_y0.data_ptr()
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_euler_bwd_workspace_bytes(mode, rows, S, int(dual)), "trajsde_euler_bwd_workspace_bytes")
+    ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_euler_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_euler_bwd")
+    return [grad_y0] + gparams
+
+
+@euler_bwd.register_fake
+def _(grad_ys, grad_g, states, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset,
+      step_offset, mode):
+    return [states.new_empty((states.shape[1], 64))] + [torch.empty_like(p) for p in params]
+
+
+def _setup_context(ctx, inputs, output):
+    (y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
+     save_states) = inputs
+    _, _, states = output
+    ctx.has_states = bool(save_states)
+    ctx.save_for_backward(states, step_tab, out_begin, out_w, *params)
+    ctx.dw, ctx.alt_mask = dw, alt_mask
+    ctx.meta = (n_outputs, seed, row_offset, step_offset, mode)
+    ctx.n_params = len(params)
+
+
+def _backward(ctx, grad_ys, grad_g, grad_states):
+    if not ctx.has_states:
+        raise RuntimeError("trajsde::euler_fwd was run with save_states=False; backward needs the saved step states")
+    states, step_tab, out_begin, out_w, *params = ctx.saved_tensors
+    n_outputs, seed, row_offset, step_offset, mode = ctx.meta
+    grads = euler_bwd(grad_ys, grad_g, states, list(params), step_tab, out_begin, out_w, n_outputs, ctx.dw, ctx.alt_mask,
+                      seed, row_offset, step_offset, mode)
+    return (grads[0], list(grads[1:]), None, None, None, None, None, None, None, None, None, None, None)
+
+
+euler_fwd.register_autograd(_backward, setup_context=_setup_context)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Brownian increments exactly as the kernels draw them (for replaying Philox runs through the oracle)
+# ---------------------------------------------------------------------------------------------------------------------
+def philox_dw(dsched: DeviceSchedule, rows: int, seed: int, device, row_offset: int = 0, step_offset: int = 0) -> torch.Tensor:
+    out = torch.empty((dsched.n_steps, rows, 64), dtype=torch.float32, device=device)
+    s = _lib.Schedule()
+    s.n_steps, s.n_outputs = dsched.n_steps, dsched.n_outputs
+    s.step_tab, s.out_begin, s.out_w = dsched.step_tab.data_ptr(), dsched.out_begin.data_ptr(), dsched.out_w.data_ptr()
+    n = _lib.Noise()
+    n.seed, n.row_offset, n.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().trajsde_philox_dw(C.byref(s), C.byref(n), rows, out.data_ptr(), _stream_ptr(device)),
+                   "trajsde_philox_dw")
+    return out
