@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — agent-SDE-steps/s of the fused SDE encoder+decoder forward on synthetic Argoverse-shaped batches.
+
+    python bench.py [--gpus N --steps K --warmup W]            our arm (one rank per GPU under torch.distributed.run for N>1)
+    python bench.py --impl reference [--steps K --warmup W]    the reference's CPU torchsde path (oracle port) on host cores
+
+A "step" is one forward pass of the SDE hot path over one synthetic batch: the encoder recurrence (21 x [one-step
+sdeint_dual + GRU jump], rows = agents + one perturbed target copy per scene) followed by the decoder solve (61 Euler
+steps, rows = 10 modes x agents).  Workload at every N: BASELINE.json configs[1] per GPU — 1024 scenes x 20 agents —
+scene-sharded with no forward collective (weak scaling; at N=8 this is configs[3]'s 8192-scene batch).
+metric = agent-SDE-steps/s = (enc_rows*21 + dec_rows*61) / step time, whole job.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "agent_sde_steps_per_s"
+UNIT = "agent-SDE-steps/s"
+ENC_STEPS, DEC_STEPS = 21, 61
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), float(d.get('bf16_tflops', 1590.5)), 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampler running during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                       '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), c[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU torchsde path restated (oracle port), timed on the host cores
+# ------------------------------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(scenes, agents, seed=0):
+    """One forward of the SDE path the way the reference runs it on CPU: internally generated Brownian increments, the
+    contract probe evaluation per sdeint call, GRU jump between encoder steps.  Returns (seconds, agent-SDE-steps)."""
+    from oracle import sde_oracle as so
+    from trajsde_b200 import synthetic as syn
+    b = syn.make_batch(scenes, agents, seed=seed)
+    enc, dec, gru = _cpu_modules()
+    pe = {k: {n: v.detach() for n, v in getattr(enc, k).net.state_dict().items()} for k in ('f_func', 'g_nus', 'g_argo')}
+    pd = {k: {n: v.detach() for n, v in getattr(dec, k).net.state_dict().items()} for k in ('f_func', 'g_func')}
+    pg = {n: v.detach() for n, v in gru.state_dict().items()}
+    ts = torch.linspace(0, 6, 61)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        dW_e = torch.randn(ENC_STEPS, b.enc_rows, 64) * (0.1 ** 0.5)
+        so.encoder_recurrence_ref(pe['f_func'], pe['g_nus'], pe['g_argo'], pg, b.enc_h0, b.aa_out, b.actors_mask, b.nus_mask,
+                                  dW_e, probe=True)
+        sched = so.euler_schedule_ref(ts, 0.1)
+        dW_d = torch.randn(DEC_STEPS, b.dec_rows, 64) * torch.sqrt(sched['h']).view(-1, 1, 1)
+        so.euler_solve_ref(pd['f_func'], pd['g_func'], b.dec_y0, ts, 0.1, dW_d, probe=True)
+    dt = time.perf_counter() - t0
+    return dt, b.enc_rows * ENC_STEPS + b.dec_rows * DEC_STEPS
+
+
+_CPU_MODS = None
+
+
+def _cpu_modules():
+    global _CPU_MODS
+    if _CPU_MODS is None:
+        from trajsde_b200 import synthetic as syn
+        _CPU_MODS = (syn.init_reference_style(syn.EncoderSDEFunc(), 1), syn.init_reference_style(syn.DecoderSDEFunc(), 2),
+                     syn.init_reference_style(syn.GRUUnit(), 3))
+    return _CPU_MODS
+
+
+def cpu_baseline(budget_s=12.0, scenes=32, agents=20):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_reference_pass(scenes, agents)             # warm-up
+    best, n, t_start = float('inf'), 0, time.perf_counter()
+    work = 0
+    while n < 3 or (time.perf_counter() - t_start < budget_s and n < 50):
+        dt, work = cpu_reference_pass(scenes, agents)
+        best = min(best, dt)
+        n += 1
+    return {"value": work / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"BASELINE configs[0]: {scenes} scenes x {agents} agents (enc {scenes * (agents + 1)} rows x 21 steps + GRU, "
+                      f"dec {scenes * agents * 10} rows x 61 steps), best of {n} passes, torch {torch.__version__} CPU, "
+                      f"oracle port of the reference torchsde path incl. its contract-probe f/g evaluation and randn increments",
+            "scenes_per_s": scenes / best}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    scenes, agents = 32, 20
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_pass(scenes, agents)
+    t0 = time.perf_counter()
+    work = 0
+    for _ in range(args.steps):
+        _, w = cpu_reference_pass(scenes, agents)
+        work += w
+    dt = time.perf_counter() - t0
+    v = work / dt
+    sample = (f"each step = one forward of BASELINE configs[0] ({scenes} scenes x {agents} agents) — a bounded sample of the "
+              f"configs[1] workload (same per-row work, 1/32 of the rows)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2-shaped SDE encoder+decoder forward, CPU sample of 32 scenes x 20 agents per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scenes_per_s": scenes * args.steps / dt,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--scenes', type=int, default=1024, help='scenes per GPU')
+    ap.add_argument('--agents', type=int, default=20)
+    ap.add_argument('--mode', default='tc_f16', choices=['tc_f16', 'exact'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch.distributed as dist
+    import trajsde_b200 as tb
+    from trajsde_b200 import encoder as enc_mod
+    from trajsde_b200 import ops, synthetic as syn
+    from trajsde_b200.schedule import encoder_schedule, euler_schedule
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mode = args.mode
+    enc_sde = syn.init_reference_style(syn.EncoderSDEFunc(), 1).to(dev)
+    dec_sde = syn.init_reference_style(syn.DecoderSDEFunc(), 2).to(dev)
+    gru = syn.init_reference_style(syn.GRUUnit(), 3).to(dev)
+    host = syn.make_batch(args.scenes, args.agents, seed=1000 + rank, pin=True)
+    E, M = host.enc_rows, host.dec_rows
+    work = E * ENC_STEPS + M * DEC_STEPS
+    ts_dec = torch.linspace(0, 6, 61)
+    sched_d, sched_e = euler_schedule(ts_dec, 0.1), encoder_schedule()
+
+    # resident inputs for `value`
+    res = {k: getattr(host, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    dW_d = torch.randn(DEC_STEPS, M, 64, device=dev, generator=gen) * torch.sqrt(torch.from_numpy(sched_d.h)).to(dev).view(-1, 1, 1)
+    dW_e = torch.randn(ENC_STEPS, E, 64, device=dev, generator=gen) * torch.sqrt(torch.from_numpy(sched_e.h)).to(dev).view(-1, 1, 1)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    dec_events = []
+
+    def step(inp, fixed_dw, seed=0, record=False):
+        with torch.no_grad():
+            lat, g = enc_mod.encoder_recurrence(enc_sde, gru, inp['enc_h0'], inp['aa_out'], inp['actors_mask'], inp['nus_mask'],
+                                                dW=dW_e if fixed_dw else None, seed=seed, mode=mode)
+            if record:
+                e0, e1 = ev(), ev()
+                e0.record()
+            ys = tb.sdeint(dec_sde, inp['dec_y0'], ts_dec, bm=dW_d if fixed_dw else None, dt=0.1, dt_min=0.1, rtol=1e-3,
+                           atol=1e-3, method='euler', mode=mode, seed=seed + 100, row_offset=rank * M)
+            if record:
+                e1.record()
+                dec_events.append((e0, e1))
+        return lat, ys
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- value: fixed dW (configs[1]), inputs resident in HBM ------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(res, True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = ops.LAUNCHES['n']
+    ms_fixed = timed(lambda i: step(res, True, record=True), args.steps)
+    launches = ops.LAUNCHES['n'] - n0
+    clocks = sampler.stop() if sampler else None
+    dec_ms = sorted(a.elapsed_time(b) for a, b in dec_events)
+    dec_ms_avg = sum(dec_ms) / len(dec_ms)
+    dec_events.clear()
+
+    # ---- Philox variant (bm=None, what the reference does in production), resident inputs -----------------------------------------
+    for i in range(2):
+        step(res, False, seed=i)
+    ms_philox = timed(lambda i: step(res, False, seed=10 + i, record=True), args.steps)
+    dec_ms_philox = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+    dec_events.clear()
+
+    # ---- e2e: public API with HOST buffers: H2D of every input from pinned memory + D2H of the results, bm=None ------------------------
+    out_lat = torch.empty((E, 64), dtype=torch.float32).pin_memory()
+    out_ys = torch.empty((M, 64), dtype=torch.float32).pin_memory()
+    h2d = sum(getattr(host, k).numel() * getattr(host, k).element_size() for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
+    d2h = out_lat.numel() * 4 + out_ys.numel() * 4
+
+    def e2e_step(i):
+        inp = {k: getattr(host, k).to(dev, non_blocking=True) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
+        lat, ys = step(inp, False, seed=20 + i)
+        out_lat.copy_(lat[-1], non_blocking=True)
+        out_ys.copy_(ys[-1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()          # the caller reads the result on the host every step
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- parity spot check at full size: 64 decoder rows against the CPU oracle under the same dW -------------------------------------
+    parity = None
+    if rank == 0:
+        from oracle import sde_oracle as so
+        idx = torch.linspace(0, M - 1, 64).long()
+        _, ys_full = step(res, True)
+        pd = {k: {n: v.detach().cpu() for n, v in getattr(dec_sde, k).net.state_dict().items()} for k in ('f_func', 'g_func')}
+        ref, _ = so.euler_solve_ref(pd['f_func'], pd['g_func'], host.dec_y0[idx], ts_dec, 0.1, dW_d[:, idx.to(dev)].cpu())
+        got = ys_full[:, idx.to(dev)].cpu()
+        parity = {"rows_checked": 64, "max_abs_err": float((got - ref).abs().max()),
+                  "max_rel_err": float(((got - ref).abs() / (ref.abs() + 1)).max()), "mode": mode}
+        del ys_full
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_gbs, bf16_tf, peak_src = peaks()
+    T = sched_d.n_outputs + 1
+    dec_bytes_fixed = M * 256 * (1 + T + DEC_STEPS)             # y0 in + ys (incl. ys[0]) out + dW in
+    dec_bytes_philox = M * 256 * (1 + T)
+    ach = dec_bytes_fixed / (dec_ms_avg * 1e-3) / 1e9
+    ach_p = dec_bytes_philox / (dec_ms_philox * 1e-3) / 1e9
+    flops = 41856.0 * M * DEC_STEPS
+    res_json = {
+        "metric": METRIC, "value": world * work / (ms_fixed / args.steps * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_fixed / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands / f32 accumulate+state" if mode == 'tc_f16' else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1] per GPU: sdesepenc+sdedec forward, {args.scenes} scenes x {args.agents} agents "
+                               f"(encoder {E} rows x 21 steps + GRU jump, decoder {M} rows x 61 steps -> 60 outputs), caller-supplied dW",
+                   "kernel_mode": mode, "scenes_per_gpu": args.scenes, "parallelism": f"scene-sharded dp{world}, no forward collective",
+                   "cache": "inputs larger than L2 (dW 3.2 GB + ys 3.2 GB per step vs 126 MB L2)",
+                   "e2e_note": "e2e uses bm=None (in-kernel Philox, like the reference's BrownianInterval default) with all inputs "
+                               "copied from pinned host memory and final latents copied back every step"},
+        "scenes_per_s": world * args.scenes / (ms_fixed / args.steps * 1e-3),
+        "philox": {"value": world * work / (ms_philox / args.steps * 1e-3), "ms_per_step": ms_philox / args.steps,
+                   "decoder_ms": dec_ms_philox, "decoder_agent_steps_per_s": M * DEC_STEPS / (dec_ms_philox * 1e-3),
+                   "roofline_frac_hbm": ach_p / hbm_gbs},
+        "decoder": {"ms": dec_ms_avg, "agent_steps_per_s": M * DEC_STEPS / (dec_ms_avg * 1e-3), "rows": M, "steps": DEC_STEPS},
+        "encoder": {"ms": ms_fixed / args.steps - dec_ms_avg, "rows": E, "steps": ENC_STEPS,
+                    "note": "21 x [fused one-step sdeint_dual launch + GRU jump on the reference PyTorch path]"},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
+                     "kernel": "euler_fwd_tc_kernel (decoder solve)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dec_bytes_fixed,
+                     "tensor_frac_of_bf16_peak": flops / (dec_ms_avg * 1e-3) / 1e12 / bf16_tf,
+                     "sfu_note": "257 MUFU ops per agent-step at 16/clk/SM (measured, profiles/) bound the kernel below both roofs"},
+        "e2e": {"value": world * work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "parity": parity,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        res_json["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(res_json))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -94,7 +94,7 @@ def diffusion_dual_ref(pg_nus: P, pg_argo: P, t, y: torch.Tensor, nus_mask: torc
 # ------------------------------------------------------------------------------------------------------------------
 def euler_solve_ref(pf: P, pg: P, y0: torch.Tensor, ts: torch.Tensor, dt: float, dW: torch.Tensor,
                     nus_mask: Optional[torch.Tensor] = None, pg_argo: Optional[P] = None,
-                    return_states: bool = False):
+                    return_states: bool = False, probe: bool = False):
     """``ys[T,rows,64], g_last[rows,1]`` (+ ``states[S+1,rows,64]``) for caller-supplied increments ``dW[S,rows,64]``.
 
     ``dW[k]`` is consumed by schedule step k (one slab per Euler step, incl. the sliver step).
@@ -104,6 +104,9 @@ def euler_solve_ref(pf: P, pg: P, y0: torch.Tensor, ts: torch.Tensor, dt: float,
     """
     sched = euler_schedule_ref(ts, dt)
     S = sched['t0'].numel()
+    if probe:   # check_contract's shape probe: one wasted f and g evaluation per call (sdeint.py:913-921); timing fidelity only
+        drift_ref(pf, ts[0], y0)
+        diffusion_ref(pg, ts[0], y0) if nus_mask is None else diffusion_dual_ref(pg, pg_argo, ts[0], y0, nus_mask)
     assert dW.shape[0] == S, f"dW must have one slab per schedule step: {dW.shape[0]} vs {S}"
     dtype = y0.dtype
     Y = [y0]
@@ -168,7 +171,7 @@ def encoder_time_pairs_ref(max_past_t: float = 2.0, historical_steps: int = 21) 
 
 def encoder_recurrence_ref(pf: P, pg_nus: P, pg_argo: P, pgru: P, h0: torch.Tensor, aa_out: torch.Tensor,
                            actors_mask: torch.Tensor, nus_mask: torch.Tensor, dW: torch.Tensor, dt: float = 0.1,
-                           max_past_t: float = 2.0):
+                           max_past_t: float = 2.0, probe: bool = False):
     """21×(one-step ``sdeint_dual`` + ``GRU_Unit``).  ``h0[rows,64]``, ``aa_out[21,rows,64]``, ``actors_mask[rows,21]``,
     ``dW[21,rows,64]`` (slab idx = loop iteration).  Returns ``latent_ys[21,rows,64]`` (post-GRU, loop order) and
     ``g[21,rows,1]`` (pre-step diffusion of each iteration)."""
@@ -177,7 +180,7 @@ def encoder_recurrence_ref(pf: P, pg_nus: P, pg_argo: P, pgru: P, h0: torch.Tens
     latent, gs = [], []
     for idx, (prev_t, t_i, t) in enumerate(encoder_time_pairs_ref(max_past_t, hist)):
         time_points = torch.tensor([prev_t, t_i])                          # enc…sep2.py:142
-        ys, g = euler_solve_ref(pf, pg_nus, prev_hidden, time_points, dt, dW[idx:idx + 1], nus_mask, pg_argo)
+        ys, g = euler_solve_ref(pf, pg_nus, prev_hidden, time_points, dt, dW[idx:idx + 1], nus_mask, pg_argo, probe=probe)
         yi_ode = ys[-1]                                                    # :165
         yi = gru_ref(pgru, yi_ode, aa_out[t].to(h0.dtype), actors_mask[:, t])  # :169
         prev_hidden = yi

@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
         log.append(f'== {src}\n{out}')
         if p.returncode != 0:
             raise RuntimeError(f'nvcc failed for {src}:\n{" ".join(cmd)}\n{out}')
-    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcuda']
+    cmd = [_nvcc(), '-shared', '-o', LIB_PATH] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}')

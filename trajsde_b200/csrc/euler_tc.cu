@@ -1,6 +1,547 @@
-// placeholder: tcgen05 forward lands here
+// Tensor-core Euler–Maruyama forward (TRAJSDE_MODE_TC_F16): persistent sm_100a kernel, tcgen05 + TMEM + TMA.
+//
+// Same reference functions as euler_exact.cu (models/utils/sdeint.py:340-384,477-485,544; dec_hivt_nusargo_sde.py:119-127,
+// 154-158,180-195; enc_hivt_nusargo_sde_sep2.py:390-398,436-440,462-482), different machine mapping:
+//
+//   * one CTA per SM, two 128-row tiles ("slots") in flight so one slot's tcgen05.mma overlaps the other's epilogue;
+//   * per slot: 4 epilogue warps (thread = one row; its 64-channel fp32 state stays in registers for ALL steps) and one
+//     MMA-issuer warp (one elected thread issues tcgen05.mma / tcgen05.commit);
+//   * drift/diffusion weights are packed once per call (fp16, 128B-swizzled K-major UMMA tiles) and staged once per CTA
+//     into shared memory with a bulk TMA copy; the five 64x64 layers of a step are three dependent MMA phases:
+//         P1: [z1f | z1g (| z1g_alt)] = y  . [W1y ; V1y (; V1y_alt)]^T        M=128, N=128 (192), K=64
+//         P2:  z2f = h1f . W2^T ,  z2g = h1g . V2^T (, z2g_alt = h1g . V2alt^T) M=128, N=64 each
+//         P3:  f   = h2f . W3^T                                                 M=128, N=64
+//     accumulators live in TMEM (fp32) and are read back with tcgen05.ld; bias + MUFU tanh + fp16 pack happen in
+//     registers and the next operand tile is written straight back to swizzled shared memory;
+//   * g's last layer (64 -> 1), the sigmoid, the Euler update y' = y + f h + g dW and the output interpolation are fused
+//     into the P3 epilogue in fp32;
+//   * HBM traffic: y0 tile in (TMA), dW tile per step in (TMA, when caller-supplied), ys tile per output out (TMA store
+//     from the same staging buffer), optional states tile per step out.  Nothing else touches global memory.
+//   * dual diffusion (encoder): each row evaluates only ITS net's activations (the other net's MMA rows are ignored), so
+//     the routing by nus_mask costs MMA columns but no extra MUFU work.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace trajsde {
-int64_t euler_fwd_tc_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
-int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs&, cudaStream_t) { return set_error(TRAJSDE_ERR_UNSUPPORTED, "TC mode not built yet"); }
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_SLOTS = 2;
+constexpr int EPI_WARPS_PER_SLOT = 4;
+constexpr int NUM_THREADS = (NUM_SLOTS * EPI_WARPS_PER_SLOT + NUM_SLOTS) * 32;  // 8 epilogue warps + 2 MMA warps = 320
+
+// ---- packed weight image (bytes) -----------------------------------------------------------------------------------------
+constexpr uint32_t IMG_B1 = 0;            // [192 rows][64] f16 SW128: W1y | V1y | V1y_alt
+constexpr uint32_t IMG_W2 = 24576;        // [64][64]
+constexpr uint32_t IMG_V2 = 32768;
+constexpr uint32_t IMG_V2A = 40960;
+constexpr uint32_t IMG_W3 = 49152;
+constexpr uint32_t IMG_VEC = 57344;       // fp32 vectors
+constexpr uint32_t IMG_BYTES = 59392;     // 58 KB
+// fp32 vector slots (float index inside IMG_VEC)
+constexpr int VEC_B2 = 0, VEC_C2 = 64, VEC_C2A = 128, VEC_B3 = 192, VEC_W3G = 256, VEC_W3GA = 320, VEC_C3 = 384, VEC_C3A = 385;
+constexpr int BIAS1_LD = 192;             // per-step layer-1 bias row: b1f | c1 | c1_alt (time features folded in)
+
+// ---- shared memory map -----------------------------------------------------------------------------------------------------
+constexpr uint32_t SLOT_BYTES = 81920;    // A0 16K | A1f 16K | A1g 16K | X 32K
+constexpr uint32_t OFF_A0 = 0, OFF_A1F = 16384, OFF_A1G = 32768, OFF_X = 49152;
+constexpr uint32_t SMEM_SLOTS = IMG_BYTES;
+constexpr uint32_t SMEM_BARS = SMEM_SLOTS + NUM_SLOTS * SLOT_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 128;
+constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack for manual 1024-B alignment
+
+struct TcParams {
+  TrajsdeEulerFwdArgs a;
+  const uint8_t* img;      // packed weight image in workspace
+  const float* bias1;      // [S][192]
+  int num_tiles;
+  int dual;
+};
+
+// ---- weight packing -----------------------------------------------------------------------------------------------------------
+__global__ void tc_pack_kernel(TrajsdeEulerFwdArgs a, uint8_t* __restrict__ img, float* __restrict__ bias1, int dual) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  __half* b1 = reinterpret_cast<__half*>(img + IMG_B1);
+  for (int idx = tid; idx < 192 * 64; idx += nth) {
+    const int n = idx >> 6, k = idx & 63, net = n >> 6, r = n & 63;
+    const float* w = net == 0 ? a.drift.w1 : net == 1 ? a.diffusion.w1 : (dual ? a.diffusion_alt.w1 : nullptr);
+    const float v = w ? w[r * TS_IN1 + k] : 0.f;
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(b1) + sw128_off_h(n, k)) = __float2half_rn(v);
+  }
+  for (int idx = tid; idx < 4 * 64 * 64; idx += nth) {
+    const int m = idx >> 12, n = (idx >> 6) & 63, k = idx & 63;
+    const float* w = m == 0 ? a.drift.w2 : m == 1 ? a.diffusion.w2 : m == 2 ? (dual ? a.diffusion_alt.w2 : nullptr) : a.drift.w3;
+    const uint32_t off = m == 0 ? IMG_W2 : m == 1 ? IMG_V2 : m == 2 ? IMG_V2A : IMG_W3;
+    const float v = w ? w[n * 64 + k] : 0.f;
+    *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(v);
+  }
+  float* vec = reinterpret_cast<float*>(img + IMG_VEC);
+  for (int i = tid; i < 512; i += nth) {
+    float v = 0.f;
+    const int c = i & 63;
+    if (i < 64) v = a.drift.b2[c];
+    else if (i < 128) v = a.diffusion.b2[c];
+    else if (i < 192) v = dual ? a.diffusion_alt.b2[c] : 0.f;
+    else if (i < 256) v = a.drift.b3[c];
+    else if (i < 320) v = a.diffusion.w3[c];
+    else if (i < 384) v = dual ? a.diffusion_alt.w3[c] : 0.f;
+    else if (i == VEC_C3) v = a.diffusion.b3[0];
+    else if (i == VEC_C3A) v = dual ? a.diffusion_alt.b3[0] : 0.f;
+    vec[i] = v;
+  }
+  const int S = a.sched.n_steps;
+  for (int idx = tid; idx < S * BIAS1_LD; idx += nth) {
+    const int k = idx / BIAS1_LD, n = idx % BIAS1_LD, net = n >> 6, r = n & 63;
+    const TrajsdeMlp* m = net == 0 ? &a.drift : net == 1 ? &a.diffusion : (dual ? &a.diffusion_alt : nullptr);
+    float v = 0.f;
+    if (m) {
+      const float sn = a.sched.step_tab[4 * k + 2], cs = a.sched.step_tab[4 * k + 3];
+      v = fmaf(m->w1[r * TS_IN1 + 65], cs, fmaf(m->w1[r * TS_IN1 + 64], sn, m->b1[r]));
+    }
+    bias1[idx] = v;
+  }
 }
+
+// ---- epilogue helpers -------------------------------------------------------------------------------------------------------
+// tanh(acc + bias) for 32 accumulator columns, packed to fp16 and stored as 4 x 16-byte chunks of an operand row.
+__device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* tile_row_base,
+                                                 uint32_t row, uint32_t chunk0) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = q * 8 + e * 2;
+      const float2 b = *reinterpret_cast<const float2*>(bias + j);
+      const float t0 = ts_tanh_approx(__uint_as_float(v[j]) + b.x);
+      const float t1 = ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y);
+      p[e] = pack_f16x2(t0, t1);
+    }
+    *reinterpret_cast<uint4*>(tile_row_base + (((chunk0 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_dw,
+                    const __grid_constant__ CUtensorMap tm_ys, const __grid_constant__ CUtensorMap tm_st) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const TrajsdeEulerFwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.sched.n_steps;
+  const bool dual = p.dual != 0;
+  const bool has_dw = a.noise.dw != nullptr;
+  const bool save_states = a.states != nullptr;
+
+  // barriers: [0] weights, per slot: opnd (128 arrivals), acc (1, tcgen05.commit), tma (1 + tx)
+  const uint32_t bar_w = base + SMEM_BARS;
+  auto bar_opnd = [&](int s) { return base + SMEM_BARS + 8u + 24u * s; };
+  auto bar_acc = [&](int s) { return base + SMEM_BARS + 16u + 24u * s; };
+  auto bar_tma = [&](int s) { return base + SMEM_BARS + 24u + 24u * s; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 96);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int s = 0; s < NUM_SLOTS; ++s) {
+      mbar_init(bar_opnd(s), EPI_WARPS_PER_SLOT * 32);
+      mbar_init(bar_acc(s), 1);
+      mbar_init(bar_tma(s), 1);
+    }
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_y0);
+    tma_prefetch_desc(&tm_dw);
+    tma_prefetch_desc(&tm_ys);
+    tma_prefetch_desc(&tm_st);
+  }
+  if (warp == NUM_SLOTS * EPI_WARPS_PER_SLOT) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {  // stage the packed weights once per CTA (bulk TMA copy)
+    mbar_arrive_expect_tx(bar_w, IMG_BYTES);
+    bulk_load_1d(base, p.img, IMG_BYTES, bar_w);
+  }
+
+  const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
+
+  if (warp < NUM_SLOTS * EPI_WARPS_PER_SLOT) {
+    // =============================================== EPILOGUE WARPS ===============================================
+    const int slot = warp / EPI_WARPS_PER_SLOT;
+    const int quad = warp % EPI_WARPS_PER_SLOT;           // TMEM lane quadrant this warp may access
+    const uint32_t row = quad * 32 + lane;                // row inside the tile == TMEM lane
+    const bool leader = (quad == 0 && lane == 0);
+    uint8_t* slot_sm = sm + SMEM_SLOTS + slot * SLOT_BYTES;
+    const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
+    uint8_t* a0_row = slot_sm + OFF_A0 + row * 128;
+    uint8_t* a1f_row = slot_sm + OFF_A1F + row * 128;
+    uint8_t* a1g_row = slot_sm + OFF_A1G + row * 128;
+    uint8_t* x_row = slot_sm + OFF_X + row * 128;         // + half*16384 + swizzled chunk
+    uint8_t* st_row = slot_sm + OFF_A1F + row * 128;      // states staging aliases A1f|A1g (32 KB, free during P3 epilogue)
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256;
+    const uint32_t bar_id = 1 + slot;
+    uint32_t par_acc = 0, par_tma = 0;
+
+    mbar_wait(bar_w, 0);
+
+    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+      const int64_t row0 = (int64_t)tile * TILE_M;
+      const int64_t grow = row0 + row;
+      const bool valid = grow < a.rows;
+      const bool use_alt = dual && valid && (a.alt_mask[grow] == 0);
+      const int gcol = use_alt ? 128 : 64;               // D1/D2 column block and bias1 offset of this row's diffusion net
+      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2);
+      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G);
+      const float c3 = vec[use_alt ? VEC_C3A : VEC_C3];
+
+      // ---- tile prologue: y0 tile -> X (TMA), registers, ys[0], A0 -----------------------------------------------
+      if (leader) {
+        mbar_arrive_expect_tx(bar_tma(slot), 32768);
+        tma_load_3d(slot_u32 + OFF_X, &tm_y0, bar_tma(slot), 0, (int)row0, 0);
+        tma_load_3d(slot_u32 + OFF_X + 16384, &tm_y0, bar_tma(slot), 32, (int)row0, 0);
+      }
+      mbar_wait(bar_tma(slot), par_tma);
+      par_tma ^= 1;
+      float y[64];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(x_row + (c >> 3) * 16384 + (((c & 7) ^ (row & 7u)) << 4));
+        y[4 * c] = v.x; y[4 * c + 1] = v.y; y[4 * c + 2] = v.z; y[4 * c + 3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(a0_row + ((q ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_opnd(slot));                       // A0 ready -> P1 of step 0
+      named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);   // everyone has read X
+      if (leader) {
+        tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, (int)row0, 0);          // ys[0] = y0
+        tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, (int)row0, 0);
+        tma_store_commit();
+        tma_store_wait_read0();
+        if (has_dw) {
+          mbar_arrive_expect_tx(bar_tma(slot), 32768);
+          tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, (int)row0, 0);
+          tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, (int)row0, 0);
+        }
+      }
+
+      for (int k = 0; k < S; ++k) {
+        const float4 stp = *reinterpret_cast<const float4*>(a.sched.step_tab + 4 * k);
+        const float h = stp.y;
+        const float* bias1 = p.bias1 + (size_t)k * BIAS1_LD;
+        named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);  // leader's store-read wait of the previous step is behind us
+
+        // ---- epilogue 1: h1f = tanh(z1f + b1f(t)), h1g = tanh(z1g + c1(t)) -> A1f, A1g --------------------------------
+        mbar_wait(bar_acc(slot), par_acc);
+        par_acc ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            tmem_ld_32x32b_x32(tm_lane + hf * 32, v);
+            tc_wait_ld();
+            act32_to_operand(v, bias1 + hf * 32, a1f_row, row, hf * 4);
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            tmem_ld_32x32b_x32(tm_lane + gcol + hf * 32, v);
+            tc_wait_ld();
+            act32_to_operand(v, bias1 + gcol + hf * 32, a1g_row, row, hf * 4);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(slot));
+
+        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 ; g = sigmoid(w3 . tanh(z2g + c2) + c3) -------------------------------
+        mbar_wait(bar_acc(slot), par_acc);
+        par_acc ^= 1;
+        tc_fence_after();
+        float gdot = 0.f;
+        {
+          uint32_t v[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            tmem_ld_32x32b_x32(tm_lane + hf * 32, v);
+            tc_wait_ld();
+            act32_to_operand(v, vec + VEC_B2 + hf * 32, a0_row, row, hf * 4);
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            tmem_ld_32x32b_x32(tm_lane + gcol + hf * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(c2v + hf * 32 + j);
+              const float4 w = *reinterpret_cast<const float4*>(w3v + hf * 32 + j);
+              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gdot);
+              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gdot);
+              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gdot);
+              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gdot);
+            }
+          }
+        }
+        const float g = __fdividef(1.0f, 1.0f + __expf(-(gdot + c3)));
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(slot));
+
+        // ---- epilogue 3: f = z3 + b3 ; y' = y + f h + g dW ; outputs ; A0 <- y' -------------------------------------------
+        if (save_states) {  // Y[k] -> states staging (aliases A1f|A1g, both consumed by P2 already)
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            *reinterpret_cast<float4*>(st_row + (c >> 3) * 16384 + (((c & 7) ^ (row & 7u)) << 4)) =
+                make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
+        }
+        const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
+        const bool has_out = oe > ob;
+        float w0 = 0.f, w1 = 1.f;
+        if (has_out) {
+          w0 = a.sched.out_w[2 * ob];
+          w1 = a.sched.out_w[2 * ob + 1];
+        }
+        const float sqrt_h = sqrtf(h);
+        mbar_wait(bar_acc(slot), par_acc);
+        par_acc ^= 1;
+        tc_fence_after();
+        if (has_dw) {
+          mbar_wait(bar_tma(slot), par_tma);
+          par_tma ^= 1;
+        }
+        {
+          uint32_t v[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            tmem_ld_32x32b_x32(tm_lane + 192 + hf * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int cc = hf * 8 + c;                    // 4-channel chunk index 0..15
+              float4* xp = reinterpret_cast<float4*>(x_row + hf * 16384 + ((c ^ (row & 7u)) << 4));
+              float4 dw;
+              if (has_dw) {
+                dw = *xp;
+              } else {
+                const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset,
+                                                 a.noise.step_offset + (uint32_t)k, (uint32_t)cc);
+                dw = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
+              }
+              const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cc * 4);
+              float yn[4];
+              yn[0] = fmaf(g, dw.x, fmaf(__uint_as_float(v[4 * c]) + b3.x, h, y[4 * cc]));
+              yn[1] = fmaf(g, dw.y, fmaf(__uint_as_float(v[4 * c + 1]) + b3.y, h, y[4 * cc + 1]));
+              yn[2] = fmaf(g, dw.z, fmaf(__uint_as_float(v[4 * c + 2]) + b3.z, h, y[4 * cc + 2]));
+              yn[3] = fmaf(g, dw.w, fmaf(__uint_as_float(v[4 * c + 3]) + b3.w, h, y[4 * cc + 3]));
+              if (has_out) {
+                *xp = make_float4(fmaf(w1, yn[0], w0 * y[4 * cc]), fmaf(w1, yn[1], w0 * y[4 * cc + 1]),
+                                  fmaf(w1, yn[2], w0 * y[4 * cc + 2]), fmaf(w1, yn[3], w0 * y[4 * cc + 3]));
+                for (int o = ob + 1; o < oe; ++o) {          // rare: several outputs completed by one step
+                  if (valid) {
+                    const float v0 = a.sched.out_w[2 * o], v1 = a.sched.out_w[2 * o + 1];
+                    float* dst = a.ys + (int64_t)(o + 1) * a.ys_t_stride + grow * a.ys_row_stride + cc * 4;
+                    *reinterpret_cast<float4*>(dst) =
+                        make_float4(fmaf(v1, yn[0], v0 * y[4 * cc]), fmaf(v1, yn[1], v0 * y[4 * cc + 1]),
+                                    fmaf(v1, yn[2], v0 * y[4 * cc + 2]), fmaf(v1, yn[3], v0 * y[4 * cc + 3]));
+                  }
+                }
+              }
+              y[4 * cc] = yn[0]; y[4 * cc + 1] = yn[1]; y[4 * cc + 2] = yn[2]; y[4 * cc + 3] = yn[3];
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(a0_row + ((q ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        if (k == S - 1 && a.g_last && valid) a.g_last[grow] = g;
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(slot));                       // A0 = y' ready -> P1 of step k+1 (or next tile: harmless extra phase)
+        named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);   // X / states staging fully written
+        if (leader) {
+          if (has_out) {
+            tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, (int)row0, ob + 1);
+            tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, (int)row0, ob + 1);
+          }
+          if (save_states) {
+            tma_store_3d(&tm_st, slot_u32 + OFF_A1F, 0, (int)row0, k);
+            tma_store_3d(&tm_st, slot_u32 + OFF_A1F + 16384, 32, (int)row0, k);
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (has_dw && k + 1 < S) {
+            mbar_arrive_expect_tx(bar_tma(slot), 32768);
+            tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, (int)row0, k + 1);
+            tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, (int)row0, k + 1);
+          }
+        }
+      }
+      // The last step's arrive on bar_opnd announced an A0 nobody multiplies: the MMA warp consumes that phase below.
+      named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);
+    }
+    if (leader) tma_store_wait_all0();
+  } else {
+    // =============================================== MMA ISSUER WARPS ===============================================
+    const int slot = warp - NUM_SLOTS * EPI_WARPS_PER_SLOT;
+    if (lane == 0) {
+      const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
+      const uint32_t d_base = tmem_base + slot * 256;
+      const uint32_t n1 = dual ? 192u : 128u;
+      const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, n1);
+      const uint32_t idesc_64 = umma_idesc_f16(TILE_M, 64);
+      const uint64_t dA0 = umma_desc_sw128(slot_u32 + OFF_A0);
+      const uint64_t dA1f = umma_desc_sw128(slot_u32 + OFF_A1F);
+      const uint64_t dA1g = umma_desc_sw128(slot_u32 + OFF_A1G);
+      const uint64_t dB1 = umma_desc_sw128(base + IMG_B1);
+      const uint64_t dW2 = umma_desc_sw128(base + IMG_W2);
+      const uint64_t dV2 = umma_desc_sw128(base + IMG_V2);
+      const uint64_t dV2a = umma_desc_sw128(base + IMG_V2A);
+      const uint64_t dW3 = umma_desc_sw128(base + IMG_W3);
+      uint32_t par_op = 0;
+      mbar_wait(bar_w, 0);
+      for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+        for (int k = 0; k < S; ++k) {
+          // P1
+          mbar_wait(bar_opnd(slot), par_op);
+          par_op ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, dA0 + 2 * kk, dB1 + 2 * kk, idesc_p1, kk > 0);
+          tc_commit(bar_acc(slot));
+          // P2
+          mbar_wait(bar_opnd(slot), par_op);
+          par_op ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, dA1f + 2 * kk, dW2 + 2 * kk, idesc_64, kk > 0);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, dA1g + 2 * kk, dV2 + 2 * kk, idesc_64, kk > 0);
+          if (dual) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, dA1g + 2 * kk, dV2a + 2 * kk, idesc_64, kk > 0);
+          }
+          tc_commit(bar_acc(slot));
+          // P3
+          mbar_wait(bar_opnd(slot), par_op);
+          par_op ^= 1;
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 192, dA0 + 2 * kk, dW3 + 2 * kk, idesc_64, kk > 0);
+          tc_commit(bar_acc(slot));
+        }
+        // swallow the trailing "A0 ready" phase of the tile's last step
+        mbar_wait(bar_opnd(slot), par_op);
+        par_op ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_SLOTS * EPI_WARPS_PER_SLOT) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 3-D fp32 tensor {64 channels, rows, slabs}; box {32, 128, 1}; 128B swizzle; OOB rows are zero-filled / clipped.
+int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t slabs, int64_t row_stride, int64_t slab_stride) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(TRAJSDE_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(slabs > 0 ? slabs : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 4, (cuuint64_t)(slab_stride > 0 ? slab_stride : row_stride * rows) * 4};
+  cuuint32_t box[3] = {32, TILE_M, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(TRAJSDE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return TRAJSDE_OK;
+}
+
+}  // namespace
+
+int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual) {
+  (void)rows;
+  (void)dual;
+  return (int64_t)IMG_BYTES + (int64_t)n_steps * BIAS1_LD * 4 + 256;
+}
+
+int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  TS_CUDA_CHECK(cudaGetDevice(&dev));
+  TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0)
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
+  TcParams p;
+  p.a = a;
+  p.img = static_cast<const uint8_t*>(a.workspace);
+  p.bias1 = reinterpret_cast<const float*>(static_cast<const uint8_t*>(a.workspace) + IMG_BYTES);
+  p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
+  p.dual = a.alt_mask != nullptr;
+  if (p.num_tiles == 0) return TRAJSDE_OK;
+
+  tc_pack_kernel<<<24, 256, 0, s>>>(a, static_cast<uint8_t*>(a.workspace),
+                                    reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + IMG_BYTES), p.dual);
+  TS_CUDA_CHECK(cudaGetLastError());
+
+  CUtensorMap tm_y0, tm_dw, tm_ys, tm_st;
+  const int T = a.sched.n_outputs + 1;
+  int rc;
+  if ((rc = make_map(&tm_y0, a.y0, a.rows, 1, a.y0_row_stride, 0)) != 0) return rc;
+  if ((rc = make_map(&tm_ys, a.ys, a.rows, T, a.ys_row_stride, a.ys_t_stride)) != 0) return rc;
+  if (a.noise.dw) {
+    if ((rc = make_map(&tm_dw, a.noise.dw, a.rows, a.sched.n_steps, 64, 0)) != 0) return rc;
+  } else {
+    tm_dw = tm_y0;
+  }
+  if (a.states) {
+    if ((rc = make_map(&tm_st, a.states, a.rows, a.sched.n_steps, 64, 0)) != 0) return rc;
+  } else {
+    tm_st = tm_y0;
+  }
+  TS_CUDA_CHECK(cudaFuncSetAttribute(euler_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+  const int pairs = (p.num_tiles + NUM_SLOTS - 1) / NUM_SLOTS;
+  const int grid = pairs < sms ? pairs : sms;
+  euler_fwd_tc_kernel<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_y0, tm_dw, tm_ys, tm_st);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
+}  // namespace trajsde

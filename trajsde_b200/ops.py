@@ -17,6 +17,10 @@ from .schedule import EulerSchedule
 
 _N_MLP = 6  # w1 b1 w2 b2 w3 b3
 
+# kernels launched by this library since import (bench.py reports the count inside its timed region)
+LAUNCHES = {'n': 0}
+_KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-pack + persistent solve
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # device-resident schedule tables
@@ -109,7 +113,7 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
             raise ValueError(f"`dW` must be float32 of shape ({S}, {rows}, 64): one slab per schedule step")
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
-    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
     a.y0, a.y0_row_stride = y0c.data_ptr(), y0c.stride(0)
     a.ys, a.ys_t_stride, a.ys_row_stride = ys.data_ptr(), ys.stride(0), ys.stride(1)
     a.g_last = g_last.data_ptr()
@@ -120,6 +124,8 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
     a.workspace, a.workspace_bytes = ws.data_ptr(), need
     with torch.cuda.device(dev):
         _lib.check(L.trajsde_euler_fwd(C.byref(a), _stream_ptr(dev)), "trajsde_euler_fwd")
+    if rows > 0:
+        LAUNCHES['n'] += _KERNELS_PER_FWD.get(mode, 1)
     return ys, g_last, states
 
 
@@ -160,7 +166,7 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     if dw is not None:
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
-    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
     states = states.contiguous()
     a.states = states.data_ptr()
     if grad_ys is not None:
@@ -219,8 +225,9 @@ def philox_dw(dsched: DeviceSchedule, rows: int, seed: int, device, row_offset: 
     s.n_steps, s.n_outputs = dsched.n_steps, dsched.n_outputs
     s.step_tab, s.out_begin, s.out_w = dsched.step_tab.data_ptr(), dsched.out_begin.data_ptr(), dsched.out_w.data_ptr()
     n = _lib.Noise()
-    n.seed, n.row_offset, n.step_offset = seed & (2**64 - 1), row_offset, step_offset
+    n.seed, n.row_offset, n.step_offset = seed & (2**63 - 1), row_offset, step_offset
     with torch.cuda.device(device):
         _lib.check(_lib.lib().trajsde_philox_dw(C.byref(s), C.byref(n), rows, out.data_ptr(), _stream_ptr(device)),
                    "trajsde_philox_dw")
+    LAUNCHES['n'] += 1
     return out

@@ -37,14 +37,14 @@ def manual_seed(seed: int) -> None:
     """Seed of the in-kernel Philox Brownian increments used when ``bm`` is None.  The op never touches torch's global
     RNG; every solver call draws an independent stream derived from (seed, call index)."""
     with _seed_lock:
-        _defaults['seed'], _defaults['calls'] = int(seed) & (2**64 - 1), 0
+        _defaults['seed'], _defaults['calls'] = int(seed) & (2**63 - 1), 0
 
 
 def _next_call_seed() -> int:
     with _seed_lock:
         k = _defaults['calls']
         _defaults['calls'] = k + 1
-        return (_defaults['seed'] + 0x9E3779B97F4A7C15 * (k + 1)) & (2**64 - 1)
+        return (_defaults['seed'] + 0x9E3779B97F4A7C15 * (k + 1)) & (2**63 - 1)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
