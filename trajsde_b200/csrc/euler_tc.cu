@@ -4,8 +4,9 @@
 // 154-158,180-195; enc_hivt_nusargo_sde_sep2.py:390-398,436-440,462-482), different machine mapping:
 //
 //   * one CTA per SM, two 128-row tiles ("slots") in flight so one slot's tcgen05.mma overlaps the other's epilogue;
-//   * per slot: 4 epilogue warps (thread = one row; its 64-channel fp32 state stays in registers for ALL steps) and one
-//     MMA-issuer warp (one elected thread issues tcgen05.mma / tcgen05.commit);
+//   * per slot: 8 epilogue warps — thread = (row, 32-channel half); its fp32 state stays in registers for ALL steps —
+//     one MMA-issuer warp (one elected thread issues tcgen05.mma / tcgen05.commit) and one IO warp (TMA loads/stores,
+//     per-step bias staging), so epilogue threads never block on a copy they did not need;
 //   * drift/diffusion weights are packed once per call (fp16, 128B-swizzled K-major UMMA tiles) and staged once per CTA
 //     into shared memory with a bulk TMA copy; the five 64x64 layers of a step are three dependent MMA phases:
 //         P1: [z1f | z1g (| z1g_alt)] = y  . [W1y ; V1y (; V1y_alt)]^T        M=128, N=128 (192), K=64
@@ -30,8 +31,12 @@ namespace {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_SLOTS = 2;
-constexpr int EPI_WARPS_PER_SLOT = 4;
-constexpr int NUM_THREADS = (NUM_SLOTS * EPI_WARPS_PER_SLOT + NUM_SLOTS) * 32;  // 8 epilogue warps + 2 MMA warps = 320
+constexpr int EPI_WARPS_PER_SLOT = 8;                       // 4 TMEM lane quadrants x 2 column halves
+constexpr int EPI_THREADS_PER_SLOT = EPI_WARPS_PER_SLOT * 32;
+constexpr int NUM_EPI_WARPS = NUM_SLOTS * EPI_WARPS_PER_SLOT;
+constexpr int WARP_MMA0 = NUM_EPI_WARPS;                    // warps 16,17: MMA issuers (slot 0,1)
+constexpr int WARP_IO0 = NUM_EPI_WARPS + NUM_SLOTS;         // warps 18,19: IO (slot 0,1)
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2 * NUM_SLOTS) * 32;  // 640
 
 // ---- packed weight image (bytes) -----------------------------------------------------------------------------------------
 constexpr uint32_t IMG_B1 = 0;            // [192 rows][64] f16 SW128: W1y | V1y | V1y_alt
@@ -49,9 +54,14 @@ constexpr int BIAS1_LD = 192;             // per-step layer-1 bias row: b1f | c1
 constexpr uint32_t SLOT_BYTES = 81920;    // A0 16K | A1f 16K | A1g 16K | X 32K
 constexpr uint32_t OFF_A0 = 0, OFF_A1F = 16384, OFF_A1G = 32768, OFF_X = 49152;
 constexpr uint32_t SMEM_SLOTS = IMG_BYTES;
-constexpr uint32_t SMEM_BARS = SMEM_SLOTS + NUM_SLOTS * SLOT_BYTES;
-constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 128;
+constexpr uint32_t SMEM_RING = SMEM_SLOTS + NUM_SLOTS * SLOT_BYTES;      // per slot: 3 x [192] fp32 layer-1 bias ring
+constexpr uint32_t RING_BYTES = 3 * BIAS1_LD * 4;
+constexpr uint32_t SMEM_GPART = SMEM_RING + NUM_SLOTS * RING_BYTES;      // per slot: [2 halves][128 rows] fp32 partial g dots
+constexpr uint32_t GPART_BYTES = 2 * TILE_M * 4;
+constexpr uint32_t SMEM_BARS = SMEM_GPART + NUM_SLOTS * GPART_BYTES;
+constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256;
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack for manual 1024-B alignment
+static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
 
 struct TcParams {
   TrajsdeEulerFwdArgs a;
@@ -111,16 +121,29 @@ __device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const 
                                                  uint32_t row, uint32_t chunk0) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    const float4 ba = *reinterpret_cast<const float4*>(bias + q * 8);
+    const float4 bb = *reinterpret_cast<const float4*>(bias + q * 8 + 4);
     uint32_t p[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = q * 8 + e * 2;
-      const float2 b = *reinterpret_cast<const float2*>(bias + j);
-      const float t0 = ts_tanh_approx(__uint_as_float(v[j]) + b.x);
-      const float t1 = ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y);
-      p[e] = pack_f16x2(t0, t1);
-    }
+    p[0] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 0]) + ba.x), ts_tanh_approx(__uint_as_float(v[q * 8 + 1]) + ba.y));
+    p[1] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 2]) + ba.z), ts_tanh_approx(__uint_as_float(v[q * 8 + 3]) + ba.w));
+    p[2] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 4]) + bb.x), ts_tanh_approx(__uint_as_float(v[q * 8 + 5]) + bb.y));
+    p[3] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 6]) + bb.z), ts_tanh_approx(__uint_as_float(v[q * 8 + 7]) + bb.w));
     *reinterpret_cast<uint4*>(tile_row_base + (((chunk0 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+
+// TMEM -> registers: 32 columns of this thread's lane; in a warp whose rows use both diffusion nets the second column block is
+// fetched too and selected per lane (tcgen05.ld is warp-collective: the address must be warp-uniform).
+__device__ __forceinline__ void ld_cols(uint32_t taddr_main, bool w_mixed, uint32_t taddr_alt, bool use_alt, uint32_t (&v)[32]) {
+  tmem_ld_32x32b_x32(taddr_main, v);
+  if (w_mixed) {
+    uint32_t v2[32];
+    tmem_ld_32x32b_x32(taddr_alt, v2);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = use_alt ? v2[j] : v[j];
+  } else {
+    tc_wait_ld();
   }
 }
 
@@ -139,19 +162,26 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const bool has_dw = a.noise.dw != nullptr;
   const bool save_states = a.states != nullptr;
 
-  // barriers: [0] weights, per slot: opnd (128 arrivals), acc (1, tcgen05.commit), tma (1 + tx)
+  // mbarriers.  [0] weights; per slot s (stride 48 B): opnd (256 epilogue arrivals), acc (tcgen05.commit), tma (TMA tx),
+  // xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), bias (IO: ring slot filled)
   const uint32_t bar_w = base + SMEM_BARS;
-  auto bar_opnd = [&](int s) { return base + SMEM_BARS + 8u + 24u * s; };
-  auto bar_acc = [&](int s) { return base + SMEM_BARS + 16u + 24u * s; };
-  auto bar_tma = [&](int s) { return base + SMEM_BARS + 24u + 24u * s; };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 96);
+  auto bar_opnd = [&](int s) { return base + SMEM_BARS + 8u + 48u * s; };
+  auto bar_acc = [&](int s) { return base + SMEM_BARS + 16u + 48u * s; };
+  auto bar_tma = [&](int s) { return base + SMEM_BARS + 24u + 48u * s; };
+  auto bar_xfull = [&](int s) { return base + SMEM_BARS + 32u + 48u * s; };
+  auto bar_xfree = [&](int s) { return base + SMEM_BARS + 40u + 48u * s; };
+  auto bar_bias = [&](int s) { return base + SMEM_BARS + 48u + 48u * s; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 128);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < NUM_SLOTS; ++s) {
-      mbar_init(bar_opnd(s), EPI_WARPS_PER_SLOT * 32);
+      mbar_init(bar_opnd(s), EPI_THREADS_PER_SLOT);
       mbar_init(bar_acc(s), 1);
       mbar_init(bar_tma(s), 1);
+      mbar_init(bar_xfull(s), EPI_THREADS_PER_SLOT);
+      mbar_init(bar_xfree(s), 1);
+      mbar_init(bar_bias(s), 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tm_y0);
@@ -159,7 +189,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     tma_prefetch_desc(&tm_ys);
     tma_prefetch_desc(&tm_st);
   }
-  if (warp == NUM_SLOTS * EPI_WARPS_PER_SLOT) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  if (warp == WARP_MMA0) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -172,22 +202,25 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
   const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
 
-  if (warp < NUM_SLOTS * EPI_WARPS_PER_SLOT) {
+  if (warp < NUM_EPI_WARPS) {
     // =============================================== EPILOGUE WARPS ===============================================
     const int slot = warp / EPI_WARPS_PER_SLOT;
-    const int quad = warp % EPI_WARPS_PER_SLOT;           // TMEM lane quadrant this warp may access
-    const uint32_t row = quad * 32 + lane;                // row inside the tile == TMEM lane
-    const bool leader = (quad == 0 && lane == 0);
+    const int wq = warp % EPI_WARPS_PER_SLOT;
+    const int quad = wq & 3;                               // TMEM lane quadrant (= warp index % 4)
+    const int hh = wq >> 2;                                // which 32-channel half of the row this thread owns
+    const uint32_t row = quad * 32 + lane;                 // row inside the tile == TMEM lane
     uint8_t* slot_sm = sm + SMEM_SLOTS + slot * SLOT_BYTES;
-    const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
     uint8_t* a0_row = slot_sm + OFF_A0 + row * 128;
     uint8_t* a1f_row = slot_sm + OFF_A1F + row * 128;
     uint8_t* a1g_row = slot_sm + OFF_A1G + row * 128;
-    uint8_t* x_row = slot_sm + OFF_X + row * 128;         // + half*16384 + swizzled chunk
-    uint8_t* st_row = slot_sm + OFF_A1F + row * 128;      // states staging aliases A1f|A1g (32 KB, free during P3 epilogue)
-    const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256;
-    const uint32_t bar_id = 1 + slot;
-    uint32_t par_acc = 0, par_tma = 0;
+    uint8_t* x_row = slot_sm + OFF_X + hh * 16384 + row * 128;      // this thread's 32 channels: 8 swizzled 16-B chunks
+    uint8_t* st_row = slot_sm + OFF_A1F + hh * 16384 + row * 128;   // states staging aliases A1f|A1g (free during P3 epilogue)
+    const float* ring = reinterpret_cast<const float*>(sm + SMEM_RING + slot * RING_BYTES);
+    float* gpart = reinterpret_cast<float*>(sm + SMEM_GPART + slot * GPART_BYTES);
+    const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + hh * 32;
+    const uint32_t pair_bar = 1 + slot * 4 + quad;         // named barrier shared by the two warps that own the same rows
+    uint32_t par_acc = 0, par_tma = 0, par_xfree = 0, par_bias = 0;
+    uint32_t gstep = 0;
 
     mbar_wait(bar_w, 0);
 
@@ -196,52 +229,51 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       const int64_t grow = row0 + row;
       const bool valid = grow < a.rows;
       const bool use_alt = dual && valid && (a.alt_mask[grow] == 0);
-      const int gcol = use_alt ? 128 : 64;               // D1/D2 column block and bias1 offset of this row's diffusion net
-      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2);
-      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G);
+      const int gcol = use_alt ? 128 : 64;                 // column block / bias offset of this row's diffusion net
+      const bool w_all_alt = __all_sync(0xffffffffu, use_alt);
+      const bool w_mixed = !w_all_alt && __any_sync(0xffffffffu, use_alt);
+      const uint32_t ucol = w_all_alt ? 128 : 64;          // warp-uniform TMEM column block (mixed warps also read 128)
+      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2) + hh * 32;
+      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G) + hh * 32;
       const float c3 = vec[use_alt ? VEC_C3A : VEC_C3];
 
-      // ---- tile prologue: y0 tile -> X (TMA), registers, ys[0], A0 -----------------------------------------------
-      if (leader) {
-        mbar_arrive_expect_tx(bar_tma(slot), 32768);
-        tma_load_3d(slot_u32 + OFF_X, &tm_y0, bar_tma(slot), 0, (int)row0, 0);
-        tma_load_3d(slot_u32 + OFF_X + 16384, &tm_y0, bar_tma(slot), 32, (int)row0, 0);
-      }
+      // ---- tile prologue: y0 tile (TMA -> X) -> registers + A0 ------------------------------------------------------
       mbar_wait(bar_tma(slot), par_tma);
       par_tma ^= 1;
-      float y[64];
+      float y[32];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(x_row + (c >> 3) * 16384 + (((c & 7) ^ (row & 7u)) << 4));
+      for (int c = 0; c < 8; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(x_row + ((c ^ (row & 7u)) << 4));
         y[4 * c] = v.x; y[4 * c + 1] = v.y; y[4 * c + 2] = v.z; y[4 * c + 3] = v.w;
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 4; ++q) {
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
-        *reinterpret_cast<uint4*>(a0_row + ((q ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async();
-      mbar_arrive(bar_opnd(slot));                       // A0 ready -> P1 of step 0
-      named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);   // everyone has read X
-      if (leader) {
-        tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, (int)row0, 0);          // ys[0] = y0
-        tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, (int)row0, 0);
-        tma_store_commit();
-        tma_store_wait_read0();
-        if (has_dw) {
-          mbar_arrive_expect_tx(bar_tma(slot), 32768);
-          tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, (int)row0, 0);
-          tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, (int)row0, 0);
-        }
-      }
+      mbar_arrive(bar_opnd(slot));                         // A0 ready -> P1 of step 0
+      mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
 
-      for (int k = 0; k < S; ++k) {
+      for (int k = 0; k < S; ++k, ++gstep) {
         const float4 stp = *reinterpret_cast<const float4*>(a.sched.step_tab + 4 * k);
         const float h = stp.y;
-        const float* bias1 = p.bias1 + (size_t)k * BIAS1_LD;
-        named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);  // leader's store-read wait of the previous step is behind us
+        const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
+        const bool has_out = oe > ob, multi_out = oe - ob > 1;
+        float w0 = 0.f, w1 = 1.f;
+        if (has_out) {
+          w0 = a.sched.out_w[2 * ob];
+          w1 = a.sched.out_w[2 * ob + 1];
+        }
+        const float* sb1 = ring + (gstep % 3u) * BIAS1_LD;
+        if (save_states) {                                 // previous step's states store must have drained A1f|A1g
+          mbar_wait(bar_xfree(slot), par_xfree);
+          par_xfree ^= 1;
+        }
+        mbar_wait(bar_bias(slot), par_bias);
+        par_bias ^= 1;
 
         // ---- epilogue 1: h1f = tanh(z1f + b1f(t)), h1g = tanh(z1g + c1(t)) -> A1f, A1g --------------------------------
         mbar_wait(bar_acc(slot), par_acc);
@@ -249,156 +281,117 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tc_fence_after();
         {
           uint32_t v[32];
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tmem_ld_32x32b_x32(tm_lane + hf * 32, v);
-            tc_wait_ld();
-            act32_to_operand(v, bias1 + hf * 32, a1f_row, row, hf * 4);
-          }
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tmem_ld_32x32b_x32(tm_lane + gcol + hf * 32, v);
-            tc_wait_ld();
-            act32_to_operand(v, bias1 + gcol + hf * 32, a1g_row, row, hf * 4);
-          }
+          tmem_ld_32x32b_x32(tm_lane, v);
+          tc_wait_ld();
+          act32_to_operand(v, sb1 + hh * 32, a1f_row, row, hh * 4);
+          ld_cols(tm_lane + ucol, w_mixed, tm_lane + 128, use_alt, v);
+          act32_to_operand(v, sb1 + gcol + hh * 32, a1g_row, row, hh * 4);
         }
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(slot));
 
-        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 ; g = sigmoid(w3 . tanh(z2g + c2) + c3) -------------------------------
+        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 ; partial of w3 . tanh(z2g + c2) ----------------------------------------
         mbar_wait(bar_acc(slot), par_acc);
         par_acc ^= 1;
         tc_fence_after();
-        float gdot = 0.f;
         {
           uint32_t v[32];
+          tmem_ld_32x32b_x32(tm_lane, v);
+          tc_wait_ld();
+          act32_to_operand(v, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
+          ld_cols(tm_lane + ucol, w_mixed, tm_lane + 128, use_alt, v);
+          float gd = 0.f;
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tmem_ld_32x32b_x32(tm_lane + hf * 32, v);
-            tc_wait_ld();
-            act32_to_operand(v, vec + VEC_B2 + hf * 32, a0_row, row, hf * 4);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(c2v + j);
+            const float4 w = *reinterpret_cast<const float4*>(w3v + j);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
           }
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tmem_ld_32x32b_x32(tm_lane + gcol + hf * 32, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(c2v + hf * 32 + j);
-              const float4 w = *reinterpret_cast<const float4*>(w3v + hf * 32 + j);
-              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gdot);
-              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gdot);
-              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gdot);
-              gdot = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gdot);
-            }
-          }
+          gpart[hh * TILE_M + row] = gd;
         }
-        const float g = __fdividef(1.0f, 1.0f + __expf(-(gdot + c3)));
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(slot));
 
         // ---- epilogue 3: f = z3 + b3 ; y' = y + f h + g dW ; outputs ; A0 <- y' -------------------------------------------
-        if (save_states) {  // Y[k] -> states staging (aliases A1f|A1g, both consumed by P2 already)
+        if (save_states) {  // Y[k] -> states staging
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            *reinterpret_cast<float4*>(st_row + (c >> 3) * 16384 + (((c & 7) ^ (row & 7u)) << 4)) =
-                make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
-        }
-        const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
-        const bool has_out = oe > ob;
-        float w0 = 0.f, w1 = 1.f;
-        if (has_out) {
-          w0 = a.sched.out_w[2 * ob];
-          w1 = a.sched.out_w[2 * ob + 1];
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<float4*>(st_row + ((c ^ (row & 7u)) << 4)) = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
         }
         const float sqrt_h = sqrtf(h);
         mbar_wait(bar_acc(slot), par_acc);
         par_acc ^= 1;
         tc_fence_after();
+        named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
+        const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3)));
+        if (!save_states) {                                  // stores of the previous step have finished reading X
+          mbar_wait(bar_xfree(slot), par_xfree);
+          par_xfree ^= 1;
+        }
         if (has_dw) {
           mbar_wait(bar_tma(slot), par_tma);
           par_tma ^= 1;
         }
         {
           uint32_t v[32];
+          tmem_ld_32x32b_x32(tm_lane + 192, v);
+          tc_wait_ld();
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            tmem_ld_32x32b_x32(tm_lane + 192 + hf * 32, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const int cc = hf * 8 + c;                    // 4-channel chunk index 0..15
-              float4* xp = reinterpret_cast<float4*>(x_row + hf * 16384 + ((c ^ (row & 7u)) << 4));
-              float4 dw;
-              if (has_dw) {
-                dw = *xp;
-              } else {
-                const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset,
-                                                 a.noise.step_offset + (uint32_t)k, (uint32_t)cc);
-                dw = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
-              }
-              const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cc * 4);
-              float yn[4];
-              yn[0] = fmaf(g, dw.x, fmaf(__uint_as_float(v[4 * c]) + b3.x, h, y[4 * cc]));
-              yn[1] = fmaf(g, dw.y, fmaf(__uint_as_float(v[4 * c + 1]) + b3.y, h, y[4 * cc + 1]));
-              yn[2] = fmaf(g, dw.z, fmaf(__uint_as_float(v[4 * c + 2]) + b3.z, h, y[4 * cc + 2]));
-              yn[3] = fmaf(g, dw.w, fmaf(__uint_as_float(v[4 * c + 3]) + b3.w, h, y[4 * cc + 3]));
-              if (has_out) {
-                *xp = make_float4(fmaf(w1, yn[0], w0 * y[4 * cc]), fmaf(w1, yn[1], w0 * y[4 * cc + 1]),
-                                  fmaf(w1, yn[2], w0 * y[4 * cc + 2]), fmaf(w1, yn[3], w0 * y[4 * cc + 3]));
-                for (int o = ob + 1; o < oe; ++o) {          // rare: several outputs completed by one step
-                  if (valid) {
-                    const float v0 = a.sched.out_w[2 * o], v1 = a.sched.out_w[2 * o + 1];
-                    float* dst = a.ys + (int64_t)(o + 1) * a.ys_t_stride + grow * a.ys_row_stride + cc * 4;
-                    *reinterpret_cast<float4*>(dst) =
-                        make_float4(fmaf(v1, yn[0], v0 * y[4 * cc]), fmaf(v1, yn[1], v0 * y[4 * cc + 1]),
-                                    fmaf(v1, yn[2], v0 * y[4 * cc + 2]), fmaf(v1, yn[3], v0 * y[4 * cc + 3]));
-                  }
+          for (int c = 0; c < 8; ++c) {
+            const int cc = hh * 8 + c;                      // 4-channel chunk index 0..15 of the row
+            float4* xp = reinterpret_cast<float4*>(x_row + ((c ^ (row & 7u)) << 4));
+            float4 dw;
+            if (has_dw) {
+              dw = *xp;
+            } else {
+              const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset,
+                                               a.noise.step_offset + (uint32_t)k, (uint32_t)cc);
+              dw = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
+            }
+            const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cc * 4);
+            float yn[4];
+            yn[0] = fmaf(g, dw.x, fmaf(__uint_as_float(v[4 * c]) + b3.x, h, y[4 * c]));
+            yn[1] = fmaf(g, dw.y, fmaf(__uint_as_float(v[4 * c + 1]) + b3.y, h, y[4 * c + 1]));
+            yn[2] = fmaf(g, dw.z, fmaf(__uint_as_float(v[4 * c + 2]) + b3.z, h, y[4 * c + 2]));
+            yn[3] = fmaf(g, dw.w, fmaf(__uint_as_float(v[4 * c + 3]) + b3.w, h, y[4 * c + 3]));
+            if (has_out) {
+              *xp = make_float4(fmaf(w1, yn[0], w0 * y[4 * c]), fmaf(w1, yn[1], w0 * y[4 * c + 1]),
+                                fmaf(w1, yn[2], w0 * y[4 * c + 2]), fmaf(w1, yn[3], w0 * y[4 * c + 3]));
+              if (multi_out && valid) {                      // rare: several outputs completed by one step -> direct stores
+                for (int o = ob + 1; o < oe; ++o) {
+                  const float v0 = a.sched.out_w[2 * o], v1 = a.sched.out_w[2 * o + 1];
+                  float* dst = a.ys + (int64_t)(o + 1) * a.ys_t_stride + grow * a.ys_row_stride + cc * 4;
+                  *reinterpret_cast<float4*>(dst) =
+                      make_float4(fmaf(v1, yn[0], v0 * y[4 * c]), fmaf(v1, yn[1], v0 * y[4 * c + 1]),
+                                  fmaf(v1, yn[2], v0 * y[4 * c + 2]), fmaf(v1, yn[3], v0 * y[4 * c + 3]));
                 }
               }
-              y[4 * cc] = yn[0]; y[4 * cc + 1] = yn[1]; y[4 * cc + 2] = yn[2]; y[4 * cc + 3] = yn[3];
             }
+            y[4 * c] = yn[0]; y[4 * c + 1] = yn[1]; y[4 * c + 2] = yn[2]; y[4 * c + 3] = yn[3];
           }
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 4; ++q) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(a0_row + ((q ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        if (k == S - 1 && a.g_last && valid) a.g_last[grow] = g;
+        if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(bar_opnd(slot));                       // A0 = y' ready -> P1 of step k+1 (or next tile: harmless extra phase)
-        named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);   // X / states staging fully written
-        if (leader) {
-          if (has_out) {
-            tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, (int)row0, ob + 1);
-            tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, (int)row0, ob + 1);
-          }
-          if (save_states) {
-            tma_store_3d(&tm_st, slot_u32 + OFF_A1F, 0, (int)row0, k);
-            tma_store_3d(&tm_st, slot_u32 + OFF_A1F + 16384, 32, (int)row0, k);
-          }
-          tma_store_commit();
-          tma_store_wait_read0();
-          if (has_dw && k + 1 < S) {
-            mbar_arrive_expect_tx(bar_tma(slot), 32768);
-            tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, (int)row0, k + 1);
-            tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, (int)row0, k + 1);
-          }
-        }
+        if (k + 1 < S) mbar_arrive(bar_opnd(slot));        // A0 = y' ready -> P1 of step k+1
+        mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
       }
-      // The last step's arrive on bar_opnd announced an A0 nobody multiplies: the MMA warp consumes that phase below.
-      named_bar_sync(bar_id, EPI_WARPS_PER_SLOT * 32);
     }
-    if (leader) tma_store_wait_all0();
-  } else {
+  } else if (warp < WARP_IO0) {
     // =============================================== MMA ISSUER WARPS ===============================================
-    const int slot = warp - NUM_SLOTS * EPI_WARPS_PER_SLOT;
+    const int slot = warp - WARP_MMA0;
     if (lane == 0) {
       const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
       const uint32_t d_base = tmem_base + slot * 256;
@@ -445,16 +438,94 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 192, dA0 + 2 * kk, dW3 + 2 * kk, idesc_64, kk > 0);
           tc_commit(bar_acc(slot));
         }
-        // swallow the trailing "A0 ready" phase of the tile's last step
-        mbar_wait(bar_opnd(slot), par_op);
-        par_op ^= 1;
       }
     }
+  } else {
+    // =============================================== IO WARPS ===============================================================
+    // TMA in/out for the slot + staging of the per-step layer-1 bias row into a 3-deep smem ring.
+    const int slot = warp - WARP_IO0;
+    const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
+    float* ring = reinterpret_cast<float*>(sm + SMEM_RING + slot * RING_BYTES);
+    uint32_t par_xfull = 0;
+    uint32_t gstep = 0;
+    int my_tiles = 0;
+    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) ++my_tiles;
+    const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)S;
+    // Bias row of global step g -> ring[g % 3].  At most ONE phase of bar_bias may be outstanding (parity waits alias after
+    // two), so the row of step g+1 is published only after the epilogue finished step g; the global read is issued early.
+    auto bias_fetch = [&](uint32_t g, float2 (&r)[3]) {
+      const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)(g % (uint32_t)S) * BIAS1_LD);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) r[i] = __ldg(src + lane + 32 * i);
+    };
+    auto bias_publish = [&](uint32_t g, const float2 (&r)[3]) {
+      float2* dst = reinterpret_cast<float2*>(ring + (g % 3u) * BIAS1_LD);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dst[lane + 32 * i] = r[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_bias(slot));
+    };
+    if (total_steps > 0) {
+      float2 r[3];
+      bias_fetch(0, r);
+      bias_publish(0, r);
+    }
+    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+      const int row0 = tile * TILE_M;
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar_tma(slot), 32768);
+        tma_load_3d(slot_u32 + OFF_X, &tm_y0, bar_tma(slot), 0, row0, 0);
+        tma_load_3d(slot_u32 + OFF_X + 16384, &tm_y0, bar_tma(slot), 32, row0, 0);
+        mbar_wait(bar_xfull(slot), par_xfull);             // every epilogue thread holds its y0
+        tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, row0, 0);              // ys[0] = y0
+        tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, row0, 0);
+        tma_store_commit();
+        tma_store_wait_read0();
+        mbar_arrive(bar_xfree(slot));
+        if (has_dw) {
+          mbar_arrive_expect_tx(bar_tma(slot), 32768);
+          tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, 0);
+          tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, 0);
+        }
+      }
+      par_xfull ^= 1;
+      for (int k = 0; k < S; ++k, ++gstep) {
+        const bool more = gstep + 1 < total_steps;
+        float2 br[3];
+        if (more) bias_fetch(gstep + 1, br);
+        if (lane == 0) mbar_wait(bar_xfull(slot), par_xfull);   // epilogue 3 of step k finished writing X / states staging
+        __syncwarp();
+        if (more) bias_publish(gstep + 1, br);
+        if (lane == 0) {
+          const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
+          if (oe > ob) {
+            tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, row0, ob + 1);
+            tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, row0, ob + 1);
+          }
+          if (save_states) {
+            tma_store_3d(&tm_st, slot_u32 + OFF_A1F, 0, row0, k);
+            tma_store_3d(&tm_st, slot_u32 + OFF_A1F + 16384, 32, row0, k);
+          }
+          tma_store_commit();
+          tma_store_wait_read0();
+          if (k + 1 < S) {
+            mbar_arrive(bar_xfree(slot));
+            if (has_dw) {
+              mbar_arrive_expect_tx(bar_tma(slot), 32768);
+              tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, k + 1);
+              tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, k + 1);
+            }
+          }
+        }
+        par_xfull ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all0();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == NUM_SLOTS * EPI_WARPS_PER_SLOT) {
+  if (warp == WARP_MMA0) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
   }
