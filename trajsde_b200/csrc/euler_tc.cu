@@ -37,6 +37,7 @@ constexpr int NUM_EPI_WARPS = NUM_SLOTS * EPI_WARPS_PER_SLOT;
 constexpr int WARP_MMA0 = NUM_EPI_WARPS;                    // warps 16,17: MMA issuers (slot 0,1)
 constexpr int WARP_IO0 = NUM_EPI_WARPS + NUM_SLOTS;         // warps 18,19: IO (slot 0,1)
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2 * NUM_SLOTS) * 32;  // 640
+constexpr int EPI_REGS = 112, AUX_REGS = 32;              // setmaxnreg split: epilogue warpgroups grow, MMA/IO warpgroup shrinks
 
 // ---- packed weight image (bytes) -----------------------------------------------------------------------------------------
 constexpr uint32_t IMG_B1 = 0;            // [192 rows][64] f16 SW128: W1y | V1y | V1y_alt
@@ -55,7 +56,8 @@ constexpr uint32_t SLOT_BYTES = 81920;    // A0 16K | A1f 16K | A1g 16K | X 32K
 constexpr uint32_t OFF_A0 = 0, OFF_A1F = 16384, OFF_A1G = 32768, OFF_X = 49152;
 constexpr uint32_t SMEM_SLOTS = IMG_BYTES;
 constexpr uint32_t SMEM_RING = SMEM_SLOTS + NUM_SLOTS * SLOT_BYTES;      // per slot: 3 x [192] fp32 layer-1 bias ring
-constexpr uint32_t RING_BYTES = 3 * BIAS1_LD * 4;
+constexpr int RING_LD = BIAS1_LD + 8;           // bias row + {h, sqrt h, w0, w1, first output, #outputs, pad, pad}
+constexpr uint32_t RING_BYTES = 3 * RING_LD * 4;
 constexpr uint32_t SMEM_GPART = SMEM_RING + NUM_SLOTS * RING_BYTES;      // per slot: [2 halves][128 rows] fp32 partial g dots
 constexpr uint32_t GPART_BYTES = 2 * TILE_M * 4;
 constexpr uint32_t SMEM_BARS = SMEM_GPART + NUM_SLOTS * GPART_BYTES;
@@ -132,21 +134,90 @@ __device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const 
   }
 }
 
-// TMEM -> registers: 32 columns of this thread's lane; in a warp whose rows use both diffusion nets the second column block is
-// fetched too and selected per lane (tcgen05.ld is warp-collective: the address must be warp-uniform).
-__device__ __forceinline__ void ld_cols(uint32_t taddr_main, bool w_mixed, uint32_t taddr_alt, bool use_alt, uint32_t (&v)[32]) {
-  tmem_ld_32x32b_x32(taddr_main, v);
-  if (w_mixed) {
+// Two TMEM column blocks -> registers with one wait: vf = f-net block, vg = this row's diffusion-net block.  In a warp whose
+// rows use both diffusion nets the alt block is fetched too and selected per lane (tcgen05.ld is warp-collective: its
+// address must be warp-uniform).
+template <bool DUAL>
+__device__ __forceinline__ void ld_fg(uint32_t tm_f, uint32_t tm_g_uniform, uint32_t tm_g_alt, bool w_mixed, bool use_alt,
+                                      uint32_t (&vf)[32], uint32_t (&vg)[32]) {
+  tmem_ld_32x32b_x32(tm_f, vf);
+  tmem_ld_32x32b_x32(tm_g_uniform, vg);
+  if (DUAL && w_mixed) {
     uint32_t v2[32];
-    tmem_ld_32x32b_x32(taddr_alt, v2);
+    tmem_ld_32x32b_x32(tm_g_alt, v2);
     tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = use_alt ? v2[j] : v[j];
+    for (int j = 0; j < 32; ++j) vg[j] = use_alt ? v2[j] : vg[j];
   } else {
     tc_wait_ld();
   }
 }
 
+struct Epi3Ctx {
+  uint8_t* x_row;
+  uint8_t* a0_row;
+  uint8_t* st_row;
+  const float* b3;      // vec + VEC_B3 + hh*32
+  uint32_t tm_y, tm_f;  // TMEM addresses of this thread's 32 state / drift columns
+  uint32_t row, hh;
+  float h, g, w0, w1;
+  bool has_out, save_states, valid;
+  // slow path only
+  int ob, nout;
+  const float* out_w;
+  float* ys_row;        // a.ys + grow * row_stride + hh*32
+  int64_t ys_t_stride;
+};
+
+// Epilogue 3: f = z3 + b3 ; y' = y + f h + g dW (dW already in this thread's X chunks) ; outputs in place ; Y, A0 <- y'.
+template <bool MULTI>
+__device__ __forceinline__ void epi3_update(const Epi3Ctx& c) {
+  uint32_t yv[32], fv[32];
+  tmem_ld_32x32b_x32(c.tm_y, yv);
+  tmem_ld_32x32b_x32(c.tm_f, fv);
+  tc_wait_ld();
+  if (c.save_states) {  // Y[k] -> states staging (aliases A1f|A1g: both consumed by P2 already)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(c.st_row + ((q ^ (c.row & 7u)) << 4)) = make_uint4(yv[4 * q], yv[4 * q + 1], yv[4 * q + 2], yv[4 * q + 3]);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4* xp = reinterpret_cast<float4*>(c.x_row + ((q ^ (c.row & 7u)) << 4));
+    const float4 dw = *xp;
+    const float4 b3 = *reinterpret_cast<const float4*>(c.b3 + 4 * q);
+    const float y0 = __uint_as_float(yv[4 * q]), y1 = __uint_as_float(yv[4 * q + 1]);
+    const float y2 = __uint_as_float(yv[4 * q + 2]), y3 = __uint_as_float(yv[4 * q + 3]);
+    const float n0 = fmaf(c.g, dw.x, fmaf(__uint_as_float(fv[4 * q]) + b3.x, c.h, y0));
+    const float n1 = fmaf(c.g, dw.y, fmaf(__uint_as_float(fv[4 * q + 1]) + b3.y, c.h, y1));
+    const float n2 = fmaf(c.g, dw.z, fmaf(__uint_as_float(fv[4 * q + 2]) + b3.z, c.h, y2));
+    const float n3 = fmaf(c.g, dw.w, fmaf(__uint_as_float(fv[4 * q + 3]) + b3.w, c.h, y3));
+    if (c.has_out)
+      *xp = make_float4(fmaf(c.w1, n0, c.w0 * y0), fmaf(c.w1, n1, c.w0 * y1), fmaf(c.w1, n2, c.w0 * y2), fmaf(c.w1, n3, c.w0 * y3));
+    if (MULTI) {  // rare: one step completes several outputs (zero-step intervals) -> direct global stores
+      if (c.valid) {
+        for (int o = 1; o < c.nout; ++o) {
+          const float v0 = c.out_w[2 * (c.ob + o)], v1 = c.out_w[2 * (c.ob + o) + 1];
+          *reinterpret_cast<float4*>(c.ys_row + (int64_t)(c.ob + o + 1) * c.ys_t_stride + 4 * q) =
+              make_float4(fmaf(v1, n0, v0 * y0), fmaf(v1, n1, v0 * y1), fmaf(v1, n2, v0 * y2), fmaf(v1, n3, v0 * y3));
+        }
+      }
+    }
+    yv[4 * q] = __float_as_uint(n0); yv[4 * q + 1] = __float_as_uint(n1);
+    yv[4 * q + 2] = __float_as_uint(n2); yv[4 * q + 3] = __float_as_uint(n3);
+  }
+  tmem_st_32x32b_x32(c.tm_y, yv);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
+    *reinterpret_cast<uint4*>(c.a0_row + (((c.hh * 4 + q) ^ (c.row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+  tc_wait_st();
+}
+
+template <bool HAS_DW, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_dw,
                     const __grid_constant__ CUtensorMap tm_ys, const __grid_constant__ CUtensorMap tm_st) {
@@ -158,19 +229,17 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const TrajsdeEulerFwdArgs& a = p.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.sched.n_steps;
-  const bool dual = p.dual != 0;
-  const bool has_dw = a.noise.dw != nullptr;
   const bool save_states = a.states != nullptr;
 
   // mbarriers.  [0] weights; per slot s (stride 48 B): opnd (256 epilogue arrivals), acc (tcgen05.commit), tma (TMA tx),
-  // xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), bias (IO: ring slot filled)
+  // xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), ring (IO: step entry filled)
   const uint32_t bar_w = base + SMEM_BARS;
   auto bar_opnd = [&](int s) { return base + SMEM_BARS + 8u + 48u * s; };
   auto bar_acc = [&](int s) { return base + SMEM_BARS + 16u + 48u * s; };
   auto bar_tma = [&](int s) { return base + SMEM_BARS + 24u + 48u * s; };
   auto bar_xfull = [&](int s) { return base + SMEM_BARS + 32u + 48u * s; };
   auto bar_xfree = [&](int s) { return base + SMEM_BARS + 40u + 48u * s; };
-  auto bar_bias = [&](int s) { return base + SMEM_BARS + 48u + 48u * s; };
+  auto bar_ring = [&](int s) { return base + SMEM_BARS + 48u + 48u * s; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 128);
 
   if (threadIdx.x == 0) {
@@ -181,7 +250,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       mbar_init(bar_tma(s), 1);
       mbar_init(bar_xfull(s), EPI_THREADS_PER_SLOT);
       mbar_init(bar_xfree(s), 1);
-      mbar_init(bar_bias(s), 1);
+      mbar_init(bar_ring(s), 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tm_y0);
@@ -204,23 +273,36 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
   if (warp < NUM_EPI_WARPS) {
     // =============================================== EPILOGUE WARPS ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));   // 16x32x112 + 4x32x32 = 640 x 96: inc only draws on what dec released
     const int slot = warp / EPI_WARPS_PER_SLOT;
     const int wq = warp % EPI_WARPS_PER_SLOT;
     const int quad = wq & 3;                               // TMEM lane quadrant (= warp index % 4)
-    const int hh = wq >> 2;                                // which 32-channel half of the row this thread owns
+    const uint32_t hh = wq >> 2;                           // which 32-channel half of the row this thread owns
     const uint32_t row = quad * 32 + lane;                 // row inside the tile == TMEM lane
     uint8_t* slot_sm = sm + SMEM_SLOTS + slot * SLOT_BYTES;
     uint8_t* a0_row = slot_sm + OFF_A0 + row * 128;
     uint8_t* a1f_row = slot_sm + OFF_A1F + row * 128;
     uint8_t* a1g_row = slot_sm + OFF_A1G + row * 128;
     uint8_t* x_row = slot_sm + OFF_X + hh * 16384 + row * 128;      // this thread's 32 channels: 8 swizzled 16-B chunks
-    uint8_t* st_row = slot_sm + OFF_A1F + hh * 16384 + row * 128;   // states staging aliases A1f|A1g (free during P3 epilogue)
     const float* ring = reinterpret_cast<const float*>(sm + SMEM_RING + slot * RING_BYTES);
     float* gpart = reinterpret_cast<float*>(sm + SMEM_GPART + slot * GPART_BYTES);
+    // TMEM columns of a slot: [0,192) P1/P2 accumulators (P3 reuses [0,64)), [192,256) the resident fp32 state Y
     const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + hh * 32;
     const uint32_t pair_bar = 1 + slot * 4 + quad;         // named barrier shared by the two warps that own the same rows
-    uint32_t par_acc = 0, par_tma = 0, par_xfree = 0, par_bias = 0;
+    uint32_t par_acc = 0, par_tma = 0, par_xfree = 0, par_ring = 0;
     uint32_t gstep = 0;
+    Epi3Ctx c3;
+    c3.x_row = x_row;
+    c3.a0_row = a0_row;
+    c3.st_row = slot_sm + OFF_A1F + hh * 16384 + row * 128;
+    c3.b3 = vec + VEC_B3 + hh * 32;
+    c3.tm_y = tm_lane + 192;
+    c3.tm_f = tm_lane;
+    c3.row = row;
+    c3.hh = hh;
+    c3.save_states = save_states;
+    c3.out_w = a.sched.out_w;
+    c3.ys_t_stride = a.ys_t_stride;
 
     mbar_wait(bar_w, 0);
 
@@ -228,64 +310,61 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int64_t grow = row0 + row;
       const bool valid = grow < a.rows;
-      const bool use_alt = dual && valid && (a.alt_mask[grow] == 0);
+      const bool use_alt = DUAL && valid && (a.alt_mask[grow] == 0);
       const int gcol = use_alt ? 128 : 64;                 // column block / bias offset of this row's diffusion net
-      const bool w_all_alt = __all_sync(0xffffffffu, use_alt);
-      const bool w_mixed = !w_all_alt && __any_sync(0xffffffffu, use_alt);
+      const bool w_all_alt = DUAL && __all_sync(0xffffffffu, use_alt);
+      const bool w_mixed = DUAL && !w_all_alt && __any_sync(0xffffffffu, use_alt);
       const uint32_t ucol = w_all_alt ? 128 : 64;          // warp-uniform TMEM column block (mixed warps also read 128)
       const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2) + hh * 32;
       const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G) + hh * 32;
-      const float c3 = vec[use_alt ? VEC_C3A : VEC_C3];
+      const float c3b = vec[use_alt ? VEC_C3A : VEC_C3];
+      c3.valid = valid;
+      c3.ys_row = a.ys + grow * a.ys_row_stride + hh * 32;
 
-      // ---- tile prologue: y0 tile (TMA -> X) -> registers + A0 ------------------------------------------------------
+      // ---- tile prologue: y0 tile (TMA -> X) -> Y (TMEM) + A0 ---------------------------------------------------------
       mbar_wait(bar_tma(slot), par_tma);
       par_tma ^= 1;
-      float y[32];
+      {
+        uint32_t yv[32];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float4 v = *reinterpret_cast<const float4*>(x_row + ((c ^ (row & 7u)) << 4));
-        y[4 * c] = v.x; y[4 * c + 1] = v.y; y[4 * c + 2] = v.z; y[4 * c + 3] = v.w;
-      }
+        for (int q = 0; q < 8; ++q) {
+          const uint4 v = *reinterpret_cast<const uint4*>(x_row + ((q ^ (row & 7u)) << 4));
+          yv[4 * q] = v.x; yv[4 * q + 1] = v.y; yv[4 * q + 2] = v.z; yv[4 * q + 3] = v.w;
+        }
+        tmem_st_32x32b_x32(tm_lane + 192, yv);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint32_t pk[4];
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
-        *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
+          *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        tc_wait_st();
       }
       fence_proxy_async();
       mbar_arrive(bar_opnd(slot));                         // A0 ready -> P1 of step 0
       mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
 
       for (int k = 0; k < S; ++k, ++gstep) {
-        const float4 stp = *reinterpret_cast<const float4*>(a.sched.step_tab + 4 * k);
-        const float h = stp.y;
-        const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
-        const bool has_out = oe > ob, multi_out = oe - ob > 1;
-        float w0 = 0.f, w1 = 1.f;
-        if (has_out) {
-          w0 = a.sched.out_w[2 * ob];
-          w1 = a.sched.out_w[2 * ob + 1];
-        }
-        const float* sb1 = ring + (gstep % 3u) * BIAS1_LD;
         if (save_states) {                                 // previous step's states store must have drained A1f|A1g
           mbar_wait(bar_xfree(slot), par_xfree);
           par_xfree ^= 1;
         }
-        mbar_wait(bar_bias(slot), par_bias);
-        par_bias ^= 1;
+        mbar_wait(bar_ring(slot), par_ring);               // this step's bias row + scalars are in the ring
+        par_ring ^= 1;
+        const float* ent = ring + (gstep % 3u) * RING_LD;
+        const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
+        const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
 
         // ---- epilogue 1: h1f = tanh(z1f + b1f(t)), h1g = tanh(z1g + c1(t)) -> A1f, A1g --------------------------------
         mbar_wait(bar_acc(slot), par_acc);
         par_acc ^= 1;
         tc_fence_after();
         {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tm_lane, v);
-          tc_wait_ld();
-          act32_to_operand(v, sb1 + hh * 32, a1f_row, row, hh * 4);
-          ld_cols(tm_lane + ucol, w_mixed, tm_lane + 128, use_alt, v);
-          act32_to_operand(v, sb1 + gcol + hh * 32, a1g_row, row, hh * 4);
+          uint32_t vf[32], vg[32];
+          ld_fg<DUAL>(tm_lane, tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, vf, vg);
+          act32_to_operand(vf, ent + hh * 32, a1f_row, row, hh * 4);
+          act32_to_operand(vg, ent + gcol + hh * 32, a1g_row, row, hh * 4);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -296,20 +375,18 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         par_acc ^= 1;
         tc_fence_after();
         {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tm_lane, v);
-          tc_wait_ld();
-          act32_to_operand(v, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
-          ld_cols(tm_lane + ucol, w_mixed, tm_lane + 128, use_alt, v);
+          uint32_t vf[32], vg[32];
+          ld_fg<DUAL>(tm_lane, tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, vf, vg);
+          act32_to_operand(vf, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
           float gd = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(c2v + j);
             const float4 w = *reinterpret_cast<const float4*>(w3v + j);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j]) + b.x), w.x, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 1]) + b.y), w.y, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 2]) + b.z), w.z, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 3]) + b.w), w.w, gd);
           }
           gpart[hh * TILE_M + row] = gd;
         }
@@ -317,71 +394,36 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tc_fence_before();
         mbar_arrive(bar_opnd(slot));
 
-        // ---- epilogue 3: f = z3 + b3 ; y' = y + f h + g dW ; outputs ; A0 <- y' -------------------------------------------
-        if (save_states) {  // Y[k] -> states staging
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<float4*>(st_row + ((c ^ (row & 7u)) << 4)) = make_float4(y[4 * c], y[4 * c + 1], y[4 * c + 2], y[4 * c + 3]);
-        }
-        const float sqrt_h = sqrtf(h);
-        mbar_wait(bar_acc(slot), par_acc);
-        par_acc ^= 1;
-        tc_fence_after();
-        named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
-        const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3)));
+        // ---- epilogue 3 -----------------------------------------------------------------------------------------------------
         if (!save_states) {                                  // stores of the previous step have finished reading X
           mbar_wait(bar_xfree(slot), par_xfree);
           par_xfree ^= 1;
         }
-        if (has_dw) {
-          mbar_wait(bar_tma(slot), par_tma);
+        if (HAS_DW) {
+          mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
           par_tma ^= 1;
-        }
-        {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tm_lane + 192, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int cc = hh * 8 + c;                      // 4-channel chunk index 0..15 of the row
-            float4* xp = reinterpret_cast<float4*>(x_row + ((c ^ (row & 7u)) << 4));
-            float4 dw;
-            if (has_dw) {
-              dw = *xp;
-            } else {
-              const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset,
-                                               a.noise.step_offset + (uint32_t)k, (uint32_t)cc);
-              dw = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
-            }
-            const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cc * 4);
-            float yn[4];
-            yn[0] = fmaf(g, dw.x, fmaf(__uint_as_float(v[4 * c]) + b3.x, h, y[4 * c]));
-            yn[1] = fmaf(g, dw.y, fmaf(__uint_as_float(v[4 * c + 1]) + b3.y, h, y[4 * c + 1]));
-            yn[2] = fmaf(g, dw.z, fmaf(__uint_as_float(v[4 * c + 2]) + b3.z, h, y[4 * c + 2]));
-            yn[3] = fmaf(g, dw.w, fmaf(__uint_as_float(v[4 * c + 3]) + b3.w, h, y[4 * c + 3]));
-            if (has_out) {
-              *xp = make_float4(fmaf(w1, yn[0], w0 * y[4 * c]), fmaf(w1, yn[1], w0 * y[4 * c + 1]),
-                                fmaf(w1, yn[2], w0 * y[4 * c + 2]), fmaf(w1, yn[3], w0 * y[4 * c + 3]));
-              if (multi_out && valid) {                      // rare: several outputs completed by one step -> direct stores
-                for (int o = ob + 1; o < oe; ++o) {
-                  const float v0 = a.sched.out_w[2 * o], v1 = a.sched.out_w[2 * o + 1];
-                  float* dst = a.ys + (int64_t)(o + 1) * a.ys_t_stride + grow * a.ys_row_stride + cc * 4;
-                  *reinterpret_cast<float4*>(dst) =
-                      make_float4(fmaf(v1, yn[0], v0 * y[4 * c]), fmaf(v1, yn[1], v0 * y[4 * c + 1]),
-                                  fmaf(v1, yn[2], v0 * y[4 * c + 2]), fmaf(v1, yn[3], v0 * y[4 * c + 3]));
-                }
-              }
-            }
-            y[4 * c] = yn[0]; y[4 * c + 1] = yn[1]; y[4 * c + 2] = yn[2]; y[4 * c + 3] = yn[3];
+        } else {                                             // draw this thread's 32 increments into X while P3 runs
+#pragma unroll 1
+          for (int q = 0; q < 8; ++q) {
+            const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
+                                             (uint32_t)(hh * 8 + q));
+            *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) = make_float4(n4.x * sc.y, n4.y * sc.y, n4.z * sc.y, n4.w * sc.y);
           }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(y[q * 8 + 2 * e], y[q * 8 + 2 * e + 1]);
-          *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
+        mbar_wait(bar_acc(slot), par_acc);
+        par_acc ^= 1;
+        tc_fence_after();
+        named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
+        const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
+        c3.h = sc.x;
+        c3.g = g;
+        c3.w0 = sc.z;
+        c3.w1 = sc.w;
+        c3.ob = so.x;
+        c3.nout = so.y;
+        c3.has_out = so.y > 0;
+        if (so.y > 1) epi3_update<true>(c3);
+        else epi3_update<false>(c3);
         if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
         fence_proxy_async();
         tc_fence_before();
@@ -391,58 +433,56 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     }
   } else if (warp < WARP_IO0) {
     // =============================================== MMA ISSUER WARPS ===============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     const int slot = warp - WARP_MMA0;
     if (lane == 0) {
       const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
       const uint32_t d_base = tmem_base + slot * 256;
-      const uint32_t n1 = dual ? 192u : 128u;
-      const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, n1);
+      const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, DUAL ? 192u : 128u);
       const uint32_t idesc_64 = umma_idesc_f16(TILE_M, 64);
-      const uint64_t dA0 = umma_desc_sw128(slot_u32 + OFF_A0);
-      const uint64_t dA1f = umma_desc_sw128(slot_u32 + OFF_A1F);
-      const uint64_t dA1g = umma_desc_sw128(slot_u32 + OFF_A1G);
-      const uint64_t dB1 = umma_desc_sw128(base + IMG_B1);
-      const uint64_t dW2 = umma_desc_sw128(base + IMG_W2);
-      const uint64_t dV2 = umma_desc_sw128(base + IMG_V2);
-      const uint64_t dV2a = umma_desc_sw128(base + IMG_V2A);
-      const uint64_t dW3 = umma_desc_sw128(base + IMG_W3);
+      // all operand descriptors share the high word (SBO / version / swizzle); only the start-address field differs
+      const uint64_t dhi = umma_desc_sw128(0);
+      auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+      const uint32_t aA0 = slot_u32 + OFF_A0, aA1f = slot_u32 + OFF_A1F, aA1g = slot_u32 + OFF_A1G;
+      const uint32_t aB1 = base + IMG_B1, aW2 = base + IMG_W2, aV2 = base + IMG_V2, aV2a = base + IMG_V2A, aW3 = base + IMG_W3;
       uint32_t par_op = 0;
       mbar_wait(bar_w, 0);
       for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
         for (int k = 0; k < S; ++k) {
-          // P1
+          // P1: [z1f | z1g (| z1g_alt)]
           mbar_wait(bar_opnd(slot), par_op);
           par_op ^= 1;
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, dA0 + 2 * kk, dB1 + 2 * kk, idesc_p1, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
           tc_commit(bar_acc(slot));
-          // P2
+          // P2: z2f, z2g (, z2g_alt)
           mbar_wait(bar_opnd(slot), par_op);
           par_op ^= 1;
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, dA1f + 2 * kk, dW2 + 2 * kk, idesc_64, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, dA1g + 2 * kk, dV2 + 2 * kk, idesc_64, kk > 0);
-          if (dual) {
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
+          if (DUAL) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, dA1g + 2 * kk, dV2a + 2 * kk, idesc_64, kk > 0);
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
           }
           tc_commit(bar_acc(slot));
-          // P3
+          // P3: drift output (reuses the z2f columns, already consumed by epilogue 2)
           mbar_wait(bar_opnd(slot), par_op);
           par_op ^= 1;
           tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 192, dA0 + 2 * kk, dW3 + 2 * kk, idesc_64, kk > 0);
+          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
           tc_commit(bar_acc(slot));
         }
       }
     }
   } else {
     // =============================================== IO WARPS ===============================================================
-    // TMA in/out for the slot + staging of the per-step layer-1 bias row into a 3-deep smem ring.
+    // TMA in/out for the slot + staging of each step's layer-1 bias row and scalars into a 3-deep smem ring.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     const int slot = warp - WARP_IO0;
     const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
     float* ring = reinterpret_cast<float*>(sm + SMEM_RING + slot * RING_BYTES);
@@ -451,24 +491,41 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     int my_tiles = 0;
     for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) ++my_tiles;
     const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)S;
-    // Bias row of global step g -> ring[g % 3].  At most ONE phase of bar_bias may be outstanding (parity waits alias after
-    // two), so the row of step g+1 is published only after the epilogue finished step g; the global read is issued early.
-    auto bias_fetch = [&](uint32_t g, float2 (&r)[3]) {
-      const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)(g % (uint32_t)S) * BIAS1_LD);
+    // Ring entry of global step g -> ring[g % 3].  At most ONE phase of bar_ring may be outstanding (parity waits alias after
+    // two), so the entry of step g+1 is published only after the epilogue finished step g; the global reads are issued early.
+    struct Ent { float2 b[3]; float4 sc; int2 so; };
+    auto ent_fetch = [&](uint32_t g, Ent& e) {
+      const int k = (int)(g % (uint32_t)S);
+      const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)k * BIAS1_LD);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) r[i] = __ldg(src + lane + 32 * i);
+      for (int i = 0; i < 3; ++i) e.b[i] = __ldg(src + lane + 32 * i);
+      if (lane == 0) {
+        const float4 st = __ldg(reinterpret_cast<const float4*>(a.sched.step_tab) + k);
+        const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
+        float w0 = 0.f, w1 = 1.f;
+        if (oe > ob) {
+          w0 = a.sched.out_w[2 * ob];
+          w1 = a.sched.out_w[2 * ob + 1];
+        }
+        e.sc = make_float4(st.y, sqrtf(st.y), w0, w1);
+        e.so = make_int2(ob, oe - ob);
+      }
     };
-    auto bias_publish = [&](uint32_t g, const float2 (&r)[3]) {
-      float2* dst = reinterpret_cast<float2*>(ring + (g % 3u) * BIAS1_LD);
+    auto ent_publish = [&](uint32_t g, const Ent& e) {
+      float* dst = ring + (g % 3u) * RING_LD;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) dst[lane + 32 * i] = r[i];
+      for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(dst)[lane + 32 * i] = e.b[i];
+      if (lane == 0) {
+        *reinterpret_cast<float4*>(dst + BIAS1_LD) = e.sc;
+        *reinterpret_cast<int2*>(dst + BIAS1_LD + 4) = e.so;
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_bias(slot));
+      if (lane == 0) mbar_arrive(bar_ring(slot));
     };
     if (total_steps > 0) {
-      float2 r[3];
-      bias_fetch(0, r);
-      bias_publish(0, r);
+      Ent e;
+      ent_fetch(0, e);
+      ent_publish(0, e);
     }
     for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
       const int row0 = tile * TILE_M;
@@ -482,7 +539,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tma_store_commit();
         tma_store_wait_read0();
         mbar_arrive(bar_xfree(slot));
-        if (has_dw) {
+        if (HAS_DW) {
           mbar_arrive_expect_tx(bar_tma(slot), 32768);
           tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, 0);
           tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, 0);
@@ -491,11 +548,11 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       par_xfull ^= 1;
       for (int k = 0; k < S; ++k, ++gstep) {
         const bool more = gstep + 1 < total_steps;
-        float2 br[3];
-        if (more) bias_fetch(gstep + 1, br);
+        Ent e;
+        if (more) ent_fetch(gstep + 1, e);
         if (lane == 0) mbar_wait(bar_xfull(slot), par_xfull);   // epilogue 3 of step k finished writing X / states staging
         __syncwarp();
-        if (more) bias_publish(gstep + 1, br);
+        if (more) ent_publish(gstep + 1, e);
         if (lane == 0) {
           const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
           if (oe > ob) {
@@ -510,7 +567,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tma_store_wait_read0();
           if (k + 1 < S) {
             mbar_arrive(bar_xfree(slot));
-            if (has_dw) {
+            if (HAS_DW) {
               mbar_arrive_expect_tx(bar_tma(slot), 32768);
               tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, k + 1);
               tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, k + 1);
@@ -607,11 +664,17 @@ int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s) {
   } else {
     tm_st = tm_y0;
   }
-  TS_CUDA_CHECK(cudaFuncSetAttribute(euler_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
   const int pairs = (p.num_tiles + NUM_SLOTS - 1) / NUM_SLOTS;
   const int grid = pairs < sms ? pairs : sms;
-  euler_fwd_tc_kernel<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_y0, tm_dw, tm_ys, tm_st);
-  TS_CUDA_CHECK(cudaGetLastError());
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_y0, tm_dw, tm_ys, tm_st);
+    return cudaGetLastError();
+  };
+  const bool hd = a.noise.dw != nullptr, du = p.dual != 0;
+  TS_CUDA_CHECK(hd ? (du ? launch(euler_fwd_tc_kernel<true, true>) : launch(euler_fwd_tc_kernel<true, false>))
+                   : (du ? launch(euler_fwd_tc_kernel<false, true>) : launch(euler_fwd_tc_kernel<false, false>)));
   return TRAJSDE_OK;
 }
 
