@@ -61,7 +61,7 @@ constexpr uint32_t RING_BYTES = 3 * RING_LD * 4;
 constexpr uint32_t SMEM_GPART = SMEM_RING + NUM_SLOTS * RING_BYTES;      // per slot: [2 halves][128 rows] fp32 partial g dots
 constexpr uint32_t GPART_BYTES = 2 * TILE_M * 4;
 constexpr uint32_t SMEM_BARS = SMEM_GPART + NUM_SLOTS * GPART_BYTES;
-constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256;
+constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256;   // 1 + 2 x 10 mbarriers, TMEM base pointer
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack for manual 1024-B alignment
 static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
 
@@ -134,13 +134,10 @@ __device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const 
   }
 }
 
-// Two TMEM column blocks -> registers with one wait: vf = f-net block, vg = this row's diffusion-net block.  In a warp whose
-// rows use both diffusion nets the alt block is fetched too and selected per lane (tcgen05.ld is warp-collective: its
-// address must be warp-uniform).
+// This row's diffusion-net column block -> registers.  In a warp whose rows use both diffusion nets the alt block is fetched
+// too and selected per lane (tcgen05.ld is warp-collective: its address must be warp-uniform).
 template <bool DUAL>
-__device__ __forceinline__ void ld_fg(uint32_t tm_f, uint32_t tm_g_uniform, uint32_t tm_g_alt, bool w_mixed, bool use_alt,
-                                      uint32_t (&vf)[32], uint32_t (&vg)[32]) {
-  tmem_ld_32x32b_x32(tm_f, vf);
+__device__ __forceinline__ void ld_g(uint32_t tm_g_uniform, uint32_t tm_g_alt, bool w_mixed, bool use_alt, uint32_t (&vg)[32]) {
   tmem_ld_32x32b_x32(tm_g_uniform, vg);
   if (DUAL && w_mixed) {
     uint32_t v2[32];
@@ -231,26 +228,30 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const int S = a.sched.n_steps;
   const bool save_states = a.states != nullptr;
 
-  // mbarriers.  [0] weights; per slot s (stride 48 B): opnd (256 epilogue arrivals), acc (tcgen05.commit), tma (TMA tx),
-  // xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), ring (IO: step entry filled)
+  // mbarriers.  [0] weights; per slot s (stride 80 B): opnd[2] (256 epilogue arrivals each), acc[2] (tcgen05.commit), tma
+  // (TMA tx), xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), ring[2] (IO:
+  // step entry filled).  opnd/acc/ring come in pairs used alternately: a parity wait can only tell apart ONE outstanding phase,
+  // and the fine-grained hand-offs below put two phases of the same kind in flight.
   const uint32_t bar_w = base + SMEM_BARS;
-  auto bar_opnd = [&](int s) { return base + SMEM_BARS + 8u + 48u * s; };
-  auto bar_acc = [&](int s) { return base + SMEM_BARS + 16u + 48u * s; };
-  auto bar_tma = [&](int s) { return base + SMEM_BARS + 24u + 48u * s; };
-  auto bar_xfull = [&](int s) { return base + SMEM_BARS + 32u + 48u * s; };
-  auto bar_xfree = [&](int s) { return base + SMEM_BARS + 40u + 48u * s; };
-  auto bar_ring = [&](int s) { return base + SMEM_BARS + 48u + 48u * s; };
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 128);
+  auto bar_opnd = [&](int s, int i) { return base + SMEM_BARS + 8u + 80u * s + 8u * i; };
+  auto bar_acc = [&](int s, int i) { return base + SMEM_BARS + 24u + 80u * s + 8u * i; };
+  auto bar_tma = [&](int s) { return base + SMEM_BARS + 40u + 80u * s; };
+  auto bar_xfull = [&](int s) { return base + SMEM_BARS + 48u + 80u * s; };
+  auto bar_xfree = [&](int s) { return base + SMEM_BARS + 56u + 80u * s; };
+  auto bar_ring = [&](int s, int i) { return base + SMEM_BARS + 64u + 80u * s + 8u * i; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 192);
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int s = 0; s < NUM_SLOTS; ++s) {
-      mbar_init(bar_opnd(s), EPI_THREADS_PER_SLOT);
-      mbar_init(bar_acc(s), 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_opnd(s, i), EPI_THREADS_PER_SLOT);
+        mbar_init(bar_acc(s, i), 1);
+        mbar_init(bar_ring(s, i), 1);
+      }
       mbar_init(bar_tma(s), 1);
       mbar_init(bar_xfull(s), EPI_THREADS_PER_SLOT);
       mbar_init(bar_xfree(s), 1);
-      mbar_init(bar_ring(s), 1);
     }
     mbar_fence_init();
     tma_prefetch_desc(&tm_y0);
@@ -289,7 +290,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     // TMEM columns of a slot: [0,192) P1/P2 accumulators (P3 reuses [0,64)), [192,256) the resident fp32 state Y
     const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + hh * 32;
     const uint32_t pair_bar = 1 + slot * 4 + quad;         // named barrier shared by the two warps that own the same rows
-    uint32_t par_acc = 0, par_tma = 0, par_xfree = 0, par_ring = 0;
+    uint32_t par_accA = 0, par_accB = 0, par_tma = 0, par_xfree = 0;
     uint32_t gstep = 0;
     Epi3Ctx c3;
     c3.x_row = x_row;
@@ -342,7 +343,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tc_wait_st();
       }
       fence_proxy_async();
-      mbar_arrive(bar_opnd(slot));                         // A0 ready -> P1 of step 0
+      mbar_arrive(bar_opnd(slot, 0));                      // A0 ready -> P1 of step 0
       mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
 
       for (int k = 0; k < S; ++k, ++gstep) {
@@ -350,49 +351,58 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           mbar_wait(bar_xfree(slot), par_xfree);
           par_xfree ^= 1;
         }
-        mbar_wait(bar_ring(slot), par_ring);               // this step's bias row + scalars are in the ring
-        par_ring ^= 1;
+        mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's bias row + scalars are in the ring
         const float* ent = ring + (gstep % 3u) * RING_LD;
         const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
         const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
 
-        // ---- epilogue 1: h1f = tanh(z1f + b1f(t)), h1g = tanh(z1g + c1(t)) -> A1f, A1g --------------------------------
-        mbar_wait(bar_acc(slot), par_acc);
-        par_acc ^= 1;
+        // ---- epilogue 1: h1f = tanh(z1f + b1f(t)) -> A1f (P2f may start), h1g = tanh(z1g + c1(t)) -> A1g -------------------
+        mbar_wait(bar_acc(slot, 0), par_accA);
+        par_accA ^= 1;
         tc_fence_after();
         {
-          uint32_t vf[32], vg[32];
-          ld_fg<DUAL>(tm_lane, tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, vf, vg);
-          act32_to_operand(vf, ent + hh * 32, a1f_row, row, hh * 4);
-          act32_to_operand(vg, ent + gcol + hh * 32, a1g_row, row, hh * 4);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm_lane, v);
+          tc_wait_ld();
+          act32_to_operand(v, ent + hh * 32, a1f_row, row, hh * 4);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(slot, 1));                  // A1f ready -> P2f
+          ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
+          act32_to_operand(v, ent + gcol + hh * 32, a1g_row, row, hh * 4);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(slot, 0));                  // A1g ready -> P2g
         }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar_opnd(slot));
 
-        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 ; partial of w3 . tanh(z2g + c2) ----------------------------------------
-        mbar_wait(bar_acc(slot), par_acc);
-        par_acc ^= 1;
+        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 (P3 may start) ; partial of w3 . tanh(z2g + c2) ----------------------------
+        mbar_wait(bar_acc(slot, 1), par_accB);
+        par_accB ^= 1;
         tc_fence_after();
         {
-          uint32_t vf[32], vg[32];
-          ld_fg<DUAL>(tm_lane, tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, vf, vg);
-          act32_to_operand(vf, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm_lane, v);
+          tc_wait_ld();
+          act32_to_operand(v, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
+          mbar_wait(bar_acc(slot, 0), par_accA);
+          par_accA ^= 1;
+          tc_fence_after();
+          ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
           float gd = 0.f;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(c2v + j);
             const float4 w = *reinterpret_cast<const float4*>(w3v + j);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j]) + b.x), w.x, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 1]) + b.y), w.y, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 2]) + b.z), w.z, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(vg[j + 3]) + b.w), w.w, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
           }
           gpart[hh * TILE_M + row] = gd;
         }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar_opnd(slot));
 
         // ---- epilogue 3 -----------------------------------------------------------------------------------------------------
         if (!save_states) {                                  // stores of the previous step have finished reading X
@@ -410,8 +420,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) = make_float4(n4.x * sc.y, n4.y * sc.y, n4.z * sc.y, n4.w * sc.y);
           }
         }
-        mbar_wait(bar_acc(slot), par_acc);
-        par_acc ^= 1;
+        mbar_wait(bar_acc(slot, 1), par_accB);
+        par_accB ^= 1;
         tc_fence_after();
         named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
         const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
@@ -427,7 +437,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
         fence_proxy_async();
         tc_fence_before();
-        if (k + 1 < S) mbar_arrive(bar_opnd(slot));        // A0 = y' ready -> P1 of step k+1
+        if (k + 1 < S) mbar_arrive(bar_opnd(slot, 0));     // A0 = y' ready -> P1 of step k+1
         mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
       }
     }
@@ -445,37 +455,42 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
       const uint32_t aA0 = slot_u32 + OFF_A0, aA1f = slot_u32 + OFF_A1F, aA1g = slot_u32 + OFF_A1G;
       const uint32_t aB1 = base + IMG_B1, aW2 = base + IMG_W2, aV2 = base + IMG_V2, aV2a = base + IMG_V2A, aW3 = base + IMG_W3;
-      uint32_t par_op = 0;
+      uint32_t par_op0 = 0, par_op1 = 0;
       mbar_wait(bar_w, 0);
       for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
         for (int k = 0; k < S; ++k) {
-          // P1: [z1f | z1g (| z1g_alt)]
-          mbar_wait(bar_opnd(slot), par_op);
-          par_op ^= 1;
+          // P1: [z1f | z1g (| z1g_alt)] = y . [W1y ; V1y (; V1y_alt)]^T
+          mbar_wait(bar_opnd(slot, 0), par_op0);
+          par_op0 ^= 1;
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
-          tc_commit(bar_acc(slot));
-          // P2: z2f, z2g (, z2g_alt)
-          mbar_wait(bar_opnd(slot), par_op);
-          par_op ^= 1;
+          tc_commit(bar_acc(slot, 0));
+          // P2f: z2f = h1f . W2^T  (overwrites the z1f columns the epilogue has already consumed)
+          mbar_wait(bar_opnd(slot, 1), par_op1);
+          par_op1 ^= 1;
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
+          tc_commit(bar_acc(slot, 1));
+          // P2g: z2g = h1g . V2^T (, z2g_alt = h1g . V2alt^T)
+          mbar_wait(bar_opnd(slot, 0), par_op0);
+          par_op0 ^= 1;
+          tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
           if (DUAL) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
           }
-          tc_commit(bar_acc(slot));
-          // P3: drift output (reuses the z2f columns, already consumed by epilogue 2)
-          mbar_wait(bar_opnd(slot), par_op);
-          par_op ^= 1;
+          tc_commit(bar_acc(slot, 0));
+          // P3: drift output f = h2f . W3^T (reuses the z2f columns, already consumed by epilogue 2)
+          mbar_wait(bar_opnd(slot, 1), par_op1);
+          par_op1 ^= 1;
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
-          tc_commit(bar_acc(slot));
+          tc_commit(bar_acc(slot, 1));
         }
       }
     }
@@ -491,8 +506,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     int my_tiles = 0;
     for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) ++my_tiles;
     const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)S;
-    // Ring entry of global step g -> ring[g % 3].  At most ONE phase of bar_ring may be outstanding (parity waits alias after
-    // two), so the entry of step g+1 is published only after the epilogue finished step g; the global reads are issued early.
+    // Ring entry of global step g -> ring[g % 3], announced on bar_ring[g & 1].  Entry g+1 is published at the start of IO
+    // iteration g, i.e. once the epilogue has finished step g-1: its slot (last read in step g-2) is free and its barrier's
+    // previous phase (entry g-1) has been consumed, so every barrier has at most one outstanding phase.
     struct Ent { float2 b[3]; float4 sc; int2 so; };
     auto ent_fetch = [&](uint32_t g, Ent& e) {
       const int k = (int)(g % (uint32_t)S);
@@ -520,7 +536,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         *reinterpret_cast<int2*>(dst + BIAS1_LD + 4) = e.so;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ring(slot));
+      if (lane == 0) mbar_arrive(bar_ring(slot, g & 1));
     };
     if (total_steps > 0) {
       Ent e;
@@ -547,14 +563,14 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       }
       par_xfull ^= 1;
       for (int k = 0; k < S; ++k, ++gstep) {
-        const bool more = gstep + 1 < total_steps;
-        Ent e;
-        if (more) ent_fetch(gstep + 1, e);
-        if (lane == 0) mbar_wait(bar_xfull(slot), par_xfull);   // epilogue 3 of step k finished writing X / states staging
-        __syncwarp();
-        if (more) ent_publish(gstep + 1, e);
+        if (gstep + 1 < total_steps) {
+          Ent e;
+          ent_fetch(gstep + 1, e);
+          ent_publish(gstep + 1, e);
+        }
         if (lane == 0) {
           const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
+          mbar_wait(bar_xfull(slot), par_xfull);           // epilogue 3 of step k finished writing X / states staging
           if (oe > ob) {
             tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, row0, ob + 1);
             tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, row0, ob + 1);
