@@ -1,0 +1,126 @@
+"""GPU parity of the fused backward (discretise-then-optimise) against fp64 autograd through the oracle — the gradients
+torch.autograd would produce through the reference solver (`adjoint: false`, yml:41): y0, every weight incl. the time
+columns W1[:,64:66], every bias."""
+import pytest
+import torch
+
+import trajsde_b200 as tb
+from helpers import DecoderSDE, EncoderSDE, init_like_reference, make_dw, net_params
+from oracle import sde_oracle as so
+from trajsde_b200 import ops
+from trajsde_b200.schedule import euler_schedule
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def oracle_grads(nets, y0, ts, dW, cot_ys, cot_g=None, nus_mask=None):
+    """fp64 autograd through oracle.euler_solve_ref. nets: list of param dicts [f, g] or [f, g_nus, g_argo]."""
+    P = [{k: v.double().clone().requires_grad_(True) for k, v in n.items()} for n in nets]
+    y = y0.double().clone().requires_grad_(True)
+    if nus_mask is None:
+        ys, g = so.euler_solve_ref(P[0], P[1], y, ts, 0.1, dW.double())
+    else:
+        ys, g = so.euler_solve_ref(P[0], P[1], y, ts, 0.1, dW.double(), nus_mask, P[2])
+    loss = (ys * cot_ys.double()).sum()
+    if cot_g is not None:
+        loss = loss + (g[:, 0] * cot_g.double()).sum()
+    leaves = [y] + [t for n in P for t in n.values()]
+    grads = torch.autograd.grad(loss, leaves)
+    names = ['y0'] + [f'net{i}.{k}' for i, n in enumerate(P) for k in n]
+    return dict(zip(names, grads))
+
+
+def rel_err(a, b):
+    return float((a.double().cpu() - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('mode,tol', [('exact', 2e-4), ('tc_f16', 3e-2)])
+@pytest.mark.parametrize('F,rows', [(10, 37), (60, 70)])
+def test_decoder_gradients_vs_fp64_autograd(mode, tol, F, rows):
+    sde = init_like_reference(DecoderSDE(), seed=F + rows, bias_std=0.2).to(DEV)
+    ts = torch.linspace(0, 0.1 * F, F + 1)
+    sched = euler_schedule(ts, 0.1)
+    g = torch.Generator().manual_seed(F)
+    y0 = torch.relu(torch.randn(rows, 64, generator=g))
+    dW = make_dw(sched.h, rows, seed=F + 1)
+    cot = torch.randn(F + 1, rows, 64, generator=g)
+    ref = oracle_grads([net_params(sde.f_func), net_params(sde.g_func)], y0, ts, dW, cot)
+
+    y = y0.to(DEV).requires_grad_(True)
+    ys = tb.sdeint(sde, y, ts, bm=dW.to(DEV), dt=0.1, method='euler', mode=mode)
+    (ys * cot.to(DEV)).sum().backward()
+    assert rel_err(y.grad, ref['y0']) < tol, ('y0', rel_err(y.grad, ref['y0']))
+    for i, net in enumerate((sde.f_func, sde.g_func)):
+        for k, prm in net.net.named_parameters():
+            e = rel_err(prm.grad, ref[f'net{i}.{k}'])
+            print(f"[{mode}] F={F} net{i}.{k}: rel err {e:.2e}")
+            assert e < tol, (i, k, e)
+
+
+@pytest.mark.parametrize('mode,tol', [('exact', 2e-4), ('tc_f16', 3e-2)])
+def test_sdeint_dual_gradients_incl_g_output(mode, tol):
+    """Encoder call site: gradients flow through ys AND through the returned diffusion g (DiffBCE consumes it,
+    losses/diff_BCE.py:11-16); rows are routed to g_nus / g_argo by nus_mask."""
+    rows = 90
+    sde = init_like_reference(EncoderSDE(), seed=5, bias_std=0.2).to(DEV)
+    ts = torch.tensor([0.3, 0.4])
+    sched = euler_schedule(ts, 0.1)
+    g = torch.Generator().manual_seed(5)
+    y0 = torch.randn(rows, 64, generator=g) * 0.5
+    mask = torch.rand(rows, generator=g) > 0.4
+    dW = make_dw(sched.h, rows, seed=6)
+    cot = torch.randn(2, rows, 64, generator=g)
+    cot_g = torch.randn(rows, generator=g)
+    nets = [net_params(sde.f_func), net_params(sde.g_nus), net_params(sde.g_argo)]
+    ref = oracle_grads(nets, y0, ts, dW, cot, cot_g, mask)
+
+    y = y0.to(DEV).requires_grad_(True)
+    ys, gg = tb.sdeint_dual(sde, y, ts, mask.to(DEV), bm=dW.to(DEV), dt=0.1, method='euler', mode=mode)
+    ((ys * cot.to(DEV)).sum() + (gg[:, 0] * cot_g.to(DEV)).sum()).backward()
+    assert rel_err(y.grad, ref['y0']) < tol
+    for i, net in enumerate((sde.f_func, sde.g_nus, sde.g_argo)):
+        for k, prm in net.net.named_parameters():
+            e = rel_err(prm.grad, ref[f'net{i}.{k}'])
+            assert e < tol, (i, k, e)
+
+
+def test_philox_backward_equals_supplied_dw_backward():
+    """The backward regenerates the forward's Philox increments: identical gradients to the supplied-dW run."""
+    sde = init_like_reference(DecoderSDE(), seed=8).to(DEV)
+    ts = torch.linspace(0, 2, 21)
+    sched = euler_schedule(ts, 0.1)
+    y0 = torch.relu(torch.randn(50, 64, generator=torch.Generator().manual_seed(8))).to(DEV)
+
+    def run(bm, seed):
+        for p_ in sde.parameters():
+            p_.grad = None
+        y = y0.clone().requires_grad_(True)
+        ys = tb.sdeint(sde, y, ts, bm=bm, dt=0.1, method='euler', mode='exact', seed=seed)
+        ys.square().mean().backward()
+        return [y.grad.clone()] + [p_.grad.clone() for p_ in sde.parameters()]
+
+    a = run(None, 31)
+    dW = ops.philox_dw(ops.DeviceSchedule.get(sched, torch.device(DEV)), 50, 31, torch.device(DEV))
+    b = run(dW, None)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_backward_is_deterministic_and_grad_free_inference():
+    sde = init_like_reference(DecoderSDE(), seed=3).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    y0 = torch.relu(torch.randn(300, 64, generator=torch.Generator().manual_seed(3))).to(DEV)
+
+    def grads():
+        for p_ in sde.parameters():
+            p_.grad = None
+        ys = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode='tc_f16', seed=5)
+        ys[1:].mean().backward()
+        return [p_.grad.clone() for p_ in sde.parameters()]
+
+    a, b = grads(), grads()
+    assert all(torch.equal(x, y) for x, y in zip(a, b))          # fixed-order reduction: bit-reproducible
+    with torch.no_grad():
+        ys = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode='tc_f16', seed=5)
+    assert not ys.requires_grad
