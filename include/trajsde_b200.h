@@ -8,7 +8,7 @@
  *                         (solver loop models/utils/sdeint.py:326-384, Euler step :467-485, f/g glue :537-566,
  *                          nets dec…sde.py:107-127,141-158,180-195 / enc…sep2.py:372-398,412-440,462-482)
  *   trajsde_euler_bwd   : torch.autograd through that solver (config `adjoint: false`, yml:41): discretise-then-optimise
- *   trajsde_enc_fwd/bwd : the encoder recurrence 21 x [sdeint_dual one step + GRU_Unit jump]
+ *   trajsde_enc_fwd     : the encoder recurrence 21 x [sdeint_dual one step + GRU_Unit jump]
  *                           enc_hivt_nusargo_sde_sep2.py:128-182 + models/utils/ode_utils.py:136-152
  *   trajsde_philox_dw   : BrownianInterval increments W(t1)-W(t0) ~ N(0,(t1-t0) I)  models/utils/sdeint.py:983-984
  *
@@ -160,6 +160,51 @@ int trajsde_euler_fwd(const TrajsdeEulerFwdArgs* args, void* cuda_stream);
 
 int64_t trajsde_euler_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
 int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* args, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused encoder recurrence: n_steps x [one Euler step of the dual-diffusion SDE + GRU_Unit jump], the loop body of
+ * LocalEncoderSDESepPara2.forward (models/encoders/enc_hivt_nusargo_sde_sep2.py:128-182) around sdeint_dual
+ * (models/utils/sdeint.py:110-197) and GRU_Unit.forward (models/utils/ode_utils.py:136-152).  The latent state of a
+ * 128-row tile stays on chip for all iterations.  Tensor-core mode only (TRAJSDE_MODE_TC_F16).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* GRU_Unit parameters, nn.Linear layout (ode_utils.py:115-133): update_gate / reset_gate / new_state_net = Linear(128,64),
+ * Tanh, Linear(64,64)(, Sigmoid).  Columns 0..63 of u1/r1 multiply h_cur, 64..127 the input; columns 0..63 of n1 multiply
+ * the input, 64..127 reset*h_cur (ode_utils.py:137,142). */
+typedef struct {
+  const float* u1; const float* ub1; const float* u2; const float* ub2;   /* update_gate   [64,128] [64] [64,64] [64] */
+  const float* r1; const float* rb1; const float* r2; const float* rb2;   /* reset_gate                                */
+  const float* n1; const float* nb1; const float* n2; const float* nb2;   /* new_state_net                             */
+} TrajsdeGru;
+
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;              /* TRAJSDE_MODE_TC_F16 */
+  int64_t rows;
+  int32_t dim;               /* 64 */
+  int32_t flags;
+  TrajsdeSchedule sched;     /* one step per loop iteration: step_tab[4*i] = t0_i, h_i, sin t0_i, cos t0_i (n_steps <= 32);
+                                out_* tables unused */
+  TrajsdeMlp drift;
+  TrajsdeMlp diffusion;      /* g_nus  (rows with alt_mask != 0, or all rows if alt_mask == NULL) */
+  TrajsdeMlp diffusion_alt;  /* g_argo (rows with alt_mask == 0) */
+  const uint8_t* alt_mask;   /* device [rows] nus_mask or NULL */
+  TrajsdeGru gru;
+  TrajsdeNoise noise;        /* dw[n_steps, rows, 64] or Philox (counter step = step_offset + iteration) */
+  const float* h0;           /* [rows,64] initial hidden state, row stride h0_row_stride elements */
+  int64_t h0_row_stride;
+  const float* aa_out;       /* [n_slots, rows, 64] GRU inputs (output of the AA encoder, enc…sep2.py:107-121) */
+  const int32_t* slot;       /* device [n_steps]: data slot consumed by iteration i (run_backwards: 20, 19, ..., 0) */
+  const uint8_t* obs_mask;   /* device [rows, n_slots] bool: actors_mask (enc…sep2.py:100); row stride obs_mask_row_stride */
+  int64_t obs_mask_row_stride;
+  float* latent;             /* out [n_steps, rows, 64]: post-GRU state of every iteration (latent_ys, :180,184) */
+  float* g_out;              /* out [n_steps, rows]: diffusion evaluated at the start of every iteration's step (:149,171) */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeEncFwdArgs;
+
+int64_t trajsde_enc_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
+int trajsde_enc_fwd(const TrajsdeEncFwdArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

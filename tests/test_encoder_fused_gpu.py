@@ -1,0 +1,92 @@
+"""Fused encoder recurrence (21 x [Euler step + GRU jump] in one kernel) against the reference loop fixture, the oracle
+and the stepwise path."""
+import pytest
+import torch
+
+import trajsde_b200 as tb
+from conftest import sub
+from helpers import EncoderSDE, init_like_reference, load_net, net_params
+from oracle import sde_oracle as so
+from trajsde_b200 import encoder as enc
+from trajsde_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def gru_from(params):
+    g = syn.GRUUnit()
+    g.load_state_dict(params)
+    return g.to(DEV)
+
+
+def test_fused_encoder_vs_reference_fixture(golden_encoder):
+    """Reference's own sdeint_dual + GRU_Unit loop (tests/golden/encoder_loop.npz): 40 rows, dual g, ragged masks."""
+    e = golden_encoder
+    sde = EncoderSDE()
+    load_net(sde.f_func, sub(e, 'f')); load_net(sde.g_nus, sub(e, 'g_nus')); load_net(sde.g_argo, sub(e, 'g_argo'))
+    sde = sde.to(DEV)
+    gru = gru_from(sub(e, 'gru'))
+    t = lambda k: torch.from_numpy(e[k]).to(DEV)  # noqa: E731
+    with torch.no_grad():
+        lat, g = enc.encoder_recurrence(sde, gru, t('h0'), t('aa_out'), t('actors_mask'), t('nus_mask'), dW=t('dW'), mode='tc_f16',
+                                        fused=True)
+    assert lat.shape == (21, 40, 64) and g.shape == (21, 40)
+    ref_lat, ref_g = torch.from_numpy(e['latent_ys']), torch.from_numpy(e['g'])[:, :, 0]
+    err, gerr = (lat.cpu() - ref_lat).abs().max().item(), (g.cpu() - ref_g).abs().max().item()
+    print(f"fused encoder vs reference fixture: latent max-abs {err:.3e}, g max-abs {gerr:.3e}")
+    assert err < 2e-2 and gerr < 3e-3
+
+
+@pytest.mark.parametrize('rows,mixed', [(1, True), (127, True), (128, False), (300, True), (1000, True)])
+def test_fused_encoder_vs_oracle_and_stepwise(rows, mixed):
+    sde = init_like_reference(EncoderSDE(), seed=rows, bias_std=0.2).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), rows + 1, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(rows)
+    h0 = (torch.randn(64, generator=g) * 0.02).repeat(rows, 1)
+    aa = torch.randn(21, rows, 64, generator=g)
+    am = torch.rand(rows, 21, generator=g) > 0.3
+    nm = (torch.rand(rows, generator=g) > 0.5) if mixed else torch.zeros(rows, dtype=torch.bool)
+    dW = torch.randn(21, rows, 64, generator=g) * 0.3
+    ref_lat, ref_g = so.encoder_recurrence_ref(net_params(sde.f_func), net_params(sde.g_nus), net_params(sde.g_argo),
+                                               {k: v.detach().cpu() for k, v in gru.state_dict().items()}, h0, aa, am, nm, dW)
+    with torch.no_grad():
+        lat, gg = enc.encoder_recurrence(sde, gru, h0.to(DEV), aa.to(DEV), am.to(DEV), nm.to(DEV), dW=dW.to(DEV), fused=True)
+        lat_s, gg_s = enc.encoder_recurrence(sde, gru, h0.to(DEV), aa.to(DEV), am.to(DEV), nm.to(DEV), dW=dW.to(DEV), fused=False,
+                                             mode='exact')
+    assert (lat_s.cpu() - ref_lat).abs().max() < 5e-5                         # stepwise exact path = oracle
+    assert (lat.cpu() - ref_lat).abs().max() < 2e-2
+    assert (gg.cpu() - ref_g[:, :, 0]).abs().max() < 3e-3
+    out = enc.eos_gather(lat, torch.nn.functional.one_hot(torch.randint(0, 21, (rows,), generator=g), 21).bool().to(DEV))
+    assert out.shape == (rows, 64)
+
+
+def test_fused_encoder_philox_deterministic_and_sharding_invariant():
+    rows = 260
+    sde = init_like_reference(EncoderSDE(), seed=1).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), 2).to(DEV)
+    b = syn.make_batch(13, 19, seed=3, mixed_sources=True)
+    h0, aa, am, nm = (x.to(DEV) for x in (b.enc_h0, b.aa_out, b.actors_mask, b.nus_mask))
+    assert h0.shape[0] == rows
+    with torch.no_grad():
+        a1, g1 = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, seed=11, fused=True)
+        a2, g2 = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, seed=11, fused=True)
+        a3, _ = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, seed=12, fused=True)
+        p1, _ = enc.encoder_recurrence(sde, gru, h0[100:], aa[:, 100:].contiguous(), am[100:], nm[100:], seed=11, fused=True,
+                                       row_offset=100)
+    assert torch.equal(a1, a2) and torch.equal(g1, g2) and not torch.equal(a1, a3)
+    assert torch.allclose(p1, a1[:, 100:], atol=1e-4, rtol=0)
+    assert torch.isfinite(a1).all() and (g1 > 0).all() and (g1 < 1).all()
+
+
+def test_fused_encoder_rejects_training_and_exact_mode():
+    sde = init_like_reference(EncoderSDE(), seed=1).to(DEV)
+    gru = syn.GRUUnit().to(DEV)
+    h0 = torch.zeros(4, 64, device=DEV)
+    aa = torch.zeros(21, 4, 64, device=DEV)
+    am = torch.ones(4, 21, dtype=torch.bool, device=DEV)
+    nm = torch.zeros(4, dtype=torch.bool, device=DEV)
+    with pytest.raises(NotImplementedError):
+        enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True)          # grad enabled + parameters require grad
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True, mode='exact')

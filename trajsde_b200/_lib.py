@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_abi_version', 'trajsde_last_error_string', 'trajsde_device_sm_count',
     'trajsde_euler_fwd_workspace_bytes', 'trajsde_euler_fwd',
     'trajsde_euler_bwd_workspace_bytes', 'trajsde_euler_bwd',
-    'trajsde_philox_dw',
+    'trajsde_philox_dw', 'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_fwd',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers

@@ -137,6 +137,40 @@ int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* a, void* cuda_stream) {
   return launch_euler_bwd_exact(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+int64_t trajsde_enc_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {
+  if (mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "fused encoder exists in TC_F16 mode only (mode %d)", mode);
+  return enc_fwd_tc_workspace_bytes(rows, n_steps, dual);
+}
+
+int trajsde_enc_fwd(const TrajsdeEncFwdArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeEncFwdArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeEncFwdArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "fused encoder exists in TC_F16 mode only (mode %d)", a->mode);
+  if (a->rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  if (a->sched.n_steps <= 0 || !a->sched.step_tab || !aligned16(a->sched.step_tab))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "schedule: n_steps=%d or step_tab null/misaligned", a->sched.n_steps);
+  int rc;
+  if ((rc = check_mlp(a->drift, "drift")) != 0) return rc;
+  if ((rc = check_mlp(a->diffusion, "diffusion")) != 0) return rc;
+  if (a->alt_mask && (rc = check_mlp(a->diffusion_alt, "diffusion_alt")) != 0) return rc;
+  const TrajsdeGru& g = a->gru;
+  if (!g.u1 || !g.ub1 || !g.u2 || !g.ub2 || !g.r1 || !g.rb1 || !g.r2 || !g.rb2 || !g.n1 || !g.nb1 || !g.n2 || !g.nb2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "gru: null weight pointer");
+  if (a->rows == 0) return TRAJSDE_OK;
+  if (!a->h0 || !a->aa_out || !a->slot || !a->obs_mask || !a->latent || !a->g_out)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h0/aa_out/slot/obs_mask/latent/g_out null");
+  if (!aligned16(a->h0) || (a->h0_row_stride & 3) || !aligned16(a->aa_out) || !aligned16(a->latent) ||
+      (a->noise.dw && !aligned16(a->noise.dw)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "h0/aa_out/latent/dw must be 16-byte aligned (row stride multiple of 4 elements)");
+  int64_t need = enc_fwd_tc_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
+  if (a->workspace_bytes < need || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  if ((rc = check_device()) != 0) return rc;
+  return launch_enc_fwd_tc(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
   if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
   int rc;

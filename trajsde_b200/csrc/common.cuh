@@ -94,6 +94,8 @@ int launch_euler_bwd_exact(const TrajsdeEulerBwdArgs& a, cudaStream_t s);
 int64_t euler_bwd_exact_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
 int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
+int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s);
+int64_t enc_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_philox_dw(const TrajsdeSchedule& sched, const TrajsdeNoise& noise, int64_t rows, float* out, cudaStream_t s);
 
 }  // namespace trajsde

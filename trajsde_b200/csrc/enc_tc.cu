@@ -1,0 +1,531 @@
+// Fused encoder recurrence (TRAJSDE_MODE_TC_F16): n_steps x [one Euler–Maruyama step of the dual-diffusion latent SDE +
+// GRU_Unit observation jump] in ONE persistent sm_100a kernel — the loop body of LocalEncoderSDESepPara2.forward
+// (models/encoders/enc_hivt_nusargo_sde_sep2.py:128-182) that the reference runs as 21 x [sdeint_dual (models/utils/sdeint.py:
+// 110-197) + GRU_Unit.forward (models/utils/ode_utils.py:136-152)] ~ 191 aten launches per iteration with two host syncs.
+//
+// Machine mapping: one 128-row tile per CTA at a time; 16 epilogue warps (thread = one row x one 16-channel quarter) + one
+// MMA-issuer warp.  The fp32 latent state of the tile lives in TMEM for all iterations; all weights (SDE 56 KB + GRU 72 KB,
+// fp16 128B-swizzled UMMA tiles) plus the per-iteration layer-1 bias rows are staged once per CTA with bulk TMA copies.
+// Per iteration eight dependent tcgen05 phases, handed over through alternating mbarrier pairs exactly like euler_tc.cu:
+//   P1  [z1f|z1g|z1g_alt] = y . [W1y;V1y;V1y_alt]^T      P2f z2f = h1f . W2^T      P2g z2g = h1g . V2^T (+alt)    P3 f = h2f . W3^T
+//   G1  [zu|zr] = [y1|x] . [U1;R1]^T (K=128)             G2  u' = tu . U2^T, r' = tr . R2^T
+//   G3  zn = [x|r*y1] . N1^T (K=128)                     G4  n = tn . N2^T
+// with  y1 = y + f h + g dW,  u = sigmoid(u'), r = sigmoid(r'),  h' = (1-u) n + u y1,  state <- mask ? h' : y1.
+// HBM traffic per row-iteration: x in (256 B), latent out (256 B), g out (4 B), mask (1 B) [+ dW in (256 B) when supplied].
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace trajsde {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 20 * 32;      // 16 epilogue warps + MMA warp + 3 idle warps (setmaxnreg works on warpgroups)
+constexpr int EPI_REGS = 112, AUX_REGS = 32;
+constexpr int S_MAX = 32;
+
+// ---- packed image (bytes) -------------------------------------------------------------------------------------------------
+constexpr uint32_t IMG_B1 = 0, IMG_W2 = 24576, IMG_V2 = 32768, IMG_V2A = 40960, IMG_W3 = 49152;
+constexpr uint32_t IMG_UR1H = 57344, IMG_UR1X = 73728, IMG_U2 = 90112, IMG_R2 = 98304;
+constexpr uint32_t IMG_N1X = 106496, IMG_N1RH = 114688, IMG_N2 = 122880;
+constexpr uint32_t IMG_VEC = 131072;     // 1024 fp32
+constexpr uint32_t IMG_BIAS1 = 135168;   // [S_MAX][192] fp32
+constexpr uint32_t IMG_BYTES = IMG_BIAS1 + S_MAX * 192 * 4;   // 159744
+constexpr int VEC_B2 = 0, VEC_C2 = 64, VEC_C2A = 128, VEC_B3 = 192, VEC_W3G = 256, VEC_W3GA = 320, VEC_C3 = 384, VEC_C3A = 385;
+constexpr int VEC_UB1 = 512, VEC_RB1 = 576, VEC_UB2 = 640, VEC_RB2 = 704, VEC_NB1 = 768, VEC_NB2 = 832;
+
+// ---- shared memory map -------------------------------------------------------------------------------------------------------
+constexpr uint32_t OFF_AH = IMG_BYTES, OFF_AX = OFF_AH + 16384, OFF_A1F = OFF_AX + 16384, OFF_A1G = OFF_A1F + 16384;
+constexpr uint32_t OFF_GPART = OFF_A1G + 16384;             // [4 quarters][128 rows] fp32
+constexpr uint32_t OFF_BARS = OFF_GPART + 4 * TILE_M * 4;
+constexpr uint32_t SMEM_TOTAL = OFF_BARS + 128;
+constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
+static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// TMEM columns
+constexpr uint32_t TM_Y = 192, TM_G1 = 256, TM_ZR = 320, TM_UP = 384, TM_RP = 448, TM_ZN = 256, TM_N = 320;
+
+struct EncParams {
+  TrajsdeEncFwdArgs a;
+  const uint8_t* img;
+  int num_tiles;
+  int dual;
+};
+
+__device__ __forceinline__ void put_h(uint8_t* img, uint32_t off, int n, int k, float v) {
+  *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(v);
+}
+
+__global__ void enc_pack_kernel(TrajsdeEncFwdArgs a, uint8_t* __restrict__ img, int dual) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int idx = tid; idx < 192 * 64; idx += nth) {
+    const int n = idx >> 6, k = idx & 63, net = n >> 6, r = n & 63;
+    const float* w = net == 0 ? a.drift.w1 : net == 1 ? a.diffusion.w1 : (dual ? a.diffusion_alt.w1 : nullptr);
+    put_h(img, IMG_B1, n, k, w ? w[r * TS_IN1 + k] : 0.f);
+  }
+  for (int idx = tid; idx < 64 * 64; idx += nth) {
+    const int n = idx >> 6, k = idx & 63;
+    put_h(img, IMG_W2, n, k, a.drift.w2[n * 64 + k]);
+    put_h(img, IMG_V2, n, k, a.diffusion.w2[n * 64 + k]);
+    put_h(img, IMG_V2A, n, k, dual ? a.diffusion_alt.w2[n * 64 + k] : 0.f);
+    put_h(img, IMG_W3, n, k, a.drift.w3[n * 64 + k]);
+    put_h(img, IMG_U2, n, k, a.gru.u2[n * 64 + k]);
+    put_h(img, IMG_R2, n, k, a.gru.r2[n * 64 + k]);
+    put_h(img, IMG_N2, n, k, a.gru.n2[n * 64 + k]);
+    put_h(img, IMG_N1X, n, k, a.gru.n1[n * 128 + k]);
+    put_h(img, IMG_N1RH, n, k, a.gru.n1[n * 128 + 64 + k]);
+    // [U1;R1]: rows 0..63 update gate, 64..127 reset gate; K-half 0 multiplies h_cur, K-half 1 the input
+    put_h(img, IMG_UR1H, n, k, a.gru.u1[n * 128 + k]);
+    put_h(img, IMG_UR1H, n + 64, k, a.gru.r1[n * 128 + k]);
+    put_h(img, IMG_UR1X, n, k, a.gru.u1[n * 128 + 64 + k]);
+    put_h(img, IMG_UR1X, n + 64, k, a.gru.r1[n * 128 + 64 + k]);
+  }
+  float* vec = reinterpret_cast<float*>(img + IMG_VEC);
+  for (int i = tid; i < 1024; i += nth) {
+    float v = 0.f;
+    const int c = i & 63;
+    if (i < 64) v = a.drift.b2[c];
+    else if (i < 128) v = a.diffusion.b2[c];
+    else if (i < 192) v = dual ? a.diffusion_alt.b2[c] : 0.f;
+    else if (i < 256) v = a.drift.b3[c];
+    else if (i < 320) v = a.diffusion.w3[c];
+    else if (i < 384) v = dual ? a.diffusion_alt.w3[c] : 0.f;
+    else if (i == VEC_C3) v = a.diffusion.b3[0];
+    else if (i == VEC_C3A) v = dual ? a.diffusion_alt.b3[0] : 0.f;
+    else if (i >= VEC_UB1 && i < VEC_UB1 + 64) v = a.gru.ub1[c];
+    else if (i >= VEC_RB1 && i < VEC_RB1 + 64) v = a.gru.rb1[c];
+    else if (i >= VEC_UB2 && i < VEC_UB2 + 64) v = a.gru.ub2[c];
+    else if (i >= VEC_RB2 && i < VEC_RB2 + 64) v = a.gru.rb2[c];
+    else if (i >= VEC_NB1 && i < VEC_NB1 + 64) v = a.gru.nb1[c];
+    else if (i >= VEC_NB2 && i < VEC_NB2 + 64) v = a.gru.nb2[c];
+    vec[i] = v;
+  }
+  float* bias1 = reinterpret_cast<float*>(img + IMG_BIAS1);
+  const int S = a.sched.n_steps;
+  for (int idx = tid; idx < S_MAX * 192; idx += nth) {
+    const int k = idx / 192, n = idx % 192, net = n >> 6, r = n & 63;
+    const TrajsdeMlp* m = net == 0 ? &a.drift : net == 1 ? &a.diffusion : (dual ? &a.diffusion_alt : nullptr);
+    float v = 0.f;
+    if (m && k < S) {
+      const float sn = a.sched.step_tab[4 * k + 2], cs = a.sched.step_tab[4 * k + 3];
+      v = fmaf(m->w1[r * TS_IN1 + 65], cs, fmaf(m->w1[r * TS_IN1 + 64], sn, m->b1[r]));
+    }
+    bias1[idx] = v;
+  }
+}
+
+// act(acc + bias) for 16 accumulator columns -> fp16 -> two 16-byte chunks of an operand row
+template <bool SIGMOID>
+__device__ __forceinline__ float act1(float x) {
+  return SIGMOID ? fmaf(0.5f, ts_tanh_approx(0.5f * x), 0.5f) : ts_tanh_approx(x);
+}
+__device__ __forceinline__ void store16_operand(const float (&t)[16], uint8_t* row_base, uint32_t row, uint32_t chunk0) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[e] = pack_f16x2(t[q * 8 + 2 * e], t[q * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(row_base + (((chunk0 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+__device__ __forceinline__ void tanh16_to_operand(const uint32_t (&v)[16], const float* __restrict__ bias, uint8_t* row_base,
+                                                  uint32_t row, uint32_t chunk0) {
+  float t[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
+    t[4 * q] = ts_tanh_approx(__uint_as_float(v[4 * q]) + b.x);
+    t[4 * q + 1] = ts_tanh_approx(__uint_as_float(v[4 * q + 1]) + b.y);
+    t[4 * q + 2] = ts_tanh_approx(__uint_as_float(v[4 * q + 2]) + b.z);
+    t[4 * q + 3] = ts_tanh_approx(__uint_as_float(v[4 * q + 3]) + b.w);
+  }
+  store16_operand(t, row_base, row, chunk0);
+}
+
+template <bool DUAL>
+__device__ __forceinline__ void ld_g16(uint32_t tm_uniform, uint32_t tm_alt, bool w_mixed, bool use_alt, uint32_t (&v)[16]) {
+  tmem_ld_32x32b_x16(tm_uniform, v);
+  if (DUAL && w_mixed) {
+    uint32_t v2[16];
+    tmem_ld_32x32b_x16(tm_alt, v2);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = use_alt ? v2[j] : v[j];
+  } else {
+    tc_wait_ld();
+  }
+}
+
+template <bool HAS_DW, bool DUAL>
+__global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const TrajsdeEncFwdArgs& a = p.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = a.sched.n_steps;
+
+  const uint32_t bar_w = base + OFF_BARS;
+  auto bar_opnd = [&](int i) { return base + OFF_BARS + 8u + 8u * i; };
+  auto bar_acc = [&](int i) { return base + OFF_BARS + 24u + 8u * i; };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 64);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_opnd(i), NUM_EPI_WARPS * 32);
+      mbar_init(bar_acc(i), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == NUM_EPI_WARPS) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {  // stage weights + bias rows once per CTA (bulk TMA copies)
+    mbar_arrive_expect_tx(bar_w, IMG_BYTES);
+    constexpr uint32_t HALF = 79872;                      // two copies: keeps each bulk copy well below 128 KB
+    bulk_load_1d(base, p.img, HALF, bar_w);
+    bulk_load_1d(base + HALF, p.img + HALF, IMG_BYTES - HALF, bar_w);
+  }
+
+  const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
+  const float* bias1_tab = reinterpret_cast<const float*>(sm + IMG_BIAS1);
+
+  if (warp < NUM_EPI_WARPS) {
+    // =============================================== EPILOGUE WARPS ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    const int quad = warp & 3;                             // TMEM lane quadrant (= warp index % 4)
+    const uint32_t cq = warp >> 2;                         // 16-channel quarter of the row owned by this thread
+    const uint32_t row = quad * 32 + lane;
+    uint8_t* ah_row = sm + OFF_AH + row * 128;
+    uint8_t* ax_row = sm + OFF_AX + row * 128;
+    uint8_t* a1f_row = sm + OFF_A1F + row * 128;
+    uint8_t* a1g_row = sm + OFF_A1G + row * 128;
+    float* gpart = reinterpret_cast<float*>(sm + OFF_GPART);
+    const uint32_t tm = tmem_base + ((uint32_t)(quad * 32) << 16) + cq * 16;
+    const uint32_t quad_bar = 1 + quad;                    // named barrier of the 4 warps that share these rows
+    uint32_t par_accA = 0, par_accB = 0;
+    mbar_wait(bar_w, 0);
+
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int64_t grow = (int64_t)tile * TILE_M + row;
+      const bool valid = grow < a.rows;
+      const bool use_alt = DUAL && valid && (a.alt_mask[grow] == 0);
+      const int gcol = use_alt ? 128 : 64;
+      const bool w_all_alt = DUAL && __all_sync(0xffffffffu, use_alt);
+      const bool w_mixed = DUAL && !w_all_alt && __any_sync(0xffffffffu, use_alt);
+      const uint32_t ucol = w_all_alt ? 128 : 64;
+      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2) + cq * 16;
+      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G) + cq * 16;
+      const float c3b = vec[use_alt ? VEC_C3A : VEC_C3];
+
+      // ---- prologue: h0 -> Y (TMEM) + AH --------------------------------------------------------------------------------
+      {
+        uint32_t yv[16];
+        float t[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) v = *reinterpret_cast<const float4*>(a.h0 + grow * a.h0_row_stride + cq * 16 + 4 * q);
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) yv[j] = __float_as_uint(t[j]);
+        tmem_st_32x32b_x16(tm + TM_Y, yv);
+        store16_operand(t, ah_row, row, cq * 2);
+        tc_wait_st();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_opnd(0));                            // AH ready -> P1 of iteration 0
+
+      for (int it = 0; it < S; ++it) {
+        const float4 stp = *reinterpret_cast<const float4*>(a.sched.step_tab + 4 * it);
+        const float h = stp.y;
+        const int slot_t = a.slot[it];
+        const float* b1row = bias1_tab + it * 192;
+        // ---- early global loads of this iteration: GRU input x, Brownian increments, observation mask ----------------------
+        float4 xv[4], dwv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dwv[q] = xv[q];
+        }
+        bool observed = false;
+        if (valid) {
+          const float* xs = a.aa_out + ((int64_t)slot_t * a.rows + grow) * 64 + cq * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) xv[q] = ld_nc_f4(xs + 4 * q);
+          if (HAS_DW) {
+            const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dwv[q] = ld_nc_f4(ds + 4 * q);
+          }
+          observed = a.obs_mask[grow * a.obs_mask_row_stride + slot_t] != 0;
+        }
+
+        // ---- epilogue 1 ------------------------------------------------------------------------------------------------------
+        mbar_wait(bar_acc(0), par_accA);                   // P1
+        par_accA ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tm, v);
+          tc_wait_ld();
+          tanh16_to_operand(v, b1row + cq * 16, a1f_row, row, cq * 2);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(1));                        // h1f -> P2f
+          ld_g16<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
+          tanh16_to_operand(v, b1row + gcol + cq * 16, a1g_row, row, cq * 2);
+          float t[16];                                     // x -> fp16 operand (AX was last read by G3 of the previous iteration)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            t[4 * q] = xv[q].x; t[4 * q + 1] = xv[q].y; t[4 * q + 2] = xv[q].z; t[4 * q + 3] = xv[q].w;
+          }
+          store16_operand(t, ax_row, row, cq * 2);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(0));                        // h1g (and x) -> P2g
+        }
+        // ---- epilogue 2 ------------------------------------------------------------------------------------------------------
+        mbar_wait(bar_acc(1), par_accB);                   // P2f
+        par_accB ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tm, v);
+          tc_wait_ld();
+          tanh16_to_operand(v, vec + VEC_B2 + cq * 16, ah_row, row, cq * 2);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(1));                        // h2f -> P3
+          mbar_wait(bar_acc(0), par_accA);                 // P2g
+          par_accA ^= 1;
+          tc_fence_after();
+          ld_g16<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
+          float gd = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(c2v + j);
+            const float4 w = *reinterpret_cast<const float4*>(w3v + j);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
+            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
+          }
+          gpart[cq * TILE_M + row] = gd;
+        }
+        // ---- epilogue 3: Euler update ----------------------------------------------------------------------------------------------
+        if (!HAS_DW) {
+          const float sqrt_h = sqrtf(h);
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
+                                             (uint32_t)(cq * 4 + q));
+            dwv[q] = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
+          }
+        }
+        mbar_wait(bar_acc(1), par_accB);                   // P3
+        par_accB ^= 1;
+        tc_fence_after();
+        named_bar_sync(quad_bar, 128);                     // the four partial diffusion dots of every row are in smem
+        const float g = __fdividef(1.0f, 1.0f + __expf(-(((gpart[row] + gpart[TILE_M + row]) + (gpart[2 * TILE_M + row] + gpart[3 * TILE_M + row])) + c3b)));
+        {
+          uint32_t yv[16], fv[16];
+          tmem_ld_32x32b_x16(tm + TM_Y, yv);
+          tmem_ld_32x32b_x16(tm, fv);
+          tc_wait_ld();
+          float t[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cq * 16 + 4 * q);
+            t[4 * q] = fmaf(g, dwv[q].x, fmaf(__uint_as_float(fv[4 * q]) + b3.x, h, __uint_as_float(yv[4 * q])));
+            t[4 * q + 1] = fmaf(g, dwv[q].y, fmaf(__uint_as_float(fv[4 * q + 1]) + b3.y, h, __uint_as_float(yv[4 * q + 1])));
+            t[4 * q + 2] = fmaf(g, dwv[q].z, fmaf(__uint_as_float(fv[4 * q + 2]) + b3.z, h, __uint_as_float(yv[4 * q + 2])));
+            t[4 * q + 3] = fmaf(g, dwv[q].w, fmaf(__uint_as_float(fv[4 * q + 3]) + b3.w, h, __uint_as_float(yv[4 * q + 3])));
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yv[j] = __float_as_uint(t[j]);
+          tmem_st_32x32b_x16(tm + TM_Y, yv);               // Y <- y1
+          store16_operand(t, ah_row, row, cq * 2);
+          if (cq == 0 && valid) a.g_out[(int64_t)it * a.rows + grow] = g;
+          tc_wait_st();
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(0));                          // y1 (and x) -> G1
+        // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
+        mbar_wait(bar_acc(0), par_accA);                   // G1
+        par_accA ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tm + TM_G1, v);
+          tc_wait_ld();
+          tanh16_to_operand(v, vec + VEC_UB1 + cq * 16, a1f_row, row, cq * 2);
+          tmem_ld_32x32b_x16(tm + TM_ZR, v);
+          tc_wait_ld();
+          tanh16_to_operand(v, vec + VEC_RB1 + cq * 16, a1g_row, row, cq * 2);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(1));                          // tu, tr -> G2
+        // ---- GRU epilogue 2: u = sigmoid(u' + ub2) (kept), r = sigmoid(r' + rb2), r * y1 -> AH ---------------------------------------------
+        float u[16];
+        mbar_wait(bar_acc(1), par_accB);                   // G2
+        par_accB ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16], yv[16];
+          tmem_ld_32x32b_x16(tm + TM_UP, v);
+          tmem_ld_32x32b_x16(tm + TM_Y, yv);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) u[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_UB2 + cq * 16 + j]);
+          tmem_ld_32x32b_x16(tm + TM_RP, v);
+          tc_wait_ld();
+          float t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            t[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_RB2 + cq * 16 + j]) * __uint_as_float(yv[j]);
+          store16_operand(t, ah_row, row, cq * 2);         // AH (y1 as fp16) was consumed by G1
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(0));                          // r*y1 -> G3
+        // ---- GRU epilogue 3: tn = tanh(zn + nb1) --------------------------------------------------------------------------------------------
+        mbar_wait(bar_acc(0), par_accA);                   // G3
+        par_accA ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tm + TM_ZN, v);
+          tc_wait_ld();
+          tanh16_to_operand(v, vec + VEC_NB1 + cq * 16, a1f_row, row, cq * 2);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(1));                          // tn -> G4
+        // ---- GRU epilogue 4: h' = (1-u) (n + nb2) + u y1 ; masked ; state, operand, latent ---------------------------------------------------
+        mbar_wait(bar_acc(1), par_accB);                   // G4
+        par_accB ^= 1;
+        tc_fence_after();
+        {
+          uint32_t v[16], yv[16];
+          tmem_ld_32x32b_x16(tm + TM_N, v);
+          tmem_ld_32x32b_x16(tm + TM_Y, yv);
+          tc_wait_ld();
+          float t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float y1 = __uint_as_float(yv[j]);
+            const float n = __uint_as_float(v[j]) + vec[VEC_NB2 + cq * 16 + j];
+            const float hn = fmaf(u[j], y1, (1.0f - u[j]) * n);
+            t[j] = observed ? hn : y1;
+            yv[j] = __float_as_uint(t[j]);
+          }
+          tmem_st_32x32b_x16(tm + TM_Y, yv);
+          store16_operand(t, ah_row, row, cq * 2);         // AH (r*y1) was consumed by G3
+          if (valid) {
+            float* dst = a.latent + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+          }
+          tc_wait_st();
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        if (it + 1 < S) mbar_arrive(bar_opnd(0));          // h' -> P1 of the next iteration
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+    if (warp == NUM_EPI_WARPS && lane == 0) {
+      // =============================================== MMA ISSUER =====================================================
+      const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, DUAL ? 192u : 128u);
+      const uint32_t idesc_64 = umma_idesc_f16(TILE_M, 64);
+      const uint32_t idesc_128 = umma_idesc_f16(TILE_M, 128);
+      const uint64_t dhi = umma_desc_sw128(0);
+      auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+      const uint32_t aAH = base + OFF_AH, aAX = base + OFF_AX, aA1f = base + OFF_A1F, aA1g = base + OFF_A1G;
+      const uint32_t d0 = tmem_base;
+      uint32_t par_op0 = 0, par_op1 = 0;
+      mbar_wait(bar_w, 0);
+      auto wait0 = [&]() { mbar_wait(bar_opnd(0), par_op0); par_op0 ^= 1; tc_fence_after(); };
+      auto wait1 = [&]() { mbar_wait(bar_opnd(1), par_op1); par_op1 ^= 1; tc_fence_after(); };
+      auto mma4 = [&](uint32_t d, uint32_t aaddr, uint32_t baddr, uint32_t idesc, bool acc_first) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d, D(aaddr + 32 * kk), D(base + baddr + 32 * kk), idesc, (acc_first || kk > 0) ? 1u : 0u);
+      };
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int it = 0; it < S; ++it) {
+          wait0(); mma4(d0, aAH, IMG_B1, idesc_p1, false); tc_commit(bar_acc(0));                          // P1
+          wait1(); mma4(d0, aA1f, IMG_W2, idesc_64, false); tc_commit(bar_acc(1));                         // P2f
+          wait0(); mma4(d0 + 64, aA1g, IMG_V2, idesc_64, false);
+          if (DUAL) mma4(d0 + 128, aA1g, IMG_V2A, idesc_64, false);
+          tc_commit(bar_acc(0));                                                                           // P2g
+          wait1(); mma4(d0, aAH, IMG_W3, idesc_64, false); tc_commit(bar_acc(1));                          // P3
+          wait0(); mma4(d0 + TM_G1, aAH, IMG_UR1H, idesc_128, false); mma4(d0 + TM_G1, aAX, IMG_UR1X, idesc_128, true);
+          tc_commit(bar_acc(0));                                                                           // G1
+          wait1(); mma4(d0 + TM_UP, aA1f, IMG_U2, idesc_64, false); mma4(d0 + TM_RP, aA1g, IMG_R2, idesc_64, false);
+          tc_commit(bar_acc(1));                                                                           // G2
+          wait0(); mma4(d0 + TM_ZN, aAX, IMG_N1X, idesc_64, false); mma4(d0 + TM_ZN, aAH, IMG_N1RH, idesc_64, true);
+          tc_commit(bar_acc(0));                                                                           // G3
+          wait1(); mma4(d0 + TM_N, aA1f, IMG_N2, idesc_64, false); tc_commit(bar_acc(1));                  // G4
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_EPI_WARPS) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int64_t enc_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual) {
+  (void)rows; (void)n_steps; (void)dual;
+  return (int64_t)IMG_BYTES + 256;
+}
+
+int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  TS_CUDA_CHECK(cudaGetDevice(&dev));
+  TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (a.sched.n_steps > S_MAX) return set_error(TRAJSDE_ERR_UNSUPPORTED, "fused encoder supports at most %d iterations, got %d", S_MAX, a.sched.n_steps);
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  EncParams p;
+  p.a = a;
+  p.img = static_cast<const uint8_t*>(a.workspace);
+  p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
+  p.dual = a.alt_mask != nullptr;
+  if (p.num_tiles == 0) return TRAJSDE_OK;
+  enc_pack_kernel<<<32, 256, 0, s>>>(a, static_cast<uint8_t*>(a.workspace), p.dual);
+  TS_CUDA_CHECK(cudaGetLastError());
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
+    return cudaGetLastError();
+  };
+  const bool hd = a.noise.dw != nullptr, du = p.dual != 0;
+  TS_CUDA_CHECK(hd ? (du ? launch(enc_fwd_tc_kernel<true, true>) : launch(enc_fwd_tc_kernel<true, false>))
+                   : (du ? launch(enc_fwd_tc_kernel<false, true>) : launch(enc_fwd_tc_kernel<false, false>)));
+  return TRAJSDE_OK;
+}
+
+}  // namespace trajsde

@@ -217,6 +217,76 @@ euler_fwd.register_autograd(_backward, setup_context=_setup_context)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# fused encoder recurrence (forward only; training uses the per-step ops, which have autograd)
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("trajsde::enc_fwd", mutates_args=(), device_types="cuda")
+def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
+            gru_params: List[torch.Tensor], step_tab: torch.Tensor, dw: Optional[torch.Tensor],
+            alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """latent[S,rows,64] (post-GRU state of every iteration), g[S,rows] (pre-step diffusion of every iteration)."""
+    dev = h0.device
+    rows, S = h0.shape[0], step_tab.shape[0]
+    dual = alt_mask is not None
+    ps = _check_params(params, dual, dev)
+    gshapes = [(64, 128), (64,), (64, 64), (64,)] * 3
+    if len(gru_params) != 12 or any(tuple(t.shape) != sh for t, sh in zip(gru_params, gshapes)):
+        raise ValueError("gru_params must be the 12 GRU_Unit tensors (update/reset/new_state: Linear(128,64), Linear(64,64))")
+    gs = [t.detach().contiguous() for t in gru_params]
+    if aa_out.dim() != 3 or aa_out.shape[1] != rows or aa_out.shape[2] != 64 or aa_out.dtype != torch.float32:
+        raise ValueError("`aa_out` must be float32 [n_slots, rows, 64]")
+    n_slots = aa_out.shape[0]
+    if tuple(obs_mask.shape) != (rows, n_slots) or obs_mask.dtype not in (torch.bool, torch.uint8):
+        raise ValueError("`actors_mask` must be bool [rows, n_slots]")
+    if slot.shape != (S,) or slot.dtype != torch.int32:
+        raise ValueError("`slot` must be int32 [n_steps]")
+    h0c = h0.detach()
+    if h0c.stride(1) != 1 or h0c.stride(0) % 4 != 0 or h0c.data_ptr() % 16 != 0:
+        h0c = h0c.contiguous()
+    aa = aa_out.detach().contiguous()
+    om = obs_mask.contiguous().view(torch.uint8)
+    latent = torch.empty((S, rows, 64), dtype=torch.float32, device=dev)
+    g_out = torch.empty((S, rows), dtype=torch.float32, device=dev)
+    a = _lib.EncFwdArgs()
+    a.struct_bytes = C.sizeof(_lib.EncFwdArgs)
+    a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
+    a.sched.n_steps, a.sched.n_outputs = S, 0
+    a.sched.step_tab = step_tab.data_ptr()
+    a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
+    mask_u8 = None
+    if dual:
+        mask_u8 = alt_mask.contiguous().view(torch.uint8)
+        a.diffusion_alt = _mlp_struct(ps[12:18])
+        a.alt_mask = mask_u8.data_ptr()
+    for name, t in zip(('u1', 'ub1', 'u2', 'ub2', 'r1', 'rb1', 'r2', 'rb2', 'n1', 'nb1', 'n2', 'nb2'), gs):
+        setattr(a.gru, name, t.data_ptr())
+    if dw is not None:
+        if tuple(dw.shape) != (S, rows, 64) or dw.dtype != torch.float32:
+            raise ValueError(f"`dW` must be float32 of shape ({S}, {rows}, 64)")
+        dw = dw.contiguous()
+        a.noise.dw = dw.data_ptr()
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    a.h0, a.h0_row_stride = h0c.data_ptr(), h0c.stride(0)
+    a.aa_out, a.slot = aa.data_ptr(), slot.data_ptr()
+    a.obs_mask, a.obs_mask_row_stride = om.data_ptr(), om.stride(0)
+    a.latent, a.g_out = latent.data_ptr(), g_out.data_ptr()
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_enc_fwd_workspace_bytes(_lib.MODE_TC_F16, rows, S, int(dual)), "trajsde_enc_fwd_workspace_bytes")
+    ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_enc_fwd(C.byref(a), _stream_ptr(dev)), "trajsde_enc_fwd")
+    if rows > 0:
+        LAUNCHES['n'] += 2
+    return latent, g_out
+
+
+@enc_fwd.register_fake
+def _(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset):
+    rows, S = h0.shape[0], step_tab.shape[0]
+    return h0.new_empty((S, rows, 64)), h0.new_empty((S, rows))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Brownian increments exactly as the kernels draw them (for replaying Philox runs through the oracle)
 # ---------------------------------------------------------------------------------------------------------------------
 def philox_dw(dsched: DeviceSchedule, rows: int, seed: int, device, row_offset: int = 0, step_offset: int = 0) -> torch.Tensor:
