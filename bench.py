@@ -178,6 +178,8 @@ def main():
     ap.add_argument('--agents', type=int, default=20)
     ap.add_argument('--mode', default='tc_f16', choices=['tc_f16', 'exact'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
+    ap.add_argument('--no-train', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
@@ -291,6 +293,43 @@ def main():
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
+    # ---- training step (BASELINE configs[2]/[3]): fwd + bwd through both solvers, one all-reduce of the flat gradient bucket, AdamW ----------
+    train = None
+    if not args.no_train:
+        from trajsde_b200.dist import FlatGradBucket
+        tb_host = syn.make_batch(args.train_scenes, args.agents, seed=2000 + rank, mixed_sources=True)
+        tr = {k: getattr(tb_host, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
+        tparams = list(enc_sde.parameters()) + list(dec_sde.parameters()) + list(gru.parameters())
+        bucket = FlatGradBucket(tparams)
+        opt = torch.optim.AdamW(tparams, lr=1e-3, weight_decay=7e-4)          # yml:2-3
+        Et, Mt = tb_host.enc_rows, tb_host.dec_rows
+
+        def train_step(i):
+            bucket.zero_()
+            y0 = tr['dec_y0'].detach().requires_grad_(True)                   # upstream (aggr_embed) needs dL/dy0 too
+            lat, g = enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], tr['aa_out'], tr['actors_mask'], tr['nus_mask'],
+                                                seed=300 + i, mode=mode, fused=False, row_offset=rank * Et)
+            ys = tb.sdeint(dec_sde, y0, ts_dec, dt=0.1, dt_min=0.1, rtol=1e-3, atol=1e-3, method='euler', mode=mode, seed=400 + i,
+                           row_offset=rank * Mt)
+            loss = ys[1:].square().mean() + lat.square().mean() + g.mean()
+            loss.backward()
+            bucket.all_reduce_mean()
+            opt.step()
+
+        for i in range(2):
+            train_step(i)
+        k_train = max(2, min(args.steps, 5))
+        ms_train = timed(train_step, k_train) / k_train
+        twork = Et * ENC_STEPS + Mt * DEC_STEPS
+        train = {"scenes_per_gpu": args.train_scenes, "ms_per_step": ms_train, "steps": k_train,
+                 "agent_steps_per_s_fwd_bwd": world * twork / (ms_train * 1e-3), "scenes_per_s_fwd_bwd": world * args.train_scenes / (ms_train * 1e-3),
+                 "allreduce_floats": bucket.numel if world > 1 else 0,
+                 "note": "fwd+bwd through encoder (21 x [fused sdeint_dual + torch GRU]) and decoder solves, exact-fp32 fused backward "
+                         "kernels (dgrad sweep + wgrad), flat-bucket NCCL all-reduce, AdamW on the SDE+GRU parameters"}
+        for p_ in tparams:
+            p_.grad = None
+        del bucket, opt
+
     # ---- parity spot check at full size: 64 decoder rows against the CPU oracle under the same dW -------------------------------------
     parity = None
     if rank == 0:
@@ -342,6 +381,7 @@ def main():
                      "sfu_note": "informational third ceiling: 257 MUFU ops per agent-step at the measured 16/clk/SM"},
         "e2e": {"value": world * work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "train": train,
         "gpu_launches": launches,
         "clocks": clocks,
         "parity": parity,

@@ -1,0 +1,59 @@
+"""Scene-sharded data parallelism for the SDE path: one process per GPU, rows of different scenes are
+independent so the forward needs NO collective; training adds ONE all-reduce of the flat fp32 gradient bucket per step
+(what torch DDP does for the reference when `--gpus > 1`, train.py:35,54 — here explicit and latency-sized: 88,003 floats
+for SDE+GRU parameters)."""
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_scenes(n_scenes: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous scene range [start, end) of `rank`; sizes differ by at most one scene."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, rem = divmod(n_scenes, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_row_offsets(n_scenes: int, agents_per_scene: int, world_size: int, rank: int, modes: int = 10) -> dict:
+    """Global row ids of this rank's first encoder / decoder row, for the `row_offset` argument of the solver calls: the
+    Philox Brownian streams are keyed by GLOBAL row id, so a sharded run draws the noise of the unsharded batch."""
+    s0, _ = shard_scenes(n_scenes, world_size, rank)
+    return {'scene_start': s0, 'enc_agent_row': s0 * agents_per_scene, 'dec_row': s0 * agents_per_scene * modes}
+
+
+class FlatGradBucket:
+    """All parameter gradients as views into ONE contiguous fp32 buffer, so a training step issues a single all-reduce."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+        off = 0
+        for p in self.params:                      # re-attach: optimizers / autograd may have replaced .grad
+            view = self.flat[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            off += p.numel()
+
+    def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
+        """SUM all-reduce of the flat bucket followed by division by the world size (DDP's gradient averaging)."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        world = dist.get_world_size(group)
+        if world == 1:
+            return None
+        self.flat.div_(world)
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
