@@ -180,6 +180,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--e2e-chunks', type=int, default=2, help='micro-batches per e2e step (H2D/compute/D2H overlap)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
@@ -276,18 +277,22 @@ def main():
     dec_ms_philox = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
     dec_events.clear()
 
-    # ---- e2e: public API with HOST buffers: H2D of every input from pinned memory + D2H of the results, bm=None ------------------------
-    out_lat = torch.empty((E, 64), dtype=torch.float32).pin_memory()
-    out_ys = torch.empty((M, 64), dtype=torch.float32).pin_memory()
-    h2d = sum(getattr(host, k).numel() * getattr(host, k).element_size() for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
-    d2h = out_lat.numel() * 4 + out_ys.numel() * 4
+    # ---- e2e: public API with HOST buffers: every step copies all inputs from pinned host memory, runs bm=None (in-kernel Philox, like
+    # the reference's default BrownianInterval) and copies the final latents back; the batch arrives as `e2e_chunks` micro-batches whose
+    # copies overlap the kernels (trajsde_b200.pipeline.HostFedSdePath) ---------------------------------------------------------------------
+    from trajsde_b200.pipeline import HostFedSdePath
+    n_chunks = args.e2e_chunks
+    cs = args.scenes // n_chunks
+    hchunks = [syn.make_batch(cs, args.agents, seed=3000 + 17 * rank + c, pin=True) for c in range(n_chunks)]
+    out_enc = [torch.empty((h.enc_rows, 64), dtype=torch.float32).pin_memory() for h in hchunks]
+    out_dec = [torch.empty((h.dec_rows, 64), dtype=torch.float32).pin_memory() for h in hchunks]
+    h2d = sum(getattr(h, k).numel() * getattr(h, k).element_size() for h in hchunks for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
+    d2h = sum(t.numel() * 4 for t in out_enc + out_dec)
+    pipe = HostFedSdePath(enc_sde, gru, dec_sde, dev, ts_dec, mode=mode)
+    e2e_work = sum(h.enc_rows * ENC_STEPS + h.dec_rows * DEC_STEPS for h in hchunks)
 
     def e2e_step(i):
-        inp = {k: getattr(host, k).to(dev, non_blocking=True) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
-        lat, ys = step(inp, False, seed=20 + i)
-        out_lat.copy_(lat[-1], non_blocking=True)
-        out_ys.copy_(ys[-1], non_blocking=True)
-        torch.cuda.current_stream().synchronize()          # the caller reads the result on the host every step
+        pipe.run(hchunks, out_enc, out_dec, seed=20 + 10 * i)
 
     for i in range(2):
         e2e_step(i)
@@ -364,8 +369,9 @@ def main():
                                f"(encoder {E} rows x 21 steps + GRU jump, decoder {M} rows x 61 steps -> 60 outputs), caller-supplied dW",
                    "kernel_mode": mode, "scenes_per_gpu": args.scenes, "parallelism": f"scene-sharded dp{world}, no forward collective",
                    "cache": "inputs larger than L2 (dW 3.2 GB + ys 3.2 GB per step vs 126 MB L2)",
-                   "e2e_note": "e2e uses bm=None (in-kernel Philox, like the reference's BrownianInterval default) with all inputs "
-                               "copied from pinned host memory and final latents copied back every step"},
+                   "e2e_note": "e2e uses bm=None (in-kernel Philox, like the reference's BrownianInterval default); every step copies all "
+                               "inputs from pinned host memory (as micro-batches whose copies overlap the kernels) and copies the final "
+                               "encoder/decoder latents back"},
         "scenes_per_s": world * args.scenes / (ms_fixed / args.steps * 1e-3),
         "philox": {"value": world * work / (ms_philox / args.steps * 1e-3), "ms_per_step": ms_philox / args.steps,
                    "decoder_ms": dec_ms_philox, "decoder_agent_steps_per_s": M * DEC_STEPS / (dec_ms_philox * 1e-3),
@@ -379,8 +385,8 @@ def main():
                      "algorithmic_bytes_per_launch": dec_bytes_fixed,
                      "tensor_frac_of_bf16_peak": flops / (dec_ms_avg * 1e-3) / 1e12 / bf16_tf,
                      "sfu_note": "informational third ceiling: 257 MUFU ops per agent-step at the measured 16/clk/SM"},
-        "e2e": {"value": world * work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": world * e2e_work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "micro_batches": n_chunks},
         "train": train,
         "gpu_launches": launches,
         "clocks": clocks,

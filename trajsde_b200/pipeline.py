@@ -1,0 +1,68 @@
+"""Host-fed execution of the SDE path: micro-batches that live in pinned host memory are copied in, solved and copied out
+on three CUDA streams so that PCIe traffic overlaps the fused kernels (rows of different scenes are independent, so a batch
+may be processed as any number of scene chunks — results are identical row for row)."""
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import encoder as enc_mod
+from .solver import sdeint
+from .synthetic import SdeBatch
+
+_KEYS = ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')
+
+
+class HostFedSdePath:
+    """Forward pass (encoder recurrence + decoder solve) over a list of pinned host micro-batches.
+
+    `run()` enqueues, for every chunk c: H2D of its inputs (copy-in stream) -> fused encoder + decoder kernels (caller's
+    stream) -> D2H of the final encoder latents and final decoder latents (copy-out stream), and returns after the last
+    D2H has landed, i.e. when the host can read the results."""
+
+    def __init__(self, enc_sde, gru, dec_sde, device, ts_dec: torch.Tensor, dt: float = 0.1, mode: Optional[str] = None):
+        self.enc_sde, self.gru, self.dec_sde = enc_sde, gru, dec_sde
+        self.device, self.ts_dec, self.dt, self.mode = torch.device(device), ts_dec, dt, mode
+        self.copy_in = torch.cuda.Stream(self.device)
+        self.copy_out = torch.cuda.Stream(self.device)
+        self._dev: List[dict] = []
+        self._ready: List[torch.cuda.Event] = []
+        self._done: List[torch.cuda.Event] = []
+        self._drained: List[torch.cuda.Event] = []
+
+    def _ensure_buffers(self, chunks: Sequence[SdeBatch]):
+        if len(self._dev) == len(chunks) and all(self._dev[i]['dec_y0'].shape == chunks[i].dec_y0.shape for i in range(len(chunks))):
+            return
+        self._dev = [{k: torch.empty_like(getattr(c, k), device=self.device) for k in _KEYS} for c in chunks]
+        self._ready = [torch.cuda.Event() for _ in chunks]
+        self._done = [torch.cuda.Event() for _ in chunks]
+        self._drained = [torch.cuda.Event() for _ in chunks]
+        for e in self._done + self._drained:
+            e.record(torch.cuda.current_stream(self.device))
+
+    def run(self, chunks: Sequence[SdeBatch], out_enc: Sequence[torch.Tensor], out_dec: Sequence[torch.Tensor], seed: int = 0,
+            enc_row_offsets: Optional[Sequence[int]] = None, dec_row_offsets: Optional[Sequence[int]] = None) -> None:
+        self._ensure_buffers(chunks)
+        cur = torch.cuda.current_stream(self.device)
+        keep = []
+        with torch.no_grad():
+            for c, hb in enumerate(chunks):
+                with torch.cuda.stream(self.copy_in):
+                    self.copy_in.wait_event(self._done[c])           # previous use of these device buffers has finished
+                    for k in _KEYS:
+                        self._dev[c][k].copy_(getattr(hb, k), non_blocking=True)
+                    self._ready[c].record(self.copy_in)
+                cur.wait_event(self._ready[c])
+                d = self._dev[c]
+                lat, _ = enc_mod.encoder_recurrence(self.enc_sde, self.gru, d['enc_h0'], d['aa_out'], d['actors_mask'], d['nus_mask'],
+                                                    dt=self.dt, seed=seed + 2 * c, mode=self.mode,
+                                                    row_offset=0 if enc_row_offsets is None else enc_row_offsets[c])
+                ys = sdeint(self.dec_sde, d['dec_y0'], self.ts_dec, dt=self.dt, dt_min=self.dt, rtol=1e-3, atol=1e-3, method='euler',
+                            mode=self.mode, seed=seed + 2 * c + 1, row_offset=0 if dec_row_offsets is None else dec_row_offsets[c])
+                self._done[c].record(cur)
+                keep.append((lat, ys))
+                with torch.cuda.stream(self.copy_out):
+                    self.copy_out.wait_event(self._done[c])
+                    out_enc[c].copy_(lat[-1], non_blocking=True)
+                    out_dec[c].copy_(ys[-1], non_blocking=True)
+        self.copy_out.synchronize()                                   # the host reads the results now
+        del keep
