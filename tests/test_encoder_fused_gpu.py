@@ -90,3 +90,30 @@ def test_fused_encoder_rejects_training_and_exact_mode():
         enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True)          # grad enabled + parameters require grad
     with torch.no_grad(), pytest.raises(NotImplementedError):
         enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True, mode='exact')
+
+
+def test_forward_ood_monte_carlo_encoder():
+    """forward_ood (enc…sep2.py:252-313): 10 passes from a zero state -> mean latent and per-actor std."""
+    sde = init_like_reference(EncoderSDE(), seed=1).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), 2).to(DEV)
+    b = syn.make_batch(6, 10, seed=3, mixed_sources=True)
+    n = 60
+    aa, am, nm, bos = b.aa_out[:, :n].contiguous().to(DEV), b.actors_mask[:n].to(DEV), b.nus_mask[:n].to(DEV), b.bos_mask.to(DEV)
+    mean, std = enc.encoder_recurrence_ood(sde, gru, aa, am, nm, bos, eval_iter=10, seed=5)
+    mean2, std2 = enc.encoder_recurrence_ood(sde, gru, aa, am, nm, bos, eval_iter=10, seed=5)
+    assert mean.shape == (n, 64) and std.shape == (n,)
+    assert torch.equal(mean, mean2) and torch.equal(std, std2)
+    assert (std > 0).all() and torch.isfinite(mean).all()
+
+
+def test_rows_major_output_layout_matches_and_is_unit_stride():
+    from helpers import DecoderSDE
+    sde = init_like_reference(DecoderSDE(), seed=4).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    y0 = torch.relu(torch.randn(300, 64, generator=torch.Generator().manual_seed(4))).to(DEV)
+    for mode in ('exact', 'tc_f16'):
+        a = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode=mode, seed=9)
+        b_ = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode=mode, seed=9, rows_major=True)
+        assert b_.shape == a.shape and torch.equal(a, b_)
+        sol_y = b_[1:].permute(1, 0, 2)                     # what SDEDecoder.forward hands to its heads (dec…sde.py:88)
+        assert sol_y.stride() == (61 * 64, 64, 1)

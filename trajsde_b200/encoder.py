@@ -83,3 +83,22 @@ def eos_gather(latent_ys: torch.Tensor, bos_mask: torch.Tensor, ref_time: int = 
     """out[n] = latent_ys[ref_time - argmax(bos_mask[n]), n]   (enc…sep2.py:187-188)."""
     eos = ref_time - torch.argmax(bos_mask.float(), dim=1)
     return latent_ys[eos, torch.arange(latent_ys.size(1), device=latent_ys.device), :]
+
+
+def encoder_recurrence_ood(sde, gru_unit, aa_out: torch.Tensor, actors_mask: torch.Tensor, nus_mask: torch.Tensor,
+                           bos_mask: torch.Tensor, *, eval_iter: int = 10, dt: float = 0.1, max_past_t: float = 2.0,
+                           seed: Optional[int] = None, mode: Optional[str] = None, ref_time: int = 20):
+    """Monte-Carlo encoder of ``forward_ood`` (enc_hivt_nusargo_sde_sep2.py:252-313): ``eval_iter`` independent passes of the
+    recurrence from a ZERO hidden state (:257), eos gather per pass (:309-310), then mean latent ``[N,64]`` and per-actor
+    std ``outs.std(0).mean(-1)`` ``[N]`` (:311-313).  Each pass is one fused-kernel launch with its own Philox stream."""
+    rows = aa_out.shape[1]
+    h0 = torch.zeros((rows, 64), dtype=torch.float32, device=aa_out.device)
+    base = _next_call_seed() if seed is None else int(seed)
+    outs = []
+    with torch.no_grad():
+        for j in range(eval_iter):
+            lat, _ = encoder_recurrence(sde, gru_unit, h0, aa_out, actors_mask, nus_mask, dt=dt, max_past_t=max_past_t,
+                                        seed=(base + 0x51ED27 * (j + 1)) & (2**63 - 1), mode=mode)
+            outs.append(eos_gather(lat, bos_mask, ref_time))
+    outs = torch.stack(outs)
+    return outs.mean(0), outs.std(0).mean(-1)

@@ -79,9 +79,11 @@ def _stream_ptr(device) -> int:
 @torch.library.custom_op("trajsde::euler_fwd", mutates_args=(), device_types="cuda")
 def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor,
               out_w: torch.Tensor, n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor],
-              seed: int, row_offset: int, step_offset: int, mode: int, save_states: bool,
+              seed: int, row_offset: int, step_offset: int, mode: int, save_states: bool, rows_major: bool,
               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """ys[T,rows,64] (T = n_outputs+1, ys[0] = y0), g_last[rows], states[S,rows,64] (empty unless save_states)."""
+    """ys[T,rows,64] (T = n_outputs+1, ys[0] = y0), g_last[rows], states[S,rows,64] (empty unless save_states).
+    ``rows_major``: allocate ys physically as [rows, T, 64] and return the [T, rows, 64] permuted view, so the reference's
+    ``[1:].permute(1, 0, 2)`` (dec_hivt_nusargo_sde.py:88) hands unit-stride rows to the decoder heads."""
     if y0.dim() != 2 or y0.shape[1] != 64 or y0.dtype != torch.float32:
         raise ValueError("`y0` must be float32 of shape (rows, 64)")
     dev = y0.device
@@ -92,7 +94,10 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
     y0c = y0.detach()
     if y0c.stride(1) != 1 or y0c.stride(0) % 4 != 0 or y0c.data_ptr() % 16 != 0:
         y0c = y0c.contiguous()
-    ys = torch.empty((n_outputs + 1, rows, 64), dtype=torch.float32, device=dev)
+    if rows_major:
+        ys = torch.empty((rows, n_outputs + 1, 64), dtype=torch.float32, device=dev).permute(1, 0, 2)
+    else:
+        ys = torch.empty((n_outputs + 1, rows, 64), dtype=torch.float32, device=dev)
     g_last = torch.empty((rows,), dtype=torch.float32, device=dev)
     states = torch.empty((S if save_states else 0, rows, 64), dtype=torch.float32, device=dev)
     a = _lib.EulerFwdArgs()
@@ -130,9 +135,11 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
 
 
 @euler_fwd.register_fake
-def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, save_states):
+def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, save_states,
+      rows_major):
     rows, S = y0.shape[0], step_tab.shape[0]
-    return (y0.new_empty((n_outputs + 1, rows, 64)), y0.new_empty((rows,)),
+    ys = y0.new_empty((rows, n_outputs + 1, 64)).permute(1, 0, 2) if rows_major else y0.new_empty((n_outputs + 1, rows, 64))
+    return (ys, y0.new_empty((rows,)),
             y0.new_empty((S if save_states else 0, rows, 64)))
 
 
@@ -194,7 +201,7 @@ def _(grad_ys, grad_g, states, params, step_tab, out_begin, out_w, n_outputs, dw
 
 def _setup_context(ctx, inputs, output):
     (y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
-     save_states) = inputs
+     save_states, _rows_major) = inputs
     _, _, states = output
     ctx.has_states = bool(save_states)
     ctx.save_for_backward(states, step_tab, out_begin, out_w, *params)
@@ -210,7 +217,7 @@ def _backward(ctx, grad_ys, grad_g, grad_states):
     n_outputs, seed, row_offset, step_offset, mode = ctx.meta
     grads = euler_bwd(grad_ys, grad_g, states, list(params), step_tab, out_begin, out_w, n_outputs, ctx.dw, ctx.alt_mask,
                       seed, row_offset, step_offset, mode)
-    return (grads[0], list(grads[1:]), None, None, None, None, None, None, None, None, None, None, None)
+    return (grads[0], list(grads[1:]), None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 euler_fwd.register_autograd(_backward, setup_context=_setup_context)

@@ -125,7 +125,7 @@ def _materialise_bm(bm, sched: EulerSchedule, rows: int, device) -> torch.Tensor
     return dW.to(device=device, dtype=torch.float32)
 
 
-def _solve(sde, params, y0, ts, dt, bm, nus_mask, mode, seed, row_offset):
+def _solve(sde, params, y0, ts, dt, bm, nus_mask, mode, seed, row_offset, rows_major=False):
     sched = euler_schedule(ts, float(dt))
     dev = y0.device
     ds = ops.DeviceSchedule.get(sched, dev)
@@ -135,7 +135,7 @@ def _solve(sde, params, y0, ts, dt, bm, nus_mask, mode, seed, row_offset):
     need_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
     mode_id = _lib.MODES[mode or _defaults['mode']]
     ys, g_last, _ = ops.euler_fwd(y0, list(params), ds.step_tab, ds.out_begin, ds.out_w, sched.n_outputs, dW, nus_mask,
-                                  int(seed), int(row_offset), 0, mode_id, need_grad)
+                                  int(seed), int(row_offset), 0, mode_id, need_grad, bool(rows_major))
     for name in ('fnfe', 'gnfe'):                      # NFE counters the reference bumps per f/g call (dec…sde.py:177,193)
         if hasattr(sde, name):
             setattr(sde, name, getattr(sde, name) + sched.n_steps)
@@ -146,11 +146,12 @@ def sdeint(sde, y0: torch.Tensor, ts, bm=None, method: Optional[str] = None, dt:
            rtol: float = 1e-5, atol: float = 1e-4, dt_min: float = 1e-5, options: Optional[Dict[str, Any]] = None,
            names: Optional[Dict[str, str]] = None, logqp: bool = False, extra: bool = False,
            extra_solver_state=None, *, mode: Optional[str] = None, seed: Optional[int] = None, row_offset: int = 0,
-           **unused_kwargs) -> torch.Tensor:
+           rows_major: bool = False, **unused_kwargs) -> torch.Tensor:
     """torchsde.sdeint for the reference decoder (dec_hivt_nusargo_sde.py:88): returns ys[T, rows, 64], ys[0] == y0.
 
     Extensions (keyword-only): ``mode`` ('exact' | 'tc_f16'), ``seed`` (Philox seed when ``bm`` is None), ``row_offset``
-    (global id of row 0, so scene-sharded ranks draw the noise of the unsharded batch)."""
+    (global id of row 0, so scene-sharded ranks draw the noise of the unsharded batch), ``rows_major`` (store ys physically as
+    [rows, T, 64]; the returned [T, rows, 64] view then makes the decoder's ``[1:].permute(1,0,2)`` unit-stride per row)."""
     _check_sde_types(sde)
     _common_checks(y0, adaptive, logqp, extra, names, options, extra_solver_state, unused_kwargs)
     if method != 'euler':
@@ -159,7 +160,7 @@ def sdeint(sde, y0: torch.Tensor, ts, bm=None, method: Optional[str] = None, dt:
     if not (hasattr(sde, 'f_func') and hasattr(sde, 'g_func')):
         raise NotImplementedError("sde must expose `f_func` and `g_func` (decoder LSDEFunc, dec…sde.py:160-167)")
     params = _mlp_params(sde.f_func, 64, 'f_func') + _mlp_params(sde.g_func, 1, 'g_func')
-    ys, _ = _solve(sde, params, y0, ts, dt, bm, None, mode, seed, row_offset)
+    ys, _ = _solve(sde, params, y0, ts, dt, bm, None, mode, seed, row_offset, rows_major)
     return ys
 
 
