@@ -1,0 +1,48 @@
+// Shared by the exact and tensor-core backward kernels: flat gradient-vector layout and the deterministic partial reduce.
+#pragma once
+#include "common.cuh"
+
+namespace trajsde {
+namespace bwd {
+
+// flat gradient vector layout (21,121 floats per (f, g) pair; g_alt appended for dual)
+constexpr int G_FW1 = 0, G_FB1 = 4224, G_FW2 = 4288, G_FB2 = 8384, G_FW3 = 8448, G_FB3 = 12544;
+constexpr int G_GW1 = 12608, G_GB1 = 16832, G_GW2 = 16896, G_GB2 = 20992, G_GW3 = 21056, G_GB3 = 21120;
+constexpr int G_TOTAL = 21121, G_PAD = 21124;
+
+constexpr int MAX_PARTIALS = 160;   // per-CTA partial vectors per pass
+
+// grads[i] = sum over CTAs (fixed order) of partial sets; set 0 -> (f, g); set 1 (dual) -> (f, g_alt)
+static __global__ void euler_bwd_reduce_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n0, int n1,
+                                        TrajsdeMlpGrad gf, TrajsdeMlpGrad gg, TrajsdeMlpGrad ga) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G_TOTAL) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = 0; c < n0; ++c) s0 += part0[(size_t)c * G_PAD + i];
+  for (int c = 0; c < n1; ++c) s1 += part1[(size_t)c * G_PAD + i];
+  if (i < G_GW1) {
+    const float v = s0 + s1;
+    if (i < G_FB1) gf.w1[i - G_FW1] = v;
+    else if (i < G_FW2) gf.b1[i - G_FB1] = v;
+    else if (i < G_FB2) gf.w2[i - G_FW2] = v;
+    else if (i < G_FW3) gf.b2[i - G_FB2] = v;
+    else if (i < G_FB3) gf.w3[i - G_FW3] = v;
+    else gf.b3[i - G_FB3] = v;
+  } else {
+    for (int set = 0; set < 2; ++set) {
+      if (set == 1 && !part1) break;
+      const TrajsdeMlpGrad& t = set == 0 ? gg : ga;
+      const float v = set == 0 ? s0 : s1;
+      if (i < G_GB1) t.w1[i - G_GW1] = v;
+      else if (i < G_GW2) t.b1[i - G_GB1] = v;
+      else if (i < G_GB2) t.w2[i - G_GW2] = v;
+      else if (i < G_GW3) t.b2[i - G_GB2] = v;
+      else if (i < G_GB3) t.w3[i - G_GW3] = v;
+      else t.b3[0] = v;
+    }
+  }
+}
+
+
+}  // namespace bwd
+}  // namespace trajsde

@@ -12,9 +12,11 @@
 //   reduce : sums the per-CTA partials in a fixed order (deterministic: no float atomics).
 // Dual diffusion (encoder): the host runs dgrad+wgrad once per diffusion net with the rows of the other net masked out (rows
 // are independent), and one reduce over both partial sets.
-#include "common.cuh"
+#include "bwd_common.cuh"
 
 namespace trajsde {
+
+using namespace bwd;
 
 namespace {
 
@@ -23,11 +25,6 @@ constexpr int BW_THREADS = 256;
 constexpr int LD = 68;               // padded row stride (floats) of weight / activation tiles
 constexpr int WSZ = 64 * LD;         // one staged 64x64 matrix
 constexpr int ASZ = BW_ROWS * LD;    // one activation tile
-
-// flat gradient vector layout (21,121 floats per (f, g) pair; g_alt appended for dual)
-constexpr int G_FW1 = 0, G_FB1 = 4224, G_FW2 = 4288, G_FB2 = 8384, G_FW3 = 8448, G_FB3 = 12544;
-constexpr int G_GW1 = 12608, G_GB1 = 16832, G_GW2 = 16896, G_GB2 = 20992, G_GW3 = 21056, G_GB3 = 21120;
-constexpr int G_TOTAL = 21121, G_PAD = 21124;
 
 struct BwdParams {
   TrajsdeEulerBwdArgs a;
@@ -571,37 +568,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1) euler_bwd_wgrad_kernel(const Bw
 #pragma unroll
     for (int j = 0; j < 4; ++j) out[G_GW3 + tx * 4 + j] = gw3g[j];
     if (tx == 0) out[G_GB3] = gc3;
-  }
-}
-
-// grads[i] = sum over CTAs (fixed order) of partial sets; set 0 -> (f, g); set 1 (dual) -> (f, g_alt)
-__global__ void euler_bwd_reduce_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int n0, int n1,
-                                        TrajsdeMlpGrad gf, TrajsdeMlpGrad gg, TrajsdeMlpGrad ga) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= G_TOTAL) return;
-  float s0 = 0.f, s1 = 0.f;
-  for (int c = 0; c < n0; ++c) s0 += part0[(size_t)c * G_PAD + i];
-  for (int c = 0; c < n1; ++c) s1 += part1[(size_t)c * G_PAD + i];
-  if (i < G_GW1) {
-    const float v = s0 + s1;
-    if (i < G_FB1) gf.w1[i - G_FW1] = v;
-    else if (i < G_FW2) gf.b1[i - G_FB1] = v;
-    else if (i < G_FB2) gf.w2[i - G_FW2] = v;
-    else if (i < G_FW3) gf.b2[i - G_FB2] = v;
-    else if (i < G_FB3) gf.w3[i - G_FW3] = v;
-    else gf.b3[i - G_FB3] = v;
-  } else {
-    for (int set = 0; set < 2; ++set) {
-      if (set == 1 && !part1) break;
-      const TrajsdeMlpGrad& t = set == 0 ? gg : ga;
-      const float v = set == 0 ? s0 : s1;
-      if (i < G_GB1) t.w1[i - G_GW1] = v;
-      else if (i < G_GW2) t.b1[i - G_GB1] = v;
-      else if (i < G_GB2) t.w2[i - G_GW2] = v;
-      else if (i < G_GW3) t.b2[i - G_GB2] = v;
-      else if (i < G_GB3) t.w3[i - G_GW3] = v;
-      else t.b3[0] = v;
-    }
   }
 }
 
