@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cmath>
+#include <cuda_bf16.h>
 #include "../trajsde_b200/csrc/tc_common.cuh"
 using namespace trajsde::tc;
 
@@ -18,7 +19,7 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo_by
   return d;
 }
 
-__global__ void k(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n_dim) {
+__global__ void k(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n_dim, int a_bf16) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -29,7 +30,8 @@ __global__ void k(const float* __restrict__ a, const float* __restrict__ b, floa
   // tiles: A0 (cols 0..63 of a), A1 (cols 64..127), B0, B1: each [128 rows][64] f16 swizzled; a,b are [128][128] fp32 row-major
   for (int idx = tid; idx < 128 * 128; idx += blockDim.x) {
     const int r = idx >> 7, c = idx & 127, t = c >> 6, cc = c & 63;
-    *reinterpret_cast<__half*>(sm + t * 16384 + sw128_off_h(r, cc)) = __float2half_rn(a[idx]);
+    if (a_bf16) *reinterpret_cast<__nv_bfloat16*>(sm + t * 16384 + sw128_off_h(r, cc)) = __float2bfloat16_rn(a[idx]);
+    else *reinterpret_cast<__half*>(sm + t * 16384 + sw128_off_h(r, cc)) = __float2half_rn(a[idx]);
     *reinterpret_cast<__half*>(sm + 32768 + t * 16384 + sw128_off_h(r, cc)) = __float2half_rn(b[idx]);
   }
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
@@ -41,7 +43,7 @@ __global__ void k(const float* __restrict__ a, const float* __restrict__ b, floa
   const uint32_t tm = tmem_ptr;
   if (tid == 0) {
     // idesc: D f32, A/B f16, a_major = b_major = MN (bits 15,16), N, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | (((uint32_t)n_dim >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | (1u << 15) | (1u << 16) | (((uint32_t)n_dim >> 3) << 17) | ((128u >> 4) << 24);
     for (int kk = 0; kk < 8; ++kk) {   // K = 128 rows, 16 per instruction -> +2048 B per step
       const uint64_t da = desc_mn_sw128(base + kk * 2048, 16384);
       const uint64_t db = desc_mn_sw128(base + 32768 + kk * 2048, 16384);
@@ -76,16 +78,26 @@ int main() {
   float *da, *db, *dout;
   cudaMalloc(&da, 65536); cudaMalloc(&db, 65536); cudaMalloc(&dout, 65536);
   cudaMemcpy(da, a.data(), 65536, cudaMemcpyHostToDevice); cudaMemcpy(db, b.data(), 65536, cudaMemcpyHostToDevice);
+  for (int a_bf16 = 0; a_bf16 < 2; ++a_bf16)
   for (int n_dim : {128, 64, 16}) {
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 128; ++n) {
+        double s = 0;
+        for (int r = 0; r < 128; ++r) {
+          const float av = a_bf16 ? __bfloat162float(__float2bfloat16_rn(a[r * 128 + m])) : __half2float(__float2half_rn(a[r * 128 + m]));
+          s += (double)av * __half2float(__float2half_rn(b[r * 128 + n]));
+        }
+        ref[m * 128 + n] = (float)s;
+      }
     cudaMemset(dout, 0, 65536);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 70000);
-    k<<<1, 128, 70000>>>(da, db, dout, n_dim);
+    k<<<1, 128, 70000>>>(da, db, dout, n_dim, a_bf16);
     cudaError_t e = cudaDeviceSynchronize();
     cudaMemcpy(got.data(), dout, 65536, cudaMemcpyDeviceToHost);
     double maxerr = 0;
     for (int m = 0; m < 128; ++m)
       for (int n = 0; n < n_dim; ++n) maxerr = fmax(maxerr, fabs(got[m * 128 + n] - ref[m * 128 + n]));
-    printf("MN-major M=128 N=%d K=128: max abs err %.3e  (%s)  sample got %.4f ref %.4f\n", n_dim, maxerr, cudaGetErrorString(e), got[5 * 128 + 7], ref[5 * 128 + 7]);
+    printf("A=%s B=f16 MN-major M=128 N=%d K=128: max abs err %.3e  (%s)  sample got %.4f ref %.4f\n", a_bf16 ? "bf16" : "f16", n_dim, maxerr, cudaGetErrorString(e), got[5 * 128 + 7], ref[5 * 128 + 7]);
   }
   return 0;
 }

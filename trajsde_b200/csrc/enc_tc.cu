@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
   uint8_t* sm = smem_raw + (base - raw);
 
   const TrajsdeEncFwdArgs& a = p.a;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = a.sched.n_steps;
 
   const uint32_t bar_w = base + OFF_BARS;
@@ -449,8 +449,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
-    if (warp == NUM_EPI_WARPS && lane == 0) {
+    if (warp == NUM_EPI_WARPS) {
       // =============================================== MMA ISSUER =====================================================
+      // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit
       const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, DUAL ? 192u : 128u);
       const uint32_t idesc_64 = umma_idesc_f16(TILE_M, 64);
       const uint32_t idesc_128 = umma_idesc_f16(TILE_M, 128);
@@ -468,19 +469,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int it = 0; it < S; ++it) {
-          wait0(); mma4(d0, aAH, IMG_B1, idesc_p1, false); tc_commit(bar_acc(0));                          // P1
-          wait1(); mma4(d0, aA1f, IMG_W2, idesc_64, false); tc_commit(bar_acc(1));                         // P2f
-          wait0(); mma4(d0 + 64, aA1g, IMG_V2, idesc_64, false);
-          if (DUAL) mma4(d0 + 128, aA1g, IMG_V2A, idesc_64, false);
-          tc_commit(bar_acc(0));                                                                           // P2g
-          wait1(); mma4(d0, aAH, IMG_W3, idesc_64, false); tc_commit(bar_acc(1));                          // P3
-          wait0(); mma4(d0 + TM_G1, aAH, IMG_UR1H, idesc_128, false); mma4(d0 + TM_G1, aAX, IMG_UR1X, idesc_128, true);
-          tc_commit(bar_acc(0));                                                                           // G1
-          wait1(); mma4(d0 + TM_UP, aA1f, IMG_U2, idesc_64, false); mma4(d0 + TM_RP, aA1g, IMG_R2, idesc_64, false);
-          tc_commit(bar_acc(1));                                                                           // G2
-          wait0(); mma4(d0 + TM_ZN, aAX, IMG_N1X, idesc_64, false); mma4(d0 + TM_ZN, aAH, IMG_N1RH, idesc_64, true);
-          tc_commit(bar_acc(0));                                                                           // G3
-          wait1(); mma4(d0 + TM_N, aA1f, IMG_N2, idesc_64, false); tc_commit(bar_acc(1));                  // G4
+          wait0();                                                                                         // P1
+          if (elect_one()) { mma4(d0, aAH, IMG_B1, idesc_p1, false); tc_commit(bar_acc(0)); }
+          __syncwarp();
+          wait1();                                                                                         // P2f
+          if (elect_one()) { mma4(d0, aA1f, IMG_W2, idesc_64, false); tc_commit(bar_acc(1)); }
+          __syncwarp();
+          wait0();                                                                                         // P2g
+          if (elect_one()) {
+            mma4(d0 + 64, aA1g, IMG_V2, idesc_64, false);
+            if (DUAL) mma4(d0 + 128, aA1g, IMG_V2A, idesc_64, false);
+            tc_commit(bar_acc(0));
+          }
+          __syncwarp();
+          wait1();                                                                                         // P3
+          if (elect_one()) { mma4(d0, aAH, IMG_W3, idesc_64, false); tc_commit(bar_acc(1)); }
+          __syncwarp();
+          wait0();                                                                                         // G1
+          if (elect_one()) {
+            mma4(d0 + TM_G1, aAH, IMG_UR1H, idesc_128, false);
+            mma4(d0 + TM_G1, aAX, IMG_UR1X, idesc_128, true);
+            tc_commit(bar_acc(0));
+          }
+          __syncwarp();
+          wait1();                                                                                         // G2
+          if (elect_one()) {
+            mma4(d0 + TM_UP, aA1f, IMG_U2, idesc_64, false);
+            mma4(d0 + TM_RP, aA1g, IMG_R2, idesc_64, false);
+            tc_commit(bar_acc(1));
+          }
+          __syncwarp();
+          wait0();                                                                                         // G3
+          if (elect_one()) {
+            mma4(d0 + TM_ZN, aAX, IMG_N1X, idesc_64, false);
+            mma4(d0 + TM_ZN, aAH, IMG_N1RH, idesc_64, true);
+            tc_commit(bar_acc(0));
+          }
+          __syncwarp();
+          wait1();                                                                                         // G4
+          if (elect_one()) { mma4(d0 + TM_N, aA1f, IMG_N2, idesc_64, false); tc_commit(bar_acc(1)); }
+          __syncwarp();
         }
       }
     }

@@ -224,8 +224,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   uint8_t* sm = smem_raw + (base - raw);
 
   const TrajsdeEulerFwdArgs& a = p.a;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = a.sched.n_steps;
+  // contiguous, balanced tile range of this CTA (sizes differ by at most one tile); its two slots take alternate tiles
+  const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
+  const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
+  const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
   const bool save_states = a.states != nullptr;
 
   // mbarriers.  [0] weights; per slot s (stride 80 B): opnd[2] (256 epilogue arrivals each), acc[2] (tcgen05.commit), tma
@@ -307,7 +311,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
     mbar_wait(bar_w, 0);
 
-    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+    for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
       const int64_t row0 = (int64_t)tile * TILE_M;
       const int64_t grow = row0 + row;
       const bool valid = grow < a.rows;
@@ -445,7 +449,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     // =============================================== MMA ISSUER WARPS ===============================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     const int slot = warp - WARP_MMA0;
-    if (lane == 0) {
+    // The whole warp runs this loop (warp-uniform control flow and operands -> descriptors live in uniform registers); one
+    // elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    {
       const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
       const uint32_t d_base = tmem_base + slot * 256;
       const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, DUAL ? 192u : 128u);
@@ -457,40 +463,52 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       const uint32_t aB1 = base + IMG_B1, aW2 = base + IMG_W2, aV2 = base + IMG_V2, aV2a = base + IMG_V2A, aW3 = base + IMG_W3;
       uint32_t par_op0 = 0, par_op1 = 0;
       mbar_wait(bar_w, 0);
-      for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+      for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
         for (int k = 0; k < S; ++k) {
           // P1: [z1f | z1g (| z1g_alt)] = y . [W1y ; V1y (; V1y_alt)]^T
           mbar_wait(bar_opnd(slot, 0), par_op0);
           par_op0 ^= 1;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
-          tc_commit(bar_acc(slot, 0));
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
+            tc_commit(bar_acc(slot, 0));
+          }
+          __syncwarp();
           // P2f: z2f = h1f . W2^T  (overwrites the z1f columns the epilogue has already consumed)
           mbar_wait(bar_opnd(slot, 1), par_op1);
           par_op1 ^= 1;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
-          tc_commit(bar_acc(slot, 1));
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
+            tc_commit(bar_acc(slot, 1));
+          }
+          __syncwarp();
           // P2g: z2g = h1g . V2^T (, z2g_alt = h1g . V2alt^T)
           mbar_wait(bar_opnd(slot, 0), par_op0);
           par_op0 ^= 1;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
-          if (DUAL) {
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
+            if (DUAL) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
+              for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
+            }
+            tc_commit(bar_acc(slot, 0));
           }
-          tc_commit(bar_acc(slot, 0));
+          __syncwarp();
           // P3: drift output f = h2f . W3^T (reuses the z2f columns, already consumed by epilogue 2)
           mbar_wait(bar_opnd(slot, 1), par_op1);
           par_op1 ^= 1;
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
-          tc_commit(bar_acc(slot, 1));
+            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
+            tc_commit(bar_acc(slot, 1));
+          }
+          __syncwarp();
         }
       }
     }
@@ -504,7 +522,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     uint32_t par_xfull = 0;
     uint32_t gstep = 0;
     int my_tiles = 0;
-    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) ++my_tiles;
+    for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) ++my_tiles;
     const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)S;
     // Ring entry of global step g -> ring[g % 3], announced on bar_ring[g & 1].  Entry g+1 is published at the start of IO
     // iteration g, i.e. once the epilogue has finished step g-1: its slot (last read in step g-2) is free and its barrier's
@@ -543,7 +561,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       ent_fetch(0, e);
       ent_publish(0, e);
     }
-    for (int tile = blockIdx.x * NUM_SLOTS + slot; tile < p.num_tiles; tile += gridDim.x * NUM_SLOTS) {
+    for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
       const int row0 = tile * TILE_M;
       if (lane == 0) {
         mbar_arrive_expect_tx(bar_tma(slot), 32768);
@@ -680,8 +698,7 @@ int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s) {
   } else {
     tm_st = tm_y0;
   }
-  const int pairs = (p.num_tiles + NUM_SLOTS - 1) / NUM_SLOTS;
-  const int grid = pairs < sms ? pairs : sms;
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;

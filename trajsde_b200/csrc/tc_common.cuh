@@ -43,6 +43,21 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One lane of the (fully converged) warp; the caller's surrounding code stays warp-uniform, so ptxas keeps the UMMA descriptors in
+// uniform registers instead of wrapping every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (measured: ~95 clk per MMA when issued
+// from an `if (lane == 0)` branch, bench_micro/phase_timeline.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- TMA -------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
