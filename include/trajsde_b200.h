@@ -124,12 +124,18 @@ typedef struct {
   int64_t workspace_bytes;
 } TrajsdeEulerFwdArgs;
 
+/* TrajsdeEulerBwdArgs.flags */
+#define TRAJSDE_BWD_FLAG_EXACT_KERNELS 1 /* run the fp32 CUDA-core backward even in TC_F16 mode (A/B validation) */
+
+/* Backward kernels by mode: EXACT_F32 -> fp32 CUDA-core dgrad sweep + wgrad (euler_bwd_exact.cu).  TC_F16 with a single
+ * diffusion net -> fused tensor-core dgrad+wgrad (euler_bwd_tc.cu; fp16 operands, fp32 accumulation, adjoint carried with a
+ * power-of-two loss scale chosen from max|grad|).  TC_F16 with alt_mask (dual diffusion) -> the fp32 kernels. */
 typedef struct {
   uint32_t struct_bytes;
   int32_t mode;
   int64_t rows;
   int32_t dim;
-  int32_t flags;
+  int32_t flags;           /* TRAJSDE_BWD_FLAG_* */
   TrajsdeSchedule sched;
   TrajsdeMlp drift;
   TrajsdeMlp diffusion;
@@ -158,6 +164,7 @@ int trajsde_device_sm_count(void);
 int64_t trajsde_euler_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
 int trajsde_euler_fwd(const TrajsdeEulerFwdArgs* args, void* cuda_stream);
 
+/* Upper bound over both backward kernel families of `mode` (valid whatever `flags` the call then uses). */
 int64_t trajsde_euler_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
 int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* args, void* cuda_stream);
 

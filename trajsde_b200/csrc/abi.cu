@@ -105,7 +105,11 @@ int trajsde_euler_fwd(const TrajsdeEulerFwdArgs* a, void* cuda_stream) {
 }
 
 int64_t trajsde_euler_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {
-  if (mode == TRAJSDE_MODE_EXACT_F32 || mode == TRAJSDE_MODE_TC_F16) return euler_bwd_exact_workspace_bytes(rows, n_steps, dual);
+  if (mode == TRAJSDE_MODE_EXACT_F32) return euler_bwd_exact_workspace_bytes(rows, n_steps, dual);
+  if (mode == TRAJSDE_MODE_TC_F16) {
+    const int64_t ex = euler_bwd_exact_workspace_bytes(rows, n_steps, dual), tc = euler_bwd_tc_workspace_bytes(rows, n_steps);
+    return ex > tc ? ex : tc;
+  }
   return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", mode);
 }
 
@@ -130,11 +134,15 @@ int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* a, void* cuda_stream) {
   if (a->rows > 0 && (!a->states || !a->grad_y0)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "states/grad_y0 null");
   if (a->grad_ys && ((a->grad_ys_row_stride & 3) || (a->grad_ys_t_stride & 3) || !aligned16(a->grad_ys)))
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_ys must be 16-byte aligned with strides multiple of 4 elements");
-  int64_t need = euler_bwd_exact_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
+  if (a->mode != TRAJSDE_MODE_EXACT_F32 && a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", a->mode);
+  const bool use_tc = a->mode == TRAJSDE_MODE_TC_F16 && !a->alt_mask && !(a->flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);
+  int64_t need = use_tc ? euler_bwd_tc_workspace_bytes(a->rows, a->sched.n_steps)
+                        : euler_bwd_exact_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
   if (a->workspace_bytes < need || (need > 0 && !a->workspace))
     return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
   if ((rc = check_device()) != 0) return rc;
-  return launch_euler_bwd_exact(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return use_tc ? launch_euler_bwd_tc(*a, s) : launch_euler_bwd_exact(*a, s);
 }
 
 int64_t trajsde_enc_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {

@@ -92,6 +92,8 @@ __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
 int launch_euler_fwd_exact(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
 int launch_euler_bwd_exact(const TrajsdeEulerBwdArgs& a, cudaStream_t s);
 int64_t euler_bwd_exact_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
+int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s);
+int64_t euler_bwd_tc_workspace_bytes(int64_t rows, int32_t n_steps);
 int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
 int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s);

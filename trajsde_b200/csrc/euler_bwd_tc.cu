@@ -1,0 +1,728 @@
+// Tensor-core backward of the fused Euler–Maruyama solve (TRAJSDE_MODE_TC_F16, single diffusion net): discretise-then-optimise,
+// i.e. what torch.autograd computes through the reference solver (config `adjoint: false`, configs/nusargo/
+// hivt_nuSArgo_sdesepenc_sdedec.yml:41; solver models/utils/sdeint.py:340-384,477-485,544; nets dec_hivt_nusargo_sde.py:119-127,
+// 154-158,180-195).  Same math as euler_bwd_exact.cu, different machine mapping: ONE persistent sm_100a kernel fuses the
+// reverse adjoint sweep (dgrad) and the weight gradients (wgrad):
+//
+//   * one CTA per SM, one 128-row tile at a time; 8 epilogue warps (thread = row x 32-channel half) + one MMA-issuer warp;
+//   * per step, five dependent tcgen05 phases (fp16 operands, fp32 accumulate in TMEM), recomputing the activations from the
+//     state Y[k] the forward call saved:
+//        P1  [z1f|z1g] = y . [W1y;V1y]^T                  P2  z2f = h1f . W2^T ,  z2g = h1g . V2^T
+//        D1  dh2f = df . W3 ,  dh1g = dz2g . V2           D2  dh1f = dz2f . W2           D3  dy = dz1f . W1y + dz1g . V1y
+//     with  df = h A',  ds = (A'.dW) g (1-g),  dz2g = ds w3 (1-h2g^2),  dz* = dh* (1-h*^2),  A = A' + dy + sum_j w0_j gy_j;
+//   * the weight gradients are MN-major tcgen05.mma products over the SAME shared-memory tiles (contraction over the 128 rows),
+//     accumulated in TMEM across all steps and tiles of the CTA and written once, as one partial vector per CTA:
+//        dW2|dV2 += [dz2f|dz2g]^T [h1f|h1g]      dW1y|dV1y += [dz1f|dz1g]^T y      dW3 += df^T h2f
+//     bias / time-column gradients are the same products against a [1, sin t, cos t] tile; they trail the dgrad MMAs of their
+//     phase, off the critical path;
+//   * the adjoint is carried SCALED by a power of two chosen from max|grad| (absmax pre-pass) so that the fp16 delta operands
+//     neither overflow nor underflow; everything leaves the kernel unscaled, in fp32;
+//   * HBM traffic per row-step: state 256 B + dW 256 B (or Philox regenerated in-kernel) + grad_ys 256 B, read once.
+// Partials are summed by the fixed-order reduce of bwd_common.cuh (bit-reproducible, no float atomics).
+#include "bwd_common.cuh"
+#include "tc_common.cuh"
+
+namespace trajsde {
+
+using namespace tc;
+using namespace bwd;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = NUM_EPI_THREADS + 128;  // + one warpgroup: MMA-issuer warp and three idle warps (setmaxnreg is per warpgroup)
+constexpr int EPI_REGS = 216, AUX_REGS = 64;        // 256 x 216 + 128 x 64 = 63488 <= 64 K registers
+
+// ---- packed weight image (bytes): fp16 SW128 K-major B operands + fp32 vectors ------------------------------------------------
+constexpr uint32_t IMG_B1 = 0;                        // [128][64]: rows 0..63 W1y, 64..127 V1y     (P1, N = 128)
+constexpr uint32_t IMG_W2 = 16384, IMG_V2 = 24576;    // forward orientation                       (P2)
+constexpr uint32_t IMG_W3T = 32768, IMG_W2T = 40960, IMG_V2T = 49152, IMG_W1YT = 57344, IMG_V1YT = 65536;   // B[n][k] = W[k][n]
+constexpr uint32_t IMG_VEC = 73728;
+constexpr int VEC_B1 = 0, VEC_W1S = 64, VEC_W1C = 128, VEC_B2 = 192, VEC_C1 = 256, VEC_V1S = 320, VEC_V1C = 384, VEC_C2 = 448,
+              VEC_W3G = 512, VEC_C3 = 576;
+constexpr uint32_t IMG_BYTES = IMG_VEC + 640 * 4;     // 76288
+
+// ---- shared memory map ------------------------------------------------------------------------------------------------------
+constexpr uint32_t OFF_TILES = 76800;                 // eight [128 rows][64] fp16 SW128 tiles, 16 KB each
+constexpr uint32_t TILE_BYTES = 16384;
+// tile roles (adjacency matters: M=128 / N=128 MN-major stacks are two consecutive tiles)
+constexpr int T_H2F = 0;      // h2f, later dz1f          [dz1f|dz1g] = tiles 0,1
+constexpr int T_DF = 1;       // df,  later dz1g          [df|y]      = tiles 1,2
+constexpr int T_Y = 2;
+constexpr int T_DZ2F = 3;     //                          [dz2f|dz2g] = tiles 3,4
+constexpr int T_DZ2G = 4;
+constexpr int T_H1F = 5;      //                          [h1f|h1g]   = tiles 5,6
+constexpr int T_H1G = 6;
+constexpr int T_TIME = 7;     // column 0 = 1, 1 = sin t_k, 2 = cos t_k, rest 0
+constexpr uint32_t OFF_XCHG = OFF_TILES + 8 * TILE_BYTES;          // q[2][128], pd[2][128] fp32
+constexpr int SCHED_MAX = 256;                        // schedule tables staged in shared memory when they fit (else read from global)
+constexpr uint32_t OFF_STAB = OFF_XCHG + 4 * TILE_M * 4;            // float4 step_tab[SCHED_MAX]
+constexpr uint32_t OFF_OBEG = OFF_STAB + SCHED_MAX * 16;           // int out_begin[SCHED_MAX + 4]
+constexpr uint32_t OFF_OUTW = OFF_OBEG + (SCHED_MAX + 4) * 4;      // float2 out_w[SCHED_MAX]
+constexpr uint32_t OFF_BARS = OFF_OUTW + SCHED_MAX * 8;
+constexpr uint32_t SMEM_TOTAL = OFF_BARS + 64;
+constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
+static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
+
+// ---- TMEM columns -------------------------------------------------------------------------------------------------------------
+constexpr uint32_t TM_R0 = 0, TM_R1 = 64, TM_E = 128;
+constexpr uint32_t TM_WGA = 192;    // 128 cols: lanes 0..63 x [0,64) = dW2, lanes 64..127 x [64,128) = dV2
+constexpr uint32_t TM_WGB = 320;    // 64 cols: lanes 0..63 dW1y, 64..127 dV1y
+constexpr uint32_t TM_WGC = 384;    // 64 cols: lanes 0..63 dW3
+constexpr uint32_t TM_SUM1 = 448, TM_SUM2 = 464, TM_SUM3 = 480;   // 16 cols each: col 0 = column sums (, 1 = x sin, 2 = x cos)
+
+struct BwdTcParams {
+  TrajsdeEulerBwdArgs a;
+  const uint8_t* img;
+  const uint32_t* amax_bits;   // max |grad| as float bits (absmax pre-pass)
+  float* partial;              // [grid][G_PAD]
+  int num_tiles;
+};
+
+// ---- pre-passes -------------------------------------------------------------------------------------------------------------------
+__global__ void bwd_tc_pack_kernel(TrajsdeEulerBwdArgs a, uint8_t* __restrict__ img, uint32_t* __restrict__ amax_bits) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) *amax_bits = 0u;
+  auto put = [&](uint32_t off, int n, int k, float v) { *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(v); };
+  for (int idx = tid; idx < 64 * 64; idx += nth) {
+    const int n = idx >> 6, k = idx & 63;
+    put(IMG_B1, n, k, a.drift.w1[n * TS_IN1 + k]);
+    put(IMG_B1, n + 64, k, a.diffusion.w1[n * TS_IN1 + k]);
+    put(IMG_W2, n, k, a.drift.w2[n * 64 + k]);
+    put(IMG_V2, n, k, a.diffusion.w2[n * 64 + k]);
+    put(IMG_W3T, n, k, a.drift.w3[k * 64 + n]);
+    put(IMG_W2T, n, k, a.drift.w2[k * 64 + n]);
+    put(IMG_V2T, n, k, a.diffusion.w2[k * 64 + n]);
+    put(IMG_W1YT, n, k, a.drift.w1[k * TS_IN1 + n]);
+    put(IMG_V1YT, n, k, a.diffusion.w1[k * TS_IN1 + n]);
+  }
+  float* vec = reinterpret_cast<float*>(img + IMG_VEC);
+  for (int i = tid; i < 640; i += nth) {
+    const int c = i & 63;
+    float v = 0.f;
+    switch (i >> 6) {
+      case 0: v = a.drift.b1[c]; break;
+      case 1: v = a.drift.w1[c * TS_IN1 + 64]; break;
+      case 2: v = a.drift.w1[c * TS_IN1 + 65]; break;
+      case 3: v = a.drift.b2[c]; break;
+      case 4: v = a.diffusion.b1[c]; break;
+      case 5: v = a.diffusion.w1[c * TS_IN1 + 64]; break;
+      case 6: v = a.diffusion.w1[c * TS_IN1 + 65]; break;
+      case 7: v = a.diffusion.b2[c]; break;
+      case 8: v = a.diffusion.w3[c]; break;
+      default: v = c == 0 ? a.diffusion.b3[0] : 0.f; break;
+    }
+    vec[i] = v;
+  }
+}
+
+// max |grad_ys| (all slabs, honouring strides) and |grad_g_last| -> *amax_bits (non-negative floats order like their bit patterns)
+__global__ void bwd_tc_absmax_kernel(TrajsdeEulerBwdArgs a, uint32_t* __restrict__ amax_bits) {
+  float m = 0.f;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (a.grad_ys) {
+    const int64_t per_slab = a.rows * 16;   // float4 units
+    for (int t = 0; t <= a.sched.n_outputs; ++t) {
+      const float* slab = a.grad_ys + (int64_t)t * a.grad_ys_t_stride;
+      for (int64_t i = tid; i < per_slab; i += nth) {
+        const float4 v = ld_nc_f4(slab + (i >> 4) * a.grad_ys_row_stride + 4 * (i & 15));
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+    }
+  }
+  if (a.grad_g_last)
+    for (int64_t i = tid; i < a.rows; i += nth) m = fmaxf(m, fabsf(a.grad_g_last[i]));
+  if (!(m <= 3.0e38f)) m = 3.0e38f;   // inf / nan in the incoming gradient: clamp (the result is garbage either way)
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+
+// ---- device helpers -----------------------------------------------------------------------------------------------------------------
+// MN-major SW128 operand descriptor: tile stored [K rows][64 x f16 = 128 B]; LBO = byte stride between 64-element MN groups
+// (consecutive tiles), SBO = 1024 B between 8-row K groups; one MMA (K = 16 rows) advances the start address by 2048 B.
+// Validated by bench_micro/mnmajor_test.cu.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(TILE_BYTES >> 4) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// this thread's 32 channels (4 swizzled 16-byte chunks) of an operand-tile row
+__device__ __forceinline__ void st_row32(uint8_t* tile_row, uint32_t row, uint32_t hh, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t p[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[e] = pack_f16x2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
+  lo = __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+  hi = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+}
+__device__ __forceinline__ void ld_row32(const uint8_t* tile_row, uint32_t row, uint32_t hh, float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile_row + (((hh * 4 + q) ^ (row & 7u)) << 4));
+    unpack_f16x2(u.x, v[q * 8 + 0], v[q * 8 + 1]);
+    unpack_f16x2(u.y, v[q * 8 + 2], v[q * 8 + 3]);
+    unpack_f16x2(u.z, v[q * 8 + 4], v[q * 8 + 5]);
+    unpack_f16x2(u.w, v[q * 8 + 6], v[q * 8 + 7]);
+  }
+}
+
+template <bool HAS_DW>
+__global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const TrajsdeEulerBwdArgs& a = p.a;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int S = a.sched.n_steps;
+  const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
+  const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
+  const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
+
+  const uint32_t bar_w = base + OFF_BARS, bar_opnd = bar_w + 8, bar_acc = bar_w + 16, bar_wg = bar_w + 24;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 32);
+  auto tile_u32 = [&](int t) { return base + OFF_TILES + (uint32_t)t * TILE_BYTES; };
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_opnd, NUM_EPI_THREADS);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_wg, 1);
+    mbar_fence_init();
+  }
+  if (warp == NUM_EPI_WARPS) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+  // time tile: zero once (only chunk 0 of every row is rewritten per step)
+  for (uint32_t i = threadIdx.x; i < TILE_BYTES / 16 && threadIdx.x < NUM_EPI_THREADS; i += NUM_EPI_THREADS)   // epilogue threads: they fence.proxy.async later
+    reinterpret_cast<uint4*>(sm + OFF_TILES + T_TIME * TILE_BYTES)[i] = make_uint4(0u, 0u, 0u, 0u);
+  // schedule tables -> shared memory (every step reads them; three dependent global round trips otherwise)
+  const bool sched_in_smem = S <= SCHED_MAX && a.sched.n_outputs <= SCHED_MAX;
+  const float4* stab = reinterpret_cast<const float4*>(a.sched.step_tab);
+  const int* obeg = a.sched.out_begin;
+  const float2* outw = reinterpret_cast<const float2*>(a.sched.out_w);
+  if (sched_in_smem) {
+    float4* s_stab = reinterpret_cast<float4*>(sm + OFF_STAB);
+    int* s_obeg = reinterpret_cast<int*>(sm + OFF_OBEG);
+    float2* s_outw = reinterpret_cast<float2*>(sm + OFF_OUTW);
+    for (int i = threadIdx.x; i < S; i += NUM_THREADS) s_stab[i] = stab[i];
+    for (int i = threadIdx.x; i <= S; i += NUM_THREADS) s_obeg[i] = obeg[i];
+    for (int i = threadIdx.x; i < a.sched.n_outputs; i += NUM_THREADS) s_outw[i] = outw[i];
+    stab = s_stab;
+    obeg = s_obeg;
+    outw = s_outw;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_w, IMG_BYTES);
+    bulk_load_1d(base, p.img, IMG_BYTES, bar_w);
+  }
+  const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
+
+  if (warp < NUM_EPI_WARPS) {
+    // =============================================== EPILOGUE WARPS ===============================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    const int quad = warp & 3;
+    const uint32_t hh = (uint32_t)warp >> 2;
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t tm = tmem_base + ((uint32_t)(quad * 32) << 16) + hh * 32;   // this thread's lane / 32-column half
+    auto trow = [&](int t) { return sm + OFF_TILES + (uint32_t)t * TILE_BYTES + row * 128; };
+    float* qbuf = reinterpret_cast<float*>(sm + OFF_XCHG);
+    float* pdbuf = qbuf + 2 * TILE_M;
+    const uint32_t pair_bar = 1 + quad;
+
+    // adjoint scale: a power of two that puts max|grad| into [2^-4, 2^-3)
+    float sigma = 1.f, inv_sigma = 1.f;
+    {
+      const float amax = __uint_as_float(*p.amax_bits);
+      if (amax > 0.f) {
+        int e;
+        frexpf(amax, &e);
+        e = max(-100, min(100, -e - 3));
+        sigma = ldexpf(1.f, e);
+        inv_sigma = ldexpf(1.f, -e);
+      }
+    }
+    float dw3g_acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dw3g_acc[j] = 0.f;
+    float dc3_acc = 0.f;
+    uint32_t hs = 0;        // hand-shake counter: acc barrier parity
+    uint32_t gstep = 0;     // steps processed by this CTA: wg barrier parity
+
+    mbar_wait(bar_w, 0);
+    const float c3 = vec[VEC_C3];
+
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      const int64_t grow = (int64_t)tile * TILE_M + row;
+      const bool valid = grow < a.rows;
+      float4 py[8], pdw[8], pgy[8];
+      auto prefetch_y_dw = [&](int k) {
+        if (valid) {
+          const float* ys = a.states + ((int64_t)k * a.rows + grow) * 64 + hh * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) py[q] = ld_nc_f4(ys + 4 * q);
+          if (HAS_DW) {
+            const float* ds = a.noise.dw + ((int64_t)k * a.rows + grow) * 64 + hh * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pdw[q] = ld_nc_f4(ds + 4 * q);
+          }
+        }
+      };
+      auto prefetch_gy = [&](int k) {
+        const int ob = obeg[k], oe = obeg[k + 1];
+        if (valid && a.grad_ys && oe > ob) {
+          const float* gs = a.grad_ys + (int64_t)(ob + 1) * a.grad_ys_t_stride + grow * a.grad_ys_row_stride + hh * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) pgy[q] = ld_nc_f4(gs + 4 * q);
+        }
+      };
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        py[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pdw[q] = py[q];
+        pgy[q] = py[q];
+      }
+      prefetch_y_dw(S - 1);
+      prefetch_gy(S - 1);
+      float adj[32];          // A = dL/dY[k+1] before the output terms, scaled by sigma
+#pragma unroll
+      for (int j = 0; j < 32; ++j) adj[j] = 0.f;
+
+      for (int k = S - 1; k >= 0; --k, ++gstep) {
+        const float4 stp = stab[k];
+        const float h = stp.y, sn = stp.z, cs = stp.w;
+        const int ob = obeg[k], oe = obeg[k + 1];
+
+        // ================= step start: A' = A + sum w1 gy ; E = A' + sum w0 gy ; df ; q = A'.dW ; y -> operand =================
+        float e_[32];
+        {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e_[j] = adj[j];
+          if (a.grad_ys && oe > ob) {
+            const float w0 = outw[ob].x, w1 = outw[ob].y;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float g4[4] = {pgy[q].x * sigma, pgy[q].y * sigma, pgy[q].z * sigma, pgy[q].w * sigma};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                adj[4 * q + e] = fmaf(w1, g4[e], adj[4 * q + e]);
+                e_[4 * q + e] = fmaf(w1 + w0, g4[e], e_[4 * q + e]);
+              }
+            }
+            for (int o = ob + 1; o < oe; ++o) {   // rare: several outputs interpolate inside the same step
+              const float v0 = outw[o].x, v1 = outw[o].y;
+              if (valid) {
+                const float* gs = a.grad_ys + (int64_t)(o + 1) * a.grad_ys_t_stride + grow * a.grad_ys_row_stride + hh * 32;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 g = ld_nc_f4(gs + 4 * q);
+                  const float g4[4] = {g.x * sigma, g.y * sigma, g.z * sigma, g.w * sigma};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    adj[4 * q + e] = fmaf(v1, g4[e], adj[4 * q + e]);
+                    e_[4 * q + e] = fmaf(v1 + v0, g4[e], e_[4 * q + e]);
+                  }
+                }
+              }
+            }
+          }
+          // q = A' . dW (this thread's half)
+          float qp = 0.f;
+          if (HAS_DW) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              qp = fmaf(adj[4 * q], pdw[q].x, qp);
+              qp = fmaf(adj[4 * q + 1], pdw[q].y, qp);
+              qp = fmaf(adj[4 * q + 2], pdw[q].z, qp);
+              qp = fmaf(adj[4 * q + 3], pdw[q].w, qp);
+            }
+          } else {
+            const float sqrt_h = sqrtf(h);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
+                                               (uint32_t)(hh * 8 + q));
+              qp = fmaf(adj[4 * q], __fmul_rn(n4.x, sqrt_h), qp);
+              qp = fmaf(adj[4 * q + 1], __fmul_rn(n4.y, sqrt_h), qp);
+              qp = fmaf(adj[4 * q + 2], __fmul_rn(n4.z, sqrt_h), qp);
+              qp = fmaf(adj[4 * q + 3], __fmul_rn(n4.w, sqrt_h), qp);
+            }
+          }
+          qbuf[hh * TILE_M + row] = valid ? qp : 0.f;
+          // E -> TMEM (read back by the last epilogue of this step)
+          {
+            uint32_t ev[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ev[j] = __float_as_uint(e_[j]);
+            tmem_st_32x32b_x32(tm + TM_E, ev);
+          }
+          // previous step's trailing weight-gradient MMAs must have finished reading Y / DF(dz1g) / TIME
+          if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);
+          float t[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = h * adj[j];
+          st_row32(trow(T_DF), row, hh, t);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            t[4 * q] = py[q].x; t[4 * q + 1] = py[q].y; t[4 * q + 2] = py[q].z; t[4 * q + 3] = py[q].w;
+          }
+          st_row32(trow(T_Y), row, hh, t);
+          if (hh == 0)
+            *reinterpret_cast<uint4*>(trow(T_TIME) + ((0u ^ (row & 7u)) << 4)) = make_uint4(pack_f16x2(1.f, sn), pack_f16x2(cs, 0.f), 0u, 0u);
+          tc_wait_st();
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // y, df, time tile -> P1
+        if (k > 0) prefetch_y_dw(k - 1);
+
+        // ================= epilogue 1: h1f, h1g ==================================================================================
+        mbar_wait(bar_acc, hs & 1);
+        ++hs;
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          float t[32];
+          tmem_ld_32x32b_x32(tm + TM_R0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = hh * 32 + j;
+            const float b = fmaf(vec[VEC_W1C + c], cs, fmaf(vec[VEC_W1S + c], sn, vec[VEC_B1 + c]));
+            t[j] = ts_tanh_approx(__uint_as_float(v[j]) + b);
+          }
+          st_row32(trow(T_H1F), row, hh, t);
+          tmem_ld_32x32b_x32(tm + TM_R1, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int c = hh * 32 + j;
+            const float b = fmaf(vec[VEC_V1C + c], cs, fmaf(vec[VEC_V1S + c], sn, vec[VEC_C1 + c]));
+            t[j] = ts_tanh_approx(__uint_as_float(v[j]) + b);
+          }
+          st_row32(trow(T_H1G), row, hh, t);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // h1f, h1g -> P2
+
+        // ================= epilogue 2: h2f ; h2g, g, ds, dz2g =====================================================================
+        mbar_wait(bar_acc, hs & 1);
+        ++hs;
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          float t[32];
+          tmem_ld_32x32b_x32(tm + TM_R0, v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = ts_tanh_approx(__uint_as_float(v[j]) + vec[VEC_B2 + hh * 32 + j]);
+          st_row32(trow(T_H2F), row, hh, t);
+          tmem_ld_32x32b_x32(tm + TM_R1, v);
+          tc_wait_ld();
+          float pd = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            t[j] = ts_tanh_approx(__uint_as_float(v[j]) + vec[VEC_C2 + hh * 32 + j]);
+            pd = fmaf(t[j], vec[VEC_W3G + hh * 32 + j], pd);
+          }
+          pdbuf[hh * TILE_M + row] = pd;
+          named_bar_sync(pair_bar, 64);                          // partner half's pd and q are in smem
+          const float s = (pdbuf[row] + pdbuf[TILE_M + row]) + c3;
+          const float g = __fdividef(1.0f, 1.0f + __expf(-s));
+          float dg = qbuf[row] + qbuf[TILE_M + row];
+          if (k == S - 1 && a.grad_g_last && valid) dg = fmaf(a.grad_g_last[grow], sigma, dg);
+          const float ds = dg * g * (1.f - g);
+          if (hh == 0) dc3_acc += ds;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            dw3g_acc[j] = fmaf(ds, t[j], dw3g_acc[j]);
+            t[j] = ds * vec[VEC_W3G + hh * 32 + j] * fmaf(-t[j], t[j], 1.f);
+          }
+          st_row32(trow(T_DZ2G), row, hh, t);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // h2f, dz2g -> D1 (+ trailing dW3 / db3)
+        if (k > 0) prefetch_gy(k - 1);
+
+        // ================= epilogue 3: dz2f = dh2f (1 - h2f^2) =====================================================================
+        mbar_wait(bar_acc, hs & 1);
+        ++hs;
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          float t[32];
+          tmem_ld_32x32b_x32(tm + TM_R0, v);
+          ld_row32(trow(T_H2F), row, hh, t);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * fmaf(-t[j], t[j], 1.f);
+          st_row32(trow(T_DZ2F), row, hh, t);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // dz2f -> D2 (+ trailing dW2|dV2 / db2|dc2)
+
+        // ================= epilogue 4: dz1f = dh1f (1 - h1f^2) -> tile H2F ; dz1g = dh1g (1 - h1g^2) -> tile DF ==========================
+        mbar_wait(bar_acc, hs & 1);
+        ++hs;
+        tc_fence_after();
+        {
+          uint32_t v[32];
+          float t[32];
+          tmem_ld_32x32b_x32(tm + TM_R0, v);
+          ld_row32(trow(T_H1F), row, hh, t);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * fmaf(-t[j], t[j], 1.f);
+          st_row32(trow(T_H2F), row, hh, t);
+          tmem_ld_32x32b_x32(tm + TM_R1, v);
+          ld_row32(trow(T_H1G), row, hh, t);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * fmaf(-t[j], t[j], 1.f);
+          st_row32(trow(T_DF), row, hh, t);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // dz1f, dz1g -> D3 (+ trailing dW1y|dV1y / db1|dc1 / time columns)
+
+        // ================= epilogue 5: A[k] = E + dy =================================================================================
+        mbar_wait(bar_acc, hs & 1);
+        ++hs;
+        tc_fence_after();
+        {
+          uint32_t v[32], ev[32];
+          tmem_ld_32x32b_x32(tm + TM_R0, v);
+          tmem_ld_32x32b_x32(tm + TM_E, ev);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) adj[j] = valid ? __uint_as_float(ev[j]) + __uint_as_float(v[j]) : 0.f;
+        }
+        tc_fence_before();
+      }
+      // ---- grad_y0 = A[0] / sigma (+ grad_ys[0]: ys[0] = y0) -----------------------------------------------------------------
+      if (valid) {
+        float* dst = a.grad_y0 + grow * 64 + hh * 32;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(adj[4 * q] * inv_sigma, adj[4 * q + 1] * inv_sigma, adj[4 * q + 2] * inv_sigma, adj[4 * q + 3] * inv_sigma);
+          if (a.grad_ys) {
+            const float4 g = ld_nc_f4(a.grad_ys + grow * a.grad_ys_row_stride + hh * 32 + 4 * q);
+            o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+          }
+          *reinterpret_cast<float4*>(dst + 4 * q) = o;
+        }
+      }
+    }
+
+    // ================= weight-gradient partials of this CTA ===============================================================================
+    if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);          // every MMA of the CTA has completed
+    tc_fence_after();
+    float* out = p.partial + (size_t)blockIdx.x * G_PAD;
+    const bool lo = quad < 2;                                    // TMEM lanes 0..63: drift net, 64..127: diffusion net
+    const int m = (int)row & 63;
+    {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tm + TM_WGA + (lo ? 0u : 64u), v);      // dW2 / dV2
+      tc_wait_ld();
+      float* d = out + (lo ? G_FW2 : G_GW2) + m * 64 + hh * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+      tmem_ld_32x32b_x32(tm + TM_WGB, v);                        // dW1y / dV1y
+      tc_wait_ld();
+      d = out + (lo ? G_FW1 : G_GW1) + m * TS_IN1 + hh * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+      tmem_ld_32x32b_x32(tm + TM_WGC, v);                        // dW3 (lanes 0..63)
+      tc_wait_ld();
+      if (lo) {
+        d = out + G_FW3 + m * 64 + hh * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+      }
+      const uint32_t tm0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+      uint32_t s1[16], s2[16], s3[16];
+      tmem_ld_32x32b_x16(tm0 + TM_SUM1, s1);
+      tmem_ld_32x32b_x16(tm0 + TM_SUM2, s2);
+      tmem_ld_32x32b_x16(tm0 + TM_SUM3, s3);
+      tc_wait_ld();
+      if (hh == 0) {
+        out[(lo ? G_FB1 : G_GB1) + m] = __uint_as_float(s1[0]) * inv_sigma;
+        out[(lo ? G_FW1 : G_GW1) + m * TS_IN1 + 64] = __uint_as_float(s1[1]) * inv_sigma;
+        out[(lo ? G_FW1 : G_GW1) + m * TS_IN1 + 65] = __uint_as_float(s1[2]) * inv_sigma;
+        out[(lo ? G_FB2 : G_GB2) + m] = __uint_as_float(s2[0]) * inv_sigma;
+        if (lo) out[G_FB3 + m] = __uint_as_float(s3[0]) * inv_sigma;
+      }
+    }
+    // w3 / c3 of the diffusion net: per-thread running sums -> column sums over the 128 rows (tiles 0,1 as fp32 scratch)
+    float* red = reinterpret_cast<float*>(sm + OFF_TILES);       // [128][64] fp32 = 32 KB
+#pragma unroll
+    for (int j = 0; j < 32; ++j) red[row * 64 + ((hh * 32 + j + row) & 63)] = dw3g_acc[j];   // rotate: conflict-free column reads
+    if (hh == 0) qbuf[row] = dc3_acc;
+    named_bar_sync(5, NUM_EPI_THREADS);
+    if (threadIdx.x < 64) {
+      float s = 0.f;
+      for (int r = 0; r < TILE_M; ++r) s += red[r * 64 + ((threadIdx.x + r) & 63)];
+      out[G_GW3 + threadIdx.x] = s * inv_sigma;
+    } else if (threadIdx.x == 64) {
+      float s = 0.f;
+      for (int r = 0; r < TILE_M; ++r) s += qbuf[r];
+      out[G_GB3] = s * inv_sigma;
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+    if (warp == NUM_EPI_WARPS) {
+    // =============================================== MMA ISSUER WARP ===============================================
+    // warp-uniform loop (descriptors in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit
+    const uint32_t idesc_128 = umma_idesc_f16(TILE_M, 128), idesc_64 = umma_idesc_f16(TILE_M, 64);
+    const uint32_t imn_128 = umma_idesc_f16_mn(TILE_M, 128), imn_64 = umma_idesc_f16_mn(TILE_M, 64), imn_16 = umma_idesc_f16_mn(TILE_M, 16);
+    const uint64_t khi = umma_desc_sw128(0), mhi = umma_desc_mn_sw128(0);
+    auto KD = [&](uint32_t addr) { return khi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+    auto MD = [&](uint32_t addr) { return mhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+    // K-major product: D[128 x N] (+)= A[128 rows][64] . B[N][64]^T
+    auto mma_k = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool acc_first) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d, KD(a_addr + 32 * kk), KD(b_addr + 32 * kk), idesc, (acc_first || kk > 0) ? 1u : 0u);
+    };
+    // MN-major product over the 128 rows: D[128 x N] (+)= [A0|A1]^T . B
+    auto mma_mn = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool acc_first) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) tc_mma_f16(d, MD(a_addr + 2048 * kk), MD(b_addr + 2048 * kk), idesc, (acc_first || kk > 0) ? 1u : 0u);
+    };
+    const uint32_t d0 = tmem_base;
+    uint32_t hs = 0;
+    bool wg_acc = false;
+    mbar_wait(bar_w, 0);
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      for (int k = S - 1; k >= 0; --k) {
+        // P1
+        mbar_wait(bar_opnd, hs & 1); ++hs;
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k(d0 + TM_R0, tile_u32(T_Y), base + IMG_B1, idesc_128, false);
+          tc_commit(bar_acc);
+        }
+        __syncwarp();
+        // P2
+        mbar_wait(bar_opnd, hs & 1); ++hs;
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k(d0 + TM_R0, tile_u32(T_H1F), base + IMG_W2, idesc_64, false);
+          mma_k(d0 + TM_R1, tile_u32(T_H1G), base + IMG_V2, idesc_64, false);
+          tc_commit(bar_acc);
+        }
+        __syncwarp();
+        // D1: dh2f, dh1g ; trailing: dW3 += df^T h2f, db3 += df^T 1
+        mbar_wait(bar_opnd, hs & 1); ++hs;
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k(d0 + TM_R0, tile_u32(T_DF), base + IMG_W3T, idesc_64, false);
+          mma_k(d0 + TM_R1, tile_u32(T_DZ2G), base + IMG_V2T, idesc_64, false);
+          tc_commit(bar_acc);
+          mma_mn(d0 + TM_WGC, tile_u32(T_DF), tile_u32(T_H2F), imn_64, wg_acc);
+          mma_mn(d0 + TM_SUM3, tile_u32(T_DF), tile_u32(T_TIME), imn_16, wg_acc);
+        }
+        __syncwarp();
+        // D2: dh1f ; trailing: dW2|dV2 += [dz2f|dz2g]^T [h1f|h1g], db2|dc2
+        mbar_wait(bar_opnd, hs & 1); ++hs;
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k(d0 + TM_R0, tile_u32(T_DZ2F), base + IMG_W2T, idesc_64, false);
+          tc_commit(bar_acc);
+          mma_mn(d0 + TM_WGA, tile_u32(T_DZ2F), tile_u32(T_H1F), imn_128, wg_acc);
+          mma_mn(d0 + TM_SUM2, tile_u32(T_DZ2F), tile_u32(T_TIME), imn_16, wg_acc);
+        }
+        __syncwarp();
+        // D3: dy = dz1f . W1y + dz1g . V1y ; trailing: dW1y|dV1y += [dz1f|dz1g]^T y, db1|dc1 and the time columns
+        mbar_wait(bar_opnd, hs & 1); ++hs;
+        tc_fence_after();
+        if (elect_one()) {
+          mma_k(d0 + TM_R0, tile_u32(T_H2F), base + IMG_W1YT, idesc_64, false);
+          mma_k(d0 + TM_R0, tile_u32(T_DF), base + IMG_V1YT, idesc_64, true);
+          tc_commit(bar_acc);
+          mma_mn(d0 + TM_WGB, tile_u32(T_H2F), tile_u32(T_Y), imn_64, wg_acc);
+          mma_mn(d0 + TM_SUM1, tile_u32(T_H2F), tile_u32(T_TIME), imn_16, wg_acc);
+          tc_commit(bar_wg);
+        }
+        __syncwarp();
+        wg_acc = true;
+      }
+    }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_EPI_WARPS) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+int64_t euler_bwd_tc_workspace_bytes(int64_t rows, int32_t n_steps) {
+  (void)rows;
+  (void)n_steps;
+  return (int64_t)76800 + 256 + (int64_t)MAX_PARTIALS * G_PAD * 4 + 256;
+}
+
+int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  TS_CUDA_CHECK(cudaGetDevice(&dev));
+  TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (sms > MAX_PARTIALS) sms = MAX_PARTIALS;
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
+  uint8_t* ws = static_cast<uint8_t*>(a.workspace);
+  BwdTcParams p;
+  p.a = a;
+  p.img = ws;
+  p.amax_bits = reinterpret_cast<uint32_t*>(ws + 76800);
+  p.partial = reinterpret_cast<float*>(ws + 76800 + 256);
+  p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (grid > 0) {
+    bwd_tc_pack_kernel<<<16, 256, 0, s>>>(a, ws, reinterpret_cast<uint32_t*>(ws + 76800));
+    TS_CUDA_CHECK(cudaGetLastError());
+    if (a.grad_ys || a.grad_g_last) {
+      bwd_tc_absmax_kernel<<<2 * sms, 512, 0, s>>>(a, reinterpret_cast<uint32_t*>(ws + 76800));
+      TS_CUDA_CHECK(cudaGetLastError());
+    }
+    auto launch = [&](auto kern) -> cudaError_t {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+      if (e != cudaSuccess) return e;
+      kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
+      return cudaGetLastError();
+    };
+    TS_CUDA_CHECK(a.noise.dw ? launch(euler_bwd_tc_kernel<true>) : launch(euler_bwd_tc_kernel<false>));
+  }
+  euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(p.partial, nullptr, grid, 0, a.grad_drift, a.grad_diffusion,
+                                                              a.grad_diffusion_alt);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
+}  // namespace trajsde

@@ -21,6 +21,9 @@ _N_MLP = 6  # w1 b1 w2 b2 w3 b3
 LAUNCHES = {'n': 0}
 _KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-pack + persistent solve
 
+# A/B switch (tests, bench): run the fp32 CUDA-core backward kernels even in 'tc_f16' mode (TRAJSDE_BWD_FLAG_EXACT_KERNELS)
+BWD_EXACT_KERNELS = False
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # device-resident schedule tables
@@ -160,7 +163,7 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     gparams = [torch.zeros_like(p) for p in ps]
     a = _lib.EulerBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EulerBwdArgs)
-    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, 0
+    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0)
     a.sched.n_steps, a.sched.n_outputs = S, n_outputs
     a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
     a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
@@ -190,6 +193,10 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     a.workspace, a.workspace_bytes = ws.data_ptr(), need
     with torch.cuda.device(dev):
         _lib.check(L.trajsde_euler_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_euler_bwd")
+    if rows > 0:
+        tc = mode == _lib.MODE_TC_F16 and not dual and not BWD_EXACT_KERNELS
+        # TC: pack + absmax + fused dgrad/wgrad + reduce; exact: (dgrad + wgrad) per diffusion net + reduce
+        LAUNCHES['n'] += 4 if tc else (5 if dual else 3)
     return [grad_y0] + gparams
 
 
