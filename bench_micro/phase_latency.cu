@@ -18,6 +18,7 @@ struct Cfg {
   int sts;           // write the operand chunks (st.shared.v4) per phase
   int iters;
   int membar;        // extra __threadfence_block() per phase
+  int wait_mode;     // 0: every epilogue warp polls the mbarrier; 1: warp 0 polls, the others wait at a named barrier
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -61,7 +62,12 @@ __global__ void __launch_bounds__(544, 1) k(Cfg c, long long* out_clk, float* si
     if (c.arrive_mode) { __syncwarp(); if (lane == 0) mbar_arrive(bar_opnd); } else mbar_arrive(bar_opnd);
     if (tid == 0) t0 = clock64();
     for (int it = 0; it < c.iters; ++it) {
-      mbar_wait(bar_acc, par);
+      if (c.wait_mode == 0) {
+        mbar_wait(bar_acc, par);
+      } else {
+        if (warp == 0) mbar_wait(bar_acc, par);
+        named_bar_sync(1, n_epi);
+      }
       par ^= 1;
       tc_fence_after();
       float v[32];
@@ -125,23 +131,28 @@ int main() {
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
   struct Named { const char* name; Cfg c; };
   std::vector<Named> v = {
-      {"8w  all-arrive  proxyfence N=64  no work       ", {8, 0, 1, 64, 0, 0, 2000, 0}},
-      {"8w  elect-arrive proxyfence N=64 no work       ", {8, 1, 1, 64, 0, 0, 2000, 0}},
-      {"8w  elect-arrive no fence  N=64  no work       ", {8, 1, 0, 64, 0, 0, 2000, 0}},
-      {"8w  all-arrive  no fence   N=64  no work       ", {8, 0, 0, 64, 0, 0, 2000, 0}},
-      {"8w  all-arrive  proxyfence N=128 no work       ", {8, 0, 1, 128, 0, 0, 2000, 0}},
-      {"8w  all-arrive  proxyfence N=64  sts           ", {8, 0, 1, 64, 0, 1, 2000, 0}},
-      {"8w  elect-arrive proxyfence N=64 sts           ", {8, 1, 1, 64, 0, 1, 2000, 0}},
-      {"8w  all-arrive  proxyfence N=64  sts+32tanh    ", {8, 0, 1, 64, 32, 1, 2000, 0}},
-      {"8w  elect-arrive proxyfence N=64 sts+32tanh    ", {8, 1, 1, 64, 32, 1, 2000, 0}},
-      {"8w  all-arrive  proxyfence+membar N=64 sts     ", {8, 0, 1, 64, 0, 1, 2000, 1}},
-      {"16w all-arrive  proxyfence N=64  no work       ", {16, 0, 1, 64, 0, 0, 2000, 0}},
-      {"16w elect-arrive proxyfence N=64 no work       ", {16, 1, 1, 64, 0, 0, 2000, 0}},
-      {"16w all-arrive  proxyfence N=64  sts           ", {16, 0, 1, 64, 0, 1, 2000, 0}},
-      {"16w elect-arrive proxyfence N=64 sts           ", {16, 1, 1, 64, 0, 1, 2000, 0}},
-      {"16w all-arrive  proxyfence N=64  sts+16tanh    ", {16, 0, 1, 64, 16, 1, 2000, 0}},
-      {"16w elect-arrive proxyfence N=64 sts+16tanh    ", {16, 1, 1, 64, 16, 1, 2000, 0}},
-      {"16w elect-arrive proxyfence N=128 sts+16tanh   ", {16, 1, 1, 128, 16, 1, 2000, 0}},
+      {"8w  all-arrive  proxyfence N=64  no work       ", {8, 0, 1, 64, 0, 0, 2000, 0, 0}},
+      {"8w  elect-arrive proxyfence N=64 no work       ", {8, 1, 1, 64, 0, 0, 2000, 0, 0}},
+      {"8w  elect-arrive no fence  N=64  no work       ", {8, 1, 0, 64, 0, 0, 2000, 0, 0}},
+      {"8w  all-arrive  no fence   N=64  no work       ", {8, 0, 0, 64, 0, 0, 2000, 0, 0}},
+      {"8w  all-arrive  proxyfence N=128 no work       ", {8, 0, 1, 128, 0, 0, 2000, 0, 0}},
+      {"8w  all-arrive  proxyfence N=64  sts           ", {8, 0, 1, 64, 0, 1, 2000, 0, 0}},
+      {"8w  elect-arrive proxyfence N=64 sts           ", {8, 1, 1, 64, 0, 1, 2000, 0, 0}},
+      {"8w  all-arrive  proxyfence N=64  sts+32tanh    ", {8, 0, 1, 64, 32, 1, 2000, 0, 0}},
+      {"8w  elect-arrive proxyfence N=64 sts+32tanh    ", {8, 1, 1, 64, 32, 1, 2000, 0, 0}},
+      {"8w  all-arrive  proxyfence+membar N=64 sts     ", {8, 0, 1, 64, 0, 1, 2000, 1, 0}},
+      {"16w all-arrive  proxyfence N=64  no work       ", {16, 0, 1, 64, 0, 0, 2000, 0, 0}},
+      {"16w elect-arrive proxyfence N=64 no work       ", {16, 1, 1, 64, 0, 0, 2000, 0, 0}},
+      {"16w all-arrive  proxyfence N=64  sts           ", {16, 0, 1, 64, 0, 1, 2000, 0, 0}},
+      {"16w elect-arrive proxyfence N=64 sts           ", {16, 1, 1, 64, 0, 1, 2000, 0, 0}},
+      {"16w all-arrive  proxyfence N=64  sts+16tanh    ", {16, 0, 1, 64, 16, 1, 2000, 0, 0}},
+      {"16w elect-arrive proxyfence N=64 sts+16tanh    ", {16, 1, 1, 64, 16, 1, 2000, 0, 0}},
+      {"16w elect-arrive proxyfence N=128 sts+16tanh   ", {16, 1, 1, 128, 16, 1, 2000, 0, 0}},
+      {"8w  all-arrive one-warp-polls N=64 sts+32tanh  ", {8, 0, 1, 64, 32, 1, 2000, 0, 1}},
+      {"8w  all-arrive one-warp-polls N=64 no work     ", {8, 0, 1, 64, 0, 0, 2000, 0, 1}},
+      {"16w all-arrive one-warp-polls N=64 sts+16tanh  ", {16, 0, 1, 64, 16, 1, 2000, 0, 1}},
+      {"16w all-arrive one-warp-polls N=64 no work     ", {16, 0, 1, 64, 0, 0, 2000, 0, 1}},
+      {"16w elect-arrive one-warp-polls N=64 sts+16tanh", {16, 1, 1, 64, 16, 1, 2000, 0, 1}},
   };
   for (auto& nv : v) {
     for (int rep = 0; rep < 2; ++rep) {

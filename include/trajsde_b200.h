@@ -10,6 +10,7 @@
  *   trajsde_euler_bwd   : torch.autograd through that solver (config `adjoint: false`, yml:41): discretise-then-optimise
  *   trajsde_enc_fwd     : the encoder recurrence 21 x [sdeint_dual one step + GRU_Unit jump]
  *                           enc_hivt_nusargo_sde_sep2.py:128-182 + models/utils/ode_utils.py:136-152
+ *   trajsde_enc_bwd     : torch.autograd through that recurrence
  *   trajsde_philox_dw   : BrownianInterval increments W(t1)-W(t0) ~ N(0,(t1-t0) I)  models/utils/sdeint.py:983-984
  *
  * Conventions
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 1
+#define TRAJSDE_ABI_VERSION 2
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -206,12 +207,62 @@ typedef struct {
   int64_t obs_mask_row_stride;
   float* latent;             /* out [n_steps, rows, 64]: post-GRU state of every iteration (latent_ys, :180,184) */
   float* g_out;              /* out [n_steps, rows]: diffusion evaluated at the start of every iteration's step (:149,171) */
+  float* y1_out;             /* out [n_steps, rows, 64] or NULL: state after the SDE step, before the GRU jump (saved for
+                                trajsde_enc_bwd) */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeEncFwdArgs;
 
 int64_t trajsde_enc_fwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
 int trajsde_enc_fwd(const TrajsdeEncFwdArgs* args, void* cuda_stream);
+
+/* Gradients of the GRU_Unit parameters (device, written — not accumulated). */
+typedef struct {
+  float* u1; float* ub1; float* u2; float* ub2;
+  float* r1; float* rb1; float* r2; float* rb2;
+  float* n1; float* nb1; float* n2; float* nb2;
+} TrajsdeGruGrad;
+
+/* Backward of the whole encoder recurrence (what autograd computes through enc…sep2.py:128-182 with `adjoint: false`): one call,
+ * a reverse sweep over the iterations that chains, per iteration, the GRU_Unit backward (fp32) and the one-step dual-diffusion
+ * SDE backward (fused tensor-core dgrad+wgrad, one pass per diffusion net).  Consumes what trajsde_enc_fwd produced with
+ * y1_out != NULL: latent (post-GRU states) and y1 (pre-GRU states); activations are recomputed. */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;              /* TRAJSDE_MODE_TC_F16 */
+  int64_t rows;
+  int32_t dim;               /* 64 */
+  int32_t flags;
+  TrajsdeSchedule sched;     /* as in TrajsdeEncFwdArgs (step_tab only) */
+  TrajsdeMlp drift;
+  TrajsdeMlp diffusion;
+  TrajsdeMlp diffusion_alt;
+  const uint8_t* alt_mask;   /* device [rows] nus_mask or NULL (single diffusion net) */
+  TrajsdeGru gru;
+  TrajsdeNoise noise;        /* the forward call's noise: dw[n_steps, rows, 64] or the same Philox seed / offsets */
+  const float* h0;           /* [rows,64] contiguous */
+  const float* aa_out;       /* [n_slots, rows, 64] */
+  int32_t n_slots;
+  int32_t reserved;
+  const int32_t* slot;       /* device [n_steps] */
+  const uint8_t* obs_mask;
+  int64_t obs_mask_row_stride;
+  const float* latent;       /* [n_steps, rows, 64] from the forward call */
+  const float* y1;           /* [n_steps, rows, 64] from the forward call (y1_out) */
+  const float* grad_latent;  /* dL/d latent [n_steps, rows, 64] or NULL */
+  const float* grad_g;       /* dL/d g_out [n_steps, rows] or NULL */
+  float* grad_h0;            /* out [rows,64] */
+  float* grad_aa_out;        /* out [n_slots, rows, 64]: slabs of the visited slots are written, the caller zero-fills the rest; or NULL */
+  TrajsdeMlpGrad grad_drift;
+  TrajsdeMlpGrad grad_diffusion;
+  TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
+  TrajsdeGruGrad grad_gru;
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeEncBwdArgs;
+
+int64_t trajsde_enc_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
+int trajsde_enc_bwd(const TrajsdeEncBwdArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

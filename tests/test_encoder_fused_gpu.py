@@ -117,3 +117,44 @@ def test_rows_major_output_layout_matches_and_is_unit_stride():
         assert b_.shape == a.shape and torch.equal(a, b_)
         sol_y = b_[1:].permute(1, 0, 2)                     # what SDEDecoder.forward hands to its heads (dec…sde.py:88)
         assert sol_y.stride() == (61 * 64, 64, 1)
+
+
+@pytest.mark.parametrize('rows,mixed', [(90, True), (200, False)])
+def test_fused_encoder_gradients_vs_fp64_autograd(rows, mixed):
+    """trajsde_enc_bwd (reverse sweep: fp32 GRU backward + tensor-core one-step SDE backward per diffusion net) against fp64
+    autograd through the oracle's recurrence: gradients of h0, aa_out, every SDE weight (f, g_nus, g_argo) and every GRU
+    weight, with cotangents on the latents AND on the per-iteration diffusion g (DiffBCE, losses/diff_BCE.py:11-16)."""
+    sde = init_like_reference(EncoderSDE(), seed=rows, bias_std=0.2).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), rows + 1, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(rows)
+    h0 = torch.randn(rows, 64, generator=g) * 0.3
+    aa = torch.randn(21, rows, 64, generator=g)
+    am = torch.rand(rows, 21, generator=g) > 0.3
+    nm = (torch.rand(rows, generator=g) > 0.5) if mixed else torch.ones(rows, dtype=torch.bool)
+    dW = torch.randn(21, rows, 64, generator=g) * 0.3
+    cot = torch.randn(21, rows, 64, generator=g)
+    cot_g = torch.randn(21, rows, generator=g)
+
+    nets = [net_params(sde.f_func), net_params(sde.g_nus), net_params(sde.g_argo), {k: v.detach().cpu() for k, v in gru.state_dict().items()}]
+    P = [{k: v.double().clone().requires_grad_(True) for k, v in n.items()} for n in nets]
+    h0d, aad = h0.double().requires_grad_(True), aa.double().requires_grad_(True)
+    lat_r, g_r = so.encoder_recurrence_ref(P[0], P[1], P[2], P[3], h0d, aad, am, nm, dW.double())
+    loss = (lat_r * cot.double()).sum() + (g_r[:, :, 0] * cot_g.double()).sum()
+    leaves = [h0d, aad] + [t for n in P for t in n.values()]
+    ref = torch.autograd.grad(loss, leaves, allow_unused=True)
+    names = ['h0', 'aa_out'] + [f'net{i}.{k}' for i, n in enumerate(P) for k in n]
+
+    h = h0.to(DEV).requires_grad_(True)
+    a = aa.to(DEV).requires_grad_(True)
+    lat, gg = enc.encoder_recurrence(sde, gru, h, a, am.to(DEV), nm.to(DEV), dW=dW.to(DEV), mode='tc_f16', fused=True)
+    ((lat * cot.to(DEV)).sum() + (gg * cot_g.to(DEV)).sum()).backward()
+    got = [h.grad, a.grad] + [p_.grad for net in (sde.f_func, sde.g_nus, sde.g_argo) for _, p_ in net.net.named_parameters()] + \
+          [gru.get_parameter(k).grad for k in nets[3]]
+    assert len(got) == len(ref)
+    for n, x, r in zip(names, got, ref):
+        if r is None or float(r.abs().max()) == 0.0:        # g_argo unused when every row is nuScenes
+            assert x is None or float(x.abs().max()) == 0.0, n
+            continue
+        e = float((x.double().cpu() - r).abs().max() / r.abs().max())
+        print(f"rows={rows} {n}: rel err {e:.2e}")
+        assert e < 3e-2, (n, e)

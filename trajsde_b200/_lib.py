@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_euler_fwd_workspace_bytes', 'trajsde_euler_fwd',
     'trajsde_euler_bwd_workspace_bytes', 'trajsde_euler_bwd',
     'trajsde_philox_dw', 'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_fwd',
+    'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -60,7 +61,17 @@ class EncFwdArgs(C.Structure):
                 ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
                 ('alt_mask', _fp), ('gru', Gru), ('noise', Noise), ('h0', _fp), ('h0_row_stride', C.c_int64),
                 ('aa_out', _fp), ('slot', _fp), ('obs_mask', _fp), ('obs_mask_row_stride', C.c_int64),
-                ('latent', _fp), ('g_out', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+                ('latent', _fp), ('g_out', _fp), ('y1_out', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class EncBwdArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
+                ('alt_mask', _fp), ('gru', Gru), ('noise', Noise), ('h0', _fp), ('aa_out', _fp), ('n_slots', C.c_int32),
+                ('reserved', C.c_int32), ('slot', _fp), ('obs_mask', _fp), ('obs_mask_row_stride', C.c_int64),
+                ('latent', _fp), ('y1', _fp), ('grad_latent', _fp), ('grad_g', _fp), ('grad_h0', _fp), ('grad_aa_out', _fp),
+                ('grad_drift', Mlp), ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('grad_gru', Gru),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 _lock = threading.Lock()
@@ -87,7 +98,7 @@ def lib():
         L.trajsde_last_error_string.restype = C.c_char_p
         L.trajsde_device_sm_count.restype = C.c_int
         for name in ('trajsde_euler_fwd_workspace_bytes', 'trajsde_euler_bwd_workspace_bytes',
-                     'trajsde_enc_fwd_workspace_bytes'):
+                     'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_bwd_workspace_bytes'):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_int64
                 getattr(L, name).argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
@@ -100,6 +111,9 @@ def lib():
         if hasattr(L, 'trajsde_enc_fwd'):
             L.trajsde_enc_fwd.restype = C.c_int
             L.trajsde_enc_fwd.argtypes = [C.POINTER(EncFwdArgs), C.c_void_p]
+        if hasattr(L, 'trajsde_enc_bwd'):
+            L.trajsde_enc_bwd.restype = C.c_int
+            L.trajsde_enc_bwd.argtypes = [C.POINTER(EncBwdArgs), C.c_void_p]
         v = L.trajsde_abi_version()
         if v != ABI_VERSION:
             raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")

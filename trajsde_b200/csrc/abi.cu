@@ -135,7 +135,7 @@ int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* a, void* cuda_stream) {
   if (a->grad_ys && ((a->grad_ys_row_stride & 3) || (a->grad_ys_t_stride & 3) || !aligned16(a->grad_ys)))
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_ys must be 16-byte aligned with strides multiple of 4 elements");
   if (a->mode != TRAJSDE_MODE_EXACT_F32 && a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", a->mode);
-  const bool use_tc = a->mode == TRAJSDE_MODE_TC_F16 && !a->alt_mask && !(a->flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);
+  const bool use_tc = a->mode == TRAJSDE_MODE_TC_F16 && !(a->flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);
   int64_t need = use_tc ? euler_bwd_tc_workspace_bytes(a->rows, a->sched.n_steps)
                         : euler_bwd_exact_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
   if (a->workspace_bytes < need || (need > 0 && !a->workspace))
@@ -177,6 +177,49 @@ int trajsde_enc_fwd(const TrajsdeEncFwdArgs* a, void* cuda_stream) {
     return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
   if ((rc = check_device()) != 0) return rc;
   return launch_enc_fwd_tc(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t trajsde_enc_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual) {
+  if (mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "fused encoder exists in TC_F16 mode only (mode %d)", mode);
+  if (rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  return enc_bwd_workspace_bytes(rows, n_steps, dual);
+}
+
+int trajsde_enc_bwd(const TrajsdeEncBwdArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeEncBwdArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeEncBwdArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "fused encoder exists in TC_F16 mode only (mode %d)", a->mode);
+  if (a->rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  if (a->sched.n_steps <= 0 || !a->sched.step_tab || !aligned16(a->sched.step_tab))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "schedule: n_steps=%d or step_tab null/misaligned", a->sched.n_steps);
+  int rc;
+  if ((rc = check_mlp(a->drift, "drift")) != 0) return rc;
+  if ((rc = check_mlp(a->diffusion, "diffusion")) != 0) return rc;
+  if (a->alt_mask && (rc = check_mlp(a->diffusion_alt, "diffusion_alt")) != 0) return rc;
+  const TrajsdeGru& g = a->gru;
+  if (!g.u1 || !g.ub1 || !g.u2 || !g.ub2 || !g.r1 || !g.rb1 || !g.r2 || !g.rb2 || !g.n1 || !g.nb1 || !g.n2 || !g.nb2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "gru: null weight pointer");
+  const TrajsdeGruGrad& gg = a->grad_gru;
+  if (!gg.u1 || !gg.ub1 || !gg.u2 || !gg.ub2 || !gg.r1 || !gg.rb1 || !gg.r2 || !gg.rb2 || !gg.n1 || !gg.nb1 || !gg.n2 || !gg.nb2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_gru: null pointer");
+  const TrajsdeMlpGrad* mg[3] = {&a->grad_drift, &a->grad_diffusion, &a->grad_diffusion_alt};
+  for (int i = 0; i < (a->alt_mask ? 3 : 2); ++i)
+    if (!mg[i]->w1 || !mg[i]->b1 || !mg[i]->w2 || !mg[i]->b2 || !mg[i]->w3 || !mg[i]->b3)
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null gradient pointer");
+  if (a->rows == 0) return TRAJSDE_OK;
+  if (!a->h0 || !a->aa_out || !a->slot || !a->obs_mask || !a->latent || !a->y1 || !a->grad_h0)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h0/aa_out/slot/obs_mask/latent/y1/grad_h0 null");
+  if (!aligned16(a->h0) || !aligned16(a->aa_out) || !aligned16(a->latent) || !aligned16(a->y1) || !aligned16(a->grad_h0) ||
+      (a->grad_latent && !aligned16(a->grad_latent)) || (a->noise.dw && !aligned16(a->noise.dw)) ||
+      (a->grad_aa_out && !aligned16(a->grad_aa_out)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "tensors must be 16-byte aligned");
+  int64_t need = enc_bwd_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
+  if (a->workspace_bytes < need || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  if ((rc = check_device()) != 0) return rc;
+  return launch_enc_bwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {

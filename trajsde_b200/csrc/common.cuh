@@ -98,6 +98,22 @@ int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s);
 int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s);
 int64_t enc_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
+// internal pieces of the tensor-core backward (euler_bwd_tc.cu), reused by the encoder backward
+int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s);
+int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride, uint32_t* amax_bits, cudaStream_t s);
+int bwd_tc_grid(int64_t rows);
+int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img, const uint32_t* amax_bits, float* partial, int filter, int accumulate,
+                cudaStream_t s);
+int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int n1, const TrajsdeMlpGrad& gf, const TrajsdeMlpGrad& gg,
+                            const TrajsdeMlpGrad& ga, cudaStream_t s);
+// GRU jump backward (gru_bwd.cu) and the encoder-recurrence backward driver (enc_bwd.cu)
+int gru_bwd_grid(int64_t rows);
+int launch_gru_bwd(const TrajsdeGru& w, int64_t rows, const float* y1, const float* aa_out, int64_t slab, const uint8_t* obs_mask,
+                   int64_t obs_mask_row_stride, const int32_t* slot, int iter, const float* carry, const float* grad_latent, float* grad_y1,
+                   float* grad_aa_out, float* partial, cudaStream_t s);
+int launch_gru_bwd_reduce(const float* partial, int n, const TrajsdeGruGrad& g, cudaStream_t s);
+int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s);
+int64_t enc_bwd_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_philox_dw(const TrajsdeSchedule& sched, const TrajsdeNoise& noise, int64_t rows, float* out, cudaStream_t s);
 
 }  // namespace trajsde

@@ -358,6 +358,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           tmem_st_32x32b_x16(tm + TM_Y, yv);               // Y <- y1
           store16_operand(t, ah_row, row, cq * 2);
           if (cq == 0 && valid) a.g_out[(int64_t)it * a.rows + grow] = g;
+          if (a.y1_out && valid) {                       // pre-GRU state, saved for the backward call
+            float* dst = a.y1_out + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+          }
           tc_wait_st();
         }
         fence_proxy_async();

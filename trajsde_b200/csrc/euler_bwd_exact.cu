@@ -620,7 +620,7 @@ int launch_euler_bwd_exact(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
     }
   }
   euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part, dual ? part + (size_t)160 * G_PAD : nullptr, wg_grid,
-                                                              dual ? wg_grid : 0, a.grad_drift, a.grad_diffusion, a.grad_diffusion_alt);
+                                                              dual ? wg_grid : 0, a.grad_drift, a.grad_diffusion, a.grad_diffusion_alt, 0);
   TS_CUDA_CHECK(cudaGetLastError());
   return TRAJSDE_OK;
 }

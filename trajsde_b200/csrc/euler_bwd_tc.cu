@@ -43,6 +43,7 @@ constexpr uint32_t IMG_VEC = 73728;
 constexpr int VEC_B1 = 0, VEC_W1S = 64, VEC_W1C = 128, VEC_B2 = 192, VEC_C1 = 256, VEC_V1S = 320, VEC_V1C = 384, VEC_C2 = 448,
               VEC_W3G = 512, VEC_C3 = 576;
 constexpr uint32_t IMG_BYTES = IMG_VEC + 640 * 4;     // 76288
+static_assert(IMG_BYTES <= BWD_TC_IMG_BYTES, "image larger than its workspace slot");
 
 // ---- shared memory map ------------------------------------------------------------------------------------------------------
 constexpr uint32_t OFF_TILES = 76800;                 // eight [128 rows][64] fp16 SW128 tiles, 16 KB each
@@ -79,12 +80,13 @@ struct BwdTcParams {
   const uint32_t* amax_bits;   // max |grad| as float bits (absmax pre-pass)
   float* partial;              // [grid][G_PAD]
   int num_tiles;
+  int filter;                  // 0: all rows; 1: only rows with alt_mask != 0; 2: only rows with alt_mask == 0 (dual diffusion passes)
+  int accumulate;              // add into the CTA's partial vector instead of overwriting it (multi-launch accumulation)
 };
 
 // ---- pre-passes -------------------------------------------------------------------------------------------------------------------
-__global__ void bwd_tc_pack_kernel(TrajsdeEulerBwdArgs a, uint8_t* __restrict__ img, uint32_t* __restrict__ amax_bits) {
+__global__ void bwd_tc_pack_kernel(TrajsdeEulerBwdArgs a, uint8_t* __restrict__ img) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-  if (tid == 0) *amax_bits = 0u;
   auto put = [&](uint32_t off, int n, int k, float v) { *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(v); };
   for (int idx = tid; idx < 64 * 64; idx += nth) {
     const int n = idx >> 6, k = idx & 63;
@@ -118,22 +120,24 @@ __global__ void bwd_tc_pack_kernel(TrajsdeEulerBwdArgs a, uint8_t* __restrict__ 
   }
 }
 
-// max |grad_ys| (all slabs, honouring strides) and |grad_g_last| -> *amax_bits (non-negative floats order like their bit patterns)
-__global__ void bwd_tc_absmax_kernel(TrajsdeEulerBwdArgs a, uint32_t* __restrict__ amax_bits) {
+// max |x| over `slabs` slabs of [rows][64] floats (slab / row strides in elements) or, with row_stride == 0, over a flat array of
+// `rows` floats -> atomicMax on *amax_bits (non-negative floats order like their bit patterns)
+__global__ void bwd_tc_absmax_kernel(const float* __restrict__ x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride,
+                                     uint32_t* __restrict__ amax_bits) {
   float m = 0.f;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
-  if (a.grad_ys) {
-    const int64_t per_slab = a.rows * 16;   // float4 units
-    for (int t = 0; t <= a.sched.n_outputs; ++t) {
-      const float* slab = a.grad_ys + (int64_t)t * a.grad_ys_t_stride;
+  if (row_stride == 0) {
+    for (int64_t i = tid; i < rows; i += nth) m = fmaxf(m, fabsf(x[i]));
+  } else {
+    const int64_t per_slab = rows * 16;   // float4 units
+    for (int t = 0; t < slabs; ++t) {
+      const float* slab = x + (int64_t)t * slab_stride;
       for (int64_t i = tid; i < per_slab; i += nth) {
-        const float4 v = ld_nc_f4(slab + (i >> 4) * a.grad_ys_row_stride + 4 * (i & 15));
+        const float4 v = ld_nc_f4(slab + (i >> 4) * row_stride + 4 * (i & 15));
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
       }
     }
   }
-  if (a.grad_g_last)
-    for (int64_t i = tid; i < a.rows; i += nth) m = fmaxf(m, fabsf(a.grad_g_last[i]));
   if (!(m <= 3.0e38f)) m = 3.0e38f;   // inf / nan in the incoming gradient: clamp (the result is garbage either way)
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
       const int64_t grow = (int64_t)tile * TILE_M + row;
-      const bool valid = grow < a.rows;
+      bool valid = grow < a.rows;
+      if (valid && p.filter) valid = (a.alt_mask[grow] != 0) == (p.filter == 1);   // other net's rows: adjoint stays zero
       float4 py[8], pdw[8], pgy[8];
       auto prefetch_y_dw = [&](int k) {
         if (valid) {
@@ -541,6 +546,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);          // every MMA of the CTA has completed
     tc_fence_after();
     float* out = p.partial + (size_t)blockIdx.x * G_PAD;
+    const bool acc_out = p.accumulate != 0;
+    auto put = [&](int idx, float v) { out[idx] = acc_out ? out[idx] + v : v; };
     const bool lo = quad < 2;                                    // TMEM lanes 0..63: drift net, 64..127: diffusion net
     const int m = (int)row & 63;
     {
@@ -549,18 +556,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       tc_wait_ld();
       float* d = out + (lo ? G_FW2 : G_GW2) + m * 64 + hh * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
       tmem_ld_32x32b_x32(tm + TM_WGB, v);                        // dW1y / dV1y
       tc_wait_ld();
       d = out + (lo ? G_FW1 : G_GW1) + m * TS_IN1 + hh * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
       tmem_ld_32x32b_x32(tm + TM_WGC, v);                        // dW3 (lanes 0..63)
       tc_wait_ld();
       if (lo) {
         d = out + G_FW3 + m * 64 + hh * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma;
+        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
       }
       const uint32_t tm0 = tmem_base + ((uint32_t)(quad * 32) << 16);
       uint32_t s1[16], s2[16], s3[16];
@@ -569,11 +576,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       tmem_ld_32x32b_x16(tm0 + TM_SUM3, s3);
       tc_wait_ld();
       if (hh == 0) {
-        out[(lo ? G_FB1 : G_GB1) + m] = __uint_as_float(s1[0]) * inv_sigma;
-        out[(lo ? G_FW1 : G_GW1) + m * TS_IN1 + 64] = __uint_as_float(s1[1]) * inv_sigma;
-        out[(lo ? G_FW1 : G_GW1) + m * TS_IN1 + 65] = __uint_as_float(s1[2]) * inv_sigma;
-        out[(lo ? G_FB2 : G_GB2) + m] = __uint_as_float(s2[0]) * inv_sigma;
-        if (lo) out[G_FB3 + m] = __uint_as_float(s3[0]) * inv_sigma;
+        put((lo ? G_FB1 : G_GB1) + m, __uint_as_float(s1[0]) * inv_sigma);
+        put((lo ? G_FW1 : G_GW1) + m * TS_IN1 + 64, __uint_as_float(s1[1]) * inv_sigma);
+        put((lo ? G_FW1 : G_GW1) + m * TS_IN1 + 65, __uint_as_float(s1[2]) * inv_sigma);
+        put((lo ? G_FB2 : G_GB2) + m, __uint_as_float(s2[0]) * inv_sigma);
+        if (lo) put(G_FB3 + m, __uint_as_float(s3[0]) * inv_sigma);
       }
     }
     // w3 / c3 of the diffusion net: per-thread running sums -> column sums over the 128 rows (tiles 0,1 as fp32 scratch)
@@ -585,11 +592,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     if (threadIdx.x < 64) {
       float s = 0.f;
       for (int r = 0; r < TILE_M; ++r) s += red[r * 64 + ((threadIdx.x + r) & 63)];
-      out[G_GW3 + threadIdx.x] = s * inv_sigma;
+      put(G_GW3 + threadIdx.x, s * inv_sigma);
     } else if (threadIdx.x == 64) {
       float s = 0.f;
       for (int r = 0; r < TILE_M; ++r) s += qbuf[r];
-      out[G_GB3] = s * inv_sigma;
+      put(G_GB3, s * inv_sigma);
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
@@ -683,44 +690,99 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
 }  // namespace
 
-int64_t euler_bwd_tc_workspace_bytes(int64_t rows, int32_t n_steps) {
-  (void)rows;
-  (void)n_steps;
-  return (int64_t)76800 + 256 + (int64_t)MAX_PARTIALS * G_PAD * 4 + 256;
+// ---- internal launch API (also used by enc_bwd.cu) ---------------------------------------------------------------------------------
+int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s) {
+  bwd_tc_pack_kernel<<<16, 256, 0, s>>>(a, img);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
 }
 
-int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
+int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride, uint32_t* amax_bits, cudaStream_t s) {
+  if (!x || rows <= 0) return TRAJSDE_OK;
   int dev = 0, sms = 0;
   TS_CUDA_CHECK(cudaGetDevice(&dev));
   TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t work = row_stride == 0 ? rows : rows * 16;
+  int64_t blocks = (work + 511) / 512;
+  if (blocks > 2 * sms) blocks = 2 * sms;
+  bwd_tc_absmax_kernel<<<(int)blocks, 512, 0, s>>>(x, slabs, rows, slab_stride, row_stride, amax_bits);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
+int bwd_tc_grid(int64_t rows) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   if (sms > MAX_PARTIALS) sms = MAX_PARTIALS;
-  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  const int64_t tiles = (rows + TILE_M - 1) / TILE_M;
+  return (int)(tiles < sms ? tiles : sms);
+}
+
+// one fused dgrad+wgrad launch over all steps of a.sched; partial[grid][G_PAD] written (or accumulated into)
+int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img, const uint32_t* amax_bits, float* partial, int filter, int accumulate,
+                cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(img) & 15u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
   if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
-  uint8_t* ws = static_cast<uint8_t*>(a.workspace);
   BwdTcParams p;
   p.a = a;
-  p.img = ws;
-  p.amax_bits = reinterpret_cast<uint32_t*>(ws + 76800);
-  p.partial = reinterpret_cast<float*>(ws + 76800 + 256);
+  p.img = img;
+  p.amax_bits = amax_bits;
+  p.partial = partial;
   p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
-  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  p.filter = filter;
+  p.accumulate = accumulate;
+  const int grid = bwd_tc_grid(a.rows);
+  if (grid <= 0) return TRAJSDE_OK;
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
+    return cudaGetLastError();
+  };
+  TS_CUDA_CHECK(a.noise.dw ? launch(euler_bwd_tc_kernel<true>) : launch(euler_bwd_tc_kernel<false>));
+  return TRAJSDE_OK;
+}
+
+int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int n1, const TrajsdeMlpGrad& gf, const TrajsdeMlpGrad& gg,
+                            const TrajsdeMlpGrad& ga, cudaStream_t s) {
+  euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part0, part1, n0, n1, gf, gg, ga, 0);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
+int64_t euler_bwd_tc_workspace_bytes(int64_t rows, int32_t n_steps) {
+  (void)rows;
+  (void)n_steps;
+  return 2 * (int64_t)BWD_TC_IMG_BYTES + 256 + 2 * (int64_t)MAX_PARTIALS * G_PAD * 4 + 256;
+}
+
+// workspace: img0 | img1 | amax (256 B) | partial0 | partial1
+int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(a.workspace);
+  uint8_t* img0 = ws;
+  uint8_t* img1 = ws + BWD_TC_IMG_BYTES;
+  uint32_t* amax = reinterpret_cast<uint32_t*>(ws + 2 * BWD_TC_IMG_BYTES);
+  float* part0 = reinterpret_cast<float*>(ws + 2 * BWD_TC_IMG_BYTES + 256);
+  float* part1 = part0 + (size_t)MAX_PARTIALS * G_PAD;
+  const bool dual = a.alt_mask != nullptr;
+  const int grid = bwd_tc_grid(a.rows);
+  int rc;
   if (grid > 0) {
-    bwd_tc_pack_kernel<<<16, 256, 0, s>>>(a, ws, reinterpret_cast<uint32_t*>(ws + 76800));
-    TS_CUDA_CHECK(cudaGetLastError());
-    if (a.grad_ys || a.grad_g_last) {
-      bwd_tc_absmax_kernel<<<2 * sms, 512, 0, s>>>(a, reinterpret_cast<uint32_t*>(ws + 76800));
-      TS_CUDA_CHECK(cudaGetLastError());
+    TS_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, s));
+    if (a.grad_ys && (rc = bwd_tc_absmax(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride, a.grad_ys_row_stride, amax, s)) != 0) return rc;
+    if (a.grad_g_last && (rc = bwd_tc_absmax(a.grad_g_last, 1, a.rows, 0, 0, amax, s)) != 0) return rc;
+    if ((rc = bwd_tc_pack(a, img0, s)) != 0) return rc;
+    if ((rc = bwd_tc_main(a, img0, amax, part0, dual ? 1 : 0, 0, s)) != 0) return rc;
+    if (dual) {   // second pass: the rows of the other diffusion net (rows are independent; the drift gradients of both passes add up)
+      TrajsdeEulerBwdArgs b = a;
+      b.diffusion = a.diffusion_alt;
+      if ((rc = bwd_tc_pack(b, img1, s)) != 0) return rc;
+      if ((rc = bwd_tc_main(b, img1, amax, part1, 2, 0, s)) != 0) return rc;
     }
-    auto launch = [&](auto kern) -> cudaError_t {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
-      if (e != cudaSuccess) return e;
-      kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
-      return cudaGetLastError();
-    };
-    TS_CUDA_CHECK(a.noise.dw ? launch(euler_bwd_tc_kernel<true>) : launch(euler_bwd_tc_kernel<false>));
   }
-  euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(p.partial, nullptr, grid, 0, a.grad_drift, a.grad_diffusion,
-                                                              a.grad_diffusion_alt);
+  euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part0, dual ? part1 : nullptr, grid, dual ? grid : 0, a.grad_drift,
+                                                              a.grad_diffusion, a.grad_diffusion_alt, 0);
   TS_CUDA_CHECK(cudaGetLastError());
   return TRAJSDE_OK;
 }

@@ -2,9 +2,10 @@
 GRU jump], diffusion read-out and the eos gather.  The AA/AL graph attention around it stays on the reference path.
 
 Two execution paths, both on our CUDA kernels:
-  * fused  (default for inference, TC mode): ONE persistent kernel for the whole recurrence (csrc/enc_tc.cu);
-  * stepwise: 21 x fused one-step `sdeint_dual` launch + the GRU jump in plain torch — differentiable (training), and the
-    only path in 'exact' mode.
+  * fused  (default in TC mode): ONE persistent kernel for the whole recurrence (csrc/enc_tc.cu); differentiable — the
+    backward is one library call (csrc/enc_bwd.cu: reverse sweep of GRU backward + one-step SDE backward kernels);
+  * stepwise: 21 x fused one-step `sdeint_dual` launch + the GRU jump in plain torch — differentiable through the
+    per-step ops, and the only path in 'exact' mode.
 """
 from typing import Optional, Tuple
 
@@ -53,19 +54,18 @@ def encoder_recurrence(sde, gru_unit, h0: torch.Tensor, aa_out: torch.Tensor, ac
     need_grad = torch.is_grad_enabled() and (h0.requires_grad or aa_out.requires_grad or
                                              any(p.requires_grad for p in params + gparams))
     if fused is None:
-        fused = mode == 'tc_f16' and not need_grad and hist <= 32
+        fused = mode == 'tc_f16' and hist <= 32
     if fused:
         if mode != 'tc_f16':
             raise NotImplementedError("the fused encoder recurrence exists in 'tc_f16' mode only")
-        if need_grad:
-            raise NotImplementedError("the fused encoder recurrence is forward-only; use fused=False for training")
         if not h0.is_cuda:
             raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
         step_tab, slots = _enc_tables(max_past_t, hist, dt, h0.device)
         if seed is None:
             seed = _next_call_seed() if dW is None else 0
-        return ops.enc_fwd(h0, aa_out, actors_mask, slots, list(params), list(gparams), step_tab, dW, nus_mask, int(seed),
-                           int(row_offset), 0)
+        latent, g, _ = ops.enc_fwd(h0, aa_out, actors_mask, slots, list(params), list(gparams), step_tab, dW, nus_mask, int(seed),
+                                   int(row_offset), 0, bool(need_grad))
+        return latent, g
     h = h0
     latent, gs = [], []
     for idx, (prev_t, t_i, t) in enumerate(encoder_time_pairs(max_past_t, hist)):

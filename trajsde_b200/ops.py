@@ -231,13 +231,15 @@ euler_fwd.register_autograd(_backward, setup_context=_setup_context)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# fused encoder recurrence (forward only; training uses the per-step ops, which have autograd)
+# fused encoder recurrence: one forward launch, one backward call (reverse sweep enqueued by the library)
 # ---------------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("trajsde::enc_fwd", mutates_args=(), device_types="cuda")
 def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
             gru_params: List[torch.Tensor], step_tab: torch.Tensor, dw: Optional[torch.Tensor],
-            alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int) -> Tuple[torch.Tensor, torch.Tensor]:
-    """latent[S,rows,64] (post-GRU state of every iteration), g[S,rows] (pre-step diffusion of every iteration)."""
+            alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int, save_y1: bool,
+            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """latent[S,rows,64] (post-GRU state of every iteration), g[S,rows] (pre-step diffusion of every iteration),
+    y1[S,rows,64] (pre-GRU state of every iteration; empty unless ``save_y1`` — the backward needs it)."""
     dev = h0.device
     rows, S = h0.shape[0], step_tab.shape[0]
     dual = alt_mask is not None
@@ -260,6 +262,7 @@ def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot
     om = obs_mask.contiguous().view(torch.uint8)
     latent = torch.empty((S, rows, 64), dtype=torch.float32, device=dev)
     g_out = torch.empty((S, rows), dtype=torch.float32, device=dev)
+    y1s = torch.empty((S if save_y1 else 0, rows, 64), dtype=torch.float32, device=dev)
     a = _lib.EncFwdArgs()
     a.struct_bytes = C.sizeof(_lib.EncFwdArgs)
     a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
@@ -283,6 +286,7 @@ def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot
     a.aa_out, a.slot = aa.data_ptr(), slot.data_ptr()
     a.obs_mask, a.obs_mask_row_stride = om.data_ptr(), om.stride(0)
     a.latent, a.g_out = latent.data_ptr(), g_out.data_ptr()
+    a.y1_out = y1s.data_ptr() if save_y1 and rows > 0 else None
     L = _lib.lib()
     need = _lib.check(L.trajsde_enc_fwd_workspace_bytes(_lib.MODE_TC_F16, rows, S, int(dual)), "trajsde_enc_fwd_workspace_bytes")
     ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
@@ -291,13 +295,107 @@ def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot
         _lib.check(L.trajsde_enc_fwd(C.byref(a), _stream_ptr(dev)), "trajsde_enc_fwd")
     if rows > 0:
         LAUNCHES['n'] += 2
-    return latent, g_out
+    return latent, g_out, y1s
 
 
 @enc_fwd.register_fake
-def _(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset):
+def _(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset, save_y1):
     rows, S = h0.shape[0], step_tab.shape[0]
-    return h0.new_empty((S, rows, 64)), h0.new_empty((S, rows))
+    return h0.new_empty((S, rows, 64)), h0.new_empty((S, rows)), h0.new_empty((S if save_y1 else 0, rows, 64))
+
+
+_GRU_NAMES = ('u1', 'ub1', 'u2', 'ub2', 'r1', 'rb1', 'r2', 'rb2', 'n1', 'nb1', 'n2', 'nb2')
+
+
+@torch.library.custom_op("trajsde::enc_bwd", mutates_args=(), device_types="cuda")
+def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], latent: torch.Tensor, y1s: torch.Tensor,
+            h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
+            gru_params: List[torch.Tensor], step_tab: torch.Tensor, dw: Optional[torch.Tensor],
+            alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int) -> List[torch.Tensor]:
+    """[grad_h0, grad_aa_out] + gradients of ``params`` + gradients of ``gru_params`` (same order / shapes)."""
+    dev = latent.device
+    S, rows = latent.shape[0], latent.shape[1]
+    dual = alt_mask is not None
+    ps = _check_params(params, dual, dev)
+    gs = [t.detach().contiguous() for t in gru_params]
+    n_slots = aa_out.shape[0]
+    grad_h0 = torch.empty((rows, 64), dtype=torch.float32, device=dev)
+    grad_aa = torch.zeros((n_slots, rows, 64), dtype=torch.float32, device=dev)
+    gparams = [torch.zeros_like(p) for p in ps]
+    ggru = [torch.zeros_like(p) for p in gs]
+    a = _lib.EncBwdArgs()
+    a.struct_bytes = C.sizeof(_lib.EncBwdArgs)
+    a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
+    a.sched.n_steps, a.sched.n_outputs = S, 0
+    a.sched.step_tab = step_tab.data_ptr()
+    a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
+    a.grad_drift, a.grad_diffusion = _mlp_struct(gparams[0:6]), _mlp_struct(gparams[6:12])
+    mask_u8 = None
+    if dual:
+        mask_u8 = alt_mask.contiguous().view(torch.uint8)
+        a.diffusion_alt, a.grad_diffusion_alt = _mlp_struct(ps[12:18]), _mlp_struct(gparams[12:18])
+        a.alt_mask = mask_u8.data_ptr()
+    for name, t, gt in zip(_GRU_NAMES, gs, ggru):
+        setattr(a.gru, name, t.data_ptr())
+        setattr(a.grad_gru, name, gt.data_ptr())
+    if dw is not None:
+        dw = dw.contiguous()
+        a.noise.dw = dw.data_ptr()
+    a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    h0c = h0.detach().contiguous()
+    aa = aa_out.detach().contiguous()
+    om = obs_mask.contiguous().view(torch.uint8)
+    lat, y1c = latent.contiguous(), y1s.contiguous()
+    a.h0, a.aa_out, a.n_slots, a.slot = h0c.data_ptr(), aa.data_ptr(), n_slots, slot.data_ptr()
+    a.obs_mask, a.obs_mask_row_stride = om.data_ptr(), om.stride(0)
+    a.latent, a.y1 = lat.data_ptr(), y1c.data_ptr()
+    if grad_latent is not None:
+        grad_latent = grad_latent.contiguous()
+        a.grad_latent = grad_latent.data_ptr()
+    if grad_g is not None:
+        grad_g = grad_g.contiguous()
+        a.grad_g = grad_g.data_ptr()
+    a.grad_h0, a.grad_aa_out = grad_h0.data_ptr(), grad_aa.data_ptr()
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_enc_bwd_workspace_bytes(_lib.MODE_TC_F16, rows, S, int(dual)), "trajsde_enc_bwd_workspace_bytes")
+    ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_enc_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_enc_bwd")
+    if rows > 0:
+        # tables + absmax x2 + pack per net + per iteration (GRU backward + one fused SDE backward per net) + two reduces
+        LAUNCHES['n'] += 3 + (2 if dual else 1) + S * (1 + (2 if dual else 1)) + 2
+    return [grad_h0, grad_aa] + gparams + ggru
+
+
+@enc_bwd.register_fake
+def _(grad_latent, grad_g, latent, y1s, h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed,
+      row_offset, step_offset):
+    return ([latent.new_empty((latent.shape[1], 64)), torch.empty_like(aa_out)] + [torch.empty_like(p) for p in params] +
+            [torch.empty_like(p) for p in gru_params])
+
+
+def _enc_setup_context(ctx, inputs, output):
+    (h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset, save_y1) = inputs
+    latent, _, y1s = output
+    ctx.has_y1 = bool(save_y1)
+    ctx.save_for_backward(latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *params, *gru_params)
+    ctx.dw, ctx.alt_mask = dw, alt_mask
+    ctx.meta = (seed, row_offset, step_offset, len(params))
+
+
+def _enc_backward(ctx, grad_latent, grad_g, grad_y1):
+    if not ctx.has_y1:
+        raise RuntimeError("trajsde::enc_fwd was run with save_y1=False; backward needs the saved pre-GRU states")
+    latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *rest = ctx.saved_tensors
+    seed, row_offset, step_offset, n_p = ctx.meta
+    params, gru_params = list(rest[:n_p]), list(rest[n_p:])
+    grads = enc_bwd(grad_latent, grad_g, latent, y1s, h0, aa_out, obs_mask, slot, params, gru_params, step_tab, ctx.dw,
+                    ctx.alt_mask, seed, row_offset, step_offset)
+    return (grads[0], grads[1], None, None, list(grads[2:2 + n_p]), list(grads[2 + n_p:]), None, None, None, None, None, None, None)
+
+
+enc_fwd.register_autograd(_enc_backward, setup_context=_enc_setup_context)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
