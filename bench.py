@@ -302,38 +302,48 @@ def main():
     train = None
     if not args.no_train:
         from trajsde_b200.dist import FlatGradBucket
-        tb_host = syn.make_batch(args.train_scenes, args.agents, seed=2000 + rank, mixed_sources=True)
-        tr = {k: getattr(tb_host, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
         tparams = list(enc_sde.parameters()) + list(dec_sde.parameters()) + list(gru.parameters())
-        bucket = FlatGradBucket(tparams)
-        opt = torch.optim.AdamW(tparams, lr=1e-3, weight_decay=7e-4)          # yml:2-3
-        Et, Mt = tb_host.enc_rows, tb_host.dec_rows
 
-        def train_step(i):
-            bucket.zero_()
-            y0 = tr['dec_y0'].detach().requires_grad_(True)                   # upstream (aggr_embed) needs dL/dy0 too
-            lat, g = enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], tr['aa_out'], tr['actors_mask'], tr['nus_mask'],
-                                                seed=300 + i, mode=mode, fused=False, row_offset=rank * Et)
-            ys = tb.sdeint(dec_sde, y0, ts_dec, dt=0.1, dt_min=0.1, rtol=1e-3, atol=1e-3, method='euler', mode=mode, seed=400 + i,
-                           row_offset=rank * Mt)
-            loss = ys[1:].square().mean() + lat.square().mean() + g.mean()
-            loss.backward()
-            bucket.all_reduce_mean()
-            opt.step()
+        def measure_train(scenes_per_gpu):
+            tb_host = syn.make_batch(scenes_per_gpu, args.agents, seed=2000 + rank, mixed_sources=True)
+            tr = {k: getattr(tb_host, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
+            bucket = FlatGradBucket(tparams)
+            opt = torch.optim.AdamW(tparams, lr=1e-3, weight_decay=7e-4)          # yml:2-3
+            Et, Mt = tb_host.enc_rows, tb_host.dec_rows
 
-        for i in range(2):
-            train_step(i)
-        k_train = max(2, min(args.steps, 5))
-        ms_train = timed(train_step, k_train) / k_train
-        twork = Et * ENC_STEPS + Mt * DEC_STEPS
-        train = {"scenes_per_gpu": args.train_scenes, "ms_per_step": ms_train, "steps": k_train,
-                 "agent_steps_per_s_fwd_bwd": world * twork / (ms_train * 1e-3), "scenes_per_s_fwd_bwd": world * args.train_scenes / (ms_train * 1e-3),
-                 "allreduce_floats": bucket.numel if world > 1 else 0,
-                 "note": "fwd+bwd through encoder (21 x [fused sdeint_dual + torch GRU]) and decoder solves, exact-fp32 fused backward "
-                         "kernels (dgrad sweep + wgrad), flat-bucket NCCL all-reduce, AdamW on the SDE+GRU parameters"}
-        for p_ in tparams:
-            p_.grad = None
-        del bucket, opt
+            def train_step(i):
+                bucket.zero_()
+                y0 = tr['dec_y0'].detach().requires_grad_(True)                   # upstream (aggr_embed / AA encoder) needs
+                aa = tr['aa_out'].detach().requires_grad_(True)                   # dL/dy0 and dL/daa_out too
+                lat, g = enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], aa, tr['actors_mask'], tr['nus_mask'],
+                                                    seed=300 + i, mode=mode, row_offset=rank * Et)
+                ys = tb.sdeint(dec_sde, y0, ts_dec, dt=0.1, dt_min=0.1, rtol=1e-3, atol=1e-3, method='euler', mode=mode, seed=400 + i,
+                               row_offset=rank * Mt)
+                loss = ys[1:].square().mean() + lat.square().mean() + g.mean()
+                loss.backward()
+                bucket.all_reduce_mean()
+                opt.step()
+
+            for i in range(3):
+                train_step(i)
+            k_train = max(3, min(args.steps, 10))
+            n0 = ops.LAUNCHES['n']
+            ms = timed(train_step, k_train) / k_train
+            twork = Et * ENC_STEPS + Mt * DEC_STEPS
+            out = {"scenes_per_gpu": scenes_per_gpu, "ms_per_step": ms, "steps": k_train,
+                   "agent_steps_per_s_fwd_bwd": world * twork / (ms * 1e-3), "scenes_per_s_fwd_bwd": world * scenes_per_gpu / (ms * 1e-3),
+                   "allreduce_floats": bucket.numel if world > 1 else 0, "gpu_launches_per_step": (ops.LAUNCHES['n'] - n0) // k_train}
+            for p_ in tparams:
+                p_.grad = None
+            del bucket, opt, tr
+            torch.cuda.empty_cache()
+            return out
+
+        train = {"note": "fwd+bwd through the fused encoder recurrence (enc_fwd_tc_kernel / trajsde_enc_bwd) and the decoder solve "
+                         "(euler_fwd_tc_kernel / fused tensor-core dgrad+wgrad euler_bwd_tc_kernel), in-kernel Philox noise, mixed "
+                         "nuScenes/Argoverse rows, flat-bucket NCCL all-reduce, AdamW on the SDE+GRU parameters",
+                 "cfg2_reference_batch": measure_train(args.train_scenes),          # BASELINE configs[2]: yml:106 batch 128
+                 "cfg3_scene_sharded": measure_train(args.scenes)}                  # BASELINE configs[3]: 8192 scenes / 8 GPUs
 
     # ---- parity spot check at full size: 64 decoder rows against the CPU oracle under the same dW -------------------------------------
     parity = None

@@ -79,15 +79,19 @@ def test_fused_encoder_philox_deterministic_and_sharding_invariant():
     assert torch.isfinite(a1).all() and (g1 > 0).all() and (g1 < 1).all()
 
 
-def test_fused_encoder_rejects_training_and_exact_mode():
+def test_fused_encoder_trains_and_rejects_exact_mode():
     sde = init_like_reference(EncoderSDE(), seed=1).to(DEV)
     gru = syn.GRUUnit().to(DEV)
     h0 = torch.zeros(4, 64, device=DEV)
     aa = torch.zeros(21, 4, 64, device=DEV)
     am = torch.ones(4, 21, dtype=torch.bool, device=DEV)
     nm = torch.zeros(4, dtype=torch.bool, device=DEV)
-    with pytest.raises(NotImplementedError):
-        enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True)          # grad enabled + parameters require grad
+    lat, g = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True, seed=3)      # grad enabled + parameters require grad
+    assert lat.requires_grad and g.requires_grad
+    (lat.sum() + g.sum()).backward()
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in gru.parameters())
+    assert sde.g_nus.net[0].weight.grad.abs().max() == 0                                 # no nuScenes row in this batch
+    assert sde.g_argo.net[0].weight.grad.abs().max() > 0
     with torch.no_grad(), pytest.raises(NotImplementedError):
         enc.encoder_recurrence(sde, gru, h0, aa, am, nm, fused=True, mode='exact')
 

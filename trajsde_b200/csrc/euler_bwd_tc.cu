@@ -62,7 +62,8 @@ constexpr int SCHED_MAX = 256;                        // schedule tables staged 
 constexpr uint32_t OFF_STAB = OFF_XCHG + 4 * TILE_M * 4;            // float4 step_tab[SCHED_MAX]
 constexpr uint32_t OFF_OBEG = OFF_STAB + SCHED_MAX * 16;           // int out_begin[SCHED_MAX + 4]
 constexpr uint32_t OFF_OUTW = OFF_OBEG + (SCHED_MAX + 4) * 4;      // float2 out_w[SCHED_MAX]
-constexpr uint32_t OFF_BARS = OFF_OUTW + SCHED_MAX * 8;
+constexpr uint32_t OFF_BROW = OFF_OUTW + SCHED_MAX * 8;            // float bias1[128]: layer-1 bias rows (f | g) of the current step
+constexpr uint32_t OFF_BARS = OFF_BROW + 128 * 4;
 constexpr uint32_t SMEM_TOTAL = OFF_BARS + 64;
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
@@ -252,6 +253,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     auto trow = [&](int t) { return sm + OFF_TILES + (uint32_t)t * TILE_BYTES + row * 128; };
     float* qbuf = reinterpret_cast<float*>(sm + OFF_XCHG);
     float* pdbuf = qbuf + 2 * TILE_M;
+    float* brow = reinterpret_cast<float*>(sm + OFF_BROW);
+    const int eid = warp * 32 + lane;                      // 0..255
     const uint32_t pair_bar = 1 + quad;
 
     // adjoint scale: a power of two that puts max|grad| into [2^-4, 2^-3)
@@ -392,6 +395,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
             t[4 * q] = py[q].x; t[4 * q + 1] = py[q].y; t[4 * q + 2] = py[q].z; t[4 * q + 3] = py[q].w;
           }
           st_row32(trow(T_Y), row, hh, t);
+          if (eid < 128) {                                       // layer-1 bias rows of this step (time features folded in)
+            const int c = eid & 63, o = eid < 64 ? 0 : VEC_C1;
+            brow[eid] = fmaf(vec[o + VEC_W1C + c], cs, fmaf(vec[o + VEC_W1S + c], sn, vec[o + VEC_B1 + c]));
+          }
           if (hh == 0)
             *reinterpret_cast<uint4*>(trow(T_TIME) + ((0u ^ (row & 7u)) << 4)) = make_uint4(pack_f16x2(1.f, sn), pack_f16x2(cs, 0.f), 0u, 0u);
           tc_wait_st();
@@ -399,7 +406,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // y, df, time tile -> P1
-        if (k > 0) prefetch_y_dw(k - 1);
+        // next step's rows: issued here so that they land while P1 / epilogue 1 run -- every later fence.proxy.async is a
+        // MEMBAR.ALL.CTA that waits for outstanding loads, so no load is issued anywhere else in the step
+        if (k > 0) {
+          prefetch_y_dw(k - 1);
+          prefetch_gy(k - 1);
+        }
 
         // ================= epilogue 1: h1f, h1g ==================================================================================
         mbar_wait(bar_acc, hs & 1);
@@ -411,20 +423,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           tmem_ld_32x32b_x32(tm + TM_R0, v);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = hh * 32 + j;
-            const float b = fmaf(vec[VEC_W1C + c], cs, fmaf(vec[VEC_W1S + c], sn, vec[VEC_B1 + c]));
-            t[j] = ts_tanh_approx(__uint_as_float(v[j]) + b);
-          }
+          for (int j = 0; j < 32; ++j) t[j] = ts_tanh_approx(__uint_as_float(v[j]) + brow[hh * 32 + j]);
           st_row32(trow(T_H1F), row, hh, t);
           tmem_ld_32x32b_x32(tm + TM_R1, v);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int c = hh * 32 + j;
-            const float b = fmaf(vec[VEC_V1C + c], cs, fmaf(vec[VEC_V1S + c], sn, vec[VEC_C1 + c]));
-            t[j] = ts_tanh_approx(__uint_as_float(v[j]) + b);
-          }
+          for (int j = 0; j < 32; ++j) t[j] = ts_tanh_approx(__uint_as_float(v[j]) + brow[64 + hh * 32 + j]);
           st_row32(trow(T_H1G), row, hh, t);
         }
         fence_proxy_async();
@@ -469,7 +473,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // h2f, dz2g -> D1 (+ trailing dW3 / db3)
-        if (k > 0) prefetch_gy(k - 1);
 
         // ================= epilogue 3: dz2f = dh2f (1 - h2f^2) =====================================================================
         mbar_wait(bar_acc, hs & 1);
