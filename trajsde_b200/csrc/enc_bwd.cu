@@ -5,7 +5,7 @@
 // One C-ABI call = one reverse sweep over the iterations, enqueued from the host without any synchronisation:
 //   for i = S-1 .. 0:   a_h   = carry (dL/dy0 of iteration i+1's SDE step) + dL/d latent[i]
 //                       GRU backward (gru_bwd.cu, fp32):      a_h -> a_y1, dL/d aa_out[slot_i], GRU weight-gradient partials
-//                       SDE step backward (euler_bwd_tc.cu):  a_y1, dL/dg[i] -> carry, SDE weight-gradient partials (one pass per diffusion net)
+//                       SDE step backward (euler_bwd_tc.cu):  a_y1, dL/dg[i] -> carry, SDE weight-gradient partials (one pass per diffusion net, same launch)
 // Partials accumulate in the workspace across the sweep and are reduced once, in fixed order (bit-reproducible).
 #include "bwd_common.cuh"
 
@@ -104,8 +104,8 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   b.grad_ys_t_stride = slab;
   b.grad_ys_row_stride = 64;
   if ((rc = bwd_tc_pack(b, w.img0, s)) != 0) return rc;
-  TrajsdeEulerBwdArgs b2 = b;
   if (dual) {
+    TrajsdeEulerBwdArgs b2 = b;
     b2.diffusion = a.diffusion_alt;
     if ((rc = bwd_tc_pack(b2, w.img1, s)) != 0) return rc;
   }
@@ -115,16 +115,13 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
                              i == S - 1 ? nullptr : w.carry, a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr, w.gbuf + slab,
                              a.grad_aa_out, w.gru_part, s)) != 0)
       return rc;
-    for (TrajsdeEulerBwdArgs* q : {&b, &b2}) {
-      q->sched.step_tab = a.sched.step_tab + 4 * i;
-      q->noise.dw = a.noise.dw ? a.noise.dw + (int64_t)i * slab : nullptr;
-      q->noise.step_offset = a.noise.step_offset + (uint32_t)i;
-      q->states = i == 0 ? a.h0 : a.latent + (int64_t)(i - 1) * slab;
-      q->grad_g_last = a.grad_g ? a.grad_g + (int64_t)i * a.rows : nullptr;
-      q->grad_y0 = i == 0 ? a.grad_h0 : w.carry;
-    }
-    if ((rc = bwd_tc_main(b, w.img0, w.amax, w.part0, dual ? 1 : 0, 1, s)) != 0) return rc;
-    if (dual && (rc = bwd_tc_main(b2, w.img1, w.amax, w.part1, 2, 1, s)) != 0) return rc;
+    b.sched.step_tab = a.sched.step_tab + 4 * i;
+    b.noise.dw = a.noise.dw ? a.noise.dw + (int64_t)i * slab : nullptr;
+    b.noise.step_offset = a.noise.step_offset + (uint32_t)i;
+    b.states = i == 0 ? a.h0 : a.latent + (int64_t)(i - 1) * slab;
+    b.grad_g_last = a.grad_g ? a.grad_g + (int64_t)i * a.rows : nullptr;
+    b.grad_y0 = i == 0 ? a.grad_h0 : w.carry;
+    if ((rc = bwd_tc_main(b, w.img0, dual ? w.img1 : nullptr, w.amax, w.part0, w.part1, 1, s)) != 0) return rc;   // both nets' passes, one launch
   }
   if ((rc = launch_euler_bwd_reduce(w.part0, dual ? w.part1 : nullptr, grid, dual ? grid : 0, a.grad_drift, a.grad_diffusion,
                                     a.grad_diffusion_alt, s)) != 0)

@@ -77,11 +77,12 @@ constexpr uint32_t TM_SUM1 = 448, TM_SUM2 = 464, TM_SUM3 = 480;   // 16 cols eac
 
 struct BwdTcParams {
   TrajsdeEulerBwdArgs a;
-  const uint8_t* img;
+  // blockIdx.y selects the pass: dual diffusion runs both nets' passes in one launch (rows are independent)
+  const uint8_t* img[2];       // packed weight image of the pass (drift + that pass's diffusion net)
+  float* partial[2];           // [gridDim.x][G_PAD] of the pass
+  int filter[2];               // 0: all rows; 1: only rows with alt_mask != 0; 2: only rows with alt_mask == 0
   const uint32_t* amax_bits;   // max |grad| as float bits (absmax pre-pass)
-  float* partial;              // [grid][G_PAD]
   int num_tiles;
-  int filter;                  // 0: all rows; 1: only rows with alt_mask != 0; 2: only rows with alt_mask == 0 (dual diffusion passes)
   int accumulate;              // add into the CTA's partial vector instead of overwriting it (multi-launch accumulation)
 };
 
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
   const TrajsdeEulerBwdArgs& a = p.a;
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int pass = blockIdx.y;
   const int S = a.sched.n_steps;
   const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
   const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_w, IMG_BYTES);
-    bulk_load_1d(base, p.img, IMG_BYTES, bar_w);
+    bulk_load_1d(base, p.img[pass], IMG_BYTES, bar_w);
   }
   const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
 
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
       const int64_t grow = (int64_t)tile * TILE_M + row;
       bool valid = grow < a.rows;
-      if (valid && p.filter) valid = (a.alt_mask[grow] != 0) == (p.filter == 1);   // other net's rows: adjoint stays zero
+      if (valid && p.filter[pass]) valid = (a.alt_mask[grow] != 0) == (p.filter[pass] == 1);   // other net's rows: adjoint stays zero
       float4 py[8], pdw[8], pgy[8];
       auto prefetch_y_dw = [&](int k) {
         if (valid) {
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     // ================= weight-gradient partials of this CTA ===============================================================================
     if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);          // every MMA of the CTA has completed
     tc_fence_after();
-    float* out = p.partial + (size_t)blockIdx.x * G_PAD;
+    float* out = p.partial[pass] + (size_t)blockIdx.x * G_PAD;
     const bool acc_out = p.accumulate != 0;
     auto put = [&](int idx, float v) { out[idx] = acc_out ? out[idx] + v : v; };
     const bool lo = quad < 2;                                    // TMEM lanes 0..63: drift net, 64..127: diffusion net
@@ -721,25 +723,32 @@ int bwd_tc_grid(int64_t rows) {
   return (int)(tiles < sms ? tiles : sms);
 }
 
-// one fused dgrad+wgrad launch over all steps of a.sched; partial[grid][G_PAD] written (or accumulated into)
-int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img, const uint32_t* amax_bits, float* partial, int filter, int accumulate,
-                cudaStream_t s) {
-  if ((reinterpret_cast<uintptr_t>(img) & 15u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+// one fused dgrad+wgrad launch over all steps of a.sched; partial[grid][G_PAD] written (or accumulated into).
+// img1 != NULL: dual diffusion — pass 0 (img0, part0) takes the rows with alt_mask != 0, pass 1 (img1 packed with a.diffusion_alt,
+// part1) the rows with alt_mask == 0; both passes run in the same launch (gridDim.y = 2).
+int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
+                int accumulate, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(img0) & 15u) != 0 || (reinterpret_cast<uintptr_t>(img1) & 15u) != 0)
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
   if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
+  const bool dual = img1 != nullptr;
   BwdTcParams p;
   p.a = a;
-  p.img = img;
+  p.img[0] = img0;
+  p.img[1] = img1;
+  p.partial[0] = part0;
+  p.partial[1] = part1;
+  p.filter[0] = dual ? 1 : 0;
+  p.filter[1] = 2;
   p.amax_bits = amax_bits;
-  p.partial = partial;
   p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
-  p.filter = filter;
   p.accumulate = accumulate;
   const int grid = bwd_tc_grid(a.rows);
   if (grid <= 0) return TRAJSDE_OK;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
+    kern<<<dim3(grid, dual ? 2 : 1), NUM_THREADS, SMEM_ALLOC, s>>>(p);
     return cudaGetLastError();
   };
   TS_CUDA_CHECK(a.noise.dw ? launch(euler_bwd_tc_kernel<true>) : launch(euler_bwd_tc_kernel<false>));
@@ -776,13 +785,12 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
     if (a.grad_ys && (rc = bwd_tc_absmax(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride, a.grad_ys_row_stride, amax, s)) != 0) return rc;
     if (a.grad_g_last && (rc = bwd_tc_absmax(a.grad_g_last, 1, a.rows, 0, 0, amax, s)) != 0) return rc;
     if ((rc = bwd_tc_pack(a, img0, s)) != 0) return rc;
-    if ((rc = bwd_tc_main(a, img0, amax, part0, dual ? 1 : 0, 0, s)) != 0) return rc;
     if (dual) {   // second pass: the rows of the other diffusion net (rows are independent; the drift gradients of both passes add up)
       TrajsdeEulerBwdArgs b = a;
       b.diffusion = a.diffusion_alt;
       if ((rc = bwd_tc_pack(b, img1, s)) != 0) return rc;
-      if ((rc = bwd_tc_main(b, img1, amax, part1, 2, 0, s)) != 0) return rc;
     }
+    if ((rc = bwd_tc_main(a, img0, dual ? img1 : nullptr, amax, part0, part1, 0, s)) != 0) return rc;
   }
   euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part0, dual ? part1 : nullptr, grid, dual ? grid : 0, a.grad_drift,
                                                               a.grad_diffusion, a.grad_diffusion_alt, 0);

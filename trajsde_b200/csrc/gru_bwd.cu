@@ -49,10 +49,16 @@ struct GruBwdParams {
   int num_tiles;
 };
 
+// [64][K] row-major global matrix -> padded smem rows, 16 bytes per access (K = 64 << k_shift6)
 __device__ __forceinline__ void stage_w(float* dst, const float* __restrict__ src, int k_dim, int ld, int tid) {
-  for (int idx = tid; idx < 64 * k_dim; idx += GB_THREADS) {
-    const int n = idx / k_dim, k = idx - n * k_dim;
-    dst[n * ld + k] = src[idx];
+  const int q_per_row = k_dim >> 2, sh = k_dim == 128 ? 5 : 4;
+  if (reinterpret_cast<uintptr_t>(src) & 15u) {   // parameter living at an odd offset of a flat buffer: scalar copy
+    for (int idx = tid; idx < 64 * k_dim; idx += GB_THREADS) dst[(idx >> (sh + 2)) * ld + (idx & (k_dim - 1))] = src[idx];
+    return;
+  }
+  for (int idx = tid; idx < 64 * q_per_row; idx += GB_THREADS) {
+    const int n = idx >> sh, k4 = idx & (q_per_row - 1);
+    *reinterpret_cast<float4*>(dst + n * ld + 4 * k4) = __ldg(reinterpret_cast<const float4*>(src) + idx);
   }
 }
 
