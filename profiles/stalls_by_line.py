@@ -3,10 +3,16 @@
     python profiles/stalls_by_line.py <report.ncu-rep> <object.o> <kernel-name-substring> [top_n]
 """
 import csv, io, re, subprocess, sys, tempfile, os, collections
+
+def first_kernel_block(rows):
+    """Source-page CSV of a multi-kernel report repeats a ("Kernel Name", ...) row + header per kernel: keep the first block."""
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    return rows[:starts[1]] if len(starts) > 1 else rows
+
 rep, obj, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 sass = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(sass)))
+rows = first_kernel_block(list(csv.reader(io.StringIO(sass))))
 h = rows[1]
 ia, isamp, isrc, iex = h.index('Address'), h.index('Warp Stall Sampling (All Samples)'), h.index('Source'), h.index('Instructions Executed')
 inst = [(r[isrc], int(r[isamp] or 0), int(r[iex] or 0)) for r in rows[2:] if len(r) > isamp]

@@ -9,6 +9,12 @@ import re
 import subprocess
 import sys
 
+
+def first_kernel_block(rows):
+    """Source-page CSV of a multi-kernel report repeats a ("Kernel Name", ...) row + header per kernel: keep the first block."""
+    starts = [i for i, r in enumerate(rows) if r and r[0] == 'Kernel Name']
+    return rows[:starts[1]] if len(starts) > 1 else rows
+
 rep = sys.argv[1]
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -32,7 +38,7 @@ for h, v in sorted(st, key=lambda t: -t[1])[:10]:
     print(f"{h.split('issue_stalled_')[1].replace('_per_issue_active.ratio', ''):28s} {v:8.3f}")
 
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
+rows = first_kernel_block(list(csv.reader(io.StringIO(src))))
 hdr = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 data = rows[2:]

@@ -285,26 +285,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       const int64_t grow = (int64_t)tile * TILE_M + row;
       bool valid = grow < a.rows;
       if (valid && p.filter[pass]) valid = (a.alt_mask[grow] != 0) == (p.filter[pass] == 1);   // other net's rows: adjoint stays zero
+      // Row prefetch, coalesced: lane L of this warp loads, for i = 0..7, the 16-byte chunk (L & 7) of tile row 32 quad + 4 i + (L >> 3)
+      // of its 32-channel half (one instruction = four full 128-byte row segments instead of 32 scattered 16-byte pieces); the
+      // registers are transposed to "thread = own row" through 4 KB of per-warp staging when the step consumes them.
       float4 py[8], pdw[8], pgy[8];
-      auto prefetch_y_dw = [&](int k) {
-        if (valid) {
-          const float* ys = a.states + ((int64_t)k * a.rows + grow) * 64 + hh * 32;
+      const int64_t lrow0 = (int64_t)tile * TILE_M + quad * 32 + (lane >> 3);     // + 4 i
+      const int lcol = hh * 32 + (lane & 7) * 4;
+      auto load_rows = [&](const float* slab, int64_t row_stride, float4 (&dst)[8]) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) py[q] = ld_nc_f4(ys + 4 * q);
-          if (HAS_DW) {
-            const float* ds = a.noise.dw + ((int64_t)k * a.rows + grow) * 64 + hh * 32;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) pdw[q] = ld_nc_f4(ds + 4 * q);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int64_t r = lrow0 + 4 * i;
+          dst[i] = r < a.rows ? ld_nc_f4(slab + r * row_stride + lcol) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+      };
+      uint8_t* stage = sm + OFF_TILES + T_H1F * TILE_BYTES + (uint32_t)warp * 4096;   // h1f|h1g tiles are idle at step start
+      auto to_own_row = [&](float4 (&v)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rl = 4 * i + (lane >> 3);
+          *reinterpret_cast<float4*>(stage + rl * 128 + ((((uint32_t)lane & 7u) ^ (rl & 7u)) << 4)) = v[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(stage + lane * 128 + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4));
+        __syncwarp();
+      };
+      auto prefetch_y_dw = [&](int k) {
+        load_rows(a.states + (int64_t)k * a.rows * 64, 64, py);
+        if (HAS_DW) load_rows(a.noise.dw + (int64_t)k * a.rows * 64, 64, pdw);
       };
       auto prefetch_gy = [&](int k) {
         const int ob = obeg[k], oe = obeg[k + 1];
-        if (valid && a.grad_ys && oe > ob) {
-          const float* gs = a.grad_ys + (int64_t)(ob + 1) * a.grad_ys_t_stride + grow * a.grad_ys_row_stride + hh * 32;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pgy[q] = ld_nc_f4(gs + 4 * q);
-        }
+        if (a.grad_ys && oe > ob) load_rows(a.grad_ys + (int64_t)(ob + 1) * a.grad_ys_t_stride, a.grad_ys_row_stride, pgy);
       };
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
@@ -326,6 +338,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         // ================= step start: A' = A + sum w1 gy ; E = A' + sum w0 gy ; df ; q = A'.dW ; y -> operand =================
         float e_[32];
         {
+          to_own_row(py);
+          if (HAS_DW) to_own_row(pdw);
+          if (a.grad_ys && oe > ob) to_own_row(pgy);
+          if (!valid) {                                            // padding / other net's rows: state and gradient read as zero
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              py[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+              pgy[q] = py[q];
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) e_[j] = adj[j];
           if (a.grad_ys && oe > ob) {
