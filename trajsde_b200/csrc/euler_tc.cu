@@ -118,13 +118,20 @@ __global__ void tc_pack_kernel(TrajsdeEulerFwdArgs a, uint8_t* __restrict__ img,
 }
 
 // ---- epilogue helpers -------------------------------------------------------------------------------------------------------
+// 32 bias values of this thread's column half -> registers.  Issued BEFORE the tcgen05.ld of the accumulators so the shared-memory
+// latency hides behind the TMEM read instead of stalling every group of eight tanh (the asm volatile tcgen05.ld keeps the order).
+struct Bias32 { float4 v[8]; };
+__device__ __forceinline__ Bias32 ld_bias32(const float* __restrict__ bias) {
+  Bias32 b;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) b.v[q] = *reinterpret_cast<const float4*>(bias + 4 * q);
+  return b;
+}
 // tanh(acc + bias) for 32 accumulator columns, packed to fp16 and stored as 4 x 16-byte chunks of an operand row.
-__device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const float* __restrict__ bias, uint8_t* tile_row_base,
-                                                 uint32_t row, uint32_t chunk0) {
+__device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const Bias32& b, uint8_t* tile_row_base, uint32_t row, uint32_t chunk0) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float4 ba = *reinterpret_cast<const float4*>(bias + q * 8);
-    const float4 bb = *reinterpret_cast<const float4*>(bias + q * 8 + 4);
+    const float4 ba = b.v[2 * q], bb = b.v[2 * q + 1];
     uint32_t p[4];
     p[0] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 0]) + ba.x), ts_tanh_approx(__uint_as_float(v[q * 8 + 1]) + ba.y));
     p[1] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 2]) + ba.z), ts_tanh_approx(__uint_as_float(v[q * 8 + 3]) + ba.w));
@@ -366,14 +373,16 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tc_fence_after();
         {
           uint32_t v[32];
+          Bias32 bf = ld_bias32(ent + hh * 32);
           tmem_ld_32x32b_x32(tm_lane, v);
           tc_wait_ld();
-          act32_to_operand(v, ent + hh * 32, a1f_row, row, hh * 4);
+          act32_to_operand(v, bf, a1f_row, row, hh * 4);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 1));                  // A1f ready -> P2f
+          bf = ld_bias32(ent + gcol + hh * 32);
           ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
-          act32_to_operand(v, ent + gcol + hh * 32, a1g_row, row, hh * 4);
+          act32_to_operand(v, bf, a1g_row, row, hh * 4);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 0));                  // A1g ready -> P2g
@@ -385,9 +394,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         tc_fence_after();
         {
           uint32_t v[32];
+          const Bias32 b2 = ld_bias32(vec + VEC_B2 + hh * 32);
           tmem_ld_32x32b_x32(tm_lane, v);
           tc_wait_ld();
-          act32_to_operand(v, vec + VEC_B2 + hh * 32, a0_row, row, hh * 4);
+          act32_to_operand(v, b2, a0_row, row, hh * 4);
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
