@@ -4,7 +4,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')
+LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
 ABI_VERSION = 2
 MODE_EXACT_F32 = 0

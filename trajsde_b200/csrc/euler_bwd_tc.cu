@@ -188,8 +188,20 @@ __device__ __forceinline__ void ld_row32(const uint8_t* tile_row, uint32_t row, 
   }
 }
 
+#ifdef TRAJSDE_BWD_TIMELINE
+}  // namespace (anonymous)
+__device__ long long g_bwd_tl[16];
+namespace {
+#define TL_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _t = clock64(); g_bwd_tl[i] += _t - tl_prev; tl_prev = _t; } } while (0)
+#else
+#define TL_MARK(i) do { } while (0)
+#endif
+
 template <bool HAS_DW>
 __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdTcParams p) {
+#ifdef TRAJSDE_BWD_TIMELINE
+  long long tl_prev = clock64();
+#endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -335,6 +347,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         const float h = stp.y, sn = stp.z, cs = stp.w;
         const int ob = obeg[k], oe = obeg[k + 1];
 
+        TL_MARK(0);   // (loop overhead / previous e5 tail)
         // ================= step start: A' = A + sum w1 gy ; E = A' + sum w0 gy ; df ; q = A'.dW ; y -> operand =================
         float e_[32];
         {
@@ -408,8 +421,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
             for (int j = 0; j < 32; ++j) ev[j] = __float_as_uint(e_[j]);
             tmem_st_32x32b_x32(tm + TM_E, ev);
           }
+          TL_MARK(1);   // SS part 1: transposes, adjoint update, q, E
           // previous step's trailing weight-gradient MMAs must have finished reading Y / DF(dz1g) / TIME
           if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);
+          TL_MARK(2);   // wait bar_wg
           float t[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = h * adj[j];
@@ -437,9 +452,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           prefetch_gy(k - 1);
         }
 
+        TL_MARK(3);   // SS part 2 + fence + arrive + prefetch issue
         // ================= epilogue 1: h1f, h1g ==================================================================================
         mbar_wait(bar_acc, hs & 1);
         ++hs;
+        TL_MARK(4);   // wait P1
         tc_fence_after();
         {
           uint32_t v[32];
@@ -459,9 +476,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // h1f, h1g -> P2
 
+        TL_MARK(5);   // e1
         // ================= epilogue 2: h2f ; h2g, g, ds, dz2g =====================================================================
         mbar_wait(bar_acc, hs & 1);
         ++hs;
+        TL_MARK(6);   // wait P2
         tc_fence_after();
         {
           uint32_t v[32];
@@ -498,9 +517,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // h2f, dz2g -> D1 (+ trailing dW3 / db3)
 
+        TL_MARK(7);   // e2
         // ================= epilogue 3: dz2f = dh2f (1 - h2f^2) =====================================================================
         mbar_wait(bar_acc, hs & 1);
         ++hs;
+        TL_MARK(8);   // wait D1
         tc_fence_after();
         {
           uint32_t v[32];
@@ -516,9 +537,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // dz2f -> D2 (+ trailing dW2|dV2 / db2|dc2)
 
+        TL_MARK(9);   // e3
         // ================= epilogue 4: dz1f = dh1f (1 - h1f^2) -> tile H2F ; dz1g = dh1g (1 - h1g^2) -> tile DF ==========================
         mbar_wait(bar_acc, hs & 1);
         ++hs;
+        TL_MARK(10);  // wait D2
         tc_fence_after();
         {
           uint32_t v[32];
@@ -540,9 +563,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // dz1f, dz1g -> D3 (+ trailing dW1y|dV1y / db1|dc1 / time columns)
 
+        TL_MARK(11);  // e4
         // ================= epilogue 5: A[k] = E + dy =================================================================================
         mbar_wait(bar_acc, hs & 1);
         ++hs;
+        TL_MARK(12);  // wait D3
         tc_fence_after();
         {
           uint32_t v[32], ev[32];
@@ -675,8 +700,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           mma_k(d0 + TM_R0, tile_u32(T_DF), base + IMG_W3T, idesc_64, false);
           mma_k(d0 + TM_R1, tile_u32(T_DZ2G), base + IMG_V2T, idesc_64, false);
           tc_commit(bar_acc);
+#ifndef TRAJSDE_BWD_NO_WGRAD
           mma_mn(d0 + TM_WGC, tile_u32(T_DF), tile_u32(T_H2F), imn_64, wg_acc);
           mma_mn(d0 + TM_SUM3, tile_u32(T_DF), tile_u32(T_TIME), imn_16, wg_acc);
+#endif
         }
         __syncwarp();
         // D2: dh1f ; trailing: dW2|dV2 += [dz2f|dz2g]^T [h1f|h1g], db2|dc2
@@ -685,8 +712,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         if (elect_one()) {
           mma_k(d0 + TM_R0, tile_u32(T_DZ2F), base + IMG_W2T, idesc_64, false);
           tc_commit(bar_acc);
+#ifndef TRAJSDE_BWD_NO_WGRAD
           mma_mn(d0 + TM_WGA, tile_u32(T_DZ2F), tile_u32(T_H1F), imn_128, wg_acc);
           mma_mn(d0 + TM_SUM2, tile_u32(T_DZ2F), tile_u32(T_TIME), imn_16, wg_acc);
+#endif
         }
         __syncwarp();
         // D3: dy = dz1f . W1y + dz1g . V1y ; trailing: dW1y|dV1y += [dz1f|dz1g]^T y, db1|dc1 and the time columns
@@ -696,8 +725,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           mma_k(d0 + TM_R0, tile_u32(T_H2F), base + IMG_W1YT, idesc_64, false);
           mma_k(d0 + TM_R0, tile_u32(T_DF), base + IMG_V1YT, idesc_64, true);
           tc_commit(bar_acc);
+#ifndef TRAJSDE_BWD_NO_WGRAD
           mma_mn(d0 + TM_WGB, tile_u32(T_H2F), tile_u32(T_Y), imn_64, wg_acc);
           mma_mn(d0 + TM_SUM1, tile_u32(T_H2F), tile_u32(T_TIME), imn_16, wg_acc);
+#endif
           tc_commit(bar_wg);
         }
         __syncwarp();
@@ -821,3 +852,12 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
 }
 
 }  // namespace trajsde
+
+#ifdef TRAJSDE_BWD_TIMELINE
+// debug build only (bench_micro/bwd_timeline.py): accumulated clocks per phase of thread 0 / CTA 0, then reset
+extern "C" int trajsde_debug_bwd_timeline(long long* out16) {
+  long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, trajsde::g_bwd_tl, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::g_bwd_tl, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
