@@ -382,6 +382,13 @@ def main():
         return
 
     hbm_gbs, bf16_tf, peak_src = peaks()
+    traffic = None
+    try:                                            # ncu-measured DRAM bytes per launch of the dominant kernel, if captured for this workload
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r1b_traffic.json')))['euler_fwd_tc_kernel<1,0>']
+        if t['rows'] == M and t['steps'] == DEC_STEPS:
+            traffic = t['dram_bytes']
+    except (OSError, KeyError, ValueError):
+        pass
     T = sched_d.n_outputs + 1
     dec_bytes_fixed = M * 256 * (1 + T + DEC_STEPS)             # y0 in + ys (incl. ys[0]) out + dW in
     dec_bytes_philox = M * 256 * (1 + T)
@@ -408,7 +415,7 @@ def main():
         "encoder": {"ms": ms_fixed / args.steps - dec_ms_avg, "rows": E, "steps": ENC_STEPS,
                     "agent_steps_per_s": E * ENC_STEPS / ((ms_fixed / args.steps - dec_ms_avg) * 1e-3),
                     "note": "one fused kernel: 21 x [Euler step of the dual-diffusion SDE + GRU jump] (enc_fwd_tc_kernel)"},
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": traffic,
                      "kernel": "euler_fwd_tc_kernel (decoder solve)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dec_bytes_fixed,
                      "tensor_frac_of_bf16_peak": flops / (dec_ms_avg * 1e-3) / 1e12 / bf16_tf,
