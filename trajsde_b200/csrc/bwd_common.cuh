@@ -11,7 +11,8 @@ constexpr int G_GW1 = 12608, G_GB1 = 16832, G_GW2 = 16896, G_GB2 = 20992, G_GW3 
 constexpr int G_TOTAL = 21121, G_PAD = 21124;
 
 constexpr int MAX_PARTIALS = 160;   // per-CTA partial vectors per pass
-constexpr int64_t BWD_TC_IMG_BYTES = 76800;   // packed weight image of euler_bwd_tc.cu (rounded up to 1 KB)
+constexpr int64_t BWD_TC_IMG_BYTES = 76800;
+constexpr int64_t GRU_TC_IMG_BYTES = 75776;   // packed GRU weight image of gru_bwd_tc.cu   // packed weight image of euler_bwd_tc.cu (rounded up to 1 KB)
 
 // GRU_Unit gradient vector layout: per gate (update, reset, new_state): w1[64,128] b1[64] w2[64,64] b2[64]
 constexpr int GRU_GATE = 8192 + 64 + 4096 + 64;   // 12416

@@ -4,7 +4,7 @@
 //
 // One C-ABI call = one reverse sweep over the iterations, enqueued from the host without any synchronisation:
 //   for i = S-1 .. 0:   a_h   = carry (dL/dy0 of iteration i+1's SDE step) + dL/d latent[i]
-//                       GRU backward (gru_bwd.cu, fp32):      a_h -> a_y1, dL/d aa_out[slot_i], GRU weight-gradient partials
+//                       GRU backward (gru_bwd_tc.cu; gru_bwd.cu = fp32 validation kernel):  a_h -> a_y1, dL/d aa_out[slot_i], GRU partials
 //                       SDE step backward (euler_bwd_tc.cu):  a_y1, dL/dg[i] -> carry, SDE weight-gradient partials (one pass per diffusion net, same launch)
 // Partials accumulate in the workspace across the sweep and are reduced once, in fixed order (bit-reproducible).
 #include "bwd_common.cuh"
@@ -28,6 +28,7 @@ struct Ws {
   uint32_t* amax;
   uint8_t* img0;
   uint8_t* img1;
+  uint8_t* gru_img;
   float* gbuf;     // [2][rows][64]: slab 0 zero (dL/d ys[0]), slab 1 = dL/d y1 of the current iteration
   float* carry;    // [rows][64]
   float* part0;
@@ -48,6 +49,7 @@ Ws carve(void* base, int64_t rows) {
   w.amax = reinterpret_cast<uint32_t*>(take(16));
   w.img0 = take(BWD_TC_IMG_BYTES);
   w.img1 = take(BWD_TC_IMG_BYTES);
+  w.gru_img = take(GRU_TC_IMG_BYTES);
   w.gbuf = reinterpret_cast<float*>(take(2 * rows * 64 * 4));
   w.carry = reinterpret_cast<float*>(take(rows * 64 * 4));
   w.part0 = reinterpret_cast<float*>(take((int64_t)MAX_PARTIALS * G_PAD * 4));
@@ -71,7 +73,8 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   const int S = a.sched.n_steps;
   const int64_t slab = a.rows * 64;
   const bool dual = a.alt_mask != nullptr;
-  const int grid = bwd_tc_grid(a.rows), ggrid = gru_bwd_grid(a.rows);
+  const bool gru_tc = !(a.flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);   // fp32 GRU kernel kept for A/B validation
+  const int grid = bwd_tc_grid(a.rows), ggrid = gru_tc ? grid : gru_bwd_grid(a.rows);
   int rc;
 
   enc_bwd_tables_kernel<<<1, 1, 0, s>>>(w.out_begin, w.out_w);
@@ -84,6 +87,8 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   // one loss scale for the whole sweep, from the incoming gradients (the carried adjoint has 2^13 of head-room above it)
   if (a.grad_latent && (rc = bwd_tc_absmax(a.grad_latent, S, a.rows, slab, 64, w.amax, s)) != 0) return rc;
   if (a.grad_g && (rc = bwd_tc_absmax(a.grad_g, 1, (int64_t)S * a.rows, 0, 0, w.amax, s)) != 0) return rc;
+
+  if (gru_tc && (rc = gru_bwd_tc_pack(a.gru, w.gru_img, s)) != 0) return rc;
 
   TrajsdeEulerBwdArgs b;
   memset(&b, 0, sizeof(b));
@@ -111,10 +116,13 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   }
 
   for (int i = S - 1; i >= 0; --i) {
-    if ((rc = launch_gru_bwd(a.gru, a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i,
-                             i == S - 1 ? nullptr : w.carry, a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr, w.gbuf + slab,
-                             a.grad_aa_out, w.gru_part, s)) != 0)
-      return rc;
+    const float* carry_in = i == S - 1 ? nullptr : w.carry;
+    const float* glat = a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr;
+    rc = gru_tc ? launch_gru_bwd_tc(a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i, carry_in,
+                                    glat, w.gbuf + slab, a.grad_aa_out, w.gru_img, w.amax, w.gru_part, s)
+                : launch_gru_bwd(a.gru, a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i,
+                                 carry_in, glat, w.gbuf + slab, a.grad_aa_out, w.gru_part, s);
+    if (rc != 0) return rc;
     b.sched.step_tab = a.sched.step_tab + 4 * i;
     b.noise.dw = a.noise.dw ? a.noise.dw + (int64_t)i * slab : nullptr;
     b.noise.step_offset = a.noise.step_offset + (uint32_t)i;

@@ -20,12 +20,13 @@
 //   * HBM traffic per row-step: state 256 B + dW 256 B (or Philox regenerated in-kernel) + grad_ys 256 B, read once.
 // Partials are summed by the fixed-order reduce of bwd_common.cuh (bit-reproducible, no float atomics).
 #include "bwd_common.cuh"
-#include "tc_common.cuh"
+#include "bwd_tc_common.cuh"
 
 namespace trajsde {
 
 using namespace tc;
 using namespace bwd;
+using namespace bwdtc;
 
 namespace {
 
@@ -144,48 +145,6 @@ __global__ void bwd_tc_absmax_kernel(const float* __restrict__ x, int slabs, int
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
-}
-
-// ---- device helpers -----------------------------------------------------------------------------------------------------------------
-// MN-major SW128 operand descriptor: tile stored [K rows][64 x f16 = 128 B]; LBO = byte stride between 64-element MN groups
-// (consecutive tiles), SBO = 1024 B between 8-row K groups; one MMA (K = 16 rows) advances the start address by 2048 B.
-// Validated by bench_micro/mnmajor_test.cu.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(TILE_BYTES >> 4) << 16;
-  d |= (uint64_t)(1024u >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-
-// this thread's 32 channels (4 swizzled 16-byte chunks) of an operand-tile row
-__device__ __forceinline__ void st_row32(uint8_t* tile_row, uint32_t row, uint32_t hh, const float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t p[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) p[e] = pack_f16x2(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-    *reinterpret_cast<uint4*>(tile_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
-  }
-}
-__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
-  lo = __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
-  hi = __half2float(__ushort_as_half((unsigned short)(w >> 16)));
-}
-__device__ __forceinline__ void ld_row32(const uint8_t* tile_row, uint32_t row, uint32_t hh, float (&v)[32]) {
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 u = *reinterpret_cast<const uint4*>(tile_row + (((hh * 4 + q) ^ (row & 7u)) << 4));
-    unpack_f16x2(u.x, v[q * 8 + 0], v[q * 8 + 1]);
-    unpack_f16x2(u.y, v[q * 8 + 2], v[q * 8 + 3]);
-    unpack_f16x2(u.z, v[q * 8 + 4], v[q * 8 + 5]);
-    unpack_f16x2(u.w, v[q * 8 + 6], v[q * 8 + 7]);
-  }
 }
 
 #ifdef TRAJSDE_BWD_TIMELINE
@@ -657,7 +616,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     // warp-uniform loop (descriptors in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit
     const uint32_t idesc_128 = umma_idesc_f16(TILE_M, 128), idesc_64 = umma_idesc_f16(TILE_M, 64);
     const uint32_t imn_128 = umma_idesc_f16_mn(TILE_M, 128), imn_64 = umma_idesc_f16_mn(TILE_M, 64), imn_16 = umma_idesc_f16_mn(TILE_M, 16);
-    const uint64_t khi = umma_desc_sw128(0), mhi = umma_desc_mn_sw128(0);
+    const uint64_t khi = umma_desc_sw128(0), mhi = umma_desc_mn_sw128(0, TILE_BYTES);
     auto KD = [&](uint32_t addr) { return khi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
     auto MD = [&](uint32_t addr) { return mhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
     // K-major product: D[128 x N] (+)= A[128 rows][64] . B[N][64]^T
