@@ -90,15 +90,25 @@ def encoder_recurrence_ood(sde, gru_unit, aa_out: torch.Tensor, actors_mask: tor
                            seed: Optional[int] = None, mode: Optional[str] = None, ref_time: int = 20):
     """Monte-Carlo encoder of ``forward_ood`` (enc_hivt_nusargo_sde_sep2.py:252-313): ``eval_iter`` independent passes of the
     recurrence from a ZERO hidden state (:257), eos gather per pass (:309-310), then mean latent ``[N,64]`` and per-actor
-    std ``outs.std(0).mean(-1)`` ``[N]`` (:311-313).  Each pass is one fused-kernel launch with its own Philox stream."""
+    std ``outs.std(0).mean(-1)`` ``[N]`` (:311-313).  In TC mode all passes run as one fused-kernel launch."""
     rows = aa_out.shape[1]
-    h0 = torch.zeros((rows, 64), dtype=torch.float32, device=aa_out.device)
     base = _next_call_seed() if seed is None else int(seed)
-    outs = []
+    mode = mode or get_default_mode()
     with torch.no_grad():
-        for j in range(eval_iter):
-            lat, _ = encoder_recurrence(sde, gru_unit, h0, aa_out, actors_mask, nus_mask, dt=dt, max_past_t=max_past_t,
-                                        seed=(base + 0x51ED27 * (j + 1)) & (2**63 - 1), mode=mode)
-            outs.append(eos_gather(lat, bos_mask, ref_time))
-    outs = torch.stack(outs)
+        if mode == 'tc_f16':
+            # the eval_iter passes are independent rows: ONE fused launch over eval_iter x rows; pass j draws the Philox stream of
+            # global rows [j*rows, (j+1)*rows) (the generator is keyed by global row), so passes get independent increments
+            k = int(eval_iter)
+            h0 = torch.zeros((k * rows, 64), dtype=torch.float32, device=aa_out.device)
+            lat, _ = encoder_recurrence(sde, gru_unit, h0, aa_out.repeat(1, k, 1), actors_mask.repeat(k, 1), nus_mask.repeat(k),
+                                        dt=dt, max_past_t=max_past_t, seed=base, mode=mode)
+            outs = eos_gather(lat, bos_mask.repeat(k, 1), ref_time).view(k, rows, 64)
+        else:
+            h0 = torch.zeros((rows, 64), dtype=torch.float32, device=aa_out.device)
+            outs = []
+            for j in range(eval_iter):
+                lat, _ = encoder_recurrence(sde, gru_unit, h0, aa_out, actors_mask, nus_mask, dt=dt, max_past_t=max_past_t,
+                                            seed=(base + 0x51ED27 * (j + 1)) & (2**63 - 1), mode=mode)
+                outs.append(eos_gather(lat, bos_mask, ref_time))
+            outs = torch.stack(outs)
     return outs.mean(0), outs.std(0).mean(-1)
