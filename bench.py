@@ -189,7 +189,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
     ap.add_argument('--no-train', action='store_true')
-    ap.add_argument('--e2e-chunks', type=int, default=2, help='micro-batches per e2e step (H2D/compute/D2H overlap)')
+    ap.add_argument('--e2e-chunks', type=int, default=2, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     out = _claim_stdout()
@@ -292,17 +292,15 @@ def main():
     # copies overlap the kernels (trajsde_b200.pipeline.HostFedSdePath) ---------------------------------------------------------------------
     from trajsde_b200.pipeline import HostFedSdePath
     n_chunks = args.e2e_chunks
-    cs = args.scenes // n_chunks
-    hchunks = [syn.make_batch(cs, args.agents, seed=3000 + 17 * rank + c, pin=True) for c in range(n_chunks)]
-    out_enc = [torch.empty((h.enc_rows, 64), dtype=torch.float32).pin_memory() for h in hchunks]
-    out_dec = [torch.empty((h.dec_rows, 64), dtype=torch.float32).pin_memory() for h in hchunks]
-    h2d = sum(getattr(h, k).numel() * getattr(h, k).element_size() for h in hchunks for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
-    d2h = sum(t.numel() * 4 for t in out_enc + out_dec)
+    out_enc = torch.empty((E, 64), dtype=torch.float32).pin_memory()
+    out_dec = torch.empty((M, 64), dtype=torch.float32).pin_memory()
+    h2d = sum(getattr(host, k).numel() * getattr(host, k).element_size() for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
+    d2h = (out_enc.numel() + out_dec.numel()) * 4
     pipe = HostFedSdePath(enc_sde, gru, dec_sde, dev, ts_dec, mode=mode)
-    e2e_work = sum(h.enc_rows * ENC_STEPS + h.dec_rows * DEC_STEPS for h in hchunks)
+    e2e_work = work
 
     def e2e_step(i):
-        pipe.run(hchunks, out_enc, out_dec, seed=20 + 10 * i)
+        pipe.run_batch(host, out_enc, out_dec, seed=20 + 10 * i, dec_chunks=n_chunks, enc_row_offset=rank * E, dec_row_offset=rank * M)
 
     for i in range(2):
         e2e_step(i)
@@ -405,8 +403,8 @@ def main():
                    "kernel_mode": mode, "scenes_per_gpu": args.scenes, "parallelism": f"scene-sharded dp{world}, no forward collective",
                    "cache": "inputs larger than L2 (dW 3.2 GB + ys 3.2 GB per step vs 126 MB L2)",
                    "e2e_note": "e2e uses bm=None (in-kernel Philox, like the reference's BrownianInterval default); every step copies all "
-                               "inputs from pinned host memory (as micro-batches whose copies overlap the kernels) and copies the final "
-                               "encoder/decoder latents back"},
+                               "inputs from pinned host memory (decoder y0 first, in row slices solved as they land; encoder inputs behind "
+                               "them) and copies the final encoder/decoder latents back (HostFedSdePath.run_batch)"},
         "scenes_per_s": world * args.scenes / (ms_fixed / args.steps * 1e-3),
         "philox": {"value": world * work / (ms_philox / args.steps * 1e-3), "ms_per_step": ms_philox / args.steps,
                    "decoder_ms": dec_ms_philox, "decoder_agent_steps_per_s": M * DEC_STEPS / (dec_ms_philox * 1e-3),
