@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 2
+#define TRAJSDE_ABI_VERSION 3
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -125,6 +125,11 @@ typedef struct {
   int64_t workspace_bytes;
 } TrajsdeEulerFwdArgs;
 
+/* bits of *status (TrajsdeEulerBwdArgs / TrajsdeEncBwdArgs): the scaled adjoint left the range in which its fp16 delta operands
+ * are exact to 2^-11 (it grew by more than ~2^17 over max|incoming gradient|): gradients of this call may be clipped — rerun with
+ * TRAJSDE_BWD_FLAG_EXACT_KERNELS or TRAJSDE_MODE_EXACT_F32. */
+#define TRAJSDE_STATUS_ADJOINT_RANGE 1
+
 /* TrajsdeEulerBwdArgs.flags */
 #define TRAJSDE_BWD_FLAG_EXACT_KERNELS 1 /* run the fp32 CUDA-core backward even in TC_F16 mode (A/B validation) */
 
@@ -152,6 +157,7 @@ typedef struct {
   TrajsdeMlpGrad grad_drift;
   TrajsdeMlpGrad grad_diffusion;
   TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
+  int32_t* status;           /* device int32 or NULL: the TC kernels OR in TRAJSDE_STATUS_* bits (never cleared by the library) */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeEulerBwdArgs;
@@ -257,6 +263,7 @@ typedef struct {
   TrajsdeMlpGrad grad_diffusion;
   TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
   TrajsdeGruGrad grad_gru;
+  int32_t* status;           /* as in TrajsdeEulerBwdArgs */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeEncBwdArgs;

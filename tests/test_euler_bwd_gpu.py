@@ -157,3 +157,22 @@ def test_tc_backward_matches_exact_backward(F, rows, use_dw):
         e = float((a - b).abs().max() / (b.abs().max() + 1e-30))
         print(f"F={F} {n}: rel err {e:.2e}")
         assert e < 1e-2, (n, e)
+
+
+def test_adjoint_range_status_bit():
+    """The TC backward carries the adjoint with a power-of-two loss scale; when the adjoint outgrows the fp16 delta range the kernel
+    raises TRAJSDE_STATUS_ADJOINT_RANGE instead of clipping silently.  Reference-style weights never get there; a drift net blown
+    up 40x (Jacobian norm >> 1 over 61 steps) does."""
+    from trajsde_b200 import _lib
+    ts = torch.linspace(0, 6, 61)
+    y0 = torch.relu(torch.randn(200, 64, generator=torch.Generator().manual_seed(1))).to(DEV)
+    for blow_up, expect in ((1.0, 0), (40.0, _lib.STATUS_ADJOINT_RANGE)):
+        sde = init_like_reference(DecoderSDE(), seed=2, bias_std=0.2).to(DEV)
+        with torch.no_grad():
+            for p_ in sde.f_func.parameters():
+                p_.mul_(blow_up)
+        ops.backward_status(DEV)                                   # clear
+        y = y0.clone().requires_grad_(True)
+        ys = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode='tc_f16', seed=5)
+        ys[-1].sum().backward()
+        assert ops.backward_status(DEV) & _lib.STATUS_ADJOINT_RANGE == expect

@@ -6,10 +6,11 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
+STATUS_ADJOINT_RANGE = 1
 
 EXPORTED_SYMBOLS = (
     'trajsde_abi_version', 'trajsde_last_error_string', 'trajsde_device_sm_count',
@@ -48,7 +49,7 @@ class EulerBwdArgs(C.Structure):
                 ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
                 ('alt_mask', _fp), ('noise', Noise), ('states', _fp), ('grad_ys', _fp), ('grad_ys_t_stride', C.c_int64),
                 ('grad_ys_row_stride', C.c_int64), ('grad_g_last', _fp), ('grad_y0', _fp), ('grad_drift', Mlp),
-                ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+                ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('status', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 class Gru(C.Structure):
@@ -71,7 +72,7 @@ class EncBwdArgs(C.Structure):
                 ('reserved', C.c_int32), ('slot', _fp), ('obs_mask', _fp), ('obs_mask_row_stride', C.c_int64),
                 ('latent', _fp), ('y1', _fp), ('grad_latent', _fp), ('grad_g', _fp), ('grad_h0', _fp), ('grad_aa_out', _fp),
                 ('grad_drift', Mlp), ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('grad_gru', Gru),
-                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+                ('status', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 _lock = threading.Lock()

@@ -108,6 +108,7 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   b.grad_ys = w.gbuf;
   b.grad_ys_t_stride = slab;
   b.grad_ys_row_stride = 64;
+  b.status = a.status;
   if ((rc = bwd_tc_pack(b, w.img0, s)) != 0) return rc;
   if (dual) {
     TrajsdeEulerBwdArgs b2 = b;

@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 #pragma unroll
     for (int j = 0; j < 32; ++j) dw3g_acc[j] = 0.f;
     float dc3_acc = 0.f;
+    float adj_peak = 0.f;   // largest |scaled adjoint| this thread has carried (range check of the fp16 delta operands)
     uint32_t hs = 0;        // hand-shake counter: acc barrier parity
     uint32_t gstep = 0;     // steps processed by this CTA: wg barrier parity
 
@@ -534,7 +535,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           tmem_ld_32x32b_x32(tm + TM_E, ev);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) adj[j] = valid ? __uint_as_float(ev[j]) + __uint_as_float(v[j]) : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            adj[j] = valid ? __uint_as_float(ev[j]) + __uint_as_float(v[j]) : 0.f;
+            adj_peak = fmaxf(adj_peak, fabsf(adj[j]));
+          }
         }
         tc_fence_before();
       }
@@ -553,6 +557,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       }
     }
 
+    if (a.status && !(adj_peak <= 16384.f)) atomicOr(a.status, TRAJSDE_STATUS_ADJOINT_RANGE);   // also catches NaN
     // ================= weight-gradient partials of this CTA ===============================================================================
     if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);          // every MMA of the CTA has completed
     tc_fence_after();

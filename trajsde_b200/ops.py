@@ -24,6 +24,28 @@ _KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-
 # A/B switch (tests, bench): run the fp32 CUDA-core backward kernels even in 'tc_f16' mode (TRAJSDE_BWD_FLAG_EXACT_KERNELS)
 BWD_EXACT_KERNELS = False
 
+# per-device int32 status word the tensor-core backward kernels OR their TRAJSDE_STATUS_* bits into (no sync on the hot path)
+_STATUS = {}
+
+
+def _status_word(device) -> torch.Tensor:
+    t = _STATUS.get(str(device))
+    if t is None:
+        t = torch.zeros((1,), dtype=torch.int32, device=device)
+        _STATUS[str(device)] = t
+    return t
+
+
+def backward_status(device, clear: bool = True) -> int:
+    """TRAJSDE_STATUS_* bits raised by tensor-core backward calls on ``device`` since the last clear (synchronises).
+    Bit ``_lib.STATUS_ADJOINT_RANGE``: the loss-scaled adjoint outgrew the fp16 delta range — gradients may be clipped; rerun
+    that step with ``ops.BWD_EXACT_KERNELS = True`` or ``mode='exact'``."""
+    t = _status_word(torch.device(device))
+    v = int(t.item())
+    if clear:
+        t.zero_()
+    return v
+
 
 # ---------------------------------------------------------------------------------------------------------------------
 # device-resident schedule tables
@@ -187,6 +209,7 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
         grad_g = grad_g.contiguous()
         a.grad_g_last = grad_g.data_ptr()
     a.grad_y0 = grad_y0.data_ptr()
+    a.status = _status_word(dev).data_ptr()
     L = _lib.lib()
     need = _lib.check(L.trajsde_euler_bwd_workspace_bytes(mode, rows, S, int(dual)), "trajsde_euler_bwd_workspace_bytes")
     ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
@@ -356,6 +379,7 @@ def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor],
         grad_g = grad_g.contiguous()
         a.grad_g = grad_g.data_ptr()
     a.grad_h0, a.grad_aa_out = grad_h0.data_ptr(), grad_aa.data_ptr()
+    a.status = _status_word(dev).data_ptr()
     L = _lib.lib()
     need = _lib.check(L.trajsde_enc_bwd_workspace_bytes(_lib.MODE_TC_F16, rows, S, int(dual)), "trajsde_enc_bwd_workspace_bytes")
     ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
