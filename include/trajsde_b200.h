@@ -11,6 +11,7 @@
  *   trajsde_enc_fwd     : the encoder recurrence 21 x [sdeint_dual one step + GRU_Unit jump]
  *                           enc_hivt_nusargo_sde_sep2.py:128-182 + models/utils/ode_utils.py:136-152
  *   trajsde_enc_bwd     : torch.autograd through that recurrence
+ *   trajsde_gru_fwd/bwd : GRU_Unit.forward as its own operator           models/utils/ode_utils.py:136-152 (enc…sep2.py:165-169)
  *   trajsde_philox_dw   : BrownianInterval increments W(t1)-W(t0) ~ N(0,(t1-t0) I)  models/utils/sdeint.py:983-984
  *
  * Conventions
@@ -270,6 +271,33 @@ typedef struct {
 
 int64_t trajsde_enc_bwd_workspace_bytes(int32_t mode, int64_t rows, int32_t n_steps, int32_t dual_diffusion);
 int trajsde_enc_bwd(const TrajsdeEncBwdArgs* args, void* cuda_stream);
+
+/* Stand-alone GRU_Unit jump (models/utils/ode_utils.py:136-152) for hosts that keep the reference's encoder loop: forward
+ * h_next = mask ? (1-u) n + u h_cur : h_cur, and its backward (what autograd computes through GRU_Unit.forward).  Tensor cores,
+ * fp16 operands / fp32 accumulation; hidden = input = units = 64 only. */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;              /* TRAJSDE_MODE_TC_F16 */
+  int64_t rows;
+  int32_t dim;               /* 64 */
+  int32_t flags;
+  TrajsdeGru gru;
+  const float* h_cur;        /* [rows,64] contiguous */
+  const float* x;            /* [rows,64] contiguous: input_tensor */
+  const uint8_t* mask;       /* [rows] bool */
+  float* h_next;             /* forward out [rows,64] */
+  const float* grad_h_next;  /* backward in  [rows,64] */
+  float* grad_h_cur;         /* backward out [rows,64] */
+  float* grad_x;             /* backward out [rows,64] */
+  TrajsdeGruGrad grad_gru;   /* backward out */
+  int32_t* status;           /* reserved (NULL) */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeGruArgs;
+
+int64_t trajsde_gru_workspace_bytes(int32_t mode, int64_t rows);
+int trajsde_gru_fwd(const TrajsdeGruArgs* args, void* cuda_stream);
+int trajsde_gru_bwd(const TrajsdeGruArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

@@ -69,6 +69,26 @@ def test_install_rebinds_reference_module_globals():
         patch.install(decoder=enc)
 
 
+def test_install_binds_fused_gru_forward_on_the_instance_only():
+    """install() also routes encoder.GRU_unit.forward (the jump at enc…sep2.py:165-169) to the fused operator — as an instance
+    attribute, so the reference class and other instances keep their forward; uninstall() removes it again."""
+    from trajsde_b200 import synthetic as syn
+    g = {'sdeint_dual': 'ORIGINAL', '__name__': 'LocalEncoderSDESepPara2'}
+    exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", g)
+    enc = g['Stage']()
+    enc.GRU_unit = syn.GRUUnit()
+    other = syn.GRUUnit()
+    saved = patch.install(encoder=enc)
+    assert 'forward' in enc.GRU_unit.__dict__ and 'forward' not in other.__dict__
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        enc.GRU_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool))
+    patch.uninstall(saved)
+    assert 'forward' not in enc.GRU_unit.__dict__
+    assert enc.GRU_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool)).shape == (3, 64)
+    enc.GRU_unit = syn.GRUUnit(n_units=100)                         # other widths stay on the reference path
+    assert 'gru' not in patch.install(encoder=enc, fuse_gru=True)
+
+
 def test_unsupported_net_layout_raises():
     from trajsde_b200.solver import _mlp_params
     import torch.nn as nn

@@ -162,3 +162,54 @@ def test_fused_encoder_gradients_vs_fp64_autograd(rows, mixed):
         e = float((x.double().cpu() - r).abs().max() / r.abs().max())
         print(f"rows={rows} {n}: rel err {e:.2e}")
         assert e < 3e-2, (n, e)
+
+
+@pytest.mark.parametrize('rows', [1, 130, 700])
+def test_gru_jump_forward_and_gradients(rows):
+    """Stand-alone fused GRU_Unit jump (trajsde_gru_fwd / trajsde_gru_bwd) against the oracle's gru_ref and fp64 autograd."""
+    gru = syn.init_reference_style(syn.GRUUnit(), rows, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(rows)
+    h, x = torch.randn(rows, 64, generator=g), torch.randn(rows, 64, generator=g)
+    m = torch.rand(rows, generator=g) > 0.3
+    cot = torch.randn(rows, 64, generator=g)
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in gru.state_dict().items()}
+    hd, xd = h.double().requires_grad_(True), x.double().requires_grad_(True)
+    ref = so.gru_ref(P, hd, xd, m)
+    gref = torch.autograd.grad((ref * cot.double()).sum(), [hd, xd] + list(P.values()))
+
+    hg, xg = h.to(DEV).requires_grad_(True), x.to(DEV).requires_grad_(True)
+    out = enc.gru_jump(gru, hg, xg, m.to(DEV))
+    assert (out.detach().cpu().double() - ref.detach()).abs().max() < 1e-2
+    assert torch.equal(out.detach()[~m.to(DEV)], hg.detach()[~m.to(DEV)])            # unobserved rows pass through untouched
+    (out * cot.to(DEV)).sum().backward()
+    got = [hg.grad, xg.grad] + [gru.get_parameter(k).grad for k in P]
+    for n, a_, r in zip(['h_cur', 'x'] + list(P), got, gref):
+        e = float((a_.double().cpu() - r).abs().max() / (r.abs().max() + 1e-30))
+        assert e < 3e-2, (n, e)
+
+
+def test_stepwise_encoder_with_installed_gru_matches_fused_recurrence():
+    """The drop-in path (reference loop: sdeint_dual + GRU_unit per iteration, both rebound by install()) and the fused recurrence
+    kernel compute the same latents from the same Brownian increments."""
+    from trajsde_b200 import patch
+    rows = 150
+    sde = init_like_reference(EncoderSDE(), seed=3, bias_std=0.2).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), 4, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(9)
+    h0 = (torch.randn(rows, 64, generator=g) * 0.1).to(DEV)
+    aa = torch.randn(21, rows, 64, generator=g).to(DEV)
+    am = (torch.rand(rows, 21, generator=g) > 0.3).to(DEV)
+    nm = (torch.rand(rows, generator=g) > 0.5).to(DEV)
+    dW = (torch.randn(21, rows, 64, generator=g) * 0.3).to(DEV)
+    glob = {'sdeint_dual': None}
+    exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", glob)
+    enc_stage = glob['Stage']()
+    enc_stage.GRU_unit = gru
+    saved = patch.install(encoder=enc_stage)
+    try:
+        with torch.no_grad():
+            lat_s, _ = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, dW=dW, fused=False)       # loop: sdeint_dual op + patched GRU
+            lat_f, _ = enc.encoder_recurrence(sde, gru, h0, aa, am, nm, dW=dW, fused=True)
+    finally:
+        patch.uninstall(saved)
+    assert (lat_s - lat_f).abs().max() < 2e-2

@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_euler_bwd_workspace_bytes', 'trajsde_euler_bwd',
     'trajsde_philox_dw', 'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_fwd',
     'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
+    'trajsde_gru_workspace_bytes', 'trajsde_gru_fwd', 'trajsde_gru_bwd',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -75,6 +76,13 @@ class EncBwdArgs(C.Structure):
                 ('status', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
+class GruArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('gru', Gru), ('h_cur', _fp), ('x', _fp), ('mask', _fp), ('h_next', _fp),
+                ('grad_h_next', _fp), ('grad_h_cur', _fp), ('grad_x', _fp), ('grad_gru', Gru), ('status', _fp),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -115,6 +123,12 @@ def lib():
         if hasattr(L, 'trajsde_enc_bwd'):
             L.trajsde_enc_bwd.restype = C.c_int
             L.trajsde_enc_bwd.argtypes = [C.POINTER(EncBwdArgs), C.c_void_p]
+        if hasattr(L, 'trajsde_gru_fwd'):
+            L.trajsde_gru_workspace_bytes.restype = C.c_int64
+            L.trajsde_gru_workspace_bytes.argtypes = [C.c_int32, C.c_int64]
+            for f in (L.trajsde_gru_fwd, L.trajsde_gru_bwd):
+                f.restype = C.c_int
+                f.argtypes = [C.POINTER(GruArgs), C.c_void_p]
         v = L.trajsde_abi_version()
         if v != ABI_VERSION:
             raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")

@@ -222,6 +222,46 @@ int trajsde_enc_bwd(const TrajsdeEncBwdArgs* a, void* cuda_stream) {
   return launch_enc_bwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+int64_t trajsde_gru_workspace_bytes(int32_t mode, int64_t rows) {
+  if (mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "the fused GRU jump exists in TC_F16 mode only (mode %d)", mode);
+  if (rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  return gru_standalone_workspace_bytes(rows);
+}
+
+static int gru_call(const TrajsdeGruArgs* a, void* cuda_stream, bool backward) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeGruArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeGruArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "the fused GRU jump exists in TC_F16 mode only (mode %d)", a->mode);
+  if (a->rows < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows < 0");
+  const TrajsdeGru& g = a->gru;
+  if (!g.u1 || !g.ub1 || !g.u2 || !g.ub2 || !g.r1 || !g.rb1 || !g.r2 || !g.rb2 || !g.n1 || !g.nb1 || !g.n2 || !g.nb2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "gru: null weight pointer");
+  if (backward) {
+    const TrajsdeGruGrad& gg = a->grad_gru;
+    if (!gg.u1 || !gg.ub1 || !gg.u2 || !gg.ub2 || !gg.r1 || !gg.rb1 || !gg.r2 || !gg.rb2 || !gg.n1 || !gg.nb1 || !gg.n2 || !gg.nb2)
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_gru: null pointer");
+  }
+  if (a->rows > 0) {
+    if (!a->h_cur || !a->x || !a->mask) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h_cur/x/mask null");
+    if (!backward && !a->h_next) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h_next null");
+    if (backward && (!a->grad_h_next || !a->grad_h_cur || !a->grad_x)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_h_next/grad_h_cur/grad_x null");
+    if (!aligned16(a->h_cur) || !aligned16(a->x) || (a->h_next && !aligned16(a->h_next)) || (a->grad_h_next && !aligned16(a->grad_h_next)) ||
+        (a->grad_h_cur && !aligned16(a->grad_h_cur)) || (a->grad_x && !aligned16(a->grad_x)))
+      return set_error(TRAJSDE_ERR_UNSUPPORTED, "tensors must be 16-byte aligned");
+  }
+  int64_t need = gru_standalone_workspace_bytes(a->rows);
+  if (a->workspace_bytes < need || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_gru_standalone(*a, backward, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int trajsde_gru_fwd(const TrajsdeGruArgs* a, void* cuda_stream) { return gru_call(a, cuda_stream, false); }
+int trajsde_gru_bwd(const TrajsdeGruArgs* a, void* cuda_stream) { return gru_call(a, cuda_stream, true); }
+
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
   if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
   int rc;

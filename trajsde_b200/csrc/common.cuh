@@ -114,7 +114,9 @@ int launch_gru_bwd(const TrajsdeGru& w, int64_t rows, const float* y1, const flo
 int gru_bwd_tc_pack(const TrajsdeGru& w, uint8_t* img, cudaStream_t s);
 int launch_gru_bwd_tc(int64_t rows, const float* y1, const float* aa_out, int64_t slab, const uint8_t* obs_mask, int64_t obs_mask_row_stride,
                       const int32_t* slot, int iter, const float* carry, const float* grad_latent, float* grad_y1, float* grad_aa_out,
-                      const uint8_t* img, const uint32_t* amax_bits, float* partial, cudaStream_t s);
+                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s);
+int launch_gru_standalone(const TrajsdeGruArgs& a, bool backward, cudaStream_t s);
+int64_t gru_standalone_workspace_bytes(int64_t rows);
 int launch_gru_bwd_reduce(const float* partial, int n, const TrajsdeGruGrad& g, cudaStream_t s);
 int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s);
 int64_t enc_bwd_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);

@@ -120,7 +120,7 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
     const float* carry_in = i == S - 1 ? nullptr : w.carry;
     const float* glat = a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr;
     rc = gru_tc ? launch_gru_bwd_tc(a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i, carry_in,
-                                    glat, w.gbuf + slab, a.grad_aa_out, w.gru_img, w.amax, w.gru_part, s)
+                                    glat, w.gbuf + slab, a.grad_aa_out, w.gru_img, w.amax, w.gru_part, nullptr, s)
                 : launch_gru_bwd(a.gru, a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i,
                                  carry_in, glat, w.gbuf + slab, a.grad_aa_out, w.gru_part, s);
     if (rc != 0) return rc;
@@ -136,6 +136,34 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
                                     a.grad_diffusion_alt, s)) != 0)
     return rc;
   return launch_gru_bwd_reduce(w.gru_part, ggrid, a.grad_gru, s);
+}
+
+// ---- stand-alone GRU_Unit forward / backward (trajsde_gru_fwd / trajsde_gru_bwd): the jump as its own operator, for the drop-in path
+// that keeps the reference's encoder loop (install() rebinds GRU_unit.forward) --------------------------------------------------------
+int64_t gru_standalone_workspace_bytes(int64_t rows) {
+  (void)rows;
+  return align256(GRU_TC_IMG_BYTES) + 256 + 256 + align256((int64_t)MAX_PARTIALS * GRU_G_PAD * 4);
+}
+
+int launch_gru_standalone(const TrajsdeGruArgs& a, bool backward, cudaStream_t s) {
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  uint8_t* ws = static_cast<uint8_t*>(a.workspace);
+  uint8_t* img = ws;
+  uint32_t* amax = reinterpret_cast<uint32_t*>(ws + align256(GRU_TC_IMG_BYTES));
+  int32_t* slot0 = reinterpret_cast<int32_t*>(ws + align256(GRU_TC_IMG_BYTES) + 256);
+  float* part = reinterpret_cast<float*>(ws + align256(GRU_TC_IMG_BYTES) + 512);
+  const int grid = bwd_tc_grid(a.rows);
+  int rc;
+  TS_CUDA_CHECK(cudaMemsetAsync(amax, 0, 512, s));                 // amax word and the single slot index (0)
+  if ((rc = gru_bwd_tc_pack(a.gru, img, s)) != 0) return rc;
+  if (!backward)
+    return launch_gru_bwd_tc(a.rows, a.h_cur, a.x, 0, a.mask, 1, slot0, 0, nullptr, nullptr, nullptr, nullptr, img, amax, part, a.h_next, s);
+  TS_CUDA_CHECK(cudaMemsetAsync(part, 0, (size_t)grid * GRU_G_PAD * 4, s));
+  if ((rc = bwd_tc_absmax(a.grad_h_next, 1, a.rows, 0, 64, amax, s)) != 0) return rc;
+  if ((rc = launch_gru_bwd_tc(a.rows, a.h_cur, a.x, 0, a.mask, 1, slot0, 0, nullptr, a.grad_h_next, a.grad_h_cur, a.grad_x, img, amax, part,
+                              nullptr, s)) != 0)
+    return rc;
+  return launch_gru_bwd_reduce(part, grid, a.grad_gru, s);
 }
 
 }  // namespace trajsde

@@ -79,6 +79,8 @@ struct GruTcParams {
   const uint32_t* amax_bits;
   float* partial;              // [grid][GRU_G_PAD], accumulated into
   int num_tiles;
+  int fwd_only;                // 1: stop after the recompute phases and write h' (the stand-alone GRU_Unit forward, trajsde_gru_fwd)
+  float* h_out;                // [rows,64], fwd_only
 };
 
 __global__ void gru_tc_pack_kernel(TrajsdeGru w, uint8_t* __restrict__ img) {
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
         load_rows_coalesced(xin, 64, row0, p.rows, hh * 32, lane, lx);
         if (p.carry) load_rows_coalesced(p.carry, 64, row0, p.rows, hh * 32, lane, lc);
         if (p.grad_latent) load_rows_coalesced(p.grad_latent, 64, row0, p.rows, hh * 32, lane, lg);
-        if (ntile > 0) mbar_wait(bar_wg, (ntile - 1) & 1);       // previous tile's weight-gradient MMAs have read every tile
+        if (ntile > 0 && !p.fwd_only) mbar_wait(bar_wg, (ntile - 1) & 1);   // previous tile's weight-gradient MMAs have read every tile
         to_own_row(stage, lane, ly);
         to_own_row(stage, lane, lx);
         if (p.carry) to_own_row(stage, lane, lc);
@@ -290,6 +292,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
+      if (p.fwd_only) {                                            // h' = mask ? (1-u) n + u y1 : y1
+        tc_fence_before();
+        if (valid) {
+          float* dst = p.h_out + grow * 64 + hh * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q + e;
+              const float n = __uint_as_float(v[j]) + vec[VEC_NB2 + hh * 32 + j];
+              o[e] = obs ? fmaf(u[j], y1[j], (1.f - u[j]) * n) : y1[j];
+            }
+            *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float n = __uint_as_float(v[j]) + vec[VEC_NB2 + hh * 32 + j];
@@ -403,7 +423,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
     }
 
     // ================= remaining weight-gradient accumulators + bias sums of this CTA -> partial =================================================
-    {
+    if (!p.fwd_only) {
       float* out = p.partial + (size_t)blockIdx.x * GRU_G_PAD;
       const bool lo = quad < 2;
       const int m = (int)row & 63;
@@ -512,6 +532,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
           tc_commit(bar_acc);
         }
         __syncwarp();
+        if (p.fwd_only) continue;
         wait_opnd();                                                // B1: d_tn = d_n . N2
         if (elect_one()) {
           mma_km(d0 + TM_W, tile_u32(T_DN), base + IMG_N2, ikm_64, false, false);
@@ -570,8 +591,10 @@ int gru_bwd_tc_pack(const TrajsdeGru& w, uint8_t* img, cudaStream_t s) {
 
 int launch_gru_bwd_tc(int64_t rows, const float* y1, const float* aa_out, int64_t slab, const uint8_t* obs_mask, int64_t obs_mask_row_stride,
                       const int32_t* slot, int iter, const float* carry, const float* grad_latent, float* grad_y1, float* grad_aa_out,
-                      const uint8_t* img, const uint32_t* amax_bits, float* partial, cudaStream_t s) {
+                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s) {
   GruTcParams p;
+  p.fwd_only = h_out_fwd_only != nullptr;
+  p.h_out = h_out_fwd_only;
   p.rows = rows;
   p.y1 = y1;
   p.x = aa_out;

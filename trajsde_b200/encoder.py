@@ -41,6 +41,14 @@ def _enc_tables(max_past_t, hist, dt, device):
     return hit
 
 
+def gru_jump(gru_unit, h_cur: torch.Tensor, input_tensor: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """``GRU_Unit.forward(h_cur, input_tensor, mask)`` (models/utils/ode_utils.py:136-152) as one tensor-core launch with a fused
+    backward; what ``install()`` binds ``encoder.GRU_unit.forward`` to.  CUDA / 64-wide layers only — no fallback."""
+    if not h_cur.is_cuda:
+        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    return ops.gru_fwd(h_cur, input_tensor, mask, _gru_params(gru_unit))
+
+
 def encoder_recurrence(sde, gru_unit, h0: torch.Tensor, aa_out: torch.Tensor, actors_mask: torch.Tensor,
                        nus_mask: torch.Tensor, *, dt: float = 0.1, max_past_t: float = 2.0, dW: Optional[torch.Tensor] = None,
                        seed: Optional[int] = None, mode: Optional[str] = None, fused: Optional[bool] = None,

@@ -423,6 +423,92 @@ enc_fwd.register_autograd(_enc_backward, setup_context=_enc_setup_context)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# stand-alone GRU_Unit jump (for the drop-in path that keeps the reference's encoder loop)
+# ---------------------------------------------------------------------------------------------------------------------
+_GRU_SHAPES = [(64, 128), (64,), (64, 64), (64,)] * 3
+
+
+def _gru_args(h_cur, x, mask, gru_params):
+    dev = h_cur.device
+    rows = h_cur.shape[0]
+    if h_cur.dim() != 2 or h_cur.shape[1] != 64 or tuple(x.shape) != (rows, 64) or h_cur.dtype != torch.float32 or x.dtype != torch.float32:
+        raise ValueError("`h_cur` and `input_tensor` must be float32 of shape (rows, 64)")
+    if tuple(mask.shape) != (rows,) or mask.dtype not in (torch.bool, torch.uint8):
+        raise ValueError("`mask` must be a bool tensor of shape (rows,)")
+    if len(gru_params) != 12 or any(tuple(t.shape) != sh for t, sh in zip(gru_params, _GRU_SHAPES)):
+        raise ValueError("gru_params must be the 12 GRU_Unit tensors (update/reset/new_state: Linear(128,64), Linear(64,64))")
+    gs = [t.detach().contiguous() for t in gru_params]
+    keep = [h_cur.detach().contiguous(), x.detach().contiguous(), mask.contiguous().view(torch.uint8)] + gs
+    a = _lib.GruArgs()
+    a.struct_bytes = C.sizeof(_lib.GruArgs)
+    a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
+    for name, t in zip(_GRU_NAMES, gs):
+        setattr(a.gru, name, t.data_ptr())
+    a.h_cur, a.x, a.mask = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr()
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_gru_workspace_bytes(_lib.MODE_TC_F16, rows), "trajsde_gru_workspace_bytes")
+    ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    keep.append(ws)
+    return a, keep, L
+
+
+@torch.library.custom_op("trajsde::gru_fwd", mutates_args=(), device_types="cuda")
+def gru_fwd(h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor, gru_params: List[torch.Tensor]) -> torch.Tensor:
+    """GRU_Unit.forward (models/utils/ode_utils.py:136-152) as one tensor-core launch: h_next[rows,64]."""
+    a, keep, L = _gru_args(h_cur, x, mask, gru_params)
+    out = torch.empty_like(keep[0])
+    a.h_next = out.data_ptr()
+    with torch.cuda.device(h_cur.device):
+        _lib.check(L.trajsde_gru_fwd(C.byref(a), _stream_ptr(h_cur.device)), "trajsde_gru_fwd")
+    if h_cur.shape[0] > 0:
+        LAUNCHES['n'] += 2
+    return out
+
+
+@gru_fwd.register_fake
+def _(h_cur, x, mask, gru_params):
+    return torch.empty_like(h_cur)
+
+
+@torch.library.custom_op("trajsde::gru_bwd", mutates_args=(), device_types="cuda")
+def gru_bwd(grad_out: torch.Tensor, h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor,
+            gru_params: List[torch.Tensor]) -> List[torch.Tensor]:
+    """[grad_h_cur, grad_x] + gradients of the 12 GRU tensors."""
+    a, keep, L = _gru_args(h_cur, x, mask, gru_params)
+    go = grad_out.contiguous()
+    gh, gx = torch.empty_like(keep[0]), torch.empty_like(keep[0])
+    gg = [torch.zeros_like(t) for t in keep[3:15]]
+    a.grad_h_next, a.grad_h_cur, a.grad_x = go.data_ptr(), gh.data_ptr(), gx.data_ptr()
+    for name, t in zip(_GRU_NAMES, gg):
+        setattr(a.grad_gru, name, t.data_ptr())
+    with torch.cuda.device(h_cur.device):
+        _lib.check(L.trajsde_gru_bwd(C.byref(a), _stream_ptr(h_cur.device)), "trajsde_gru_bwd")
+    if h_cur.shape[0] > 0:
+        LAUNCHES['n'] += 4
+    return [gh, gx] + gg
+
+
+@gru_bwd.register_fake
+def _(grad_out, h_cur, x, mask, gru_params):
+    return [torch.empty_like(h_cur), torch.empty_like(x)] + [torch.empty_like(p) for p in gru_params]
+
+
+def _gru_setup_context(ctx, inputs, output):
+    h_cur, x, mask, gru_params = inputs
+    ctx.save_for_backward(h_cur, x, mask, *gru_params)
+
+
+def _gru_backward(ctx, grad_out):
+    h_cur, x, mask, *gru_params = ctx.saved_tensors
+    grads = gru_bwd(grad_out, h_cur, x, mask, list(gru_params))
+    return grads[0], grads[1], None, list(grads[2:])
+
+
+gru_fwd.register_autograd(_gru_backward, setup_context=_gru_setup_context)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # Brownian increments exactly as the kernels draw them (for replaying Philox runs through the oracle)
 # ---------------------------------------------------------------------------------------------------------------------
 def philox_dw(dsched: DeviceSchedule, rows: int, seed: int, device, row_offset: int = 0, step_offset: int = 0) -> torch.Tensor:

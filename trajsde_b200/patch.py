@@ -5,7 +5,7 @@ decoder's ``sdeint`` and the encoder's ``sdeint_dual`` are module globals of the
 two names is the whole integration."""
 from typing import Optional
 
-from .solver import sdeint, sdeint_dual
+from .solver import get_default_mode, sdeint, sdeint_dual
 
 
 def _globals_of(obj):
@@ -16,9 +16,20 @@ def _globals_of(obj):
     return g
 
 
-def install(model=None, decoder=None, encoder=None) -> dict:
+def _is_64_wide_gru(gru) -> bool:
+    try:
+        shapes = [tuple(getattr(gru, n)[i].weight.shape) for n in ('update_gate', 'reset_gate', 'new_state_net') for i in (0, 2)]
+    except (AttributeError, IndexError, TypeError):
+        return False
+    return shapes == [(64, 128), (64, 64)] * 3
+
+
+def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True) -> dict:
     """Rebind ``sdeint`` (decoder module) and ``sdeint_dual`` (encoder module).  Pass the LightningModule-style ``model``
-    (with ``.decoder`` / ``.encoder``) or the stage modules directly.  Returns the originals for ``uninstall``."""
+    (with ``.decoder`` / ``.encoder``) or the stage modules directly.  With ``fuse_gru`` the encoder's ``GRU_unit`` instance
+    (the jump between SDE steps, enc…sep2.py:165-169) also gets its ``forward`` bound to the fused ``gru_jump`` — an instance
+    attribute, the reference class is untouched — when the default mode is 'tc_f16' and its layers are 64 wide.  Returns the
+    originals for ``uninstall``."""
     decoder = decoder if decoder is not None else getattr(model, 'decoder', None)
     encoder = encoder if encoder is not None else getattr(model, 'encoder', None)
     saved = {}
@@ -34,9 +45,24 @@ def install(model=None, decoder=None, encoder=None) -> dict:
             raise KeyError("encoder module has no global `sdeint_dual`")
         saved['encoder'] = (g, 'sdeint_dual', g['sdeint_dual'])
         g['sdeint_dual'] = sdeint_dual
+        gru = getattr(encoder, 'GRU_unit', None)
+        if fuse_gru and gru is not None and get_default_mode() == 'tc_f16' and _is_64_wide_gru(gru):
+            from .encoder import gru_jump
+
+            def fused_forward(h_cur, input_tensor, mask, _gru=gru):
+                return gru_jump(_gru, h_cur, input_tensor, mask)
+
+            saved['gru'] = (gru, 'forward', gru.__dict__.get('forward'))
+            gru.forward = fused_forward
     return saved
 
 
 def uninstall(saved: Optional[dict]) -> None:
-    for g, name, orig in (saved or {}).values():
-        g[name] = orig
+    for key, (g, name, orig) in (saved or {}).items():
+        if key == 'gru':
+            if orig is None:
+                g.__dict__.pop('forward', None)          # back to the class's forward
+            else:
+                g.forward = orig
+        else:
+            g[name] = orig
