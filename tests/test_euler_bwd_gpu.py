@@ -176,3 +176,33 @@ def test_adjoint_range_status_bit():
         ys = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode='tc_f16', seed=5)
         ys[-1].sum().backward()
         assert ops.backward_status(DEV) & _lib.STATUS_ADJOINT_RANGE == expect
+
+
+def test_registered_torch_ops_equal_the_eager_fast_path():
+    """solver.py / encoder.py call thin autograd.Function wrappers; the registered torch.library ops (trajsde::euler_fwd/bwd,
+    gru_fwd/bwd) wrap the same implementations and must give identical outputs and gradients through the dispatcher."""
+    from trajsde_b200 import synthetic as syn
+    sde = init_like_reference(DecoderSDE(), seed=4).to(DEV)
+    ts = torch.linspace(0, 2, 21)
+    y0 = torch.relu(torch.randn(100, 64, generator=torch.Generator().manual_seed(4))).to(DEV)
+
+    def run(dispatcher):
+        ops.USE_DISPATCHER = dispatcher
+        try:
+            for p_ in sde.parameters():
+                p_.grad = None
+            y = y0.clone().requires_grad_(True)
+            ys = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode='tc_f16', seed=5)
+            ys[1:].square().sum().backward()
+            return [ys.detach().clone(), y.grad.clone()] + [p_.grad.clone() for p_ in sde.parameters()]
+        finally:
+            ops.USE_DISPATCHER = False
+
+    for a, b in zip(run(False), run(True)):
+        assert torch.equal(a, b)
+    assert torch.ops.trajsde.euler_fwd is not None and torch.ops.trajsde.gru_fwd is not None and torch.ops.trajsde.enc_fwd is not None
+    gru = syn.init_reference_style(syn.GRUUnit(), 1).to(DEV)
+    h = torch.randn(70, 64, device=DEV)
+    m = torch.rand(70, device=DEV) > 0.5
+    gp = [p_ for p_ in gru.parameters()]
+    assert torch.equal(ops.gru_call(h, h * 0.5, m, gp), torch.ops.trajsde.gru_fwd(h, h * 0.5, m, gp))

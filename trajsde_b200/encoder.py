@@ -46,7 +46,7 @@ def gru_jump(gru_unit, h_cur: torch.Tensor, input_tensor: torch.Tensor, mask: to
     backward; what ``install()`` binds ``encoder.GRU_unit.forward`` to.  CUDA / 64-wide layers only — no fallback."""
     if not h_cur.is_cuda:
         raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-    return ops.gru_fwd(h_cur, input_tensor, mask, _gru_params(gru_unit))
+    return ops.gru_call(h_cur, input_tensor, mask, _gru_params(gru_unit))
 
 
 def encoder_recurrence(sde, gru_unit, h0: torch.Tensor, aa_out: torch.Tensor, actors_mask: torch.Tensor,
@@ -71,9 +71,8 @@ def encoder_recurrence(sde, gru_unit, h0: torch.Tensor, aa_out: torch.Tensor, ac
         step_tab, slots = _enc_tables(max_past_t, hist, dt, h0.device)
         if seed is None:
             seed = _next_call_seed() if dW is None else 0
-        latent, g, _ = ops.enc_fwd(h0, aa_out, actors_mask, slots, list(params), list(gparams), step_tab, dW, nus_mask, int(seed),
-                                   int(row_offset), 0, bool(need_grad))
-        return latent, g
+        return ops.enc_call(h0, aa_out, actors_mask, slots, list(params), list(gparams), step_tab, dW, nus_mask, int(seed),
+                            int(row_offset), 0, bool(need_grad))
     h = h0
     latent, gs = [], []
     for idx, (prev_t, t_i, t) in enumerate(encoder_time_pairs(max_past_t, hist)):

@@ -182,7 +182,7 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     dual = alt_mask is not None
     ps = _check_params(params, dual, dev)
     grad_y0 = torch.empty((rows, 64), dtype=torch.float32, device=dev)
-    gparams = [torch.zeros_like(p) for p in ps]
+    gparams = [torch.empty_like(p) for p in ps]       # the fixed-order reduce writes every element
     a = _lib.EulerBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EulerBwdArgs)
     a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0)
@@ -344,8 +344,8 @@ def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor],
     n_slots = aa_out.shape[0]
     grad_h0 = torch.empty((rows, 64), dtype=torch.float32, device=dev)
     grad_aa = torch.zeros((n_slots, rows, 64), dtype=torch.float32, device=dev)
-    gparams = [torch.zeros_like(p) for p in ps]
-    ggru = [torch.zeros_like(p) for p in gs]
+    gparams = [torch.empty_like(p) for p in ps]       # the fixed-order reduces write every element
+    ggru = [torch.empty_like(p) for p in gs]
     a = _lib.EncBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EncBwdArgs)
     a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
@@ -478,7 +478,7 @@ def gru_bwd(grad_out: torch.Tensor, h_cur: torch.Tensor, x: torch.Tensor, mask: 
     a, keep, L = _gru_args(h_cur, x, mask, gru_params)
     go = grad_out.contiguous()
     gh, gx = torch.empty_like(keep[0]), torch.empty_like(keep[0])
-    gg = [torch.zeros_like(t) for t in keep[3:15]]
+    gg = [torch.empty_like(t) for t in keep[3:15]]
     a.grad_h_next, a.grad_h_cur, a.grad_x = go.data_ptr(), gh.data_ptr(), gx.data_ptr()
     for name, t in zip(_GRU_NAMES, gg):
         setattr(a.grad_gru, name, t.data_ptr())
@@ -506,6 +506,117 @@ def _gru_backward(ctx, grad_out):
 
 
 gru_fwd.register_autograd(_gru_backward, setup_context=_gru_setup_context)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# eager fast path
+# ---------------------------------------------------------------------------------------------------------------------
+# The torch.library operators above are the registered ops (dispatcher, fake tensors, torch.compile).  Eager callers — solver.py,
+# encoder.py, i.e. the drop-in functions — go through thin autograd.Function wrappers over the SAME implementations: that skips
+# ~0.2 ms of dispatcher / pytree work per call, which is what the reference's 21-iteration encoder loop is made of.
+# TRAJSDE_USE_DISPATCHER=1 routes everything through the registered ops instead.
+import os as _os
+
+USE_DISPATCHER = _os.environ.get('TRAJSDE_USE_DISPATCHER', '0') == '1'
+
+
+def _raw(op):
+    return getattr(op, '_init_fn', op)
+
+
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+class _EulerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, rows_major, *params):
+        ys, g_last, states = _raw(euler_fwd)(y0, list(params), step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset,
+                                             step_offset, mode, True, rows_major)
+        ctx.save_for_backward(states, step_tab, out_begin, out_w, *params)
+        ctx.dw, ctx.alt_mask = dw, alt_mask
+        ctx.meta = (n_outputs, seed, row_offset, step_offset, mode)
+        ctx.set_materialize_grads(False)               # an unused output arrives as None, not as a zero tensor
+        return ys, g_last
+
+    @staticmethod
+    def backward(ctx, grad_ys, grad_g):
+        states, step_tab, out_begin, out_w, *params = ctx.saved_tensors
+        n_outputs, seed, row_offset, step_offset, mode = ctx.meta
+        grads = _raw(euler_bwd)(grad_ys, grad_g, states, list(params), step_tab, out_begin, out_w, n_outputs, ctx.dw, ctx.alt_mask,
+                                seed, row_offset, step_offset, mode)
+        return (grads[0],) + (None,) * 11 + tuple(grads[1:])
+
+
+def euler_call(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, save_states,
+               rows_major):
+    """ys, g_last of the fused solve, differentiable w.r.t. y0 and params when ``save_states``."""
+    if USE_DISPATCHER:
+        ys, g_last, _ = euler_fwd(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
+                                  save_states, rows_major)
+        return ys, g_last
+    if save_states and _needs_grad(y0, *params):
+        return _EulerFn.apply(y0, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, rows_major,
+                              *params)
+    ys, g_last, _ = _raw(euler_fwd)(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
+                                    False, rows_major)
+    return ys, g_last
+
+
+class _GruFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h_cur, x, mask, *gru_params):
+        ctx.save_for_backward(h_cur, x, mask, *gru_params)
+        return _raw(gru_fwd)(h_cur, x, mask, list(gru_params))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h_cur, x, mask, *gru_params = ctx.saved_tensors
+        grads = _raw(gru_bwd)(grad_out, h_cur, x, mask, list(gru_params))
+        return (grads[0], grads[1], None) + tuple(grads[2:])
+
+
+def gru_call(h_cur, x, mask, gru_params):
+    if USE_DISPATCHER:
+        return gru_fwd(h_cur, x, mask, gru_params)
+    if _needs_grad(h_cur, x, *gru_params):
+        return _GruFn.apply(h_cur, x, mask, *gru_params)
+    return _raw(gru_fwd)(h_cur, x, mask, gru_params)
+
+
+class _EncFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h0, aa_out, obs_mask, slot, step_tab, dw, alt_mask, seed, row_offset, step_offset, n_p, *all_params):
+        params, gru_params = list(all_params[:n_p]), list(all_params[n_p:])
+        latent, g, y1s = _raw(enc_fwd)(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset,
+                                       step_offset, True)
+        ctx.save_for_backward(latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *all_params)
+        ctx.dw, ctx.alt_mask = dw, alt_mask
+        ctx.meta = (seed, row_offset, step_offset, n_p)
+        ctx.set_materialize_grads(False)
+        return latent, g
+
+    @staticmethod
+    def backward(ctx, grad_latent, grad_g):
+        latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *all_params = ctx.saved_tensors
+        seed, row_offset, step_offset, n_p = ctx.meta
+        grads = _raw(enc_bwd)(grad_latent, grad_g, latent, y1s, h0, aa_out, obs_mask, slot, list(all_params[:n_p]), list(all_params[n_p:]),
+                              step_tab, ctx.dw, ctx.alt_mask, seed, row_offset, step_offset)
+        return (grads[0], grads[1]) + (None,) * 9 + tuple(grads[2:])
+
+
+def enc_call(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset, need_grad):
+    """latent, g of the fused encoder recurrence, differentiable when ``need_grad``."""
+    if USE_DISPATCHER:
+        latent, g, _ = enc_fwd(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset,
+                               need_grad)
+        return latent, g
+    if need_grad:
+        return _EncFn.apply(h0, aa_out, obs_mask, slot, step_tab, dw, alt_mask, seed, row_offset, step_offset, len(params),
+                            *params, *gru_params)
+    latent, g, _ = _raw(enc_fwd)(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset,
+                                 False)
+    return latent, g
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -134,8 +134,8 @@ def _solve(sde, params, y0, ts, dt, bm, nus_mask, mode, seed, row_offset, rows_m
         seed = _next_call_seed() if dW is None else 0
     need_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params))
     mode_id = _lib.MODES[mode or _defaults['mode']]
-    ys, g_last, _ = ops.euler_fwd(y0, list(params), ds.step_tab, ds.out_begin, ds.out_w, sched.n_outputs, dW, nus_mask,
-                                  int(seed), int(row_offset), 0, mode_id, need_grad, bool(rows_major))
+    ys, g_last = ops.euler_call(y0, list(params), ds.step_tab, ds.out_begin, ds.out_w, sched.n_outputs, dW, nus_mask,
+                                int(seed), int(row_offset), 0, mode_id, need_grad, bool(rows_major))
     for name in ('fnfe', 'gnfe'):                      # NFE counters the reference bumps per f/g call (dec…sde.py:177,193)
         if hasattr(sde, name):
             setattr(sde, name, getattr(sde, name) + sched.n_steps)
