@@ -103,7 +103,7 @@ int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s);
 int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride, uint32_t* amax_bits, cudaStream_t s);
 int bwd_tc_grid(int64_t rows);
 int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
-                int accumulate, cudaStream_t s);
+                int accumulate, cudaStream_t s, bool pdl = false);
 int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int n1, const TrajsdeMlpGrad& gf, const TrajsdeMlpGrad& gg,
                             const TrajsdeMlpGrad& ga, cudaStream_t s);
 // GRU jump backward (gru_bwd.cu) and the encoder-recurrence backward driver (enc_bwd.cu)
@@ -114,7 +114,7 @@ int launch_gru_bwd(const TrajsdeGru& w, int64_t rows, const float* y1, const flo
 int gru_bwd_tc_pack(const TrajsdeGru& w, uint8_t* img, cudaStream_t s);
 int launch_gru_bwd_tc(int64_t rows, const float* y1, const float* aa_out, int64_t slab, const uint8_t* obs_mask, int64_t obs_mask_row_stride,
                       const int32_t* slot, int iter, const float* carry, const float* grad_latent, float* grad_y1, float* grad_aa_out,
-                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s);
+                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s, bool pdl = false);
 int launch_gru_standalone(const TrajsdeGruArgs& a, bool backward, cudaStream_t s);
 int64_t gru_standalone_workspace_bytes(int64_t rows);
 int launch_gru_bwd_reduce(const float* partial, int n, const TrajsdeGruGrad& g, cudaStream_t s);

@@ -120,7 +120,7 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
     const float* carry_in = i == S - 1 ? nullptr : w.carry;
     const float* glat = a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr;
     rc = gru_tc ? launch_gru_bwd_tc(a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i, carry_in,
-                                    glat, w.gbuf + slab, a.grad_aa_out, w.gru_img, w.amax, w.gru_part, nullptr, s)
+                                    glat, w.gbuf + slab, a.grad_aa_out, w.gru_img, w.amax, w.gru_part, nullptr, s, i < S - 1)
                 : launch_gru_bwd(a.gru, a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i,
                                  carry_in, glat, w.gbuf + slab, a.grad_aa_out, w.gru_part, s);
     if (rc != 0) return rc;
@@ -130,7 +130,9 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
     b.states = i == 0 ? a.h0 : a.latent + (int64_t)(i - 1) * slab;
     b.grad_g_last = a.grad_g ? a.grad_g + (int64_t)i * a.rows : nullptr;
     b.grad_y0 = i == 0 ? a.grad_h0 : w.carry;
-    if ((rc = bwd_tc_main(b, w.img0, dual ? w.img1 : nullptr, w.amax, w.part0, w.part1, 1, s)) != 0) return rc;   // both nets' passes, one launch
+    // both nets' passes in one launch; launched with programmatic stream serialisation: its prologue (barriers, TMEM) overlaps the GRU
+    // kernel's tail, and it lets the next iteration's GRU kernel do the same (the chain is dependent, the prologues are not)
+    if ((rc = bwd_tc_main(b, w.img0, dual ? w.img1 : nullptr, w.amax, w.part0, w.part1, 1, s, true)) != 0) return rc;
   }
   if ((rc = launch_euler_bwd_reduce(w.part0, dual ? w.part1 : nullptr, grid, dual ? grid : 0, a.grad_drift, a.grad_diffusion,
                                     a.grad_diffusion_alt, s)) != 0)

@@ -178,6 +178,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 32);
   auto tile_u32 = [&](int t) { return base + OFF_TILES + (uint32_t)t * TILE_BYTES; };
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_opnd, NUM_EPI_THREADS);
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   // time tile: zero once (only chunk 0 of every row is rewritten per step)
   for (uint32_t i = threadIdx.x; i < TILE_BYTES / 16 && threadIdx.x < NUM_EPI_THREADS; i += NUM_EPI_THREADS)   // epilogue threads: they fence.proxy.async later
     reinterpret_cast<uint4*>(sm + OFF_TILES + T_TIME * TILE_BYTES)[i] = make_uint4(0u, 0u, 0u, 0u);
+  pdl_wait();   // nothing above touches global memory; everything below may depend on the previous kernel of the stream
   // schedule tables -> shared memory (every step reads them; three dependent global round trips otherwise)
   const bool sched_in_smem = S <= SCHED_MAX && a.sched.n_outputs <= SCHED_MAX;
   const float4* stab = reinterpret_cast<const float4*>(a.sched.step_tab);
@@ -744,7 +746,7 @@ int bwd_tc_grid(int64_t rows) {
 // img1 != NULL: dual diffusion — pass 0 (img0, part0) takes the rows with alt_mask != 0, pass 1 (img1 packed with a.diffusion_alt,
 // part1) the rows with alt_mask == 0; both passes run in the same launch (gridDim.y = 2).
 int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
-                int accumulate, cudaStream_t s) {
+                int accumulate, cudaStream_t s, bool pdl) {
   if ((reinterpret_cast<uintptr_t>(img0) & 15u) != 0 || (reinterpret_cast<uintptr_t>(img1) & 15u) != 0)
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
   if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
@@ -765,8 +767,17 @@ int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    kern<<<dim3(grid, dual ? 2 : 1), NUM_THREADS, SMEM_ALLOC, s>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, dual ? 2 : 1);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_ALLOC;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, p);
   };
   TS_CUDA_CHECK(a.noise.dw ? launch(euler_bwd_tc_kernel<true>) : launch(euler_bwd_tc_kernel<false>));
   return TRAJSDE_OK;
@@ -807,7 +818,7 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
       b.diffusion = a.diffusion_alt;
       if ((rc = bwd_tc_pack(b, img1, s)) != 0) return rc;
     }
-    if ((rc = bwd_tc_main(a, img0, dual ? img1 : nullptr, amax, part0, part1, 0, s)) != 0) return rc;
+    if ((rc = bwd_tc_main(a, img0, dual ? img1 : nullptr, amax, part0, part1, 0, s, false)) != 0) return rc;
   }
   euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part0, dual ? part1 : nullptr, grid, dual ? grid : 0, a.grad_drift,
                                                               a.grad_diffusion, a.grad_diffusion_alt, 0);

@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 32);
   auto tile_u32 = [&](int t) { return base + OFF_TILES + (uint32_t)t * TILE_BYTES; };
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     mbar_init(bar_opnd, NUM_EPI_THREADS);
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // nothing above touches global memory; everything below may depend on the previous kernel of the stream
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(bar_w, IMG_BYTES);
     bulk_load_1d(base, p.img, IMG_BYTES, bar_w);
@@ -591,7 +593,7 @@ int gru_bwd_tc_pack(const TrajsdeGru& w, uint8_t* img, cudaStream_t s) {
 
 int launch_gru_bwd_tc(int64_t rows, const float* y1, const float* aa_out, int64_t slab, const uint8_t* obs_mask, int64_t obs_mask_row_stride,
                       const int32_t* slot, int iter, const float* carry, const float* grad_latent, float* grad_y1, float* grad_aa_out,
-                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s) {
+                      const uint8_t* img, const uint32_t* amax_bits, float* partial, float* h_out_fwd_only, cudaStream_t s, bool pdl) {
   GruTcParams p;
   p.fwd_only = h_out_fwd_only != nullptr;
   p.h_out = h_out_fwd_only;
@@ -614,8 +616,17 @@ int launch_gru_bwd_tc(int64_t rows, const float* y1, const float* aa_out, int64_
   const int grid = bwd_tc_grid(rows);
   if (grid <= 0) return TRAJSDE_OK;
   TS_CUDA_CHECK(cudaFuncSetAttribute(gru_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
-  gru_bwd_tc_kernel<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p);
-  TS_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_ALLOC;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  TS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gru_bwd_tc_kernel, p));
   return TRAJSDE_OK;
 }
 

@@ -58,6 +58,12 @@ __device__ __forceinline__ bool elect_one() {
 // warp index as a value the compiler knows to be warp-uniform
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 
+// ---- programmatic dependent launch (chains of short dependent kernels: the encoder backward sweep) ------------------------------------
+// pdl_launch_dependents(): lets the next kernel of the stream start its prologue (barrier init, TMEM alloc) while this grid runs;
+// pdl_wait(): blocks until the previous grid has completed and its memory is visible.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA -------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
