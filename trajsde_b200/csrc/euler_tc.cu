@@ -141,6 +141,22 @@ __device__ __forceinline__ void act32_to_operand(const uint32_t (&v)[32], const 
   }
 }
 
+// Same burst, result written as the A operand of the next MMA in TENSOR memory (16 packed columns of this thread's lane): no
+// st.shared, no fence.proxy.async (= MEMBAR.ALL.CTA) — 260 clk less per dependent phase (bench_micro/tmem_a_test.cu).
+__device__ __forceinline__ void act32_to_tmem(const uint32_t (&v)[32], const Bias32& b, uint32_t taddr) {
+  uint32_t p[16];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 ba = b.v[2 * q], bb = b.v[2 * q + 1];
+    p[4 * q + 0] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 0]) + ba.x), ts_tanh_approx(__uint_as_float(v[q * 8 + 1]) + ba.y));
+    p[4 * q + 1] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 2]) + ba.z), ts_tanh_approx(__uint_as_float(v[q * 8 + 3]) + ba.w));
+    p[4 * q + 2] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 4]) + bb.x), ts_tanh_approx(__uint_as_float(v[q * 8 + 5]) + bb.y));
+    p[4 * q + 3] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[q * 8 + 6]) + bb.z), ts_tanh_approx(__uint_as_float(v[q * 8 + 7]) + bb.w));
+  }
+  tmem_st_32x32b_x16(taddr, p);
+  tc_wait_st();
+}
+
 // This row's diffusion-net column block -> registers.  In a warp whose rows use both diffusion nets the alt block is fetched
 // too and selected per lane (tcgen05.ld is warp-collective: its address must be warp-uniform).
 template <bool DUAL>
@@ -163,6 +179,7 @@ struct Epi3Ctx {
   uint8_t* st_row;
   const float* b3;      // vec + VEC_B3 + hh*32
   uint32_t tm_y, tm_f;  // TMEM addresses of this thread's 32 state / drift columns
+  uint32_t tm_oa;       // TMEM address of this thread's 16 packed operand columns (TMEM_A variants)
   uint32_t row, hh;
   float h, g, w0, w1;
   bool has_out, save_states, valid;
@@ -174,7 +191,7 @@ struct Epi3Ctx {
 };
 
 // Epilogue 3: f = z3 + b3 ; y' = y + f h + g dW (dW already in this thread's X chunks) ; outputs in place ; Y, A0 <- y'.
-template <bool MULTI>
+template <bool MULTI, bool TMEM_A>
 __device__ __forceinline__ void epi3_update(const Epi3Ctx& c) {
   uint32_t yv[32], fv[32];
   tmem_ld_32x32b_x32(c.tm_y, yv);
@@ -211,12 +228,19 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c) {
     yv[4 * q + 2] = __float_as_uint(n2); yv[4 * q + 3] = __float_as_uint(n3);
   }
   tmem_st_32x32b_x32(c.tm_y, yv);
+  if (TMEM_A) {
+    uint32_t pk[16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t pk[4];
+    for (int e = 0; e < 16; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[2 * e]), __uint_as_float(yv[2 * e + 1]));
+    tmem_st_32x32b_x16(c.tm_oa, pk);
+  } else {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
-    *reinterpret_cast<uint4*>(c.a0_row + (((c.hh * 4 + q) ^ (c.row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    for (int q = 0; q < 4; ++q) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
+      *reinterpret_cast<uint4*>(c.a0_row + (((c.hh * 4 + q) ^ (c.row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
   }
   tc_wait_st();
 }
@@ -300,6 +324,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     float* gpart = reinterpret_cast<float*>(sm + SMEM_GPART + slot * GPART_BYTES);
     // TMEM columns of a slot: [0,192) P1/P2 accumulators (P3 reuses [0,64)), [192,256) the resident fp32 state Y
     const uint32_t tm_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + hh * 32;
+    // single-diffusion variants keep the MMA A operands in the TMEM columns the dual variant needs for its second diffusion net:
+    // OA = [128,160): y -> h1f -> h2f -> y' (each written after the MMA that read the previous content has completed), OB = [160,192): h1g
+    constexpr bool TMEM_A = !DUAL;
+    const uint32_t tm_oa = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + 128 + hh * 16, tm_ob = tm_oa + 32;
     const uint32_t pair_bar = 1 + slot * 4 + quad;         // named barrier shared by the two warps that own the same rows
     uint32_t par_accA = 0, par_accB = 0, par_tma = 0, par_xfree = 0;
     uint32_t gstep = 0;
@@ -309,6 +337,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     c3.st_row = slot_sm + OFF_A1F + hh * 16384 + row * 128;
     c3.b3 = vec + VEC_B3 + hh * 32;
     c3.tm_y = tm_lane + 192;
+    c3.tm_oa = tm_oa;
     c3.tm_f = tm_lane;
     c3.row = row;
     c3.hh = hh;
@@ -344,15 +373,23 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           yv[4 * q] = v.x; yv[4 * q + 1] = v.y; yv[4 * q + 2] = v.z; yv[4 * q + 3] = v.w;
         }
         tmem_st_32x32b_x32(tm_lane + 192, yv);
+        if (TMEM_A) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[4];
+          for (int e = 0; e < 16; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[2 * e]), __uint_as_float(yv[2 * e + 1]));
+          tmem_st_32x32b_x16(tm_oa, pk);
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
-          *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int q = 0; q < 4; ++q) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[e] = pack_f16x2(__uint_as_float(yv[q * 8 + 2 * e]), __uint_as_float(yv[q * 8 + 2 * e + 1]));
+            *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
         tc_wait_st();
       }
+      tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_opnd(slot, 0));                      // A0 ready -> P1 of step 0
       mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
@@ -376,14 +413,22 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           Bias32 bf = ld_bias32(ent + hh * 32);
           tmem_ld_32x32b_x32(tm_lane, v);
           tc_wait_ld();
-          act32_to_operand(v, bf, a1f_row, row, hh * 4);
-          fence_proxy_async();
+          if (TMEM_A) {
+            act32_to_tmem(v, bf, tm_oa);
+          } else {
+            act32_to_operand(v, bf, a1f_row, row, hh * 4);
+            fence_proxy_async();
+          }
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 1));                  // A1f ready -> P2f
           bf = ld_bias32(ent + gcol + hh * 32);
           ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
-          act32_to_operand(v, bf, a1g_row, row, hh * 4);
-          fence_proxy_async();
+          if (TMEM_A) {
+            act32_to_tmem(v, bf, tm_ob);
+          } else {
+            act32_to_operand(v, bf, a1g_row, row, hh * 4);
+            fence_proxy_async();
+          }
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 0));                  // A1g ready -> P2g
         }
@@ -397,8 +442,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           const Bias32 b2 = ld_bias32(vec + VEC_B2 + hh * 32);
           tmem_ld_32x32b_x32(tm_lane, v);
           tc_wait_ld();
-          act32_to_operand(v, b2, a0_row, row, hh * 4);
-          fence_proxy_async();
+          if (TMEM_A) {
+            act32_to_tmem(v, b2, tm_oa);
+          } else {
+            act32_to_operand(v, b2, a0_row, row, hh * 4);
+            fence_proxy_async();
+          }
           tc_fence_before();
           mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
           mbar_wait(bar_acc(slot, 0), par_accA);
@@ -446,8 +495,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         c3.ob = so.x;
         c3.nout = so.y;
         c3.has_out = so.y > 0;
-        if (so.y > 1) epi3_update<true>(c3);
-        else epi3_update<false>(c3);
+        if (so.y > 1) epi3_update<true, TMEM_A>(c3);
+        else epi3_update<false, TMEM_A>(c3);
         if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
         fence_proxy_async();
         tc_fence_before();
@@ -470,6 +519,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       const uint64_t dhi = umma_desc_sw128(0);
       auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
       const uint32_t aA0 = slot_u32 + OFF_A0, aA1f = slot_u32 + OFF_A1F, aA1g = slot_u32 + OFF_A1G;
+      constexpr bool TMEM_A = !DUAL;
+      const uint32_t t_oa = d_base + 128, t_ob = d_base + 160;   // TMEM operand columns (lane field 0: all 128 rows)
       const uint32_t aB1 = base + IMG_B1, aW2 = base + IMG_W2, aV2 = base + IMG_V2, aV2a = base + IMG_V2A, aW3 = base + IMG_W3;
       uint32_t par_op0 = 0, par_op1 = 0;
       mbar_wait(bar_w, 0);
@@ -481,7 +532,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aB1 + 32 * kk), idesc_p1, kk > 0);
+              else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
+            }
             tc_commit(bar_acc(slot, 0));
           }
           __syncwarp();
@@ -491,7 +545,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW2 + 32 * kk), idesc_64, kk > 0);
+              else tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
+            }
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
@@ -501,7 +558,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (TMEM_A) tc_mma_f16_ts(d_base + 64, t_ob + 8 * kk, D(aV2 + 32 * kk), idesc_64, kk > 0);
+              else tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
+            }
             if (DUAL) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
@@ -515,7 +575,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW3 + 32 * kk), idesc_64, kk > 0);
+              else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
+            }
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
