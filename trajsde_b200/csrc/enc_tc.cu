@@ -22,9 +22,10 @@ using namespace tc;
 namespace {
 
 constexpr int TILE_M = 128;
-constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 20 * 32;      // 16 epilogue warps + MMA warp + 3 idle warps (setmaxnreg works on warpgroups)
-constexpr int EPI_REGS = 112, AUX_REGS = 32;
+constexpr int NUM_EPI_WARPS = 8;           // thread = one row x one 32-channel half
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = NUM_EPI_THREADS + 128;   // + one warpgroup: MMA-issuer warp and three idle warps (setmaxnreg is per warpgroup)
+constexpr int EPI_REGS = 216, AUX_REGS = 64;
 constexpr int S_MAX = 32;
 
 // ---- packed image (bytes) -------------------------------------------------------------------------------------------------
@@ -37,16 +38,18 @@ constexpr uint32_t IMG_BYTES = IMG_BIAS1 + S_MAX * 192 * 4;   // 159744
 constexpr int VEC_B2 = 0, VEC_C2 = 64, VEC_C2A = 128, VEC_B3 = 192, VEC_W3G = 256, VEC_W3GA = 320, VEC_C3 = 384, VEC_C3A = 385;
 constexpr int VEC_UB1 = 512, VEC_RB1 = 576, VEC_UB2 = 640, VEC_RB2 = 704, VEC_NB1 = 768, VEC_NB2 = 832;
 
-// ---- shared memory map -------------------------------------------------------------------------------------------------------
-constexpr uint32_t OFF_AH = IMG_BYTES, OFF_AX = OFF_AH + 16384, OFF_A1F = OFF_AX + 16384, OFF_A1G = OFF_A1F + 16384;
-constexpr uint32_t OFF_GPART = OFF_A1G + 16384;             // [4 quarters][128 rows] fp32
-constexpr uint32_t OFF_BARS = OFF_GPART + 4 * TILE_M * 4;
+// ---- shared memory map: weights + bias rows only — every MMA A operand lives in tensor memory ---------------------------------
+constexpr uint32_t OFF_GPART = IMG_BYTES;                    // [2 halves][128 rows] fp32 partial diffusion dots
+constexpr uint32_t OFF_BARS = OFF_GPART + 2 * TILE_M * 4;
 constexpr uint32_t SMEM_TOTAL = OFF_BARS + 128;
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
 
-// TMEM columns
-constexpr uint32_t TM_Y = 192, TM_G1 = 256, TM_ZR = 320, TM_UP = 384, TM_RP = 448, TM_ZN = 256, TM_N = 320;
+// ---- TMEM columns ----------------------------------------------------------------------------------------------------------------
+// [0,192)   accumulators: SDE phases (P1 192 wide in the dual variant), then reused by the GRU phases (G1 [zu|zr] 128, G2 u'|r', G3 zn, G4 n)
+// [192,256) fp32 latent state Y
+// [256,384) A operands, fp16 pairs (32 columns each): AH (y / h2f / y1 / r*y1 / h'), AX (x), A1F (h1f / tu / tn), A1G (h1g / tr)
+constexpr uint32_t TM_Y = 192, TM_AH = 256, TM_AX = 288, TM_A1F = 320, TM_A1G = 352;
 
 struct EncParams {
   TrajsdeEncFwdArgs a;
@@ -117,43 +120,40 @@ __global__ void enc_pack_kernel(TrajsdeEncFwdArgs a, uint8_t* __restrict__ img, 
   }
 }
 
-// act(acc + bias) for 16 accumulator columns -> fp16 -> two 16-byte chunks of an operand row
+// fp16 pairs of this thread's 32 values -> its 16 packed operand columns
+__device__ __forceinline__ void st_operand32(uint32_t taddr, const float (&t)[32]) {
+  uint32_t p[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) p[e] = pack_f16x2(t[2 * e], t[2 * e + 1]);
+  tmem_st_32x32b_x16(taddr, p);
+}
 template <bool SIGMOID>
 __device__ __forceinline__ float act1(float x) {
   return SIGMOID ? fmaf(0.5f, ts_tanh_approx(0.5f * x), 0.5f) : ts_tanh_approx(x);
 }
-__device__ __forceinline__ void store16_operand(const float (&t)[16], uint8_t* row_base, uint32_t row, uint32_t chunk0) {
+// tanh(acc + bias) for 32 accumulator columns -> operand columns
+__device__ __forceinline__ void tanh32_to_operand(const uint32_t (&v)[32], const float* __restrict__ bias, uint32_t taddr) {
+  float t[32];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t p[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) p[e] = pack_f16x2(t[q * 8 + 2 * e], t[q * 8 + 2 * e + 1]);
-    *reinterpret_cast<uint4*>(row_base + (((chunk0 + q) ^ (row & 7u)) << 4)) = make_uint4(p[0], p[1], p[2], p[3]);
-  }
-}
-__device__ __forceinline__ void tanh16_to_operand(const uint32_t (&v)[16], const float* __restrict__ bias, uint8_t* row_base,
-                                                  uint32_t row, uint32_t chunk0) {
-  float t[16];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(bias + 4 * q);
     t[4 * q] = ts_tanh_approx(__uint_as_float(v[4 * q]) + b.x);
     t[4 * q + 1] = ts_tanh_approx(__uint_as_float(v[4 * q + 1]) + b.y);
     t[4 * q + 2] = ts_tanh_approx(__uint_as_float(v[4 * q + 2]) + b.z);
     t[4 * q + 3] = ts_tanh_approx(__uint_as_float(v[4 * q + 3]) + b.w);
   }
-  store16_operand(t, row_base, row, chunk0);
+  st_operand32(taddr, t);
 }
 
 template <bool DUAL>
-__device__ __forceinline__ void ld_g16(uint32_t tm_uniform, uint32_t tm_alt, bool w_mixed, bool use_alt, uint32_t (&v)[16]) {
-  tmem_ld_32x32b_x16(tm_uniform, v);
+__device__ __forceinline__ void ld_g32(uint32_t tm_uniform, uint32_t tm_alt, bool w_mixed, bool use_alt, uint32_t (&v)[32]) {
+  tmem_ld_32x32b_x32(tm_uniform, v);
   if (DUAL && w_mixed) {
-    uint32_t v2[16];
-    tmem_ld_32x32b_x16(tm_alt, v2);
+    uint32_t v2[32];
+    tmem_ld_32x32b_x32(tm_alt, v2);
     tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = use_alt ? v2[j] : v[j];
+    for (int j = 0; j < 32; ++j) v[j] = use_alt ? v2[j] : v[j];
   } else {
     tc_wait_ld();
   }
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar_opnd(i), NUM_EPI_WARPS * 32);
+      mbar_init(bar_opnd(i), NUM_EPI_THREADS);
       mbar_init(bar_acc(i), 1);
     }
     mbar_fence_init();
@@ -203,15 +203,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
     // =============================================== EPILOGUE WARPS ===============================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
     const int quad = warp & 3;                             // TMEM lane quadrant (= warp index % 4)
-    const uint32_t cq = warp >> 2;                         // 16-channel quarter of the row owned by this thread
+    const uint32_t hh = (uint32_t)warp >> 2;               // 32-channel half of the row owned by this thread
     const uint32_t row = quad * 32 + lane;
-    uint8_t* ah_row = sm + OFF_AH + row * 128;
-    uint8_t* ax_row = sm + OFF_AX + row * 128;
-    uint8_t* a1f_row = sm + OFF_A1F + row * 128;
-    uint8_t* a1g_row = sm + OFF_A1G + row * 128;
     float* gpart = reinterpret_cast<float*>(sm + OFF_GPART);
-    const uint32_t tm = tmem_base + ((uint32_t)(quad * 32) << 16) + cq * 16;
-    const uint32_t quad_bar = 1 + quad;                    // named barrier of the 4 warps that share these rows
+    const uint32_t tml = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t tm = tml + hh * 32;                     // accumulator / state columns of this thread
+    const uint32_t o_ah = tml + TM_AH + hh * 16, o_ax = tml + TM_AX + hh * 16, o_a1f = tml + TM_A1F + hh * 16, o_a1g = tml + TM_A1G + hh * 16;
+    const uint32_t pair_bar = 1 + quad;                    // named barrier of the two warps that share these rows
     uint32_t par_accA = 0, par_accB = 0;
     mbar_wait(bar_w, 0);
 
@@ -223,27 +221,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
       const bool w_all_alt = DUAL && __all_sync(0xffffffffu, use_alt);
       const bool w_mixed = DUAL && !w_all_alt && __any_sync(0xffffffffu, use_alt);
       const uint32_t ucol = w_all_alt ? 128 : 64;
-      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2) + cq * 16;
-      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G) + cq * 16;
+      const float* c2v = vec + (use_alt ? VEC_C2A : VEC_C2) + hh * 32;
+      const float* w3v = vec + (use_alt ? VEC_W3GA : VEC_W3G) + hh * 32;
       const float c3b = vec[use_alt ? VEC_C3A : VEC_C3];
 
       // ---- prologue: h0 -> Y (TMEM) + AH --------------------------------------------------------------------------------
       {
-        uint32_t yv[16];
-        float t[16];
+        uint32_t yv[32];
+        float t[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) v = *reinterpret_cast<const float4*>(a.h0 + grow * a.h0_row_stride + cq * 16 + 4 * q);
+          if (valid) v = *reinterpret_cast<const float4*>(a.h0 + grow * a.h0_row_stride + hh * 32 + 4 * q);
           t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
         }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) yv[j] = __float_as_uint(t[j]);
-        tmem_st_32x32b_x16(tm + TM_Y, yv);
-        store16_operand(t, ah_row, row, cq * 2);
+        for (int j = 0; j < 32; ++j) yv[j] = __float_as_uint(t[j]);
+        tmem_st_32x32b_x32(tm + TM_Y, yv);
+        st_operand32(o_ah, t);
         tc_wait_st();
       }
-      fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_opnd(0));                            // AH ready -> P1 of iteration 0
 
@@ -253,21 +250,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         const int slot_t = a.slot[it];
         const float* b1row = bias1_tab + it * 192;
         // ---- early global loads of this iteration: GRU input x, Brownian increments, observation mask ----------------------
-        float4 xv[4], dwv[4];
+        float4 xv[8], dwv[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
           xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           dwv[q] = xv[q];
         }
         bool observed = false;
         if (valid) {
-          const float* xs = a.aa_out + ((int64_t)slot_t * a.rows + grow) * 64 + cq * 16;
+          const float* xs = a.aa_out + ((int64_t)slot_t * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) xv[q] = ld_nc_f4(xs + 4 * q);
+          for (int q = 0; q < 8; ++q) xv[q] = ld_nc_f4(xs + 4 * q);
           if (HAS_DW) {
-            const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+            const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dwv[q] = ld_nc_f4(ds + 4 * q);
+            for (int q = 0; q < 8; ++q) dwv[q] = ld_nc_f4(ds + 4 * q);
           }
           observed = a.obs_mask[grow * a.obs_mask_row_stride + slot_t] != 0;
         }
@@ -277,22 +274,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         par_accA ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tm, v);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm, v);
           tc_wait_ld();
-          tanh16_to_operand(v, b1row + cq * 16, a1f_row, row, cq * 2);
-          fence_proxy_async();
+          tanh32_to_operand(v, b1row + hh * 32, o_a1f);
+          tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_opnd(1));                        // h1f -> P2f
-          ld_g16<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
-          tanh16_to_operand(v, b1row + gcol + cq * 16, a1g_row, row, cq * 2);
-          float t[16];                                     // x -> fp16 operand (AX was last read by G3 of the previous iteration)
+          ld_g32<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
+          tanh32_to_operand(v, b1row + gcol + hh * 32, o_a1g);
+          float t[32];                                     // x -> fp16 operand (AX was last read by G3 of the previous iteration)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 8; ++q) {
             t[4 * q] = xv[q].x; t[4 * q + 1] = xv[q].y; t[4 * q + 2] = xv[q].z; t[4 * q + 3] = xv[q].w;
           }
-          store16_operand(t, ax_row, row, cq * 2);
-          fence_proxy_async();
+          st_operand32(o_ax, t);
+          tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_opnd(0));                        // h1g (and x) -> P2g
         }
@@ -301,20 +298,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         par_accB ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tm, v);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm, v);
           tc_wait_ld();
-          tanh16_to_operand(v, vec + VEC_B2 + cq * 16, ah_row, row, cq * 2);
-          fence_proxy_async();
+          tanh32_to_operand(v, vec + VEC_B2 + hh * 32, o_ah);
+          tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_opnd(1));                        // h2f -> P3
           mbar_wait(bar_acc(0), par_accA);                 // P2g
           par_accA ^= 1;
           tc_fence_after();
-          ld_g16<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
+          ld_g32<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
           float gd = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
+          for (int j = 0; j < 32; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(c2v + j);
             const float4 w = *reinterpret_cast<const float4*>(w3v + j);
             gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
@@ -322,50 +319,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
             gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
             gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
           }
-          gpart[cq * TILE_M + row] = gd;
+          gpart[hh * TILE_M + row] = gd;
         }
         // ---- epilogue 3: Euler update ----------------------------------------------------------------------------------------------
         if (!HAS_DW) {
           const float sqrt_h = sqrtf(h);
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
             const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
-                                             (uint32_t)(cq * 4 + q));
+                                             (uint32_t)(hh * 8 + q));
             dwv[q] = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
           }
         }
         mbar_wait(bar_acc(1), par_accB);                   // P3
         par_accB ^= 1;
         tc_fence_after();
-        named_bar_sync(quad_bar, 128);                     // the four partial diffusion dots of every row are in smem
-        const float g = __fdividef(1.0f, 1.0f + __expf(-(((gpart[row] + gpart[TILE_M + row]) + (gpart[2 * TILE_M + row] + gpart[3 * TILE_M + row])) + c3b)));
+        named_bar_sync(pair_bar, 64);                      // both partial diffusion dots of every row are in smem
+        const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
         {
-          uint32_t yv[16], fv[16];
-          tmem_ld_32x32b_x16(tm + TM_Y, yv);
-          tmem_ld_32x32b_x16(tm, fv);
+          uint32_t yv[32], fv[32];
+          tmem_ld_32x32b_x32(tm + TM_Y, yv);
+          tmem_ld_32x32b_x32(tm, fv);
           tc_wait_ld();
-          float t[16];
+          float t[32];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + cq * 16 + 4 * q);
+          for (int q = 0; q < 8; ++q) {
+            const float4 b3 = *reinterpret_cast<const float4*>(vec + VEC_B3 + hh * 32 + 4 * q);
             t[4 * q] = fmaf(g, dwv[q].x, fmaf(__uint_as_float(fv[4 * q]) + b3.x, h, __uint_as_float(yv[4 * q])));
             t[4 * q + 1] = fmaf(g, dwv[q].y, fmaf(__uint_as_float(fv[4 * q + 1]) + b3.y, h, __uint_as_float(yv[4 * q + 1])));
             t[4 * q + 2] = fmaf(g, dwv[q].z, fmaf(__uint_as_float(fv[4 * q + 2]) + b3.z, h, __uint_as_float(yv[4 * q + 2])));
             t[4 * q + 3] = fmaf(g, dwv[q].w, fmaf(__uint_as_float(fv[4 * q + 3]) + b3.w, h, __uint_as_float(yv[4 * q + 3])));
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) yv[j] = __float_as_uint(t[j]);
-          tmem_st_32x32b_x16(tm + TM_Y, yv);               // Y <- y1
-          store16_operand(t, ah_row, row, cq * 2);
-          if (cq == 0 && valid) a.g_out[(int64_t)it * a.rows + grow] = g;
-          if (a.y1_out && valid) {                       // pre-GRU state, saved for the backward call
-            float* dst = a.y1_out + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+          for (int j = 0; j < 32; ++j) yv[j] = __float_as_uint(t[j]);
+          tmem_st_32x32b_x32(tm + TM_Y, yv);               // Y <- y1
+          st_operand32(o_ah, t);
+          if (hh == 0 && valid) a.g_out[(int64_t)it * a.rows + grow] = g;
+          if (a.y1_out && valid) {                         // pre-GRU state, saved for the backward call
+            float* dst = a.y1_out + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+            for (int q = 0; q < 8; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
           }
           tc_wait_st();
         }
-        fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(0));                          // y1 (and x) -> G1
         // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
@@ -373,38 +369,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         par_accA ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tm + TM_G1, v);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm, v);
           tc_wait_ld();
-          tanh16_to_operand(v, vec + VEC_UB1 + cq * 16, a1f_row, row, cq * 2);
-          tmem_ld_32x32b_x16(tm + TM_ZR, v);
+          tanh32_to_operand(v, vec + VEC_UB1 + hh * 32, o_a1f);
+          tmem_ld_32x32b_x32(tm + 64, v);
           tc_wait_ld();
-          tanh16_to_operand(v, vec + VEC_RB1 + cq * 16, a1g_row, row, cq * 2);
+          tanh32_to_operand(v, vec + VEC_RB1 + hh * 32, o_a1g);
+          tc_wait_st();
         }
-        fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(1));                          // tu, tr -> G2
         // ---- GRU epilogue 2: u = sigmoid(u' + ub2) (kept), r = sigmoid(r' + rb2), r * y1 -> AH ---------------------------------------------
-        float u[16];
+        float u[32];
         mbar_wait(bar_acc(1), par_accB);                   // G2
         par_accB ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16], yv[16];
-          tmem_ld_32x32b_x16(tm + TM_UP, v);
-          tmem_ld_32x32b_x16(tm + TM_Y, yv);
+          uint32_t v[32], yv[32];
+          tmem_ld_32x32b_x32(tm, v);
+          tmem_ld_32x32b_x32(tm + TM_Y, yv);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) u[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_UB2 + cq * 16 + j]);
-          tmem_ld_32x32b_x16(tm + TM_RP, v);
+          for (int j = 0; j < 32; ++j) u[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_UB2 + hh * 32 + j]);
+          tmem_ld_32x32b_x32(tm + 64, v);
           tc_wait_ld();
-          float t[16];
+          float t[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            t[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_RB2 + cq * 16 + j]) * __uint_as_float(yv[j]);
-          store16_operand(t, ah_row, row, cq * 2);         // AH (y1 as fp16) was consumed by G1
+          for (int j = 0; j < 32; ++j)
+            t[j] = act1<true>(__uint_as_float(v[j]) + vec[VEC_RB2 + hh * 32 + j]) * __uint_as_float(yv[j]);
+          st_operand32(o_ah, t);                           // AH (y1 as fp16) was consumed by G1
+          tc_wait_st();
         }
-        fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(0));                          // r*y1 -> G3
         // ---- GRU epilogue 3: tn = tanh(zn + nb1) --------------------------------------------------------------------------------------------
@@ -412,12 +408,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         par_accA ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tm + TM_ZN, v);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tm, v);
           tc_wait_ld();
-          tanh16_to_operand(v, vec + VEC_NB1 + cq * 16, a1f_row, row, cq * 2);
+          tanh32_to_operand(v, vec + VEC_NB1 + hh * 32, o_a1f);
+          tc_wait_st();
         }
-        fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd(1));                          // tn -> G4
         // ---- GRU epilogue 4: h' = (1-u) (n + nb2) + u y1 ; masked ; state, operand, latent ---------------------------------------------------
@@ -425,29 +421,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         par_accB ^= 1;
         tc_fence_after();
         {
-          uint32_t v[16], yv[16];
-          tmem_ld_32x32b_x16(tm + TM_N, v);
-          tmem_ld_32x32b_x16(tm + TM_Y, yv);
+          uint32_t v[32], yv[32];
+          tmem_ld_32x32b_x32(tm, v);
+          tmem_ld_32x32b_x32(tm + TM_Y, yv);
           tc_wait_ld();
-          float t[16];
+          float t[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
             const float y1 = __uint_as_float(yv[j]);
-            const float n = __uint_as_float(v[j]) + vec[VEC_NB2 + cq * 16 + j];
+            const float n = __uint_as_float(v[j]) + vec[VEC_NB2 + hh * 32 + j];
             const float hn = fmaf(u[j], y1, (1.0f - u[j]) * n);
             t[j] = observed ? hn : y1;
             yv[j] = __float_as_uint(t[j]);
           }
-          tmem_st_32x32b_x16(tm + TM_Y, yv);
-          store16_operand(t, ah_row, row, cq * 2);         // AH (r*y1) was consumed by G3
+          tmem_st_32x32b_x32(tm + TM_Y, yv);
+          st_operand32(o_ah, t);                           // AH (r*y1) was consumed by G3
           if (valid) {
-            float* dst = a.latent + ((int64_t)it * a.rows + grow) * 64 + cq * 16;
+            float* dst = a.latent + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+            for (int q = 0; q < 8; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
           }
           tc_wait_st();
         }
-        fence_proxy_async();
         tc_fence_before();
         if (it + 1 < S) mbar_arrive(bar_opnd(0));          // h' -> P1 of the next iteration
       }
@@ -456,21 +451,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     if (warp == NUM_EPI_WARPS) {
       // =============================================== MMA ISSUER =====================================================
-      // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit
+      // warp-uniform loop (descriptors stay in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit.
+      // A operands come from tensor memory (fp16 pairs, 8 columns per K = 16 instruction), B operands from the staged weight tiles.
       const uint32_t idesc_p1 = umma_idesc_f16(TILE_M, DUAL ? 192u : 128u);
       const uint32_t idesc_64 = umma_idesc_f16(TILE_M, 64);
       const uint32_t idesc_128 = umma_idesc_f16(TILE_M, 128);
       const uint64_t dhi = umma_desc_sw128(0);
       auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
-      const uint32_t aAH = base + OFF_AH, aAX = base + OFF_AX, aA1f = base + OFF_A1F, aA1g = base + OFF_A1G;
       const uint32_t d0 = tmem_base;
+      const uint32_t aAH = d0 + TM_AH, aAX = d0 + TM_AX, aA1f = d0 + TM_A1F, aA1g = d0 + TM_A1G;
       uint32_t par_op0 = 0, par_op1 = 0;
       mbar_wait(bar_w, 0);
       auto wait0 = [&]() { mbar_wait(bar_opnd(0), par_op0); par_op0 ^= 1; tc_fence_after(); };
       auto wait1 = [&]() { mbar_wait(bar_opnd(1), par_op1); par_op1 ^= 1; tc_fence_after(); };
-      auto mma4 = [&](uint32_t d, uint32_t aaddr, uint32_t baddr, uint32_t idesc, bool acc_first) {
+      auto mma4 = [&](uint32_t d, uint32_t a_tmem, uint32_t baddr, uint32_t idesc, bool acc_first) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d, D(aaddr + 32 * kk), D(base + baddr + 32 * kk), idesc, (acc_first || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < 4; ++kk) tc_mma_f16_ts(d, a_tmem + 8 * kk, D(base + baddr + 32 * kk), idesc, (acc_first || kk > 0) ? 1u : 0u);
       };
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         for (int it = 0; it < S; ++it) {
@@ -490,29 +486,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           wait1();                                                                                         // P3
           if (elect_one()) { mma4(d0, aAH, IMG_W3, idesc_64, false); tc_commit(bar_acc(1)); }
           __syncwarp();
-          wait0();                                                                                         // G1
+          wait0();                                                                                         // G1: [zu|zr] -> [0,128)
           if (elect_one()) {
-            mma4(d0 + TM_G1, aAH, IMG_UR1H, idesc_128, false);
-            mma4(d0 + TM_G1, aAX, IMG_UR1X, idesc_128, true);
+            mma4(d0, aAH, IMG_UR1H, idesc_128, false);
+            mma4(d0, aAX, IMG_UR1X, idesc_128, true);
             tc_commit(bar_acc(0));
           }
           __syncwarp();
-          wait1();                                                                                         // G2
+          wait1();                                                                                         // G2: u' -> [0,64), r' -> [64,128)
           if (elect_one()) {
-            mma4(d0 + TM_UP, aA1f, IMG_U2, idesc_64, false);
-            mma4(d0 + TM_RP, aA1g, IMG_R2, idesc_64, false);
+            mma4(d0, aA1f, IMG_U2, idesc_64, false);
+            mma4(d0 + 64, aA1g, IMG_R2, idesc_64, false);
             tc_commit(bar_acc(1));
           }
           __syncwarp();
-          wait0();                                                                                         // G3
+          wait0();                                                                                         // G3: zn -> [0,64)
           if (elect_one()) {
-            mma4(d0 + TM_ZN, aAX, IMG_N1X, idesc_64, false);
-            mma4(d0 + TM_ZN, aAH, IMG_N1RH, idesc_64, true);
+            mma4(d0, aAX, IMG_N1X, idesc_64, false);
+            mma4(d0, aAH, IMG_N1RH, idesc_64, true);
             tc_commit(bar_acc(0));
           }
           __syncwarp();
-          wait1();                                                                                         // G4
-          if (elect_one()) { mma4(d0 + TM_N, aA1f, IMG_N2, idesc_64, false); tc_commit(bar_acc(1)); }
+          wait1();                                                                                         // G4: n -> [0,64)
+          if (elect_one()) { mma4(d0, aA1f, IMG_N2, idesc_64, false); tc_commit(bar_acc(1)); }
           __syncwarp();
         }
       }
