@@ -26,7 +26,7 @@ int set_error(int code, const char* fmt, ...);
 
 // ---- Philox4x32-10 + Box–Muller ----------------------------------------------------------------------------------
 // Stream definition: key = (seed_lo, seed_hi); counter = (grow_lo, grow_hi, step, chunk) where
-// grow = global row id, step = step_offset + k, chunk = channel/4.  One call -> 4 uint32 -> 4 standard normals for
+// grow = global row id, step = step_offset + k, chunk = channel/4.  One call -> 4 uint32 -> 4 increments N(0, h) for
 // channels 4*chunk .. 4*chunk+3 via two Box–Muller pairs.
 __host__ __device__ __forceinline__ uint32_t ts_mulhi(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -54,17 +54,35 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // uniform in (0,1]: (x + 0.5) * 2^-32 evaluated in fp32 (never 0).
 __device__ __forceinline__ float ts_u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
-// 4 standard normals for (global row, step, chunk).
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t grow, uint32_t step, uint32_t chunk) {
-  uint4 r = philox4x32_10(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), step, chunk),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-  float u0 = ts_u01(r.x), u1 = ts_u01(r.y), u2 = ts_u01(r.z), u3 = ts_u01(r.w);
-  float r0 = sqrtf(-2.0f * __logf(u0));
-  float r1 = sqrtf(-2.0f * __logf(u2));
+// 4 Brownian increments N(0, h) for (global row, step, chunk): Box–Muller on the four Philox words, radius scaled by sqrt(h).
+// Every kernel (and trajsde_philox_dw, which dumps the stream for replays) calls THIS function, and every product is an explicit
+// round-to-nearest multiply, so the increments are bit-identical wherever they are drawn.  The transcendental steps are single
+// MUFU instructions (lg2 / sqrt / sin / cos .approx): u = (x + 0.5) 2^-32 lies in [1.2e-10, 1], so no denormal or range handling is
+// needed, and the angle 2 pi u is formed directly by the integer -> float conversion FMA.
+__device__ __forceinline__ float ts_lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ts_sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void ts_sincos_approx(float x, float& s, float& c) {
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
+}
+__device__ __forceinline__ float4 philox_dw4(uint64_t seed, uint64_t grow, uint32_t step, uint32_t chunk, float sqrt_h) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), step, chunk),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u)
+  const float r0 = __fmul_rn(ts_sqrt_approx(__fmul_rn(ts_lg2_approx(ts_u01(r.x)), -1.3862943611198906f)), sqrt_h);
+  const float r1 = __fmul_rn(ts_sqrt_approx(__fmul_rn(ts_lg2_approx(ts_u01(r.z)), -1.3862943611198906f)), sqrt_h);
   float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u1, &s0, &c0);
-  __sincosf(6.283185307179586f * u3, &s1, &c1);
-  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+  ts_sincos_approx(__fmaf_rn((float)r.y, 1.4629180792671596e-09f, 7.314590396335798e-10f), s0, c0);   // 2 pi (x + 0.5) 2^-32
+  ts_sincos_approx(__fmaf_rn((float)r.w, 1.4629180792671596e-09f, 7.314590396335798e-10f), s1, c1);
+  return make_float4(__fmul_rn(r0, c0), __fmul_rn(r0, s0), __fmul_rn(r1, c1), __fmul_rn(r1, s1));
 }
 
 // ---- small math helpers -------------------------------------------------------------------------------------------

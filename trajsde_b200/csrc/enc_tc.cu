@@ -326,9 +326,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           const float sqrt_h = sqrtf(h);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
-                                             (uint32_t)(hh * 8 + q));
-            dwv[q] = make_float4(n4.x * sqrt_h, n4.y * sqrt_h, n4.z * sqrt_h, n4.w * sqrt_h);
+            dwv[q] = philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
+                                (uint32_t)(hh * 8 + q), sqrt_h);
           }
         }
         mbar_wait(bar_acc(1), par_accB);                   // P3

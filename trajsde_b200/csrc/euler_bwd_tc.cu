@@ -367,12 +367,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
             const float sqrt_h = sqrtf(h);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
-                                               (uint32_t)(hh * 8 + q));
-              qp = fmaf(adj[4 * q], __fmul_rn(n4.x, sqrt_h), qp);
-              qp = fmaf(adj[4 * q + 1], __fmul_rn(n4.y, sqrt_h), qp);
-              qp = fmaf(adj[4 * q + 2], __fmul_rn(n4.z, sqrt_h), qp);
-              qp = fmaf(adj[4 * q + 3], __fmul_rn(n4.w, sqrt_h), qp);
+              const float4 n4 = philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
+                                           (uint32_t)(hh * 8 + q), sqrt_h);
+              qp = fmaf(adj[4 * q], n4.x, qp);
+              qp = fmaf(adj[4 * q + 1], n4.y, qp);
+              qp = fmaf(adj[4 * q + 2], n4.z, qp);
+              qp = fmaf(adj[4 * q + 3], n4.w, qp);
             }
           }
           qbuf[hh * TILE_M + row] = valid ? qp : 0.f;

@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(EX_THREADS, 1) euler_fwd_exact_kernel(const Ex
             dw = valid[i] ? a.noise.dw[((int64_t)k * a.rows + r[i]) * 64 + tx + 16 * j] : 0.f;
           } else {
             const int c = tx + 16 * j;
-            const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)r[i] + a.noise.row_offset,
-                                             a.noise.step_offset + (uint32_t)k, (uint32_t)(c >> 2));
-            const float nn = (c & 3) == 0 ? n4.x : (c & 3) == 1 ? n4.y : (c & 3) == 2 ? n4.z : n4.w;
-            dw = __fmul_rn(nn, sqrt_h);
+            const float4 n4 = philox_dw4(a.noise.seed, (uint64_t)r[i] + a.noise.row_offset,
+                                         a.noise.step_offset + (uint32_t)k, (uint32_t)(c >> 2), sqrt_h);
+            dw = (c & 3) == 0 ? n4.x : (c & 3) == 1 ? n4.y : (c & 3) == 2 ? n4.z : n4.w;
           }
           yn[j] = __fadd_rn(__fadd_rn(y[i][j], __fmul_rn(f[i][j], h)), __fmul_rn(g, dw));
         }
@@ -285,9 +284,8 @@ __global__ void philox_dw_kernel(TrajsdeSchedule sched, TrajsdeNoise noise, int6
     const int64_t row = rk % rows;
     const int k = (int)(rk / rows);
     const float sqrt_h = sqrtf(sched.step_tab[4 * k + 1]);
-    float4 n4 = philox_normal4(noise.seed, (uint64_t)row + noise.row_offset, noise.step_offset + (uint32_t)k, chunk);
-    float4 o = make_float4(__fmul_rn(n4.x, sqrt_h), __fmul_rn(n4.y, sqrt_h), __fmul_rn(n4.z, sqrt_h), __fmul_rn(n4.w, sqrt_h));
-    *reinterpret_cast<float4*>(out + idx * 4) = o;
+    *reinterpret_cast<float4*>(out + idx * 4) =
+        philox_dw4(noise.seed, (uint64_t)row + noise.row_offset, noise.step_offset + (uint32_t)k, chunk, sqrt_h);
   }
 }
 

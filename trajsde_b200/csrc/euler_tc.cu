@@ -476,12 +476,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
           par_tma ^= 1;
         } else {                                             // draw this thread's 32 increments into X while P3 runs
-#pragma unroll 1
-          for (int q = 0; q < 8; ++q) {
-            const float4 n4 = philox_normal4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
-                                             (uint32_t)(hh * 8 + q));
-            *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) = make_float4(n4.x * sc.y, n4.y * sc.y, n4.z * sc.y, n4.w * sc.y);
-          }
+#pragma unroll 2
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
+                philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
         }
         mbar_wait(bar_acc(slot, 1), par_accB);
         par_accB ^= 1;
