@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         const int ob = obeg[k], oe = obeg[k + 1];
 
         TL_MARK(0);   // (loop overhead / previous e5 tail)
-        // ================= step start: A' = A + sum w1 gy ; E = A' + sum w0 gy ; df ; q = A'.dW ; y -> operand =================
+        // ================= step start: y -> operand (P1 starts) ; A' = A + sum w1 gy ; E = A' + sum w0 gy ; df ; q = A'.dW =================
         float e_[32];
         {
           to_own_row(py);
@@ -323,6 +323,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
               pgy[q] = py[q];
             }
           }
+          TL_MARK(1);   // SS part 1: transposes
+          // previous step's trailing weight-gradient MMAs must have finished reading Y / DF(dz1g) / TIME
+          if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);
+          TL_MARK(2);   // wait bar_wg
+          // P1 needs only y (and the bias rows): hand it over first, so that its hand-shake and MMAs run under the adjoint update below
+          float t[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            t[4 * q] = py[q].x; t[4 * q + 1] = py[q].y; t[4 * q + 2] = py[q].z; t[4 * q + 3] = py[q].w;
+          }
+          st_row32(trow(T_Y), row, hh, t);
+          if (eid < 128) {                                       // layer-1 bias rows of this step (time features folded in)
+            const int c = eid & 63, o = eid < 64 ? 0 : VEC_C1;
+            brow[eid] = fmaf(vec[o + VEC_W1C + c], cs, fmaf(vec[o + VEC_W1S + c], sn, vec[o + VEC_B1 + c]));
+          }
+          if (hh == 0)
+            *reinterpret_cast<uint4*>(trow(T_TIME) + ((0u ^ (row & 7u)) << 4)) = make_uint4(pack_f16x2(1.f, sn), pack_f16x2(cs, 0.f), 0u, 0u);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd);                                   // y, time tile -> P1
+        {
 #pragma unroll
           for (int j = 0; j < 32; ++j) e_[j] = adj[j];
           if (a.grad_ys && oe > ob) {
@@ -383,31 +405,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
             for (int j = 0; j < 32; ++j) ev[j] = __float_as_uint(e_[j]);
             tmem_st_32x32b_x32(tm + TM_E, ev);
           }
-          TL_MARK(1);   // SS part 1: transposes, adjoint update, q, E
-          // previous step's trailing weight-gradient MMAs must have finished reading Y / DF(dz1g) / TIME
-          if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);
-          TL_MARK(2);   // wait bar_wg
+          // df -> operand tile (read by D1 and its trailing dW3 product; made visible by the fence of epilogue 1)
           float t[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) t[j] = h * adj[j];
           st_row32(trow(T_DF), row, hh, t);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            t[4 * q] = py[q].x; t[4 * q + 1] = py[q].y; t[4 * q + 2] = py[q].z; t[4 * q + 3] = py[q].w;
-          }
-          st_row32(trow(T_Y), row, hh, t);
-          if (eid < 128) {                                       // layer-1 bias rows of this step (time features folded in)
-            const int c = eid & 63, o = eid < 64 ? 0 : VEC_C1;
-            brow[eid] = fmaf(vec[o + VEC_W1C + c], cs, fmaf(vec[o + VEC_W1S + c], sn, vec[o + VEC_B1 + c]));
-          }
-          if (hh == 0)
-            *reinterpret_cast<uint4*>(trow(T_TIME) + ((0u ^ (row & 7u)) << 4)) = make_uint4(pack_f16x2(1.f, sn), pack_f16x2(cs, 0.f), 0u, 0u);
           tc_wait_st();
         }
-        fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(bar_opnd);                                   // y, df, time tile -> P1
-        // next step's rows: issued here so that they land while P1 / epilogue 1 run -- every later fence.proxy.async is a
+        // next step's rows: issued here so that they land while epilogue 1 runs -- every later fence.proxy.async is a
         // MEMBAR.ALL.CTA that waits for outstanding loads, so no load is issued anywhere else in the step
         if (k > 0) {
           prefetch_y_dw(k - 1);
