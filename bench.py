@@ -382,9 +382,14 @@ def main():
     hbm_gbs, bf16_tf, peak_src = peaks()
     traffic = None
     try:                                            # ncu-measured DRAM bytes per launch of the dominant kernel, if captured for this workload
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'r1b_traffic.json')))['euler_fwd_tc_kernel<1,0>']
-        if t['rows'] == M and t['steps'] == DEC_STEPS:
-            traffic = t['dram_bytes']
+        for name in ('r1e_traffic.json', 'r1b_traffic.json'):       # latest capture first
+            fp = os.path.join(ROOT, 'profiles', name)
+            if not os.path.isfile(fp):
+                continue
+            t = json.load(open(fp))['euler_fwd_tc_kernel<1,0>']
+            if t['rows'] == M and t['steps'] == DEC_STEPS:
+                traffic = t['dram_bytes']
+                break
     except (OSError, KeyError, ValueError):
         pass
     T = sched_d.n_outputs + 1
