@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 3
+#define TRAJSDE_ABI_VERSION 4
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -298,6 +298,42 @@ typedef struct {
 int64_t trajsde_gru_workspace_bytes(int32_t mode, int64_t rows);
 int trajsde_gru_fwd(const TrajsdeGruArgs* args, void* cuda_stream);
 int trajsde_gru_bwd(const TrajsdeGruArgs* args, void* cuda_stream);
+
+/* Fused decoder heads over the solver outputs: for every (row, t) latent x[t][row][0..63]
+ *     out[h][row][t][0..1] = W2_h . relu(LayerNorm(W1_h x + b1_h)) + b2_h          h = 0 (self.decoder), 1 (self.scale)
+ * replaces the two nn.Sequential calls of SDEDecoder.forward (models/decoders/dec_hivt_nusargo_sde.py:50-61, 96, 98); the ELU,
+ * +1 and +min_scale of :98-99 stay with the caller (they act on the 2-channel result).  Forward only (inference); fp16 operands /
+ * fp32 accumulation for the 64x64 layers, fp32 LayerNorm and projections; dim = 64 only. */
+typedef struct {
+  const float* w1;   /* [64,64] net[0].weight */
+  const float* b1;   /* [64]    net[0].bias */
+  const float* ln_g; /* [64]    net[1].weight */
+  const float* ln_b; /* [64]    net[1].bias */
+  const float* w2;   /* [2,64]  net[3].weight */
+  const float* b2;   /* [2]     net[3].bias */
+} TrajsdeHead;
+
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;              /* TRAJSDE_MODE_TC_F16 */
+  int64_t rows;
+  int32_t dim;               /* 64 */
+  int32_t flags;
+  int32_t n_t;               /* time slabs of x (60 for the reference decoder) */
+  int32_t n_heads;           /* 1 (uncertain = False) or 2 */
+  TrajsdeHead head[2];
+  float ln_eps;              /* nn.LayerNorm eps (1e-5) */
+  float reserved;
+  const float* x;            /* element (t, row, c) at x + t * x_t_stride + row * x_row_stride + c; 16-byte aligned, strides % 4 == 0 */
+  int64_t x_row_stride;
+  int64_t x_t_stride;
+  float* out[2];             /* per head [rows, n_t, 2] contiguous */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeHeadsArgs;
+
+int64_t trajsde_heads_workspace_bytes(int32_t mode);
+int trajsde_heads_fwd(const TrajsdeHeadsArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

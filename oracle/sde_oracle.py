@@ -205,6 +205,11 @@ def decoder_loc_head_ref(phead: P, sol_y: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.linear(torch.relu(x), phead['3.weight'], phead['3.bias'])
 
 
+def decoder_scale_ref(phead: P, sol_y: torch.Tensor, min_scale: float) -> torch.Tensor:
+    """self.scale head + dec…sde.py:98-99: elu(head(sol_y)) + 1 + min_scale (same layer stack as self.decoder)."""
+    return torch.nn.functional.elu(decoder_loc_head_ref(phead, sol_y), alpha=1.0) + 1.0 + min_scale
+
+
 def min_ade_fde_ref(loc: torch.Tensor, target: torch.Tensor, reg_mask: torch.Tensor) -> Tuple[float, float]:
     """loc[modes,N,T,2], target[N,T,2], reg_mask[N,T] -> (minADE, minFDE) with best mode by ADE ('nuScenes' branch,
     ade_t.py:55-57) and FDE at each agent's last valid slot."""

@@ -4,7 +4,7 @@
 
 Fixtures (all float32 unless noted, seeds fixed):
   decoder_solve.npz   reference SDEDecoder.lsde_func + torchsde.sdeint call (dec…sde.py:88): 48 rows, 61 steps, dW supplied;
-                      weights (non-zero biases), y0, dW, ys, Brownian query times (ta,tb), loc/scale head outputs.
+                      weights (non-zero biases), y0, dW, ys, Brownian query times (ta,tb), loc/scale head parameters and outputs.
   encoder_loop.npz    reference sdeint_dual + GRU_Unit loop (enc…sep2.py:128-182): 40 rows, 21 steps, dual g, masks.
   schedule.npz        step schedules for the grids of SURVEY App. A (F = 10,20,30,50,60,100,200 and the encoder pairs),
                       from the literal torch replay + the (ta,tb) the reference solver actually queried.
@@ -44,6 +44,8 @@ def decoder_fixture():
     d.update(flat('f', rr.net_params(dec.lsde_func.f_func.net)))
     d.update(flat('g', rr.net_params(dec.lsde_func.g_func.net)))
     d.update(flat('head', rr.net_params(dec.decoder)))
+    d.update(flat('scale_head', rr.net_params(dec.scale)))
+    d['min_scale'] = np.float64(dec.min_scale)
     np.savez_compressed(os.path.join(OUT, 'decoder_solve.npz'), **d)
     print('decoder_solve: ys', ys.shape, 'queries', len(queries), 'fnfe', dec.lsde_func.fnfe)
 

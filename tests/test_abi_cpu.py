@@ -29,16 +29,17 @@ def test_struct_sizes_match_header(tmp_path):
     """ctypes mirrors must have the C sizes (compiled with gcc from the header)."""
     import subprocess
     src = tmp_path / 'sz.c'
-    src.write_text('#include "trajsde_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include "trajsde_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(TrajsdeEulerFwdArgs),sizeof(TrajsdeEulerBwdArgs),sizeof(TrajsdeSchedule),sizeof(TrajsdeNoise),'
                    'sizeof(TrajsdeMlp),sizeof(TrajsdeEncFwdArgs),sizeof(TrajsdeGru),sizeof(TrajsdeEncBwdArgs),'
-                   'sizeof(TrajsdeGruGrad));return 0;}\n')
+                   'sizeof(TrajsdeGruGrad),sizeof(TrajsdeGruArgs),sizeof(TrajsdeHead),sizeof(TrajsdeHeadsArgs));return 0;}\n')
     exe = tmp_path / 'sz'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_lib.EulerFwdArgs), C.sizeof(_lib.EulerBwdArgs), C.sizeof(_lib.Schedule),
                      C.sizeof(_lib.Noise), C.sizeof(_lib.Mlp), C.sizeof(_lib.EncFwdArgs), C.sizeof(_lib.Gru),
-                     C.sizeof(_lib.EncBwdArgs), C.sizeof(_lib.Gru)]
+                     C.sizeof(_lib.EncBwdArgs), C.sizeof(_lib.Gru), C.sizeof(_lib.GruArgs), C.sizeof(_lib.Head),
+                     C.sizeof(_lib.HeadsArgs)]
 
 
 def test_invalid_arguments_return_status_and_message():
@@ -60,6 +61,11 @@ def test_invalid_arguments_return_status_and_message():
     assert L.trajsde_enc_bwd(C.byref(e), None) == -2 and b'TC_F16' in L.trajsde_last_error_string()
     assert L.trajsde_enc_bwd_workspace_bytes(_lib.MODE_TC_F16, 1000, 21, 1) > 0
     assert L.trajsde_euler_fwd_workspace_bytes(99, 10, 10, 0) == -2
+    h = _lib.HeadsArgs()
+    assert L.trajsde_heads_fwd(C.byref(h), None) == -1 and b'ABI mismatch' in L.trajsde_last_error_string()
+    h.struct_bytes, h.dim, h.mode, h.n_heads = C.sizeof(h), 64, _lib.MODE_TC_F16, 3
+    assert L.trajsde_heads_fwd(C.byref(h), None) == -1 and b'n_heads' in L.trajsde_last_error_string()
+    assert L.trajsde_heads_workspace_bytes(_lib.MODE_TC_F16) > 0 and L.trajsde_heads_workspace_bytes(_lib.MODE_EXACT_F32) == -2
     with pytest.raises(_lib.TrajsdeError):
         _lib.check(-2, "x")
 

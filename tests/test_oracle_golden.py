@@ -23,6 +23,8 @@ def test_decoder_heads_vs_golden(golden_decoder):
     d = golden_decoder
     loc = so.decoder_loc_head_ref(sub(d, 'head'), torch.from_numpy(d['ys'])[1:].permute(1, 0, 2))
     assert torch.allclose(loc, torch.from_numpy(d['loc']), atol=1e-5, rtol=1e-5)
+    scale = so.decoder_scale_ref(sub(d, 'scale_head'), torch.from_numpy(d['ys'])[1:].permute(1, 0, 2), float(d['min_scale']))
+    assert torch.allclose(scale, torch.from_numpy(d['scale']), atol=1e-5, rtol=1e-5)
 
 
 def test_encoder_loop_vs_golden(golden_encoder):

@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_philox_dw', 'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_fwd',
     'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
     'trajsde_gru_workspace_bytes', 'trajsde_gru_fwd', 'trajsde_gru_bwd',
+    'trajsde_heads_workspace_bytes', 'trajsde_heads_fwd',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -83,6 +84,18 @@ class GruArgs(C.Structure):
                 ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
+class Head(C.Structure):
+    """One decoder head (nn.Sequential(Linear, LayerNorm, ReLU, Linear(64, 2)), dec_hivt_nusargo_sde.py:50-61)."""
+    _fields_ = [(n, _fp) for n in ('w1', 'b1', 'ln_g', 'ln_b', 'w2', 'b2')]
+
+
+class HeadsArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('n_t', C.c_int32), ('n_heads', C.c_int32), ('head', Head * 2), ('ln_eps', C.c_float),
+                ('reserved', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('out', _fp * 2),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -129,6 +142,10 @@ def lib():
             for f in (L.trajsde_gru_fwd, L.trajsde_gru_bwd):
                 f.restype = C.c_int
                 f.argtypes = [C.POINTER(GruArgs), C.c_void_p]
+        L.trajsde_heads_workspace_bytes.restype = C.c_int64
+        L.trajsde_heads_workspace_bytes.argtypes = [C.c_int32]
+        L.trajsde_heads_fwd.restype = C.c_int
+        L.trajsde_heads_fwd.argtypes = [C.POINTER(HeadsArgs), C.c_void_p]
         v = L.trajsde_abi_version()
         if v != ABI_VERSION:
             raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")

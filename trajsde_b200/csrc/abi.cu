@@ -262,6 +262,36 @@ static int gru_call(const TrajsdeGruArgs* a, void* cuda_stream, bool backward) {
 int trajsde_gru_fwd(const TrajsdeGruArgs* a, void* cuda_stream) { return gru_call(a, cuda_stream, false); }
 int trajsde_gru_bwd(const TrajsdeGruArgs* a, void* cuda_stream) { return gru_call(a, cuda_stream, true); }
 
+int64_t trajsde_heads_workspace_bytes(int32_t mode) {
+  if (mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "the fused decoder heads exist in TC_F16 mode only (mode %d)", mode);
+  return heads_workspace_bytes();
+}
+
+int trajsde_heads_fwd(const TrajsdeHeadsArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeHeadsArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeHeadsArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "the fused decoder heads exist in TC_F16 mode only (mode %d)", a->mode);
+  if (a->rows < 0 || a->n_t < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows / n_t < 0");
+  if (a->n_heads != 1 && a->n_heads != 2) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_heads %d (1 or 2)", a->n_heads);
+  for (int h = 0; h < a->n_heads; ++h) {
+    const TrajsdeHead& hd = a->head[h];
+    if (!hd.w1 || !hd.b1 || !hd.ln_g || !hd.ln_b || !hd.w2 || !hd.b2)
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "head[%d]: null parameter pointer", h);
+    if (a->rows > 0 && a->n_t > 0 && !a->out[h]) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "out[%d] null", h);
+  }
+  if (a->rows == 0 || a->n_t == 0) return TRAJSDE_OK;
+  if (!a->x || !aligned16(a->x) || (a->x_row_stride & 3) != 0 || (a->x_t_stride & 3) != 0 || a->x_row_stride < 64 || a->x_t_stride < 64)
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "x must be 16-byte aligned with row / t strides that are multiples of 4 elements and >= 64");
+  const int64_t need = heads_workspace_bytes();
+  if (a->workspace_bytes < need || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_heads_fwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
   if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
   int rc;

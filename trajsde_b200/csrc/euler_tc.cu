@@ -729,6 +729,10 @@ int make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t slabs, int6
 
 }  // namespace
 
+int tc_make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t slabs, int64_t row_stride, int64_t slab_stride) {
+  return make_map(m, ptr, rows, slabs, row_stride, slab_stride);
+}
+
 int64_t euler_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual) {
   (void)rows;
   (void)dual;

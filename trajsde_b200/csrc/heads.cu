@@ -1,0 +1,297 @@
+// Fused decoder heads over the solver's outputs: for every (row, t) latent x = sol_y[row, t, :64]
+//     loc   = W2d . relu(LayerNorm(W1d x + b1d)) + b2d          (self.decoder, models/decoders/dec_hivt_nusargo_sde.py:50-54, 96)
+//     scale = W2s . relu(LayerNorm(W1s x + b1s)) + b2s          (self.scale,   dec_hivt_nusargo_sde.py:56-61, 98; ELU/+1/+min_scale stay with the caller)
+// The reference runs ~10 aten kernels per head, each a full pass over the [M, 60, 64] tensor (3.15 GB at configs[1]); here the
+// latents are read ONCE (TMA, 128B-swizzled fp32 tiles), both heads' first layers are one tcgen05 product per 128-point tile
+// ([128 x 64] . [W1d; W1s]^T, fp16 operands from tensor memory, fp32 accumulate), and LayerNorm / ReLU / the 64 -> 2 projections run
+// in the epilogue with thread = (point, head): the whole normalisation is register-local.  HBM per point: 256 B in, 16 B out.
+//
+//   * persistent CTAs, two per SM (84 KB of shared memory, 256 TMEM columns each); 8 epilogue warps + one MMA-issuer warp + one IO warp;
+//   * a tile = 128 consecutive rows at one output time; a CTA walks a contiguous range of tiles in the order that is unit-stride
+//     in memory (t fastest for rows_major latents, rows fastest for time-major ones);
+//   * software pipeline: the operand of tile i+1 (fp32 smem -> fp16 pairs -> TMEM) is staged before the accumulator of tile i is
+//     drained, and MMA(i+1) is released as soon as those 64 registers are loaded, so it runs under tile i's LayerNorm arithmetic.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace trajsde {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int WARP_MMA = NUM_EPI_WARPS, WARP_IO = NUM_EPI_WARPS + 1;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;   // 320
+constexpr int NBUF = 2;
+
+// packed image: [128][64] fp16 SW128 K-major B operand (rows 0..63 head 0, 64..127 head 1) + fp32 vectors
+constexpr uint32_t IMG_W1 = 0;
+constexpr uint32_t IMG_VEC = 16384;
+// vector slots (float index), per head h: + h * 64 (w2: + h * 128)
+constexpr int VEC_B1 = 0, VEC_G = 128, VEC_BETA = 256, VEC_W2 = 384, VEC_B2 = 640;   // w2: [head][2][64]; b2: [head][2]
+constexpr uint32_t IMG_BYTES = IMG_VEC + 648 * 4;        // 18976
+constexpr uint32_t OFF_X = 19456;                        // 1024-aligned: NBUF x 32 KB fp32 tiles (two 16 KB boxes of 32 channels)
+constexpr uint32_t X_BYTES = 32768;
+constexpr uint32_t OFF_BARS = OFF_X + NBUF * X_BYTES;    // w, full[NBUF], empty[NBUF], opnd, acc
+constexpr uint32_t SMEM_TOTAL = OFF_BARS + 128;
+constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
+static_assert(2 * (SMEM_ALLOC + 1024) <= 232448, "two CTAs per SM must fit");
+
+// TMEM columns (256 allocated): [0,128) accumulator (head 0 | head 1), [128,192) two operand buffers of 32 columns (fp16 pairs)
+constexpr uint32_t TM_ACC = 0, TM_A = 128;
+
+struct HeadsParams {
+  TrajsdeHeadsArgs a;
+  const uint8_t* img;
+  int row_tiles;
+  int64_t num_tiles;     // row_tiles * n_t
+  int t_fastest;         // tile index = rt * n_t + t   (else t * row_tiles + rt)
+};
+
+__global__ void heads_pack_kernel(TrajsdeHeadsArgs a, uint8_t* __restrict__ img) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int idx = tid; idx < 128 * 64; idx += nth) {
+    const int n = idx >> 6, k = idx & 63, h = n >> 6;
+    const float v = h < a.n_heads ? a.head[h].w1[(n & 63) * 64 + k] : 0.f;
+    *reinterpret_cast<__half*>(img + IMG_W1 + sw128_off_h(n, k)) = __float2half_rn(v);
+  }
+  float* vec = reinterpret_cast<float*>(img + IMG_VEC);
+  for (int i = tid; i < 648; i += nth) {
+    float v = 0.f;
+    if (i < VEC_W2) {
+      const int h = (i >> 6) & 1, c = i & 63;
+      if (h < a.n_heads) v = i < VEC_G ? a.head[h].b1[c] : i < VEC_BETA ? a.head[h].ln_g[c] : a.head[h].ln_b[c];
+    } else if (i < VEC_B2) {
+      const int h = (i - VEC_W2) >> 7, j = (i - VEC_W2) & 127;
+      if (h < a.n_heads) v = a.head[h].w2[j];
+    } else if (i < VEC_B2 + 4) {
+      const int h = (i - VEC_B2) >> 1;
+      if (h < a.n_heads) v = a.head[h].b2[(i - VEC_B2) & 1];
+    }
+    vec[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsParams p, const __grid_constant__ CUtensorMap tm_x) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const TrajsdeHeadsArgs& a = p.a;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+
+  // contiguous, balanced tile range of this CTA
+  const int64_t tq = p.num_tiles / gridDim.x, tr = p.num_tiles % gridDim.x;
+  const int64_t tile_lo = (int64_t)blockIdx.x * tq + min((int64_t)blockIdx.x, tr);
+  const int n_my = (int)(tq + ((int64_t)blockIdx.x < tr ? 1 : 0));
+  auto tile_coord = [&](int i, int& rt, int& t) {
+    const int64_t g = tile_lo + i;
+    if (p.t_fastest) {
+      rt = (int)(g / a.n_t);
+      t = (int)(g % a.n_t);
+    } else {
+      t = (int)(g / p.row_tiles);
+      rt = (int)(g % p.row_tiles);
+    }
+  };
+
+  const uint32_t bar_w = base + OFF_BARS;
+  auto bar_full = [&](int b) { return base + OFF_BARS + 8u + 8u * b; };
+  auto bar_empty = [&](int b) { return base + OFF_BARS + 8u + 8u * NBUF + 8u * b; };
+  const uint32_t bar_opnd = base + OFF_BARS + 8u + 16u * NBUF, bar_acc = bar_opnd + 8u;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 96);
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_w, 1);
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(bar_full(b), 1);
+      mbar_init(bar_empty(b), NUM_EPI_THREADS);
+    }
+    mbar_init(bar_opnd, NUM_EPI_THREADS);
+    mbar_init(bar_acc, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == WARP_MMA) tmem_alloc(smem_u32(tmem_ptr_smem), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar_w, IMG_BYTES);
+    bulk_load_1d(base, p.img, IMG_BYTES, bar_w);
+  }
+  const float* vec = reinterpret_cast<const float*>(sm + IMG_VEC);
+
+  if (warp < NUM_EPI_WARPS) {
+    // =============================================== EPILOGUE WARPS ===============================================
+    const int quad = warp & 3;                              // TMEM lane quadrant
+    const uint32_t hh = (uint32_t)warp >> 2;                // operand staging: 32-channel half of the row; epilogue: head index
+    const uint32_t row = quad * 32 + lane;
+    const uint32_t tml = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const bool head_on = (int)hh < a.n_heads;
+    float* outp = head_on ? a.out[hh] : nullptr;
+    uint32_t par_acc = 0;
+
+    // fp32 tile (this thread's 32 channels) -> fp16 pairs -> operand buffer `ab` in tensor memory; releases the smem buffer
+    auto stage_operand = [&](int i) {
+      const int b = i % NBUF;
+      mbar_wait(bar_full(b), (uint32_t)(i / NBUF) & 1u);   // buffer b is filled for the (i / NBUF)-th time
+      const uint8_t* xr = sm + OFF_X + b * X_BYTES + hh * 16384 + row * 128;
+      uint32_t pk[16];
+#pragma unroll
+      for (uint32_t q = 0; q < 8; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(xr + ((q ^ (row & 7u)) << 4));
+        pk[2 * q] = pack_f16x2(v.x, v.y);
+        pk[2 * q + 1] = pack_f16x2(v.z, v.w);
+      }
+      tmem_st_32x32b_x16(tml + TM_A + (uint32_t)(i & 1) * 32 + hh * 16, pk);
+      mbar_arrive(bar_empty(b));                           // the IO warp may refill this buffer
+      tc_wait_st();
+    };
+
+    mbar_wait(bar_w, 0);
+    if (n_my > 0) {
+      stage_operand(0);
+      tc_fence_before();
+      mbar_arrive(bar_opnd);
+    }
+    for (int i = 0; i < n_my; ++i) {
+      int rt, t;
+      tile_coord(i, rt, t);
+      if (i + 1 < n_my) stage_operand(i + 1);
+      mbar_wait(bar_acc, par_acc);
+      par_acc ^= 1;
+      tc_fence_after();
+      float v[64];
+      {
+        uint32_t u0[32], u1[32];
+        tmem_ld_32x32b_x32(tml + TM_ACC + hh * 64, u0);
+        tmem_ld_32x32b_x32(tml + TM_ACC + hh * 64 + 32, u1);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          v[j] = __uint_as_float(u0[j]);
+          v[32 + j] = __uint_as_float(u1[j]);
+        }
+      }
+      tc_fence_before();
+      if (i + 1 < n_my) mbar_arrive(bar_opnd);             // accumulator drained, next operand staged -> MMA(i+1)
+      if (head_on) {
+        const float* b1 = vec + VEC_B1 + hh * 64;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(b1 + j);
+          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+        }
+        const float mean = s * (1.0f / 64.0f);
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          v[j] -= mean;
+          ss = fmaf(v[j], v[j], ss);
+        }
+        const float rstd = rsqrtf(ss * (1.0f / 64.0f) + a.ln_eps);
+        const float* gm = vec + VEC_G + hh * 64;
+        const float* bt = vec + VEC_BETA + hh * 64;
+        const float* w2 = vec + VEC_W2 + hh * 128;
+        float o0 = vec[VEC_B2 + hh * 2], o1 = vec[VEC_B2 + hh * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 64; j += 4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gm + j);
+          const float4 b4 = *reinterpret_cast<const float4*>(bt + j);
+          const float4 wa = *reinterpret_cast<const float4*>(w2 + j);
+          const float4 wb = *reinterpret_cast<const float4*>(w2 + 64 + j);
+          const float r0 = fmaxf(fmaf(v[j] * rstd, g4.x, b4.x), 0.f);
+          const float r1 = fmaxf(fmaf(v[j + 1] * rstd, g4.y, b4.y), 0.f);
+          const float r2 = fmaxf(fmaf(v[j + 2] * rstd, g4.z, b4.z), 0.f);
+          const float r3 = fmaxf(fmaf(v[j + 3] * rstd, g4.w, b4.w), 0.f);
+          o0 = fmaf(r0, wa.x, o0); o0 = fmaf(r1, wa.y, o0); o0 = fmaf(r2, wa.z, o0); o0 = fmaf(r3, wa.w, o0);
+          o1 = fmaf(r0, wb.x, o1); o1 = fmaf(r1, wb.y, o1); o1 = fmaf(r2, wb.z, o1); o1 = fmaf(r3, wb.w, o1);
+        }
+        const int64_t grow = (int64_t)rt * TILE_M + row;
+        if (grow < a.rows) *reinterpret_cast<float2*>(outp + (grow * a.n_t + t) * 2) = make_float2(o0, o1);
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // =============================================== MMA ISSUER =====================================================
+    const uint32_t idesc = umma_idesc_f16(TILE_M, 128);
+    const uint64_t dhi = umma_desc_sw128(0);
+    auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
+    uint32_t par_op = 0;
+    mbar_wait(bar_w, 0);
+    for (int i = 0; i < n_my; ++i) {
+      mbar_wait(bar_opnd, par_op);
+      par_op ^= 1;
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          tc_mma_f16_ts(tmem_base + TM_ACC, tmem_base + TM_A + (uint32_t)(i & 1) * 32 + 8 * kk, D(base + IMG_W1 + 32 * kk), idesc, kk > 0);
+        tc_commit(bar_acc);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================================== IO WARP ==========================================================
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int b = i % NBUF;
+        if (i >= NBUF) mbar_wait(bar_empty(b), (uint32_t)(i / NBUF - 1) & 1u);   // its previous content has been staged
+        int rt, t;
+        tile_coord(i, rt, t);
+        const uint32_t dst = base + OFF_X + b * X_BYTES;
+        mbar_arrive_expect_tx(bar_full(b), X_BYTES);
+        tma_load_3d(dst, &tm_x, bar_full(b), 0, rt * TILE_M, t);
+        tma_load_3d(dst + 16384, &tm_x, bar_full(b), 32, rt * TILE_M, t);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+}  // namespace
+
+int64_t heads_workspace_bytes() { return (int64_t)IMG_BYTES + 256; }
+
+int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s) {
+  int dev = 0, sms = 0;
+  TS_CUDA_CHECK(cudaGetDevice(&dev));
+  TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0)
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
+  if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported");
+  HeadsParams p;
+  p.a = a;
+  p.img = static_cast<const uint8_t*>(a.workspace);
+  p.row_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
+  p.num_tiles = (int64_t)p.row_tiles * a.n_t;
+  p.t_fastest = a.x_t_stride < a.x_row_stride ? 1 : 0;
+  if (p.num_tiles == 0) return TRAJSDE_OK;
+
+  heads_pack_kernel<<<16, 256, 0, s>>>(a, static_cast<uint8_t*>(a.workspace));
+  TS_CUDA_CHECK(cudaGetLastError());
+  CUtensorMap tm_x;
+  int rc;
+  if ((rc = tc_make_map(&tm_x, a.x, a.rows, a.n_t, a.x_row_stride, a.x_t_stride)) != 0) return rc;
+  TS_CUDA_CHECK(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
+  const int64_t max_ctas = 2 * (int64_t)sms;
+  const int grid = (int)(p.num_tiles < max_ctas ? p.num_tiles : max_ctas);
+  heads_fwd_kernel<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_x);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
+}  // namespace trajsde

@@ -200,4 +200,8 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 }
 
 }  // namespace tc
+
+// 3-D fp32 tensor map {64 channels, rows, slabs} with box {32, 128, 1} and 128-byte swizzle (defined in euler_tc.cu); strides in elements
+int tc_make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t slabs, int64_t row_stride, int64_t slab_stride);
+
 }  // namespace trajsde

@@ -1,0 +1,155 @@
+"""Fused decoder heads: ``self.decoder(sol_y)`` and ``self.scale(sol_y)`` of the reference's ``SDEDecoder.forward``
+(models/decoders/dec_hivt_nusargo_sde.py:50-61, 96, 98) as ONE launch that reads the solver's latents once.
+
+    loc, scale_raw = decoder_heads(dec.decoder, dec.scale, sol_y)        # sol_y [rows, T, 64], any row / time strides
+    scale = F.elu_(scale_raw, alpha=1.0) + 1.0 + min_scale               # :98-99 stays with the caller
+
+Forward only: inference / ``torch.no_grad()``.  Under autograd the reference's own ``nn.Sequential`` heads run (they are outside
+the solver path and stay on the reference PyTorch path); ``decoder_heads`` itself raises instead of falling back silently.
+"""
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .ops import LAUNCHES, _stream_ptr
+
+_HEAD_SHAPES = [(64, 64), (64,), (64,), (64,), (2, 64), (2,)]
+
+
+def head_params(head: torch.nn.Module) -> List[torch.Tensor]:
+    """[w1, b1, ln_g, ln_b, w2, b2] of ``nn.Sequential(Linear(64,64), LayerNorm(64), ReLU, Linear(64,2))`` (dec…sde.py:50-54)."""
+    lin1, ln, lin2 = head[0], head[1], head[3]
+    ps = [lin1.weight, lin1.bias, ln.weight, ln.bias, lin2.weight, lin2.bias]
+    if any(tuple(p.shape) != sh for p, sh in zip(ps, _HEAD_SHAPES)):
+        raise NotImplementedError("fused decoder heads support Linear(64,64) / LayerNorm(64) / ReLU / Linear(64,2) only")
+    return ps
+
+
+@torch.library.custom_op("trajsde::heads_fwd", mutates_args=(), device_types="cuda")
+def heads_fwd(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x[rows, T, 64] (last dim unit-stride) -> (out0[rows, T, 2], out1[rows, T, 2]); out1 is empty when n_heads == 1."""
+    if x.dim() != 3 or x.shape[2] != 64 or x.dtype != torch.float32 or (x.numel() > 0 and x.stride(2) != 1):
+        raise ValueError("`sol_y` must be float32 of shape (rows, T, 64) with a unit-stride last dimension")
+    if n_heads not in (1, 2) or len(params) != 6 * n_heads:
+        raise ValueError("params: 6 tensors per head")
+    rows, T = x.shape[0], x.shape[1]
+    dev = x.device
+    ps = [p.detach().contiguous() for p in params]
+    a = _lib.HeadsArgs()
+    a.struct_bytes = C.sizeof(_lib.HeadsArgs)
+    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, 0, T, n_heads
+    for h in range(n_heads):
+        for name, t in zip(('w1', 'b1', 'ln_g', 'ln_b', 'w2', 'b2'), ps[6 * h:6 * h + 6]):
+            setattr(a.head[h], name, t.data_ptr())
+    a.ln_eps = ln_eps
+    xd = x.detach()
+    if rows > 0 and T > 0 and (xd.data_ptr() % 16 != 0 or xd.stride(0) % 4 != 0 or xd.stride(1) % 4 != 0):
+        xd = xd.contiguous()
+    a.x, a.x_row_stride, a.x_t_stride = xd.data_ptr(), max(xd.stride(0), 64), max(xd.stride(1), 64)
+    outs = [torch.empty((rows, T, 2), dtype=torch.float32, device=dev),
+            torch.empty((rows, T, 2) if n_heads == 2 else (0, T, 2), dtype=torch.float32, device=dev)]
+    for h in range(n_heads):
+        a.out[h] = outs[h].data_ptr()
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_heads_workspace_bytes(_lib.MODE_TC_F16), "trajsde_heads_workspace_bytes")
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_heads_fwd(C.byref(a), _stream_ptr(dev)), "trajsde_heads_fwd")
+    if rows > 0 and T > 0:
+        LAUNCHES['n'] += 2
+    return outs[0], outs[1]
+
+
+@heads_fwd.register_fake
+def _(x, params, n_heads, ln_eps):
+    rows, T = x.shape[0], x.shape[1]
+    return x.new_empty((rows, T, 2)), x.new_empty((rows, T, 2) if n_heads == 2 else (0, T, 2))
+
+
+def _fusable(x: torch.Tensor, heads) -> bool:
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for h in heads for p in h.parameters()))
+    return x.is_cuda and not need_grad
+
+
+def decoder_heads(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], sol_y: torch.Tensor):
+    """(loc[rows,T,2], scale_raw[rows,T,2] or None) = (loc_head(sol_y), scale_head(sol_y)) in one fused launch."""
+    heads = [loc_head] + ([scale_head] if scale_head is not None else [])
+    if not sol_y.is_cuda:
+        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if not _fusable(sol_y, heads):
+        raise NotImplementedError("the fused decoder heads are forward-only: call them under torch.no_grad() / with frozen inputs, "
+                                  "or use the reference nn.Sequential heads for training")
+    eps = {float(h[1].eps) for h in heads}
+    if len(eps) != 1:
+        raise NotImplementedError("both heads must share the LayerNorm eps")
+    params = [p for h in heads for p in head_params(h)]
+    o0, o1 = heads_fwd(sol_y, params, len(heads), eps.pop())
+    return o0, (o1 if scale_head is not None else None)
+
+
+class FusedHeadPair:
+    """No-edit drop-in for ``SDEDecoder.forward``'s two head calls: ``install_heads`` binds ``loc_forward`` / ``scale_forward`` as the
+    ``forward`` of the decoder's ``self.decoder`` / ``self.scale`` instances.  The first call on a given ``sol_y`` runs the fused
+    launch and keeps the other head's result for the call that follows (dec…sde.py:96 then :98).  Calls that need autograd go to
+    the original ``nn.Sequential.forward`` — the reference PyTorch path."""
+
+    def __init__(self, loc_head, scale_head):
+        self.loc_head, self.scale_head = loc_head, scale_head
+        self._key, self._pending = None, None
+
+    @staticmethod
+    def _key_of(x):
+        return (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()))
+
+    def _both(self, x):
+        return decoder_heads(self.loc_head, self.scale_head, x)
+
+    def loc_forward(self, x):
+        if not (_fusable(x, [self.loc_head, self.scale_head]) and x.dim() == 3):
+            return torch.nn.Sequential.forward(self.loc_head, x)
+        if self._key == self._key_of(x) and self._pending is not None and self._pending[0] == 'loc':
+            out, self._key, self._pending = self._pending[1], None, None
+            return out
+        loc, scale = self._both(x)
+        self._key, self._pending = self._key_of(x), ('scale', scale)
+        return loc
+
+    def scale_forward(self, x):
+        if not (_fusable(x, [self.loc_head, self.scale_head]) and x.dim() == 3):
+            return torch.nn.Sequential.forward(self.scale_head, x)
+        if self._key == self._key_of(x) and self._pending is not None and self._pending[0] == 'scale':
+            out, self._key, self._pending = self._pending[1], None, None
+            return out
+        loc, scale = self._both(x)
+        self._key, self._pending = self._key_of(x), ('loc', loc)
+        return scale
+
+
+def install_heads(decoder) -> dict:
+    """Bind the fused pair on ``decoder.decoder`` / ``decoder.scale`` (instance attributes; classes untouched).  Returns what
+    ``uninstall_heads`` needs.  No-op (empty dict) when the decoder has no ``scale`` head (``uncertain: false``) or other widths."""
+    loc, scale = getattr(decoder, 'decoder', None), getattr(decoder, 'scale', None)
+    if loc is None or scale is None:
+        return {}
+    try:
+        head_params(loc), head_params(scale)
+    except (NotImplementedError, IndexError, AttributeError, TypeError):
+        return {}
+    pair = FusedHeadPair(loc, scale)
+    saved = {'loc': (loc, loc.__dict__.get('forward')), 'scale': (scale, scale.__dict__.get('forward')), 'pair': pair}
+    loc.forward = pair.loc_forward
+    scale.forward = pair.scale_forward
+    return saved
+
+
+def uninstall_heads(saved: Optional[dict]) -> None:
+    for key in ('loc', 'scale'):
+        if saved and key in saved:
+            mod, orig = saved[key]
+            if orig is None:
+                mod.__dict__.pop('forward', None)
+            else:
+                mod.forward = orig
