@@ -189,6 +189,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-heads', action='store_true')
     ap.add_argument('--e2e-chunks', type=int, default=2, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -305,6 +306,32 @@ def main():
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- decoder heads on the solver output: fused launch vs the reference nn.Sequential heads, inference ----------------
+    heads = None
+    if not args.no_heads:
+        import torch.nn as nn
+        from trajsde_b200 import heads as hd
+        mk = lambda sd: syn.init_reference_style(nn.Sequential(nn.Linear(64, 64), nn.LayerNorm(64), nn.ReLU(inplace=True),  # noqa: E731
+                                                               nn.Linear(64, 2)), sd).to(dev)
+        loc_h, sc_h = mk(7), mk(8)
+        with torch.no_grad():
+            ys_rm = tb.sdeint(dec_sde, res['dec_y0'], ts_dec, bm=dW_d, dt=0.1, method='euler', mode=mode, rows_major=True)
+            sol_y = ys_rm[1:].permute(1, 0, 2)                                   # dec…sde.py:88: unit-stride rows here
+            for _ in range(2):
+                hd.decoder_heads(loc_h, sc_h, sol_y)
+            ms_heads = timed(lambda i: hd.decoder_heads(loc_h, sc_h, sol_y), args.steps) / args.steps
+            loc_f, sc_f = hd.decoder_heads(loc_h, sc_h, sol_y)
+            loc_h(sol_y[:128])
+            ms_heads_eager = timed(lambda i: (loc_h(sol_y), sc_h(sol_y)), 2) / 2
+            err = max(float((loc_f - loc_h(sol_y)).abs().max()), float((sc_f - sc_h(sol_y)).abs().max()))
+        hbytes = M * sched_d.n_outputs * (256 + 16)
+        heads = {"kernel": "heads_fwd_kernel (self.decoder + self.scale of SDEDecoder.forward, one launch)", "ms": ms_heads,
+                 "points_per_s": world * M * sched_d.n_outputs / (ms_heads * 1e-3), "reference_torch_ms": ms_heads_eager,
+                 "roofline_frac_hbm": hbytes / (ms_heads * 1e-3) / 1e9 / peaks()[0], "algorithmic_bytes": hbytes,
+                 "max_abs_diff_vs_torch_fp32": err, "layout": "rows_major solver output"}
+        del ys_rm, sol_y, loc_f, sc_f
+        torch.cuda.empty_cache()
 
     # ---- training step (BASELINE configs[2]/[3]): fwd + bwd through both solvers, one all-reduce of the flat gradient bucket, AdamW ----------
     train = None
@@ -425,6 +452,7 @@ def main():
                      "sfu_note": "informational third ceiling: 257 MUFU ops per agent-step at the measured 16/clk/SM"},
         "e2e": {"value": world * e2e_work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "micro_batches": n_chunks},
+        "heads": heads,
         "train": train,
         "gpu_launches": launches,
         "clocks": clocks,

@@ -99,3 +99,27 @@ def test_unsupported_net_layout_raises():
     with pytest.raises(NotImplementedError):
         _mlp_params(n, 32, 'f')
     assert len(_mlp_params(EncoderSDE().g_argo, 1, 'g')) == 6
+
+
+def test_install_binds_fused_heads_on_the_instances_only():
+    """install() binds the fused head pair on decoder.decoder / decoder.scale (dec…sde.py:50-61) as instance attributes; inputs the
+    fused launch does not serve (autograd, non-CUDA) run the reference's own nn.Sequential; uninstall() restores the class forward."""
+    import torch.nn as nn
+
+    def head():
+        return nn.Sequential(nn.Linear(64, 64), nn.LayerNorm(64), nn.ReLU(inplace=True), nn.Linear(64, 2))
+
+    g = {'sdeint': 'ORIGINAL', '__name__': 'SDEDecoder', 'nn': nn, 'head': head}
+    exec("class Stage(nn.Module):\n    def __init__(self):\n        super().__init__()\n        self.decoder, self.scale = head(), head()\n"
+         "    def forward(self):\n        return sdeint\n", g)
+    dec = g['Stage']()
+    x = torch.randn(3, 5, 64)
+    want = dec.decoder(x)
+    saved = patch.install(decoder=dec)
+    assert 'heads' in saved and 'forward' in dec.decoder.__dict__ and 'forward' in dec.scale.__dict__
+    assert torch.equal(dec.decoder(x), want)                  # CPU tensor: the reference module's own forward
+    patch.uninstall(saved)
+    assert 'forward' not in dec.decoder.__dict__ and 'forward' not in dec.scale.__dict__
+    narrow = g['Stage']()
+    narrow.decoder = nn.Sequential(nn.Linear(32, 32), nn.LayerNorm(32), nn.ReLU(), nn.Linear(32, 2))
+    assert 'heads' not in patch.install(decoder=narrow)       # other widths: left alone

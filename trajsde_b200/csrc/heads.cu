@@ -47,15 +47,25 @@ struct HeadsParams {
   TrajsdeHeadsArgs a;
   const uint8_t* img;
   int row_tiles;
-  int64_t num_tiles;     // row_tiles * n_t
+  uint32_t num_tiles;    // row_tiles * n_t
   int t_fastest;         // tile index = rt * n_t + t   (else t * row_tiles + rt)
 };
 
 __global__ void heads_pack_kernel(TrajsdeHeadsArgs a, uint8_t* __restrict__ img) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // LayerNorm subtracts the channel mean of z = W1 x + b1, which is linear in x: mean_n(z) = (mean_n W1[n,:]) . x + mean(b1).  The image
+  // holds the CENTRED layer W1 - 1 (mean_n W1)^T, b1 - mean(b1), so the accumulator already is z - mean(z) and the epilogue needs
+  // neither the sum over channels nor the subtraction (the fp16 rounding of the centred weights leaves a residual mean of order
+  // 2^-11 |z|, far below the operand rounding itself).
   for (int idx = tid; idx < 128 * 64; idx += nth) {
     const int n = idx >> 6, k = idx & 63, h = n >> 6;
-    const float v = h < a.n_heads ? a.head[h].w1[(n & 63) * 64 + k] : 0.f;
+    float v = 0.f;
+    if (h < a.n_heads) {
+      const float* w = a.head[h].w1;
+      float cm = 0.f;
+      for (int m = 0; m < 64; ++m) cm += w[m * 64 + k];
+      v = w[(n & 63) * 64 + k] - cm * (1.0f / 64.0f);
+    }
     *reinterpret_cast<__half*>(img + IMG_W1 + sw128_off_h(n, k)) = __float2half_rn(v);
   }
   float* vec = reinterpret_cast<float*>(img + IMG_VEC);
@@ -63,7 +73,15 @@ __global__ void heads_pack_kernel(TrajsdeHeadsArgs a, uint8_t* __restrict__ img)
     float v = 0.f;
     if (i < VEC_W2) {
       const int h = (i >> 6) & 1, c = i & 63;
-      if (h < a.n_heads) v = i < VEC_G ? a.head[h].b1[c] : i < VEC_BETA ? a.head[h].ln_g[c] : a.head[h].ln_b[c];
+      if (h < a.n_heads) {
+        if (i < VEC_G) {
+          float bm = 0.f;
+          for (int m = 0; m < 64; ++m) bm += a.head[h].b1[m];
+          v = a.head[h].b1[c] - bm * (1.0f / 64.0f);
+        } else {
+          v = i < VEC_BETA ? a.head[h].ln_g[c] : a.head[h].ln_b[c];
+        }
+      }
     } else if (i < VEC_B2) {
       const int h = (i - VEC_W2) >> 7, j = (i - VEC_W2) & 127;
       if (h < a.n_heads) v = a.head[h].w2[j];
@@ -84,18 +102,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
 
   // contiguous, balanced tile range of this CTA
-  const int64_t tq = p.num_tiles / gridDim.x, tr = p.num_tiles % gridDim.x;
-  const int64_t tile_lo = (int64_t)blockIdx.x * tq + min((int64_t)blockIdx.x, tr);
-  const int n_my = (int)(tq + ((int64_t)blockIdx.x < tr ? 1 : 0));
+  const uint32_t tq = p.num_tiles / gridDim.x, tr = p.num_tiles % gridDim.x;
+  const uint32_t tile_lo = blockIdx.x * tq + min(blockIdx.x, tr);
+  const int n_my = (int)(tq + (blockIdx.x < tr ? 1u : 0u));
+  const uint32_t fast_n = p.t_fastest ? (uint32_t)a.n_t : (uint32_t)p.row_tiles;
   auto tile_coord = [&](int i, int& rt, int& t) {
-    const int64_t g = tile_lo + i;
-    if (p.t_fastest) {
-      rt = (int)(g / a.n_t);
-      t = (int)(g % a.n_t);
-    } else {
-      t = (int)(g / p.row_tiles);
-      rt = (int)(g % p.row_tiles);
-    }
+    const uint32_t g = tile_lo + (uint32_t)i, hi = g / fast_n, lo = g - hi * fast_n;
+    rt = (int)(p.t_fastest ? hi : lo);
+    t = (int)(p.t_fastest ? lo : hi);
   };
 
   const uint32_t bar_w = base + OFF_BARS;
@@ -182,26 +196,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
       tc_fence_before();
       if (i + 1 < n_my) mbar_arrive(bar_opnd);             // accumulator drained, next operand staged -> MMA(i+1)
       if (head_on) {
+        // the accumulator holds z - mean(z) up to the centred bias (see heads_pack_kernel): variance = mean of squares; four
+        // independent partial sums keep the dependent chains short next to the 4-cycle FMA latency
         const float* b1 = vec + VEC_B1 + hh * 64;
-        float s = 0.f;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
           const float4 b = *reinterpret_cast<const float4*>(b1 + j);
           v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          s += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+          s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1); s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
         }
-        const float mean = s * (1.0f / 64.0f);
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          v[j] -= mean;
-          ss = fmaf(v[j], v[j], ss);
-        }
-        const float rstd = rsqrtf(ss * (1.0f / 64.0f) + a.ln_eps);
+        const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f) + a.ln_eps);
         const float* gm = vec + VEC_G + hh * 64;
         const float* bt = vec + VEC_BETA + hh * 64;
         const float* w2 = vec + VEC_W2 + hh * 128;
-        float o0 = vec[VEC_B2 + hh * 2], o1 = vec[VEC_B2 + hh * 2 + 1];
+        float o0a = vec[VEC_B2 + hh * 2], o1a = vec[VEC_B2 + hh * 2 + 1], o0b = 0.f, o1b = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
           const float4 g4 = *reinterpret_cast<const float4*>(gm + j);
@@ -212,9 +221,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
           const float r1 = fmaxf(fmaf(v[j + 1] * rstd, g4.y, b4.y), 0.f);
           const float r2 = fmaxf(fmaf(v[j + 2] * rstd, g4.z, b4.z), 0.f);
           const float r3 = fmaxf(fmaf(v[j + 3] * rstd, g4.w, b4.w), 0.f);
-          o0 = fmaf(r0, wa.x, o0); o0 = fmaf(r1, wa.y, o0); o0 = fmaf(r2, wa.z, o0); o0 = fmaf(r3, wa.w, o0);
-          o1 = fmaf(r0, wb.x, o1); o1 = fmaf(r1, wb.y, o1); o1 = fmaf(r2, wb.z, o1); o1 = fmaf(r3, wb.w, o1);
+          o0a = fmaf(r0, wa.x, o0a); o0b = fmaf(r1, wa.y, o0b); o0a = fmaf(r2, wa.z, o0a); o0b = fmaf(r3, wa.w, o0b);
+          o1a = fmaf(r0, wb.x, o1a); o1b = fmaf(r1, wb.y, o1b); o1a = fmaf(r2, wb.z, o1a); o1b = fmaf(r3, wb.w, o1b);
         }
+        const float o0 = o0a + o0b, o1 = o1a + o1b;
         const int64_t grow = (int64_t)rt * TILE_M + row;
         if (grow < a.rows) *reinterpret_cast<float2*>(outp + (grow * a.n_t + t) * 2) = make_float2(o0, o1);
       }
@@ -227,7 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
     uint32_t par_op = 0;
     mbar_wait(bar_w, 0);
     for (int i = 0; i < n_my; ++i) {
-      mbar_wait(bar_opnd, par_op);
+      mbar_wait_suspend(bar_opnd, par_op);                 // MMA(i) was released a whole LayerNorm epilogue ahead of its consumer
       par_op ^= 1;
       tc_fence_after();
       if (elect_one()) {
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
     if (lane == 0) {
       for (int i = 0; i < n_my; ++i) {
         const int b = i % NBUF;
-        if (i >= NBUF) mbar_wait(bar_empty(b), (uint32_t)(i / NBUF - 1) & 1u);   // its previous content has been staged
+        if (i >= NBUF) mbar_wait_suspend(bar_empty(b), (uint32_t)(i / NBUF - 1) & 1u);   // its previous content has been staged
         int rt, t;
         tile_coord(i, rt, t);
         const uint32_t dst = base + OFF_X + b * X_BYTES;
@@ -277,7 +287,8 @@ int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s) {
   p.a = a;
   p.img = static_cast<const uint8_t*>(a.workspace);
   p.row_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
-  p.num_tiles = (int64_t)p.row_tiles * a.n_t;
+  if ((int64_t)p.row_tiles * a.n_t >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows x n_t too large");
+  p.num_tiles = (uint32_t)p.row_tiles * (uint32_t)a.n_t;
   p.t_fastest = a.x_t_stride < a.x_row_stride ? 1 : 0;
   if (p.num_tiles == 0) return TRAJSDE_OK;
 
@@ -287,7 +298,7 @@ int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s) {
   int rc;
   if ((rc = tc_make_map(&tm_x, a.x, a.rows, a.n_t, a.x_row_stride, a.x_t_stride)) != 0) return rc;
   TS_CUDA_CHECK(cudaFuncSetAttribute(heads_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC));
-  const int64_t max_ctas = 2 * (int64_t)sms;
+  const uint32_t max_ctas = 2u * (uint32_t)sms;
   const int grid = (int)(p.num_tiles < max_ctas ? p.num_tiles : max_ctas);
   heads_fwd_kernel<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_x);
   TS_CUDA_CHECK(cudaGetLastError());

@@ -32,8 +32,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+#ifdef TRAJSDE_MBAR_SUSPEND_ALL
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait_suspend(bar, parity, 20000u)) {
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
+  }
+}
+#endif
+
+// Suspending wait: try_wait with a suspend-time hint compiles to TRYWAIT + NANOSLEEP.SYNCS (the warp is parked until the barrier
+// signals or the hint elapses) instead of a bare polling loop, whose ~3 instructions per poll take issue slots from the epilogue
+// warps of the same SM sub-partition (ncu: 21 % of all executed instructions in heads_fwd_kernel came from polling).
+__device__ __forceinline__ bool mbar_try_wait_suspend(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_suspend(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait_suspend(bar, parity, 20000u)) {
   }
 }
 

@@ -24,12 +24,13 @@ def _is_64_wide_gru(gru) -> bool:
     return shapes == [(64, 128), (64, 64)] * 3
 
 
-def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True) -> dict:
+def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True, fuse_heads: bool = True) -> dict:
     """Rebind ``sdeint`` (decoder module) and ``sdeint_dual`` (encoder module).  Pass the LightningModule-style ``model``
     (with ``.decoder`` / ``.encoder``) or the stage modules directly.  With ``fuse_gru`` the encoder's ``GRU_unit`` instance
     (the jump between SDE steps, enc…sep2.py:165-169) also gets its ``forward`` bound to the fused ``gru_jump`` — an instance
-    attribute, the reference class is untouched — when the default mode is 'tc_f16' and its layers are 64 wide.  Returns the
-    originals for ``uninstall``."""
+    attribute, the reference class is untouched — when the default mode is 'tc_f16' and its layers are 64 wide.  With
+    ``fuse_heads`` the decoder's ``self.decoder`` / ``self.scale`` heads run as one fused launch under ``no_grad``.
+    Returns the originals for ``uninstall``."""
     decoder = decoder if decoder is not None else getattr(model, 'decoder', None)
     encoder = encoder if encoder is not None else getattr(model, 'encoder', None)
     saved = {}
@@ -39,6 +40,13 @@ def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True) -> di
             raise KeyError("decoder module has no global `sdeint` (expected `from torchsde import sdeint`)")
         saved['decoder'] = (g, 'sdeint', g['sdeint'])
         g['sdeint'] = sdeint
+        if fuse_heads and get_default_mode() == 'tc_f16':
+            # self.decoder / self.scale (dec…sde.py:50-61): one fused launch for both heads under no_grad; autograd calls keep
+            # running the reference nn.Sequential (trajsde_b200/heads.py)
+            from .heads import install_heads
+            hs = install_heads(decoder)
+            if hs:
+                saved['heads'] = (hs, None, None)
     if encoder is not None:
         g = _globals_of(encoder)
         if 'sdeint_dual' not in g:
@@ -59,7 +67,10 @@ def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True) -> di
 
 def uninstall(saved: Optional[dict]) -> None:
     for key, (g, name, orig) in (saved or {}).items():
-        if key == 'gru':
+        if key == 'heads':
+            from .heads import uninstall_heads
+            uninstall_heads(g)
+        elif key == 'gru':
             if orig is None:
                 g.__dict__.pop('forward', None)          # back to the class's forward
             else:
