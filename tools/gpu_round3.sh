@@ -1,0 +1,9 @@
+#!/bin/bash
+# GPU visit (1 GPU): smoke, full tests, sweep, final bench line, reference arm.  usage: bash tools/gpu_round3.sh <tag>
+tag=${1:-x}
+mkdir -p gpurun_out
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.txt 2>&1; tail -3 gpurun_out/pytest_gpu_$tag.txt
+timeout 400 python bench_sweep.py --out gpurun_out/sweep_$tag.json > gpurun_out/sweep_$tag.txt 2>&1; tail -3 gpurun_out/sweep_$tag.txt
+timeout 400 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_${tag}_err.txt; cut -c1-400 gpurun_out/bench_$tag.json; tail -3 gpurun_out/bench_${tag}_err.txt
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>/dev/null; cut -c1-300 gpurun_out/bench_ref_$tag.json
