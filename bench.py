@@ -210,6 +210,8 @@ def main():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from trajsde_b200.dist import bind_host_to_gpu
+    cores_bound = bind_host_to_gpu(local) if world > 1 else None      # host-fed path: pinned buffers next to this rank's GPU
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -451,7 +453,8 @@ def main():
                      "tensor_frac_of_bf16_peak": flops / (dec_ms_avg * 1e-3) / 1e12 / bf16_tf,
                      "sfu_note": "informational third ceiling: 257 MUFU ops per agent-step at the measured 16/clk/SM"},
         "e2e": {"value": world * e2e_work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "micro_batches": n_chunks},
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "micro_batches": n_chunks,
+                "host_cores_bound_per_rank": cores_bound},
         "heads": heads,
         "train": train,
         "gpu_launches": launches,

@@ -57,3 +57,25 @@ class FlatGradBucket:
             return None
         self.flat.div_(world)
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def bind_host_to_gpu(local_rank: int) -> Optional[int]:
+    """Pin this process (and the pinned host buffers it allocates afterwards) to the CPU cores next to GPU `local_rank` — NVML's
+    CPU affinity mask of the device, i.e. its NUMA node.  One rank per GPU feeds its GPU over its own PCIe link; without this a rank
+    scheduled on the other socket pays the inter-socket hop on every host->device byte.  Returns the number of cores bound, or None
+    when NVML / sched_setaffinity is unavailable (then nothing changes)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:                                        # noqa: BLE001 — an optimisation only; never fatal
+        return None
