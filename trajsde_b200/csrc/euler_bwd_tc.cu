@@ -412,13 +412,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
           st_row32(trow(T_DF), row, hh, t);
           tc_wait_st();
         }
-        // next step's rows: issued here so that they land while epilogue 1 runs -- every later fence.proxy.async is a
-        // MEMBAR.ALL.CTA that waits for outstanding loads, so no load is issued anywhere else in the step
-        if (k > 0) {
-          prefetch_y_dw(k - 1);
-          prefetch_gy(k - 1);
-        }
-
         TL_MARK(3);   // SS part 2 + fence + arrive + prefetch issue
         // ================= epilogue 1: h1f, h1g ==================================================================================
         mbar_wait(bar_acc, hs & 1);
@@ -442,6 +435,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(bar_opnd);                                   // h1f, h1g -> P2
+        // next step's rows.  Every fence.proxy.async is a MEMBAR.ALL.CTA that waits for outstanding loads, so they are issued where
+        // the distance to the next fence is longest: the P2 hand-shake plus the 128 tanh of epilogue 2 (~2.3 k clk) lie ahead here,
+        // against ~1 k clk when they were issued at the step start
+        if (k > 0) {
+          prefetch_y_dw(k - 1);
+          prefetch_gy(k - 1);
+        }
 
         TL_MARK(5);   // e1
         // ================= epilogue 2: h2f ; h2g, g, ds, dz2g =====================================================================
