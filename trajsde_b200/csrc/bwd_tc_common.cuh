@@ -77,5 +77,64 @@ __device__ __forceinline__ void to_own_row(uint8_t* stage4k, int lane, float4 (&
   __syncwarp();
 }
 
+// Column sums over the warp's 32 rows: on return lane L holds sum over lanes of v[L] (butterfly transpose-reduce, 31 shuffles).
+__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? a16[i] : a16[i + 8], keep = up ? a16[i + 8] : a16[i];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? a8[i] : a8[i + 4], keep = up ? a8[i + 4] : a8[i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? a4[i] : a4[i + 2], keep = up ? a4[i + 2] : a4[i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const bool up = lane & 1;
+  const float send = up ? a2[0] : a2[1], keep = up ? a2[1] : a2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// Weight-gradient flush: d[0..31] = v * scale (+ d[0..31]) for this thread's 32 consecutive floats of the CTA's partial vector.
+// The lanes of a warp write 128-byte rows that lie 256+ bytes apart, so the cost is the number of store (and, when accumulating,
+// load) instructions: 16-byte accesses where the row is 16-byte aligned, 8-byte ones otherwise (rows of the 66-wide W1 gradients
+// start on odd multiples of 8 bytes) instead of 32 scalar read-modify-writes (measured: 27 k -> 9 k clk per launch of the one-step
+// backward, bench_micro/bwd_fixed_cost.py).
+__device__ __forceinline__ void flush_row32(float* d, const uint32_t (&v)[32], float scale, bool accumulate) {
+  if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 o = accumulate ? *reinterpret_cast<const float4*>(d + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = fmaf(__uint_as_float(v[4 * q]), scale, o.x);
+      o.y = fmaf(__uint_as_float(v[4 * q + 1]), scale, o.y);
+      o.z = fmaf(__uint_as_float(v[4 * q + 2]), scale, o.z);
+      o.w = fmaf(__uint_as_float(v[4 * q + 3]), scale, o.w);
+      *reinterpret_cast<float4*>(d + 4 * q) = o;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      float2 o = accumulate ? *reinterpret_cast<const float2*>(d + 2 * q) : make_float2(0.f, 0.f);
+      o.x = fmaf(__uint_as_float(v[2 * q]), scale, o.x);
+      o.y = fmaf(__uint_as_float(v[2 * q + 1]), scale, o.y);
+      *reinterpret_cast<float2*>(d + 2 * q) = o;
+    }
+  }
+}
+
 }  // namespace bwdtc
 }  // namespace trajsde

@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
     mbar_wait(bar_w, 0);
     const float c3 = vec[VEC_C3];
+    TL_MARK(13);  // kernel prologue: barriers, TMEM, tables, weight image
 
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
       const int64_t grow = (int64_t)tile * TILE_M + row;
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       }
     }
 
+    TL_MARK(0);   // last step's tail + grad_y0 stores
     if (a.status && !(adj_peak <= 16384.f)) atomicOr(a.status, TRAJSDE_STATUS_ADJOINT_RANGE);   // also catches NaN
     // ================= weight-gradient partials of this CTA ===============================================================================
     if (gstep > 0) mbar_wait(bar_wg, (gstep - 1) & 1);          // every MMA of the CTA has completed
@@ -578,19 +580,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       tmem_ld_32x32b_x32(tm + TM_WGA + (lo ? 0u : 64u), v);      // dW2 / dV2
       tc_wait_ld();
       float* d = out + (lo ? G_FW2 : G_GW2) + m * 64 + hh * 32;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
+      flush_row32(d, v, inv_sigma, acc_out);
       tmem_ld_32x32b_x32(tm + TM_WGB, v);                        // dW1y / dV1y
       tc_wait_ld();
       d = out + (lo ? G_FW1 : G_GW1) + m * TS_IN1 + hh * 32;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
+      flush_row32(d, v, inv_sigma, acc_out);
       tmem_ld_32x32b_x32(tm + TM_WGC, v);                        // dW3 (lanes 0..63)
       tc_wait_ld();
       if (lo) {
         d = out + G_FW3 + m * 64 + hh * 32;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(v[j]) * inv_sigma + (acc_out ? d[j] : 0.f);
+        flush_row32(d, v, inv_sigma, acc_out);
       }
       const uint32_t tm0 = tmem_base + ((uint32_t)(quad * 32) << 16);
       uint32_t s1[16], s2[16], s3[16];
@@ -606,21 +605,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         if (lo) put(G_FB3 + m, __uint_as_float(s3[0]) * inv_sigma);
       }
     }
-    // w3 / c3 of the diffusion net: per-thread running sums -> column sums over the 128 rows (tiles 0,1 as fp32 scratch)
-    float* red = reinterpret_cast<float*>(sm + OFF_TILES);       // [128][64] fp32 = 32 KB
+    // w3 / c3 of the diffusion net: per-thread running sums -> column sums over the warp's 32 rows (butterfly), then over the four
+    // row quadrants through 1 KB of shared memory
+    {
+      float* red = reinterpret_cast<float*>(sm + OFF_TILES);     // [8 warps][32] + [8] fp32 scratch (operand tiles are idle now)
+      red[warp * 32 + lane] = colsum32(dw3g_acc, lane);          // column hh*32 + lane, rows of this warp
+      float cs = dc3_acc;                                        // hh == 0 threads carry the c3 sums, the others 0
 #pragma unroll
-    for (int j = 0; j < 32; ++j) red[row * 64 + ((hh * 32 + j + row) & 63)] = dw3g_acc[j];   // rotate: conflict-free column reads
-    if (hh == 0) qbuf[row] = dc3_acc;
-    named_bar_sync(5, NUM_EPI_THREADS);
-    if (threadIdx.x < 64) {
-      float s = 0.f;
-      for (int r = 0; r < TILE_M; ++r) s += red[r * 64 + ((threadIdx.x + r) & 63)];
-      put(G_GW3 + threadIdx.x, s * inv_sigma);
-    } else if (threadIdx.x == 64) {
-      float s = 0.f;
-      for (int r = 0; r < TILE_M; ++r) s += qbuf[r];
-      put(G_GB3, s * inv_sigma);
+      for (int off = 16; off >= 1; off >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, off);
+      if (lane == 0) red[256 + warp] = cs;
+      named_bar_sync(5, NUM_EPI_THREADS);
+      if (threadIdx.x < 64) {
+        const int h2 = threadIdx.x >> 5, l2 = threadIdx.x & 31;
+        const float s4 = (red[(h2 * 4 + 0) * 32 + l2] + red[(h2 * 4 + 1) * 32 + l2]) + (red[(h2 * 4 + 2) * 32 + l2] + red[(h2 * 4 + 3) * 32 + l2]);
+        put(G_GW3 + threadIdx.x, s4 * inv_sigma);
+      } else if (threadIdx.x == 64) {
+        put(G_GB3, ((red[256] + red[257]) + (red[258] + red[259])) * inv_sigma);
+      }
     }
+    TL_MARK(14);  // weight-gradient flush
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     if (warp == NUM_EPI_WARPS) {

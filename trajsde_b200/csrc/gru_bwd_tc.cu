@@ -106,37 +106,6 @@ __global__ void gru_tc_pack_kernel(TrajsdeGru w, uint8_t* __restrict__ img) {
   }
 }
 
-// Column sums over the warp's 32 rows: on return lane L holds sum over lanes of v[L] (butterfly transpose-reduce, 31 shuffles).
-__device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
-  float a16[16], a8[8], a4[4], a2[2];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool up = lane & 16;
-    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-    a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? a16[i] : a16[i + 8], keep = up ? a16[i + 8] : a16[i];
-    a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? a8[i] : a8[i + 4], keep = up ? a8[i + 4] : a8[i];
-    a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 2;
-    const float send = up ? a4[i] : a4[i + 2], keep = up ? a4[i + 2] : a4[i];
-    a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  const bool up = lane & 1;
-  const float send = up ? a2[0] : a2[1], keep = up ? a2[1] : a2[0];
-  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
 
 __device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, ts_tanh_approx(0.5f * x), 0.5f); }
 
@@ -414,12 +383,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
         float* d = out + (lo ? GRU_U1 : GRU_R1) + m * 128;
         tmem_ld_32x32b_x32(tm + TM_W, v);                          // columns hh*32 .. of [0,64): h_cur part
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[hh * 32 + j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d + hh * 32, v, inv_sigma, true);
         tmem_ld_32x32b_x32(tm + TM_W + 64, v);                     // [64,128): input part
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[64 + hh * 32 + j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d + 64 + hh * 32, v, inv_sigma, true);
       }
       tc_fence_before();
     }
@@ -435,28 +402,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gru_bwd_tc_kernel(const GruTcP
         float* d = out + GRU_N1 + m * 128;
         tmem_ld_32x32b_x32(tm + TM_GN1, v);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[hh * 32 + j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d + hh * 32, v, inv_sigma, true);
         tmem_ld_32x32b_x32(tm + TM_GN1 + 64, v);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[64 + hh * 32 + j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d + 64 + hh * 32, v, inv_sigma, true);
         d = out + GRU_U2 + m * 64 + hh * 32;
         tmem_ld_32x32b_x32(tm + TM_G2, v);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d, v, inv_sigma, true);
       } else {
         float* d = out + GRU_N2 + m * 64 + hh * 32;
         tmem_ld_32x32b_x32(tm + TM_GN2, v);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d, v, inv_sigma, true);
         d = out + GRU_R2 + m * 64 + hh * 32;
         tmem_ld_32x32b_x32(tm + TM_G2 + 64, v);
         tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) d[j] += __uint_as_float(v[j]) * inv_sigma;
+        flush_row32(d, v, inv_sigma, true);
       }
       // bias gradients: this lane's column (hh*32 + lane) summed over the warp's rows -> combine the four row quadrants
       float* bsum = reinterpret_cast<float*>(sm + OFF_BSUM) + warp * 6 * 32;
