@@ -13,7 +13,7 @@ rows = int(sys.argv[1]) if len(sys.argv) > 1 else 204800
 sde = init_like_reference(DecoderSDE(), seed=1).to(DEV)
 ts = torch.linspace(0, 6, 61); y0 = torch.relu(torch.randn(rows, 64, device=DEV))
 dW = torch.randn(61, rows, 64, device=DEV) * 0.3
-names = ['loop/e5 tail', 'SS: transpose, A\', q, E', 'wait bar_wg', 'SS: df,y,bias,fence,arrive,prefetch', 'wait P1', 'e1', 'wait P2', 'e2',
+names = ['loop / e5 tail / tile tail', 'SS: transposes', 'wait bar_wg', 'SS: y, arrive, adjoint, q, E, df', 'wait P1', 'e1 + prefetch issue', 'wait P2', 'e2',
          'wait D1', 'e3', 'wait D2', 'e4', 'wait D3']
 L = _lib.lib()
 for label, bm in (('supplied dW', dW), ('philox', None)):
