@@ -115,23 +115,22 @@ __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
 // start on odd multiples of 8 bytes) instead of 32 scalar read-modify-writes (measured: 27 k -> 9 k clk per launch of the one-step
 // backward, bench_micro/bwd_fixed_cost.py).
 __device__ __forceinline__ void flush_row32(float* d, const uint32_t (&v)[32], float scale, bool accumulate) {
+  // accumulate: vector reductions (red.global.add.v4/v2.f32) instead of load + add + store — no round trip to L2 in front of the
+  // stores.  Every address is owned by ONE thread of ONE CTA and launches are stream-ordered, so the sums stay bit-reproducible.
   if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float4 o = accumulate ? *reinterpret_cast<const float4*>(d + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      o.x = fmaf(__uint_as_float(v[4 * q]), scale, o.x);
-      o.y = fmaf(__uint_as_float(v[4 * q + 1]), scale, o.y);
-      o.z = fmaf(__uint_as_float(v[4 * q + 2]), scale, o.z);
-      o.w = fmaf(__uint_as_float(v[4 * q + 3]), scale, o.w);
-      *reinterpret_cast<float4*>(d + 4 * q) = o;
+      const float4 o = make_float4(__uint_as_float(v[4 * q]) * scale, __uint_as_float(v[4 * q + 1]) * scale,
+                                   __uint_as_float(v[4 * q + 2]) * scale, __uint_as_float(v[4 * q + 3]) * scale);
+      if (accumulate) atomicAdd(reinterpret_cast<float4*>(d + 4 * q), o);
+      else *reinterpret_cast<float4*>(d + 4 * q) = o;
     }
   } else {
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
-      float2 o = accumulate ? *reinterpret_cast<const float2*>(d + 2 * q) : make_float2(0.f, 0.f);
-      o.x = fmaf(__uint_as_float(v[2 * q]), scale, o.x);
-      o.y = fmaf(__uint_as_float(v[2 * q + 1]), scale, o.y);
-      *reinterpret_cast<float2*>(d + 2 * q) = o;
+      const float2 o = make_float2(__uint_as_float(v[2 * q]) * scale, __uint_as_float(v[2 * q + 1]) * scale);
+      if (accumulate) atomicAdd(reinterpret_cast<float2*>(d + 2 * q), o);
+      else *reinterpret_cast<float2*>(d + 2 * q) = o;
     }
   }
 }
