@@ -390,18 +390,9 @@ def main():
                  "cfg2_reference_batch": measure_train(args.train_scenes),          # BASELINE configs[2]: yml:106 batch 128
                  "cfg3_scene_sharded": measure_train(args.scenes)}                  # BASELINE configs[3]: 8192 scenes / 8 GPUs
 
-    # ---- parity spot check at full size: 64 decoder rows against the CPU oracle under the same dW -------------------------------------
-    parity = None
-    if rank == 0:
-        from oracle import sde_oracle as so
-        idx = torch.linspace(0, M - 1, 64).long()
-        _, ys_full = step(res, True)
-        pd = {k: {n: v.detach().cpu() for n, v in getattr(dec_sde, k).net.state_dict().items()} for k in ('f_func', 'g_func')}
-        ref, _ = so.euler_solve_ref(pd['f_func'], pd['g_func'], host.dec_y0[idx], ts_dec, 0.1, dW_d[:, idx.to(dev)].cpu())
-        got = ys_full[:, idx.to(dev)].cpu()
-        parity = {"rows_checked": 64, "max_abs_err": float((got - ref).abs().max()),
-                  "max_rel_err": float(((got - ref).abs() / (ref.abs() + 1)).max()), "mode": mode}
-        del ys_full
+    # parity is NOT checked here: the oracle is test infrastructure (tests/test_full_size_gpu.py checks this very workload against it);
+    # in this file only the cpu_baseline / reference-arm legs execute oracle code, as the thing being timed on the host cores
+    parity = {"checked_by": "tests/test_full_size_gpu.py, tests/test_euler_fwd_gpu.py (pytest -m gpu)", "mode": mode}
 
     if rank != 0:
         if world > 1:
