@@ -1,3 +1,4 @@
+"""Manual gradient check of the fused encoder backward against fp64 autograd of the oracle (dev script; not collected by pytest)."""
 import sys, os
 R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0,R); sys.path.insert(0,os.path.join(R,'tests'))
 import torch, time
