@@ -206,3 +206,31 @@ def test_registered_torch_ops_equal_the_eager_fast_path():
     m = torch.rand(70, device=DEV) > 0.5
     gp = [p_ for p_ in gru.parameters()]
     assert torch.equal(ops.gru_call(h, h * 0.5, m, gp), torch.ops.trajsde.gru_fwd(h, h * 0.5, m, gp))
+
+
+def test_loss_scale_sampled_absmax_falls_back_to_the_full_scan():
+    """The loss scale of the tensor-core backward comes from a SAMPLED scan of the incoming gradient (every 8th block of 32 rows) for
+    large inputs; when every sampled row carries a zero gradient the full scan must run, else a 1e-7-sized gradient would be carried
+    unscaled and flushed to zero by the fp16 delta operands.  Gradient lives only in unsampled rows here; exact mode is the reference."""
+    rows, F = 70_000, 2
+    sde = init_like_reference(DecoderSDE(), seed=5, bias_std=0.2).to(DEV)
+    ts = torch.linspace(0, 0.1 * F, F + 1)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    y0 = torch.relu(torch.randn(rows, 64, device=DEV, generator=g))
+    cot = torch.randn(F + 1, rows, 64, device=DEV, generator=g) * 1e-7
+    sampled_rows = ((torch.arange(rows, device=DEV) >> 5) % 8) == 0
+    cot[:, sampled_rows] = 0.0
+    out = {}
+    for mode in ('exact', 'tc_f16'):
+        for p in sde.parameters():
+            p.grad = None
+        y = y0.clone().requires_grad_(True)
+        ys = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode=mode, seed=3)
+        ys.backward(cot)
+        out[mode] = (y.grad.clone(), [p.grad.clone() for p in sde.parameters()])
+    gy_e, gw_e = out['exact']
+    gy_t, gw_t = out['tc_f16']
+    assert gy_e.abs().max() > 0
+    assert (gy_t - gy_e).abs().max() <= 3e-2 * gy_e.abs().max()
+    for a, b in zip(gw_t, gw_e):
+        assert (a - b).abs().max() <= 3e-2 * b.abs().max() + 1e-14

@@ -219,7 +219,8 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     if rows > 0:
         tc = mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS
         # TC: pack + absmax + fused dgrad/wgrad + reduce; exact: (dgrad + wgrad) per diffusion net + reduce
-        LAUNCHES['n'] += (5 if dual else 4) if tc else (5 if dual else 3)
+        sampled = tc and grad_ys is not None and rows * grad_ys.shape[0] >= (1 << 16)   # sampled absmax + its conditional full scan
+        LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
     return [grad_y0] + gparams
 
 
@@ -388,7 +389,7 @@ def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor],
         _lib.check(L.trajsde_enc_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_enc_bwd")
     if rows > 0:
         # tables + absmax x2 + pack per net + per iteration (GRU backward + one fused SDE backward per net) + two reduces
-        LAUNCHES['n'] += 3 + (2 if dual else 1) + S * 2 + 2
+        LAUNCHES['n'] += 3 + (2 if dual else 1) + S * 2 + 2 + int(grad_latent is not None and rows * S >= (1 << 16))
     return [grad_h0, grad_aa] + gparams + ggru
 
 
