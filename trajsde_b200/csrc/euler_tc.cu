@@ -395,9 +395,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
 
       for (int k = 0; k < S; ++k, ++gstep) {
-        if (save_states) {                                 // previous step's states store must have drained A1f|A1g
-          mbar_wait(bar_xfree(slot), par_xfree);
-          par_xfree ^= 1;
+        if (save_states && !TMEM_A) {                      // previous step's states store must have drained A1f|A1g before epilogue 1
+          mbar_wait(bar_xfree(slot), par_xfree);           // writes h1f there (the TMEM-operand variants write that staging area only
+          par_xfree ^= 1;                                  // in epilogue 3 and wait there)
         }
         mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's bias row + scalars are in the ring
         const float* ent = ring + (gstep % 3u) * RING_LD;
@@ -468,7 +468,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         }
 
         // ---- epilogue 3 -----------------------------------------------------------------------------------------------------
-        if (!save_states) {                                  // stores of the previous step have finished reading X
+        if (!save_states || TMEM_A) {                        // stores of the previous step have finished reading X (and the states staging)
           mbar_wait(bar_xfree(slot), par_xfree);
           par_xfree ^= 1;
         }
