@@ -59,13 +59,15 @@ constexpr int T_H1F = 5;      //                          [h1f|h1g]   = tiles 5,
 constexpr int T_H1G = 6;
 constexpr int T_TIME = 7;     // column 0 = 1, 1 = sin t_k, 2 = cos t_k, rest 0
 constexpr uint32_t OFF_XCHG = OFF_TILES + 8 * TILE_BYTES;          // q[2][128], pd[2][128] fp32
-constexpr int SCHED_MAX = 256;                        // schedule tables staged in shared memory when they fit (else read from global)
+constexpr int SCHED_MAX = 128;                        // schedule tables staged in shared memory when they fit (else read from global)
 constexpr uint32_t OFF_STAB = OFF_XCHG + 4 * TILE_M * 4;            // float4 step_tab[SCHED_MAX]
 constexpr uint32_t OFF_OBEG = OFF_STAB + SCHED_MAX * 16;           // int out_begin[SCHED_MAX + 4]
 constexpr uint32_t OFF_OUTW = OFF_OBEG + (SCHED_MAX + 4) * 4;      // float2 out_w[SCHED_MAX]
 constexpr uint32_t OFF_BROW = OFF_OUTW + SCHED_MAX * 8;            // float bias1[128]: layer-1 bias rows (f | g) of the current step
-constexpr uint32_t OFF_BARS = OFF_BROW + 128 * 4;
+constexpr uint32_t OFF_DWT = OFF_BROW + 128 * 4;      // Philox variant: [128 rows][64] fp16 increments of the step, drawn by the aux warps
+constexpr uint32_t OFF_BARS = OFF_DWT + TILE_BYTES;   // w, opnd, acc, wg, dwfull, dwempty
 constexpr uint32_t SMEM_TOTAL = OFF_BARS + 64;
+constexpr int NUM_DW_WARPS = 3, NUM_DW_THREADS = NUM_DW_WARPS * 32;   // the three warps of the issuer's warpgroup that were idle
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
 
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
 
   const uint32_t bar_w = base + OFF_BARS, bar_opnd = bar_w + 8, bar_acc = bar_w + 16, bar_wg = bar_w + 24;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 32);
+  const uint32_t bar_dwfull = bar_w + 32, bar_dwempty = bar_w + 40;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + OFF_BARS + 48);
   auto tile_u32 = [&](int t) { return base + OFF_TILES + (uint32_t)t * TILE_BYTES; };
 
   pdl_launch_dependents();
@@ -193,6 +196,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     mbar_init(bar_opnd, NUM_EPI_THREADS);
     mbar_init(bar_acc, 1);
     mbar_init(bar_wg, 1);
+    mbar_init(bar_dwfull, NUM_DW_THREADS);
+    mbar_init(bar_dwempty, NUM_EPI_THREADS);
     mbar_fence_init();
   }
   if (warp == NUM_EPI_WARPS) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
@@ -396,16 +401,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
               qp = fmaf(adj[4 * q + 3], pdw[q].w, qp);
             }
           } else {
-            const float sqrt_h = sqrtf(h);
+            // the increments of this step, drawn again by the aux warps while the previous step ran (fp16: q is a 64-term dot product
+            // that feeds fp16 delta operands anyway)
+            mbar_wait(bar_dwfull, gstep & 1);
+            float t[32];
+            ld_row32(sm + OFF_DWT + row * 128, row, hh, t);
+            mbar_arrive(bar_dwempty);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 n4 = philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k,
-                                           (uint32_t)(hh * 8 + q), sqrt_h);
-              qp = fmaf(adj[4 * q], n4.x, qp);
-              qp = fmaf(adj[4 * q + 1], n4.y, qp);
-              qp = fmaf(adj[4 * q + 2], n4.z, qp);
-              qp = fmaf(adj[4 * q + 3], n4.w, qp);
-            }
+            for (int j = 0; j < 32; ++j) qp = fmaf(adj[j], t[j], qp);
           }
           qbuf[hh * TILE_M + row] = valid ? qp : 0.f;
           // E -> TMEM (read back by the last epilogue of this step)
@@ -635,6 +638,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     TL_MARK(14);  // weight-gradient flush
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
+    if (!HAS_DW && warp > NUM_EPI_WARPS) {
+      // =============================================== INCREMENT PRODUCERS (Philox variant) =========================================
+      // The three warps next to the MMA issuer regenerate the forward's Brownian increments of step k into the fp16 tile OFF_DWT while
+      // the epilogue warps are busy with step k+1; the epilogue reads its row for q = A'.dW and hands the tile back.  Keyed by (global
+      // row, step, channel / 4) like every other draw of the stream.
+      const uint32_t t = (uint32_t)(warp - NUM_EPI_WARPS - 1) * 32u + (uint32_t)lane;      // 0..95
+      uint32_t n = 0;                                                                    // tiles-steps produced: dwempty parity
+      for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const uint64_t grow0 = (uint64_t)tile * TILE_M + a.noise.row_offset;
+        for (int k = S - 1; k >= 0; --k, ++n) {
+          const float sqrt_h = sqrtf(stab[k].y);
+          if (n > 0) mbar_wait(bar_dwempty, (n - 1) & 1);                                // every epilogue thread has read the previous tile
+          for (uint32_t item = t; item < 2u * TILE_M; item += NUM_DW_THREADS) {
+            const uint32_t r = item & (TILE_M - 1), h2 = item >> 7;
+            uint8_t* tr = sm + OFF_DWT + r * 128;
+#pragma unroll 1
+            for (uint32_t c = 0; c < 4; ++c) {                                           // 16-byte chunk = 8 channels = two Philox calls
+              const float4 n0 = philox_dw4(a.noise.seed, grow0 + r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c, sqrt_h);
+              const float4 n1 = philox_dw4(a.noise.seed, grow0 + r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c + 1, sqrt_h);
+              *reinterpret_cast<uint4*>(tr + (((h2 * 4 + c) ^ (r & 7u)) << 4)) =
+                  make_uint4(pack_f16x2(n0.x, n0.y), pack_f16x2(n0.z, n0.w), pack_f16x2(n1.x, n1.y), pack_f16x2(n1.z, n1.w));
+            }
+          }
+          mbar_arrive(bar_dwfull);
+        }
+      }
+    }
     if (warp == NUM_EPI_WARPS) {
     // =============================================== MMA ISSUER WARP ===============================================
     // warp-uniform loop (descriptors in uniform registers); one elected lane issues tcgen05.mma / tcgen05.commit
