@@ -62,7 +62,7 @@ def test_install_rebinds_reference_module_globals():
     enc, ge = make('LocalEncoderSDESepPara2', 'sdeint_dual')
     model = types.SimpleNamespace(decoder=dec, encoder=enc)
     saved = patch.install(model)
-    assert dec.forward() is tb.sdeint and enc.forward() is tb.sdeint_dual
+    assert dec.forward() is patch._sdeint_rows_major and enc.forward() is tb.sdeint_dual     # decoder: sdeint with rows-major storage
     patch.uninstall(saved)
     assert dec.forward() == 'ORIGINAL' and enc.forward() == 'ORIGINAL'
     with pytest.raises(KeyError):

@@ -234,3 +234,24 @@ def test_loss_scale_sampled_absmax_falls_back_to_the_full_scan():
     assert (gy_t - gy_e).abs().max() <= 3e-2 * gy_e.abs().max()
     for a, b in zip(gw_t, gw_e):
         assert (a - b).abs().max() <= 3e-2 * b.abs().max() + 1e-14
+
+
+@pytest.mark.parametrize('mode', ['exact', 'tc_f16'])
+def test_rows_major_storage_gives_the_same_gradients(mode):
+    """install() binds the decoder's sdeint with rows-major storage; the reference consumes `ys[1:].permute(1,0,2)` (dec…sde.py:88).
+    Same loss through both storage layouts -> same gradients (the backward reads grad_ys through its strides)."""
+    sde = init_like_reference(DecoderSDE(), seed=6, bias_std=0.2).to(DEV)
+    ts = torch.linspace(0, 2, 21)
+    g = torch.Generator().manual_seed(2)
+    y0 = torch.relu(torch.randn(150, 64, generator=g)).to(DEV)
+    w = torch.randn(150, 20, 64, generator=g).to(DEV)
+    out = []
+    for rm in (False, True):
+        for p in sde.parameters():
+            p.grad = None
+        y = y0.clone().requires_grad_(True)
+        sol_y = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode=mode, seed=12, rows_major=rm)[1:].permute(1, 0, 2)
+        (sol_y * w).sum().backward()
+        out.append([y.grad.clone()] + [p.grad.clone() for p in sde.parameters()])
+    for a, b in zip(*out):
+        assert torch.allclose(a, b, atol=1e-6 * float(b.abs().max()) + 1e-12, rtol=1e-5)

@@ -24,6 +24,12 @@ def _is_64_wide_gru(gru) -> bool:
     return shapes == [(64, 128), (64, 64)] * 3
 
 
+def _sdeint_rows_major(sde, y0, ts, *args, **kwargs):
+    """`sdeint` with the rows-major storage default (same values, same shape; only the strides of the returned tensor differ)."""
+    kwargs.setdefault('rows_major', True)
+    return sdeint(sde, y0, ts, *args, **kwargs)
+
+
 def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True, fuse_heads: bool = True) -> dict:
     """Rebind ``sdeint`` (decoder module) and ``sdeint_dual`` (encoder module).  Pass the LightningModule-style ``model``
     (with ``.decoder`` / ``.encoder``) or the stage modules directly.  With ``fuse_gru`` the encoder's ``GRU_unit`` instance
@@ -39,7 +45,9 @@ def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True, fuse_
         if 'sdeint' not in g:
             raise KeyError("decoder module has no global `sdeint` (expected `from torchsde import sdeint`)")
         saved['decoder'] = (g, 'sdeint', g['sdeint'])
-        g['sdeint'] = sdeint
+        # the decoder consumes `sdeint(...)[1:].permute(1, 0, 2)` (dec…sde.py:88): store the solution rows-major ([rows, T, 64] memory,
+        # returned as the same [T, rows, 64] view) so that this view has unit-stride rows for the heads that read it
+        g['sdeint'] = _sdeint_rows_major
         if fuse_heads and get_default_mode() == 'tc_f16':
             # self.decoder / self.scale (dec…sde.py:50-61): one fused launch for both heads under no_grad; autograd calls keep
             # running the reference nn.Sequential (trajsde_b200/heads.py)
