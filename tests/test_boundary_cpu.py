@@ -123,3 +123,23 @@ def test_install_binds_fused_heads_on_the_instances_only():
     narrow = g['Stage']()
     narrow.decoder = nn.Sequential(nn.Linear(32, 32), nn.LayerNorm(32), nn.ReLU(), nn.Linear(32, 2))
     assert 'heads' not in patch.install(decoder=narrow)       # other widths: left alone
+
+
+def test_install_on_the_live_reference_decoder():
+    """With /root/reference present (dev container): install() on a real `SDEDecoder` instance swaps the module global its forward
+    calls (dec…sde.py:11, 88) and binds the fused head pair on its `decoder` / `scale` instances; uninstall() restores both."""
+    from oracle import ref_runner as rr
+    if not rr.reference_available():
+        pytest.skip("reference tree absent (GPU box)")
+    dec = rr.build_reference_decoder(seed=0)
+    g = type(dec).forward.__globals__
+    orig = g['sdeint']
+    saved = patch.install(decoder=dec)
+    try:
+        assert g['sdeint'] is patch._sdeint_rows_major and g['sdeint'] is not orig
+        assert 'heads' in saved and 'forward' in dec.decoder.__dict__ and 'forward' in dec.scale.__dict__
+        x = torch.randn(4, 60, 64)
+        assert torch.equal(dec.decoder(x), torch.nn.Sequential.forward(dec.decoder, x))      # CPU input: the reference module itself
+    finally:
+        patch.uninstall(saved)
+    assert g['sdeint'] is orig and 'forward' not in dec.decoder.__dict__ and 'forward' not in dec.scale.__dict__
