@@ -119,7 +119,7 @@ int64_t enc_fwd_tc_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 // internal pieces of the tensor-core backward (euler_bwd_tc.cu), reused by the encoder backward
 int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s);
 int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride, uint32_t* amax_bits, cudaStream_t s);
-int bwd_tc_grid(int64_t rows);
+int bwd_tc_grid(int64_t rows, bool dual = false);
 int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
                 int accumulate, cudaStream_t s, bool pdl = false);
 int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int n1, const TrajsdeMlpGrad& gf, const TrajsdeMlpGrad& gg,

@@ -74,7 +74,7 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   const int64_t slab = a.rows * 64;
   const bool dual = a.alt_mask != nullptr;
   const bool gru_tc = !(a.flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);   // fp32 GRU kernel kept for A/B validation
-  const int grid = bwd_tc_grid(a.rows), ggrid = gru_tc ? grid : gru_bwd_grid(a.rows);
+  const int grid = bwd_tc_grid(a.rows, dual), ggrid = gru_tc ? bwd_tc_grid(a.rows) : gru_bwd_grid(a.rows);
   int rc;
 
   enc_bwd_tables_kernel<<<1, 1, 0, s>>>(w.out_begin, w.out_w);

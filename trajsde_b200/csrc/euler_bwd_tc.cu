@@ -786,10 +786,13 @@ int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, 
   return TRAJSDE_OK;
 }
 
-int bwd_tc_grid(int64_t rows) {
+// CTAs per pass.  Dual diffusion launches two passes (gridDim.y = 2) of one-CTA-per-SM kernels: half the SMs per pass keeps both passes
+// resident at once — one wave with one prologue and one weight-gradient flush per CTA instead of two waves.
+int bwd_tc_grid(int64_t rows, bool dual) {
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   if (sms > MAX_PARTIALS) sms = MAX_PARTIALS;
+  if (dual && sms > 1) sms /= 2;
   const int64_t tiles = (rows + TILE_M - 1) / TILE_M;
   return (int)(tiles < sms ? tiles : sms);
 }
@@ -814,7 +817,7 @@ int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t
   p.amax_bits = amax_bits;
   p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
   p.accumulate = accumulate;
-  const int grid = bwd_tc_grid(a.rows);
+  const int grid = bwd_tc_grid(a.rows, dual);
   if (grid <= 0) return TRAJSDE_OK;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
@@ -858,7 +861,7 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
   float* part0 = reinterpret_cast<float*>(ws + 2 * BWD_TC_IMG_BYTES + 256);
   float* part1 = part0 + (size_t)MAX_PARTIALS * G_PAD;
   const bool dual = a.alt_mask != nullptr;
-  const int grid = bwd_tc_grid(a.rows);
+  const int grid = bwd_tc_grid(a.rows, dual);
   int rc;
   if (grid > 0) {
     TS_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, s));
