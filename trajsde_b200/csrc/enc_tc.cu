@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
     const uint32_t o_ah = tml + TM_AH + hh * 16, o_ax = tml + TM_AX + hh * 16, o_a1f = tml + TM_A1F + hh * 16, o_a1g = tml + TM_A1G + hh * 16;
     const uint32_t pair_bar = 1 + quad;                    // named barrier of the two warps that share these rows
     uint32_t par_accA = 0, par_accB = 0;
+    // per-iteration scalars live in lane registers (S <= 32): lane i holds the slot index and the step size of iteration i
+    const int lane_slot = lane < S ? a.slot[lane] : 0;
+    const float lane_h = lane < S ? a.sched.step_tab[4 * lane + 1] : 0.f;
     mbar_wait(bar_w, 0);
 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -244,10 +247,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
       tc_fence_before();
       mbar_arrive(bar_opnd(0));                            // AH ready -> P1 of iteration 0
 
+      // observation mask of this row for all iterations as one bit mask (21 independent byte loads here instead of one dependent
+      // load at the top of every iteration)
+      uint32_t obs_bits = 0;
+      {
+        const uint8_t* mrow = a.obs_mask + (valid ? grow : 0) * a.obs_mask_row_stride;   // rows past the end read row 0 and are never stored
+        for (int it = 0; it < S; ++it) {
+          const int sl = __shfl_sync(0xffffffffu, lane_slot, it);                      // warp-uniform: outside any divergent branch
+          obs_bits |= (mrow[sl] != 0 ? 1u : 0u) << it;
+        }
+      }
+
       for (int it = 0; it < S; ++it) {
-        const float4 stp = *reinterpret_cast<const float4*>(a.sched.step_tab + 4 * it);
-        const float h = stp.y;
-        const int slot_t = a.slot[it];
+        const float h = __shfl_sync(0xffffffffu, lane_h, it);                // step size / slot index of iteration `it`: held by lane `it`
+        const int slot_t = __shfl_sync(0xffffffffu, lane_slot, it);
         const float* b1row = bias1_tab + it * 192;
         // ---- early global loads of this iteration: GRU input x, Brownian increments, observation mask ----------------------
         float4 xv[8], dwv[8];
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           dwv[q] = xv[q];
         }
-        bool observed = false;
+        const bool observed = (obs_bits >> it) & 1u;
         if (valid) {
           const float* xs = a.aa_out + ((int64_t)slot_t * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
@@ -266,7 +279,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
 #pragma unroll
             for (int q = 0; q < 8; ++q) dwv[q] = ld_nc_f4(ds + 4 * q);
           }
-          observed = a.obs_mask[grow * a.obs_mask_row_stride + slot_t] != 0;
         }
 
         // ---- epilogue 1 ------------------------------------------------------------------------------------------------------
