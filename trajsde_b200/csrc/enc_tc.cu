@@ -242,6 +242,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         for (int j = 0; j < 32; ++j) yv[j] = __float_as_uint(t[j]);
         tmem_st_32x32b_x32(tm + TM_Y, yv);
         st_operand32(o_ah, t);
+        // GRU input x of iteration 0 -> AX.  Later iterations fetch theirs one GRU phase ahead (after the Euler update of the previous
+        // iteration) and store it once G3 has read the old one, so epilogue 1 never waits for a global load.
+        const int slot0 = __shfl_sync(0xffffffffu, lane_slot, 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) v = ld_nc_f4(a.aa_out + ((int64_t)slot0 * a.rows + grow) * 64 + hh * 32 + 4 * q);
+          t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+        }
+        st_operand32(o_ax, t);
         tc_wait_st();
       }
       tc_fence_before();
@@ -260,20 +270,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
 
       for (int it = 0; it < S; ++it) {
         const float h = __shfl_sync(0xffffffffu, lane_h, it);                // step size / slot index of iteration `it`: held by lane `it`
-        const int slot_t = __shfl_sync(0xffffffffu, lane_slot, it);
+        const int slot_next = __shfl_sync(0xffffffffu, lane_slot, (it + 1) & 31);
         const float* b1row = bias1_tab + it * 192;
-        // ---- early global loads of this iteration: GRU input x, Brownian increments, observation mask ----------------------
-        float4 xv[8], dwv[8];
+        // ---- early global loads of this iteration: Brownian increments ------------------------------------------------------
+        float4 dwv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          xv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          dwv[q] = xv[q];
-        }
+        for (int q = 0; q < 8; ++q) dwv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool observed = (obs_bits >> it) & 1u;
         if (valid) {
-          const float* xs = a.aa_out + ((int64_t)slot_t * a.rows + grow) * 64 + hh * 32;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) xv[q] = ld_nc_f4(xs + 4 * q);
           if (HAS_DW) {
             const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
@@ -295,15 +299,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           mbar_arrive(bar_opnd(1));                        // h1f -> P2f
           ld_g32<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
           tanh32_to_operand(v, b1row + gcol + hh * 32, o_a1g);
-          float t[32];                                     // x -> fp16 operand (AX was last read by G3 of the previous iteration)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            t[4 * q] = xv[q].x; t[4 * q + 1] = xv[q].y; t[4 * q + 2] = xv[q].z; t[4 * q + 3] = xv[q].w;
-          }
-          st_operand32(o_ax, t);
           tc_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_opnd(0));                        // h1g (and x) -> P2g
+          mbar_arrive(bar_opnd(0));                        // h1g -> P2g
         }
         // ---- epilogue 2 ------------------------------------------------------------------------------------------------------
         mbar_wait(bar_acc(1), par_accB);                   // P2f
@@ -374,7 +372,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           tc_wait_st();
         }
         tc_fence_before();
-        mbar_arrive(bar_opnd(0));                          // y1 (and x) -> G1
+        mbar_arrive(bar_opnd(0));                          // y1 -> G1 (x is in AX since the previous iteration / the tile prologue)
+        // next iteration's GRU input: in flight during G1..G3, stored to AX after G3 (its last reader this iteration)
+        float4 xn[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && it + 1 < S) {
+          const float* xs = a.aa_out + ((int64_t)slot_next * a.rows + grow) * 64 + hh * 32;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xn[q] = ld_nc_f4(xs + 4 * q);
+        }
         // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
         mbar_wait(bar_acc(0), par_accA);                   // G1
         par_accA ^= 1;
@@ -423,6 +430,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           tmem_ld_32x32b_x32(tm, v);
           tc_wait_ld();
           tanh32_to_operand(v, vec + VEC_NB1 + hh * 32, o_a1f);
+          float t[32];                                     // x of the next iteration -> AX (G3 of this iteration has completed)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            t[4 * q] = xn[q].x; t[4 * q + 1] = xn[q].y; t[4 * q + 2] = xn[q].z; t[4 * q + 3] = xn[q].w;
+          }
+          st_operand32(o_ax, t);
           tc_wait_st();
         }
         tc_fence_before();

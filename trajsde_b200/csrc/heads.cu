@@ -29,19 +29,21 @@ constexpr int NBUF = 2;
 
 // packed image: [128][64] fp16 SW128 K-major B operand (rows 0..63 head 0, 64..127 head 1) + fp32 vectors
 constexpr uint32_t IMG_W1 = 0;
-constexpr uint32_t IMG_VEC = 16384;
+constexpr uint32_t IMG_WB = 16384;       // [128][64] fp16 SW128, only k = 0, 1 used: centred layer-1 bias as hi + lo fp16 (A operand there is 1, 1)
+constexpr uint32_t IMG_VEC = 32768;
 // vector slots (float index), per head h: + h * 64 (w2: + h * 128)
 constexpr int VEC_B1 = 0, VEC_G = 128, VEC_BETA = 256, VEC_W2 = 384, VEC_B2 = 640;   // w2: [head][2][64]; b2: [head][2]
-constexpr uint32_t IMG_BYTES = IMG_VEC + 648 * 4;        // 18976
-constexpr uint32_t OFF_X = 19456;                        // 1024-aligned: NBUF x 32 KB fp32 tiles (two 16 KB boxes of 32 channels)
+constexpr uint32_t IMG_BYTES = IMG_VEC + 648 * 4;        // 35360
+constexpr uint32_t OFF_X = 35840;                        // 1024-aligned: NBUF x 32 KB fp32 tiles (two 16 KB boxes of 32 channels)
 constexpr uint32_t X_BYTES = 32768;
 constexpr uint32_t OFF_BARS = OFF_X + NBUF * X_BYTES;    // w, full[NBUF], empty[NBUF], opnd, acc
 constexpr uint32_t SMEM_TOTAL = OFF_BARS + 128;
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(2 * (SMEM_ALLOC + 1024) <= 232448, "two CTAs per SM must fit");
 
-// TMEM columns (256 allocated): [0,128) accumulator (head 0 | head 1), [128,192) two operand buffers of 32 columns (fp16 pairs)
-constexpr uint32_t TM_ACC = 0, TM_A = 128;
+// TMEM columns (256 allocated): [0,128) accumulator (head 0 | head 1), [128,224) two operand buffers of 48 columns: 32 of fp16 pairs
+// (K = 64 channels) + 16 whose first column is (1, 1) and the rest 0 (K block of the bias product)
+constexpr uint32_t TM_ACC = 0, TM_A = 128, TM_A_STRIDE = 48;
 
 struct HeadsParams {
   TrajsdeHeadsArgs a;
@@ -67,6 +69,16 @@ __global__ void heads_pack_kernel(TrajsdeHeadsArgs a, uint8_t* __restrict__ img)
       v = w[(n & 63) * 64 + k] - cm * (1.0f / 64.0f);
     }
     *reinterpret_cast<__half*>(img + IMG_W1 + sw128_off_h(n, k)) = __float2half_rn(v);
+    // bias tile: k = 0 holds the fp16 head of the centred bias, k = 1 its fp16 remainder (their sum is exact to 2^-22), k >= 2 zero
+    float bv = 0.f;
+    if (h < a.n_heads && k < 2) {
+      float bm = 0.f;
+      for (int m = 0; m < 64; ++m) bm += a.head[h].b1[m];
+      const float bc = a.head[h].b1[n & 63] - bm * (1.0f / 64.0f);
+      const float hi = __half2float(__float2half_rn(bc));
+      bv = k == 0 ? hi : bc - hi;
+    }
+    *reinterpret_cast<__half*>(img + IMG_WB + sw128_off_h(n, k)) = __float2half_rn(bv);
   }
   float* vec = reinterpret_cast<float*>(img + IMG_VEC);
   for (int i = tid; i < 648; i += nth) {
@@ -163,11 +175,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
         pk[2 * q] = pack_f16x2(v.x, v.y);
         pk[2 * q + 1] = pack_f16x2(v.z, v.w);
       }
-      tmem_st_32x32b_x16(tml + TM_A + (uint32_t)(i & 1) * 32 + hh * 16, pk);
+      tmem_st_32x32b_x16(tml + TM_A + (uint32_t)(i & 1) * TM_A_STRIDE + hh * 16, pk);
       mbar_arrive(bar_empty(b));                           // the IO warp may refill this buffer
       tc_wait_st();
     };
 
+    if (hh == 0) {                                           // constant K block of the bias product: (1, 1) then zeros, both buffers
+      uint32_t ones[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ones[j] = 0u;
+      ones[0] = 0x3C003C00u;                                 // fp16 pair (1.0, 1.0)
+      tmem_st_32x32b_x16(tml + TM_A + 32, ones);
+      tmem_st_32x32b_x16(tml + TM_A + TM_A_STRIDE + 32, ones);
+      tc_wait_st();
+    }
     mbar_wait(bar_w, 0);
     if (n_my > 0) {
       stage_operand(0);
@@ -196,14 +217,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
       tc_fence_before();
       if (i + 1 < n_my) mbar_arrive(bar_opnd);             // accumulator drained, next operand staged -> MMA(i+1)
       if (head_on) {
-        // the accumulator holds z - mean(z) up to the centred bias (see heads_pack_kernel): variance = mean of squares; four
+        // the accumulator holds z - mean(z), centred bias included (see heads_pack_kernel): variance = mean of squares; four
         // independent partial sums keep the dependent chains short next to the 4-cycle FMA latency
-        const float* b1 = vec + VEC_B1 + hh * 64;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int j = 0; j < 64; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(b1 + j);
-          v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1); s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
         }
         const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f) + a.ln_eps);
@@ -243,7 +261,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
-          tc_mma_f16_ts(tmem_base + TM_ACC, tmem_base + TM_A + (uint32_t)(i & 1) * 32 + 8 * kk, D(base + IMG_W1 + 32 * kk), idesc, kk > 0);
+          tc_mma_f16_ts(tmem_base + TM_ACC, tmem_base + TM_A + (uint32_t)(i & 1) * TM_A_STRIDE + 8 * kk, D(base + IMG_W1 + 32 * kk), idesc, kk > 0);
+        tc_mma_f16_ts(tmem_base + TM_ACC, tmem_base + TM_A + (uint32_t)(i & 1) * TM_A_STRIDE + 32, D(base + IMG_WB), idesc, 1);   // + 1 . b1'^T
         tc_commit(bar_acc);
       }
       __syncwarp();
