@@ -41,7 +41,7 @@ constexpr uint32_t IMG_B1 = 0;                        // [128][64]: rows 0..63 W
 constexpr uint32_t IMG_W2 = 16384, IMG_V2 = 24576;    // forward orientation                       (P2)
 constexpr uint32_t IMG_W3T = 32768, IMG_W2T = 40960, IMG_V2T = 49152, IMG_W1YT = 57344, IMG_V1YT = 65536;   // B[n][k] = W[k][n]
 constexpr uint32_t IMG_VEC = 73728;
-constexpr int VEC_B1 = 0, VEC_W1S = 64, VEC_W1C = 128, VEC_B2 = 192, VEC_C1 = 256, VEC_V1S = 320, VEC_V1C = 384, VEC_C2 = 448,
+constexpr int VEC_B1 = 0, VEC_W1S = 64, VEC_W1C = 128, VEC_B2 = 192, VEC_C1 = 256, VEC_C2 = 448,   // [320,448): diffusion time columns, addressed as VEC_C1 + VEC_W1S / VEC_W1C
               VEC_W3G = 512, VEC_C3 = 576;
 constexpr uint32_t IMG_BYTES = IMG_VEC + 640 * 4;     // 76288
 static_assert(IMG_BYTES <= BWD_TC_IMG_BYTES, "image larger than its workspace slot");

@@ -23,7 +23,7 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
-constexpr int WARP_MMA = NUM_EPI_WARPS, WARP_IO = NUM_EPI_WARPS + 1;
+constexpr int WARP_MMA = NUM_EPI_WARPS;                 // warp 8: MMA issuer, warp 9: IO (TMA loads)
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;   // 320
 constexpr int NBUF = 2;
 
@@ -32,7 +32,7 @@ constexpr uint32_t IMG_W1 = 0;
 constexpr uint32_t IMG_WB = 16384;       // [128][64] fp16 SW128, only k = 0, 1 used: centred layer-1 bias as hi + lo fp16 (A operand there is 1, 1)
 constexpr uint32_t IMG_VEC = 32768;
 // vector slots (float index), per head h: + h * 64 (w2: + h * 128)
-constexpr int VEC_B1 = 0, VEC_G = 128, VEC_BETA = 256, VEC_W2 = 384, VEC_B2 = 640;   // w2: [head][2][64]; b2: [head][2]
+constexpr int VEC_G = 128, VEC_BETA = 256, VEC_W2 = 384, VEC_B2 = 640;   // [0,128) unused (the bias rides the MMA); w2: [head][2][64]; b2: [head][2]
 constexpr uint32_t IMG_BYTES = IMG_VEC + 648 * 4;        // 35360
 constexpr uint32_t OFF_X = 35840;                        // 1024-aligned: NBUF x 32 KB fp32 tiles (two 16 KB boxes of 32 channels)
 constexpr uint32_t X_BYTES = 32768;
@@ -85,15 +85,7 @@ __global__ void heads_pack_kernel(TrajsdeHeadsArgs a, uint8_t* __restrict__ img)
     float v = 0.f;
     if (i < VEC_W2) {
       const int h = (i >> 6) & 1, c = i & 63;
-      if (h < a.n_heads) {
-        if (i < VEC_G) {
-          float bm = 0.f;
-          for (int m = 0; m < 64; ++m) bm += a.head[h].b1[m];
-          v = a.head[h].b1[c] - bm * (1.0f / 64.0f);
-        } else {
-          v = i < VEC_BETA ? a.head[h].ln_g[c] : a.head[h].ln_b[c];
-        }
-      }
+      if (h < a.n_heads && i >= VEC_G) v = i < VEC_BETA ? a.head[h].ln_g[c] : a.head[h].ln_b[c];
     } else if (i < VEC_B2) {
       const int h = (i - VEC_W2) >> 7, j = (i - VEC_W2) & 127;
       if (h < a.n_heads) v = a.head[h].w2[j];
