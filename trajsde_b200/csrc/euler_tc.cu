@@ -282,7 +282,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_opnd(s, i), EPI_THREADS_PER_SLOT);
         mbar_init(bar_acc(s, i), 1);
-        mbar_init(bar_ring(s, i), 1);
+        mbar_init(bar_ring(s, i), 32);                     // every lane of the IO warp releases its own ring stores
       }
       mbar_init(bar_tma(s), 1);
       mbar_init(bar_xfull(s), EPI_THREADS_PER_SLOT);
@@ -624,12 +624,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         *reinterpret_cast<float4*>(dst + BIAS1_LD) = e.sc;
         *reinterpret_cast<int2*>(dst + BIAS1_LD + 4) = e.so;
       }
-      // __syncwarp does two jobs here: it orders every lane's ring stores before lane 0's release-arrive (bar.warp.sync is a
-      // synchronising operation of the memory model, the release is cumulative), and it paces the warp — lane 0 blocks on bar_xfull
-      // below, and without the rendezvous lanes 1..31 would run ahead and publish entries whose ring slots are still in use
-      // (compute-sanitizer racecheck does not model this pairing and reports the ring as a potential RAW hazard)
+      // every lane release-arrives for its own stores; the __syncwarp paces the warp: lane 0 blocks on bar_xfull below, and without
+      // the rendezvous lanes 1..31 would run ahead and publish entries whose ring slots are still in use
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ring(slot, g & 1));
+      mbar_arrive(bar_ring(slot, g & 1));
     };
     if (total_steps > 0) {
       Ent e;
