@@ -1,3 +1,4 @@
+# A/B of the shipped library against a variant build (first: EXTRA="-D..." bash bench_micro/build_variant_lib.sh); run under gpurun from the repo root
 for v in base var; do
   if [ $v = var ]; then export TRAJSDE_LIB_PATH=$PWD/bench_micro/libtrajsde_b200_var.so; else unset TRAJSDE_LIB_PATH; fi
   echo "== $v"
