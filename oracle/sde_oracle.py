@@ -222,3 +222,94 @@ def min_ade_fde_ref(loc: torch.Tensor, target: torch.Tensor, reg_mask: torch.Ten
     n = torch.arange(m.size(0))
     last = m.size(1) - 1 - torch.argmax(m.flip(1).float(), dim=1)
     return float(ade[best, n].mean()), float(l2[best, n, last].mean())
+
+
+def ade_t_ref(pred: torch.Tensor, target: torch.Tensor, reg_mask: torch.Tensor) -> float:
+    """ADE_T.update/compute, 'nuScenes' branch (metrics/ade_t.py:44-66): pred[modes,N,T,2], target[N,T,2], reg_mask[N,T]; best mode
+    by masked ADE, averaged over the actors that have any valid future slot."""
+    l2 = torch.norm(pred - target.unsqueeze(0), p=2, dim=-1)                # :48
+    keep = reg_mask.any(-1)                                                 # :49
+    l2, m = l2[:, keep].clone(), reg_mask[keep]                             # :50
+    l2[:, ~m] = 0                                                           # :51
+    ade = l2.sum(-1) / m.sum(-1).unsqueeze(0)                               # :54
+    best = torch.argmin(ade, dim=0)                                         # :57
+    return float(ade[best, torch.arange(int(keep.sum()))].sum() / keep.sum())   # :68-73
+
+
+def fde_t_ref(pred: torch.Tensor, target: torch.Tensor, reg_mask: torch.Tensor, source: torch.Tensor, end_idcs=(59, 29)) -> float:
+    """FDE_T.update/compute (metrics/fde_t.py:45-57): displacement at the per-source end slot (actors sorted by source), best mode by
+    that displacement, over the actors whose end slot is valid."""
+    NA = pred.size(1)
+    c0, c1 = int((source == 0).sum()), int((source == 1).sum())
+    end = torch.repeat_interleave(torch.tensor(list(end_idcs)), torch.tensor([c0, c1]))   # :48-49
+    n = torch.arange(NA)
+    l2 = torch.norm(pred[:, n, end, :] - target[n, end].unsqueeze(0), p=2, dim=-1)          # :51
+    ok = reg_mask[n, end]                                                                   # :52
+    l2 = l2[:, ok]
+    best = torch.argmin(l2, dim=0)
+    return float(l2[best, torch.arange(int(ok.sum()))].sum() / ok.sum())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY §8(f)-4 and row (g): the decoder stage around the solve and the two training losses
+#   SDEDecoder.forward   models/decoders/dec_hivt_nusargo_sde.py:77-105  (aggr_embed :26-29,82 ; heads :50-61,95-99 ; pi :63-67,92-94)
+#   L2                   losses/L2.py:10-27
+#   DiffBCE              losses/diff_BCE.py:11-16
+# ------------------------------------------------------------------------------------------------------------------
+def _lin_ln_relu(p: P, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """nn.Sequential(Linear, LayerNorm, ReLU) with state_dict keys ``{prefix}.0.*`` / ``{prefix}.1.*``."""
+    z = torch.nn.functional.linear(x, p[f'{prefix}.0.weight'].to(x.dtype), p[f'{prefix}.0.bias'].to(x.dtype))
+    z = torch.nn.functional.layer_norm(z, (z.size(-1),), p[f'{prefix}.1.weight'].to(x.dtype), p[f'{prefix}.1.bias'].to(x.dtype))
+    return torch.relu(z)
+
+
+def aggr_embed_ref(p: P, local_embed: torch.Tensor, global_embed: torch.Tensor) -> torch.Tensor:
+    """hidden_0[modes*N, 64] = aggr_embed(cat(global_embed, local_embed.expand(modes, N, 64)))   dec…sde.py:82-85.
+    ``p``: the decoder's state_dict (keys ``aggr_embed.0.weight`` [64,128], ``aggr_embed.0.bias``, ``aggr_embed.1.weight/bias``)."""
+    modes = global_embed.size(0)
+    x = torch.cat((global_embed, local_embed.expand(modes, *local_embed.shape)), dim=-1)
+    return _lin_ln_relu(p, 'aggr_embed', x).reshape(modes * local_embed.size(0), -1)
+
+
+def decoder_forward_ref(p: P, local_embed: torch.Tensor, global_embed: torch.Tensor, padding_mask: torch.Tensor, dW: torch.Tensor,
+                        ts: Optional[torch.Tensor] = None, dt: float = 0.1, min_scale: float = 0.001, future_steps: int = 60):
+    """The whole ``SDEDecoder.forward`` (dec…sde.py:77-105) with caller-supplied increments: returns the reference's ``out`` dict
+    (``loc`` [modes,N,F,4] = cat(loc, scale), ``pi`` [N,modes], ``reg_mask`` [N,F]) plus ``hidden_0`` and ``ys`` for step-wise checks.
+    ``p`` = the decoder's state_dict; works in the dtype of the embeddings."""
+    dtype = local_embed.dtype
+    modes, N = global_embed.size(0), local_embed.size(0)
+    ts = torch.linspace(0, 6, future_steps + 1) if ts is None else ts                      # :72
+    hidden_0 = aggr_embed_ref(p, local_embed, global_embed)
+    sub = lambda pre: {k[len(pre) + 1:]: v for k, v in p.items() if k.startswith(pre + '.')}  # noqa: E731
+    ys, _ = euler_solve_ref(sub('lsde_func.f_func.net'), sub('lsde_func.g_func.net'), hidden_0, ts, dt, dW.to(dtype))
+    sol_y = ys[1:].permute(1, 0, 2)                                                        # :88
+    xpi = torch.cat((local_embed.expand(modes, *local_embed.shape), global_embed), dim=-1)   # :92-93
+    pi = torch.nn.functional.linear(_lin_ln_relu(p, 'pi', xpi), p['pi.3.weight'].to(dtype), p['pi.3.bias'].to(dtype)).squeeze(-1).t()
+    cast = lambda d: {k: v.to(dtype) for k, v in d.items()}                                # noqa: E731
+    loc = decoder_loc_head_ref(cast(sub('decoder')), sol_y).view(modes, N, future_steps, 2)  # :95
+    scale = torch.nn.functional.elu(decoder_loc_head_ref(cast(sub('scale')), sol_y), alpha=1.0).view(modes, -1, future_steps, 2) + 1.0
+    scale = scale + min_scale                                                              # :98-99
+    return {'loc': torch.cat((loc, scale), dim=-1), 'pi': pi, 'reg_mask': ~padding_mask[:, -future_steps:],   # :100,104
+            'hidden_0': hidden_0, 'ys': ys}
+
+
+def l2_loss_ref(loc4: torch.Tensor, target: torch.Tensor, reg_mask: torch.Tensor) -> torch.Tensor:
+    """losses/L2.py:10-27: best mode per actor by mean masked displacement, then the mean displacement of that mode over the valid
+    (actor, slot) pairs.  ``loc4`` [modes,N,F,4] (cat of loc and scale, :12), target [N,F,2], reg_mask [N,F]."""
+    loc, _ = loc4.chunk(2, dim=-1)                                          # :12
+    l2 = torch.norm(target.unsqueeze(0) - loc, p=2, dim=-1)                 # :15
+    ade = l2.clone()
+    ade[:, ~reg_mask] = 0                                                   # :17-18
+    best = torch.argmin(ade.mean(-1), dim=0)                                # :19
+    minl2 = l2[best, torch.arange(l2.size(1))]                              # :20
+    if reg_mask.sum() > 0:
+        return minl2[reg_mask].mean()                                       # :22-24
+    return torch.zeros((), dtype=loc4.dtype)                                # :27 (returns the int 0)
+
+
+def diff_bce_ref(diff_in: torch.Tensor, diff_out: torch.Tensor) -> torch.Tensor:
+    """losses/diff_BCE.py:11-16 with the labels the encoder attaches (enc…sep2.py:194-195: in -> 0, out -> 1), mean reduction;
+    nn.BCELoss clamps each log term at -100."""
+    loss_in = -torch.clamp(torch.log1p(-diff_in), min=-100.0).mean()
+    loss_out = -torch.clamp(torch.log(diff_out), min=-100.0).mean()
+    return loss_in + loss_out

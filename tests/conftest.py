@@ -50,3 +50,8 @@ def golden_encoder():
 @pytest.fixture(scope='session')
 def golden_schedule():
     return load_golden('schedule.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_stage():
+    return load_golden('decoder_stage.npz')

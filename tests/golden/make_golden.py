@@ -6,6 +6,9 @@ Fixtures (all float32 unless noted, seeds fixed):
   decoder_solve.npz   reference SDEDecoder.lsde_func + torchsde.sdeint call (dec…sde.py:88): 48 rows, 61 steps, dW supplied;
                       weights (non-zero biases), y0, dW, ys, Brownian query times (ta,tb), loc/scale head parameters and outputs.
   encoder_loop.npz    reference sdeint_dual + GRU_Unit loop (enc…sep2.py:128-182): 40 rows, 21 steps, dual g, masks.
+  decoder_stage.npz   the reference's whole `SDEDecoder.forward` (dec…sde.py:77-105: aggr_embed -> sdeint -> heads -> elu -> cat, pi) on
+                      seeded embeddings with supplied dW, its `L2` / `DiffBCE` losses (losses/L2.py, losses/diff_BCE.py) with their
+                      gradients through the reference solver, and `ADE_T` / `FDE_T` (metrics/ade_t.py, metrics/fde_t.py) of the result.
   schedule.npz        step schedules for the grids of SURVEY App. A (F = 10,20,30,50,60,100,200 and the encoder pairs),
                       from the literal torch replay + the (ta,tb) the reference solver actually queried.
 Cannot run on the GPU box (/root/reference absent there) — the outputs are committed.
@@ -102,8 +105,76 @@ def schedule_fixture():
     print('schedule: grids', [k for k in d if k.endswith('/h')])
 
 
+def stage_fixture():
+    """SDEDecoder.forward + losses + metrics, run verbatim from the reference (training-mode graph: gradients included)."""
+    from importlib.machinery import SourceFileLoader
+    m = rr.load_reference()
+    ref = rr.REFERENCE_ROOT
+    L2 = SourceFileLoader('L2', os.path.join(ref, 'losses/L2.py')).load_module('L2').L2
+    DiffBCE = SourceFileLoader('DiffBCE', os.path.join(ref, 'losses/diff_BCE.py')).load_module('DiffBCE').DiffBCE
+    ADE_T = SourceFileLoader('ADE_T', os.path.join(ref, 'metrics/ade_t.py')).load_module('ADE_T').ADE_T
+    FDE_T = SourceFileLoader('FDE_T', os.path.join(ref, 'metrics/fde_t.py')).load_module('FDE_T').FDE_T
+    dec = rr.build_reference_decoder(seed=5, bias_std=0.1).train()
+    g = torch.Generator().manual_seed(777)
+    N, modes, F_, H = 12, 10, 60, 21
+    local_embed = torch.randn(N, 64, generator=g).requires_grad_(True)
+    global_embed = torch.randn(modes, N, 64, generator=g).requires_grad_(True)
+    source = torch.tensor([0] * 5 + [1] * 7)                    # per-actor here: one agent per scene, nuScenes scenes first
+    pad = torch.ones(N, H + F_, dtype=torch.bool)               # padding_mask: True = padded
+    pad[source == 0, 0:H:5] = False                             # nuScenes-shaped: past slots {0,5,..,20}, future slots {4,9,..,59}
+    pad[source == 0, H + 4::5] = False
+    pad[source == 1, 1:H] = False                               # Argoverse-shaped: past 1..20, future 0..29
+    pad[source == 1, H:H + 30] = False
+    pad[3, H + 40:] = True                                      # ragged: one actor loses its tail, one has no future at all
+    pad[9, H:] = True
+    y = torch.randn(N, F_, 2, generator=g).cumsum(1) * 0.5
+    data = {'padding_mask': pad, 'y': y}
+    sched = so.euler_schedule_ref(dec.ts_pred, dec.min_stepsize)
+    S = sched['h'].numel()
+    dW = torch.randn(S, modes * N, 64, generator=g) * torch.sqrt(sched['h']).view(S, 1, 1)
+    glob = type(dec).forward.__globals__
+    orig = glob['sdeint']
+    captured = {}
+
+    def sdeint_with_dw(sde, y0, ts, **kw):
+        captured['hidden_0'] = y0.detach().clone()
+        ys = orig(sde, y0, ts, bm=m['torchsde'].FixedIncrements(dW), **kw)
+        captured['ys'] = ys.detach().clone()
+        return ys
+
+    glob['sdeint'] = sdeint_with_dw
+    try:
+        out = dec(data, local_embed, global_embed)
+    finally:
+        glob['sdeint'] = orig
+    diff_in = (torch.rand(4, 64, generator=g) * 0.8 + 0.1).requires_grad_(True)      # what the encoder hands DiffBCE: g in (0,1), repeated
+    diff_out = (torch.rand(4, 64, generator=g) * 0.8 + 0.1).requires_grad_(True)
+    out['diff_in'], out['diff_out'] = diff_in, diff_out
+    out['label_in'], out['label_out'] = torch.full_like(diff_in, 0), torch.full_like(diff_out, 1)   # enc…sep2.py:194-195
+    l2 = L2(reduction='mean')(data, out)
+    bce = DiffBCE(reduction='mean')(data, out)
+    (l2 + bce).backward()                                        # loss_weights [1, 1]  (yml:86)
+    agent_index = torch.arange(N)
+    ade, fde = ADE_T('nuScenes', [59, 29]), FDE_T('nuScenes', [59, 29])
+    pred = out['loc'][:, agent_index, :, :2].detach()
+    ade.update(pred, y[agent_index], out['reg_mask'][agent_index], source)
+    fde.update(pred, y[agent_index], out['reg_mask'][agent_index], source)
+    d = dict(local_embed=local_embed.detach().numpy(), global_embed=global_embed.detach().numpy(), padding_mask=pad.numpy(), y=y.numpy(),
+             source=source.numpy(), dW=dW.numpy(), hidden_0=captured['hidden_0'].numpy(), ys=captured['ys'].numpy(),
+             loc=out['loc'].detach().numpy(), pi=out['pi'].detach().numpy(), reg_mask=out['reg_mask'].numpy(),
+             diff_in=diff_in.detach().numpy(), diff_out=diff_out.detach().numpy(), loss_l2=np.float64(l2.item()),
+             loss_bce=np.float64(bce.item()), ade=np.float64(float(ade.compute())), fde=np.float64(float(fde.compute())),
+             grad_local_embed=local_embed.grad.numpy(), grad_global_embed=global_embed.grad.numpy(),
+             grad_diff_in=diff_in.grad.numpy(), grad_diff_out=diff_out.grad.numpy(), min_scale=np.float64(dec.min_scale))
+    d.update({f'param/{k}': v.detach().numpy() for k, v in dec.state_dict().items()})
+    d.update({f'grad/{k}': (p.grad.numpy() if p.grad is not None else np.zeros(tuple(p.shape), np.float32)) for k, p in dec.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, 'decoder_stage.npz'), **d)
+    print('decoder_stage: loc', tuple(out['loc'].shape), 'L2', l2.item(), 'BCE', bce.item(), 'ADE', float(ade.compute()), 'FDE', float(fde.compute()))
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)       # fixture bytes must not depend on the thread count of the generating host
     decoder_fixture()
     encoder_fixture()
     schedule_fixture()
+    stage_fixture()

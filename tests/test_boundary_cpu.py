@@ -70,22 +70,22 @@ def test_install_rebinds_reference_module_globals():
 
 
 def test_install_binds_fused_gru_forward_on_the_instance_only():
-    """install() also routes encoder.GRU_unit.forward (the jump at enc…sep2.py:165-169) to the fused operator — as an instance
+    """install() also routes encoder.gru_unit.forward (the jump at enc…sep2.py:165-169) to the fused operator — as an instance
     attribute, so the reference class and other instances keep their forward; uninstall() removes it again."""
     from trajsde_b200 import synthetic as syn
     g = {'sdeint_dual': 'ORIGINAL', '__name__': 'LocalEncoderSDESepPara2'}
     exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", g)
     enc = g['Stage']()
-    enc.GRU_unit = syn.GRUUnit()
+    enc.gru_unit = syn.GRUUnit()
     other = syn.GRUUnit()
     saved = patch.install(encoder=enc)
-    assert 'forward' in enc.GRU_unit.__dict__ and 'forward' not in other.__dict__
+    assert 'forward' in enc.gru_unit.__dict__ and 'forward' not in other.__dict__
     with pytest.raises(RuntimeError, match='no CPU fallback'):
-        enc.GRU_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool))
+        enc.gru_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool))
     patch.uninstall(saved)
-    assert 'forward' not in enc.GRU_unit.__dict__
-    assert enc.GRU_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool)).shape == (3, 64)
-    enc.GRU_unit = syn.GRUUnit(n_units=100)                         # other widths stay on the reference path
+    assert 'forward' not in enc.gru_unit.__dict__
+    assert enc.gru_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool)).shape == (3, 64)
+    enc.gru_unit = syn.GRUUnit(n_units=100)                         # other widths stay on the reference path
     assert 'gru' not in patch.install(encoder=enc, fuse_gru=True)
 
 
@@ -143,3 +143,84 @@ def test_install_on_the_live_reference_decoder():
     finally:
         patch.uninstall(saved)
     assert g['sdeint'] is orig and 'forward' not in dec.decoder.__dict__ and 'forward' not in dec.scale.__dict__
+
+
+REF_ENC_KW = dict(historical_steps=21, node_dim=2, edge_dim=2, embed_dim=64, num_heads=8, dropout=0.1, parallel=True, local_radius=50,
+                  sde_layers=2, ref_time=20, max_past_t=2, run_backwards=True, minimum_step=0.1, rtol=0.001, atol=0.001, method='euler')
+
+
+def test_install_on_the_live_reference_encoder_binds_the_gru_jump():
+    """The reference encoder names its jump module `gru_unit` (enc…sep2.py:49; state_dict `encoder.gru_unit.*`): install() on a real
+    `LocalEncoderSDESepPara2` instance must rebind `sdeint_dual` AND the GRU jump, and uninstall() must restore both."""
+    from oracle import ref_runner as rr
+    if not rr.reference_available():
+        pytest.skip("reference tree absent (GPU box)")
+    enc = rr.load_reference()['enc'].LocalEncoderSDESepPara2(**REF_ENC_KW)
+    g = type(enc).forward.__globals__
+    orig = g['sdeint_dual']
+    saved = patch.install(encoder=enc)
+    try:
+        assert g['sdeint_dual'] is tb.sdeint_dual
+        assert 'gru' in saved and 'forward' in enc.gru_unit.__dict__
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            enc.gru_unit(h_cur=torch.zeros(3, 64), input_tensor=torch.zeros(3, 64), mask=torch.ones(3, dtype=torch.bool))
+    finally:
+        patch.uninstall(saved)
+    assert g['sdeint_dual'] is orig and 'forward' not in enc.gru_unit.__dict__
+    assert any(k.startswith('gru_unit.') for k in enc.state_dict())
+
+
+def test_default_seed_follows_torch_seed_and_rank(monkeypatch):
+    """bm=None default seeding: derived from torch.initial_seed() (so torch.manual_seed / pl.seed_everything reproduce a run and an
+    unseeded process draws fresh noise, like BrownianInterval(entropy=None)), mixed with the distributed rank."""
+    from trajsde_b200 import solver as mod
+    saved = dict(mod._defaults)
+    try:
+        mod._defaults.update(seed=None, torch_seed=None, calls=0)
+        torch.manual_seed(1234)
+        a = [mod._next_call_seed() for _ in range(3)]
+        torch.manual_seed(1234)
+        mod._defaults.update(seed=None, torch_seed=None, calls=0)
+        assert a == [mod._next_call_seed() for _ in range(3)] and len(set(a)) == 3
+        torch.manual_seed(99)                                    # re-seeding torch mid-run restarts the stream from the new seed
+        b = mod._next_call_seed()
+        assert b not in a
+        torch.manual_seed(1234)
+        assert mod._next_call_seed() == a[0]
+        monkeypatch.setattr(mod, '_rank', lambda: 3)
+        mod._defaults.update(seed=None, torch_seed=None, calls=0)
+        assert mod._next_call_seed() != a[0]                     # another rank, another stream
+        tb.manual_seed(5)                                        # explicit library seed: torch's seed no longer matters
+        c = mod._next_call_seed()
+        torch.manual_seed(7)
+        tb.manual_seed(5)
+        assert mod._next_call_seed() == c
+    finally:
+        mod._defaults.update(saved)
+
+
+def test_device_schedule_cache_is_keyed_by_content():
+    import inspect
+    from trajsde_b200 import ops
+    src = inspect.getsource(ops.DeviceSchedule.get)
+    assert 'id(' not in src and 'tobytes' in src
+
+
+def test_adjoint_range_policy_api():
+    from trajsde_b200 import ops
+    with pytest.raises(ValueError):
+        ops.set_adjoint_range_policy('maybe')
+    ops.set_adjoint_range_policy('raise')
+    ops.set_adjoint_range_policy('warn')
+    assert issubclass(ops.AdjointRangeError, FloatingPointError)
+    ops.poll_status()                                             # no device touched yet: a no-op
+
+
+def test_fused_head_pair_key_handles_inference_tensors():
+    """Lightning runs validate/test/predict under torch.inference_mode(): inference tensors have no version counter."""
+    from trajsde_b200.heads import FusedHeadPair
+    with torch.inference_mode():
+        x = torch.zeros(2, 3, 64)
+        assert FusedHeadPair._key_of(x)[1] is None
+    y = torch.zeros(2, 3, 64)
+    assert FusedHeadPair._key_of(y)[1] == y._version

@@ -189,7 +189,7 @@ def test_gru_jump_forward_and_gradients(rows):
 
 
 def test_stepwise_encoder_with_installed_gru_matches_fused_recurrence():
-    """The drop-in path (reference loop: sdeint_dual + GRU_unit per iteration, both rebound by install()) and the fused recurrence
+    """The drop-in path (reference loop: sdeint_dual + gru_unit per iteration, both rebound by install()) and the fused recurrence
     kernel compute the same latents from the same Brownian increments."""
     from trajsde_b200 import patch
     rows = 150
@@ -204,7 +204,7 @@ def test_stepwise_encoder_with_installed_gru_matches_fused_recurrence():
     glob = {'sdeint_dual': None}
     exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", glob)
     enc_stage = glob['Stage']()
-    enc_stage.GRU_unit = gru
+    enc_stage.gru_unit = gru
     saved = patch.install(encoder=enc_stage)
     try:
         with torch.no_grad():

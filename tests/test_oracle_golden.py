@@ -77,3 +77,63 @@ def test_oracle_vs_live_reference_encoder():
                                         rr.net_params(lsde.g_argo.net), rr.net_params(gru), h0, aa, am, nm, dW)
     assert (lat - lat_ref).abs().max() < 2e-6
     assert (gs.repeat(1, 1, 64) - g_ref).abs().max() < 5e-7
+
+
+# ---- decoder stage, losses, metrics (SURVEY §8(f)-4, row g): oracle vs the reference's own SDEDecoder.forward / L2 / DiffBCE / ADE_T / FDE_T ----
+def _stage_inputs(d, dtype=torch.float32):
+    p = {k[len('param/'):]: torch.from_numpy(d[k]).to(dtype) for k in d if k.startswith('param/')}
+    le = torch.from_numpy(d['local_embed']).to(dtype)
+    ge = torch.from_numpy(d['global_embed']).to(dtype)
+    return p, le, ge, torch.from_numpy(d['padding_mask']), torch.from_numpy(d['dW'])
+
+
+def test_decoder_stage_forward_vs_golden(golden_stage):
+    d = golden_stage
+    p, le, ge, pad, dW = _stage_inputs(d)
+    out = so.decoder_forward_ref(p, le, ge, pad, dW, min_scale=float(d['min_scale']))
+    assert torch.allclose(out['hidden_0'], torch.from_numpy(d['hidden_0']), atol=1e-6, rtol=1e-6)      # aggr_embed
+    assert torch.allclose(out['ys'], torch.from_numpy(d['ys']), atol=2e-5, rtol=1e-5)                  # solve from the oracle's own hidden_0
+    assert torch.allclose(out['loc'], torch.from_numpy(d['loc']), atol=2e-5, rtol=1e-5)                # [10,12,60,4] = cat(loc, scale)
+    assert torch.allclose(out['pi'], torch.from_numpy(d['pi']), atol=1e-5, rtol=1e-5)
+    assert torch.equal(out['reg_mask'], torch.from_numpy(d['reg_mask']))
+
+
+def test_losses_and_metrics_vs_golden(golden_stage):
+    d = golden_stage
+    loc, y, rm = torch.from_numpy(d['loc']), torch.from_numpy(d['y']), torch.from_numpy(d['reg_mask'])
+    assert abs(float(so.l2_loss_ref(loc, y, rm)) - float(d['loss_l2'])) < 1e-6
+    assert abs(float(so.diff_bce_ref(torch.from_numpy(d['diff_in']), torch.from_numpy(d['diff_out']))) - float(d['loss_bce'])) < 1e-6
+    assert abs(so.ade_t_ref(loc[..., :2], y, rm) - float(d['ade'])) < 1e-5
+    assert abs(so.fde_t_ref(loc[..., :2], y, rm, torch.from_numpy(d['source'])) - float(d['fde'])) < 1e-5
+    ade2, _ = so.min_ade_fde_ref(loc[..., :2], y, rm)          # the older helper agrees with the ADE_T restatement
+    assert abs(ade2 - float(d['ade'])) < 1e-5
+
+
+def test_training_gradients_through_the_stage_vs_golden(golden_stage):
+    """fp64 autograd of the oracle chain (aggr_embed -> solve -> heads -> L2, + DiffBCE) reproduces the gradients the reference's
+    own forward/backward produced in fp32 — this is the oracle the GPU training-step tests lean on."""
+    d = golden_stage
+    p, le, ge, pad, dW = _stage_inputs(d, torch.float64)
+    for v in p.values():
+        v.requires_grad_(True)
+    le.requires_grad_(True); ge.requires_grad_(True)
+    di = torch.from_numpy(d['diff_in']).double().requires_grad_(True)
+    do = torch.from_numpy(d['diff_out']).double().requires_grad_(True)
+    out = so.decoder_forward_ref(p, le, ge, pad, dW.double(), min_scale=float(d['min_scale']))
+    loss = so.l2_loss_ref(out['loc'], torch.from_numpy(d['y']).double(), out['reg_mask']) + so.diff_bce_ref(di, do)
+    loss.backward()
+
+    def close(a, b, name):
+        b = torch.from_numpy(b).double()
+        assert (a - b).abs().max() <= 2e-4 * b.abs().max() + 1e-9, name
+
+    close(le.grad, d['grad_local_embed'], 'local_embed')
+    close(ge.grad, d['grad_global_embed'], 'global_embed')
+    close(di.grad, d['grad_diff_in'], 'diff_in')
+    close(do.grad, d['grad_diff_out'], 'diff_out')
+    for k in ('aggr_embed.0.weight', 'aggr_embed.1.bias', 'lsde_func.f_func.net.0.weight', 'lsde_func.f_func.net.4.bias',
+              'lsde_func.g_func.net.0.weight', 'lsde_func.g_func.net.4.weight', 'decoder.0.weight', 'decoder.1.weight', 'decoder.3.weight',
+              'decoder.3.bias'):
+        close(p[k].grad, d['grad/' + k], k)
+    # the scale head and pi do not reach L2 (loc only, losses/L2.py:12,15): their reference gradients are exactly zero
+    assert not d['grad/scale.0.weight'].any() and not d['grad/pi.0.weight'].any()

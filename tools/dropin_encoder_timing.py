@@ -11,7 +11,7 @@ b = syn.make_batch(scenes, 20, seed=5, mixed_sources=True)
 tr = {k: getattr(b, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask')}
 glob = {'sdeint_dual': None}
 exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", glob)
-stage = glob['Stage'](); stage.GRU_unit = gru
+stage = glob['Stage'](); stage.gru_unit = gru
 
 
 def step(i, fused):

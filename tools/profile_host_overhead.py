@@ -9,7 +9,7 @@ b = syn.make_batch(128, 20, seed=5, mixed_sources=True)
 tr = {k: getattr(b, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask')}
 glob = {'sdeint_dual': None}
 exec("class Stage:\n    def forward(self):\n        return sdeint_dual\n", glob)
-stage = glob['Stage'](); stage.GRU_unit = gru
+stage = glob['Stage'](); stage.gru_unit = gru
 patch.install(encoder=stage)
 def step(i):
     aa = tr['aa_out'].detach().requires_grad_(True)

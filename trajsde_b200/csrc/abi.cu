@@ -208,7 +208,29 @@ int trajsde_enc_bwd(const TrajsdeEncBwdArgs* a, void* cuda_stream) {
   for (int i = 0; i < (a->alt_mask ? 3 : 2); ++i)
     if (!mg[i]->w1 || !mg[i]->b1 || !mg[i]->w2 || !mg[i]->b2 || !mg[i]->w3 || !mg[i]->b3)
       return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null gradient pointer");
-  if (a->rows == 0) return TRAJSDE_OK;
+  if (a->rows == 0) {
+    // an empty shard still owes its caller defined parameter gradients (they are accumulated into .grad and all-reduced): zeros
+    if ((rc = check_device()) != 0) return rc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    for (int i = 0; i < (a->alt_mask ? 3 : 2); ++i) {
+      const size_t n3 = i == 0 ? 64 * 64 : 64, nb3 = i == 0 ? 64 : 1;
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->w1, 0, sizeof(float) * 64 * 66, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->b1, 0, sizeof(float) * 64, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->w2, 0, sizeof(float) * 64 * 64, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->b2, 0, sizeof(float) * 64, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->w3, 0, sizeof(float) * n3, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->b3, 0, sizeof(float) * nb3, s));
+    }
+    float* const w128[3] = {gg.u1, gg.r1, gg.n1};
+    float* const w64[3] = {gg.u2, gg.r2, gg.n2};
+    float* const bias[6] = {gg.ub1, gg.ub2, gg.rb1, gg.rb2, gg.nb1, gg.nb2};
+    for (int i = 0; i < 3; ++i) {
+      TS_CUDA_CHECK(cudaMemsetAsync(w128[i], 0, sizeof(float) * 64 * 128, s));
+      TS_CUDA_CHECK(cudaMemsetAsync(w64[i], 0, sizeof(float) * 64 * 64, s));
+    }
+    for (int i = 0; i < 6; ++i) TS_CUDA_CHECK(cudaMemsetAsync(bias[i], 0, sizeof(float) * 64, s));
+    return TRAJSDE_OK;
+  }
   if (!a->h0 || !a->aa_out || !a->slot || !a->obs_mask || !a->latent || !a->y1 || !a->grad_h0)
     return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h0/aa_out/slot/obs_mask/latent/y1/grad_h0 null");
   if (!aligned16(a->h0) || !aligned16(a->aa_out) || !aligned16(a->latent) || !aligned16(a->y1) || !aligned16(a->grad_h0) ||

@@ -141,7 +141,7 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
 }
 
 // ---- stand-alone GRU_Unit forward / backward (trajsde_gru_fwd / trajsde_gru_bwd): the jump as its own operator, for the drop-in path
-// that keeps the reference's encoder loop (install() rebinds GRU_unit.forward) --------------------------------------------------------
+// that keeps the reference's encoder loop (install() rebinds gru_unit.forward) --------------------------------------------------------
 int64_t gru_standalone_workspace_bytes(int64_t rows) {
   (void)rows;
   return align256(GRU_TC_IMG_BYTES) + 256 + 256 + align256((int64_t)MAX_PARTIALS * GRU_G_PAD * 4);

@@ -43,7 +43,7 @@ def _enc_tables(max_past_t, hist, dt, device):
 
 def gru_jump(gru_unit, h_cur: torch.Tensor, input_tensor: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """``GRU_Unit.forward(h_cur, input_tensor, mask)`` (models/utils/ode_utils.py:136-152) as one tensor-core launch with a fused
-    backward; what ``install()`` binds ``encoder.GRU_unit.forward`` to.  CUDA / 64-wide layers only — no fallback."""
+    backward; what ``install()`` binds ``encoder.gru_unit.forward`` to.  CUDA / 64-wide layers only — no fallback."""
     if not h_cur.is_cuda:
         raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
     return ops.gru_call(h_cur, input_tensor, mask, _gru_params(gru_unit))

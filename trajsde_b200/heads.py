@@ -102,7 +102,9 @@ class FusedHeadPair:
 
     @staticmethod
     def _key_of(x):
-        return (x.data_ptr(), x._version, tuple(x.shape), tuple(x.stride()))
+        # inference tensors (torch.inference_mode(): Lightning's validate / test / predict loops) do not track a version counter
+        version = None if x.is_inference() else x._version
+        return (x.data_ptr(), version, tuple(x.shape), tuple(x.stride()))
 
     def _both(self, x):
         return decoder_heads(self.loc_head, self.scale_head, x)

@@ -7,6 +7,7 @@ The ops do not own parameters: they read the caller's ``nn.Linear`` tensors on e
 unchanged) and return gradients for them through ``register_autograd``.
 """
 import ctypes as C
+import os as _os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -24,26 +25,101 @@ _KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-
 # A/B switch (tests, bench): run the fp32 CUDA-core backward kernels even in 'tc_f16' mode (TRAJSDE_BWD_FLAG_EXACT_KERNELS)
 BWD_EXACT_KERNELS = False
 
-# per-device int32 status word the tensor-core backward kernels OR their TRAJSDE_STATUS_* bits into (no sync on the hot path)
+# per-device int32 status word the tensor-core backward kernels OR their TRAJSDE_STATUS_* bits into.  The word is never read on the
+# hot path: after every tensor-core backward call a snapshot is copied to pinned host memory on the same stream (4 bytes, no sync)
+# and the NEXT call into this module looks at the snapshot once its copy event has completed — so a clipped gradient surfaces within
+# one optimizer step as a warning or an exception (policy below) without ever blocking the stream.
+ADJOINT_RANGE_POLICIES = ('warn', 'raise', 'ignore')
+_POLICY = {'adjoint_range': _os.environ.get('TRAJSDE_ADJOINT_RANGE', 'warn')}
+if _POLICY['adjoint_range'] not in ADJOINT_RANGE_POLICIES:
+    raise ValueError(f"TRAJSDE_ADJOINT_RANGE must be one of {ADJOINT_RANGE_POLICIES}")
+
+
+class AdjointRangeError(FloatingPointError):
+    """Raised (policy 'raise') when a tensor-core backward call reported TRAJSDE_STATUS_ADJOINT_RANGE."""
+
+
+_ADJOINT_MSG = ("trajsde_b200: a tensor-core backward call reported TRAJSDE_STATUS_ADJOINT_RANGE — the loss-scaled adjoint outgrew the "
+                "fp16 delta range, so the gradients of that step may be clipped.  Rerun the step with ops.BWD_EXACT_KERNELS = True or "
+                "mode='exact' (policy: trajsde_b200.ops.set_adjoint_range_policy('warn' | 'raise' | 'ignore'), env TRAJSDE_ADJOINT_RANGE)")
+
+
+class _StatusMonitor:
+    def __init__(self, device: torch.device):
+        self.word = torch.zeros((1,), dtype=torch.int32, device=device)
+        self.host = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        self.event: Optional[torch.cuda.Event] = None
+        self.seen = 0                                      # bits reported so far and not yet cleared by backward_status()
+
+    def snapshot(self):
+        """Enqueue a 4-byte D2H copy of the status word behind the backward kernels just launched (if none is pending)."""
+        if _POLICY['adjoint_range'] == 'ignore' or self.event is not None:
+            return
+        self.host.copy_(self.word, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(self.word.device))
+
+    def poll(self, block: bool = False):
+        if self.event is None or not (block or self.event.query()):
+            return
+        if block:
+            self.event.synchronize()
+        self.event = None
+        v = int(self.host[0])
+        new_bits = v & ~self.seen
+        self.seen |= v
+        if new_bits & _lib.STATUS_ADJOINT_RANGE:
+            pol = _POLICY['adjoint_range']
+            if pol == 'raise':
+                self.word.zero_()
+                self.seen = 0
+                raise AdjointRangeError(_ADJOINT_MSG)
+            if pol == 'warn':
+                import warnings
+                warnings.warn(_ADJOINT_MSG, RuntimeWarning, stacklevel=3)
+
+
 _STATUS = {}
 
 
+def _monitor(device) -> _StatusMonitor:
+    m = _STATUS.get(str(device))
+    if m is None:
+        m = _StatusMonitor(torch.device(device))
+        _STATUS[str(device)] = m
+    return m
+
+
 def _status_word(device) -> torch.Tensor:
-    t = _STATUS.get(str(device))
-    if t is None:
-        t = torch.zeros((1,), dtype=torch.int32, device=device)
-        _STATUS[str(device)] = t
-    return t
+    return _monitor(device).word
+
+
+def set_adjoint_range_policy(policy: str) -> None:
+    """What happens when a tensor-core backward reports a clipped adjoint: 'warn' (default, RuntimeWarning at the next call into the
+    library), 'raise' (AdjointRangeError at the next call) or 'ignore' (poll ``backward_status`` yourself)."""
+    if policy not in ADJOINT_RANGE_POLICIES:
+        raise ValueError(f"policy must be one of {ADJOINT_RANGE_POLICIES}")
+    _POLICY['adjoint_range'] = policy
+
+
+def poll_status(device=None, block: bool = False) -> None:
+    """Look at the pending status snapshots (non-blocking unless ``block``); called by every op of this module on entry, and by
+    ``FlatGradBucket.all_reduce_mean`` / user code once per optimizer step with ``block=True`` for a same-step guarantee."""
+    for key, m in list(_STATUS.items()):
+        if device is None or key == str(torch.device(device)):
+            m.poll(block)
 
 
 def backward_status(device, clear: bool = True) -> int:
     """TRAJSDE_STATUS_* bits raised by tensor-core backward calls on ``device`` since the last clear (synchronises).
     Bit ``_lib.STATUS_ADJOINT_RANGE``: the loss-scaled adjoint outgrew the fp16 delta range — gradients may be clipped; rerun
     that step with ``ops.BWD_EXACT_KERNELS = True`` or ``mode='exact'``."""
-    t = _status_word(torch.device(device))
-    v = int(t.item())
+    m = _monitor(torch.device(device))
+    v = int(m.word.item())
     if clear:
-        t.zero_()
+        m.word.zero_()
+        m.seen = 0
+        m.event = None
     return v
 
 
@@ -63,14 +139,15 @@ class DeviceSchedule:
 
     @classmethod
     def get(cls, sched: EulerSchedule, device: torch.device) -> "DeviceSchedule":
-        key = (id(sched), str(device))
+        # keyed by the schedule's CONTENT (step starts / sizes / output map), never by object identity
+        key = (sched.t0.tobytes(), sched.h.tobytes(), sched.out_k.tobytes(), sched.w0.tobytes(), sched.w1.tobytes(), str(device))
         hit = cls._cache.get(key)
-        if hit is None or hit[0] is not sched:
+        if hit is None:
             if len(cls._cache) > 256:
                 cls._cache.clear()
-            hit = (sched, cls(sched, device))
+            hit = cls(sched, device)
             cls._cache[key] = hit
-        return hit[1]
+        return hit
 
 
 def _mlp_struct(ts: Sequence[torch.Tensor]) -> _lib.Mlp:
@@ -101,8 +178,7 @@ def _stream_ptr(device) -> int:
 # ---------------------------------------------------------------------------------------------------------------------
 # forward
 # ---------------------------------------------------------------------------------------------------------------------
-@torch.library.custom_op("trajsde::euler_fwd", mutates_args=(), device_types="cuda")
-def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor,
+def _euler_fwd_impl(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor,
               out_w: torch.Tensor, n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor],
               seed: int, row_offset: int, step_offset: int, mode: int, save_states: bool, rows_major: bool,
               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -112,6 +188,7 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
     if y0.dim() != 2 or y0.shape[1] != 64 or y0.dtype != torch.float32:
         raise ValueError("`y0` must be float32 of shape (rows, 64)")
     dev = y0.device
+    _monitor(dev).poll()
     rows = y0.shape[0]
     S = step_tab.shape[0]
     dual = alt_mask is not None
@@ -159,6 +236,9 @@ def euler_fwd(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torch.Tens
     return ys, g_last, states
 
 
+euler_fwd = torch.library.custom_op("trajsde::euler_fwd", _euler_fwd_impl, mutates_args=(), device_types="cuda")
+
+
 @euler_fwd.register_fake
 def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, save_states,
       rows_major):
@@ -171,13 +251,13 @@ def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row
 # ---------------------------------------------------------------------------------------------------------------------
 # backward
 # ---------------------------------------------------------------------------------------------------------------------
-@torch.library.custom_op("trajsde::euler_bwd", mutates_args=(), device_types="cuda")
-def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], states: torch.Tensor,
+def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], states: torch.Tensor,
               params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor, out_w: torch.Tensor,
               n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor], seed: int, row_offset: int,
               step_offset: int, mode: int) -> List[torch.Tensor]:
     """[grad_y0] + gradients of every tensor in ``params`` (same order/shapes)."""
     dev = states.device
+    _monitor(dev).poll()
     S, rows = states.shape[0], states.shape[1]
     dual = alt_mask is not None
     ps = _check_params(params, dual, dev)
@@ -216,12 +296,17 @@ def euler_bwd(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], s
     a.workspace, a.workspace_bytes = ws.data_ptr(), need
     with torch.cuda.device(dev):
         _lib.check(L.trajsde_euler_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_euler_bwd")
+        if rows > 0 and mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS:
+            _monitor(dev).snapshot()
     if rows > 0:
         tc = mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS
         # TC: pack + absmax + fused dgrad/wgrad + reduce; exact: (dgrad + wgrad) per diffusion net + reduce
         sampled = tc and grad_ys is not None and rows * grad_ys.shape[0] >= (1 << 16)   # sampled absmax + its conditional full scan
         LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
     return [grad_y0] + gparams
+
+
+euler_bwd = torch.library.custom_op("trajsde::euler_bwd", _euler_bwd_impl, mutates_args=(), device_types="cuda")
 
 
 @euler_bwd.register_fake
@@ -257,14 +342,14 @@ euler_fwd.register_autograd(_backward, setup_context=_setup_context)
 # ---------------------------------------------------------------------------------------------------------------------
 # fused encoder recurrence: one forward launch, one backward call (reverse sweep enqueued by the library)
 # ---------------------------------------------------------------------------------------------------------------------
-@torch.library.custom_op("trajsde::enc_fwd", mutates_args=(), device_types="cuda")
-def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
+def _enc_fwd_impl(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
             gru_params: List[torch.Tensor], step_tab: torch.Tensor, dw: Optional[torch.Tensor],
             alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int, save_y1: bool,
             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """latent[S,rows,64] (post-GRU state of every iteration), g[S,rows] (pre-step diffusion of every iteration),
     y1[S,rows,64] (pre-GRU state of every iteration; empty unless ``save_y1`` — the backward needs it)."""
     dev = h0.device
+    _monitor(dev).poll()
     rows, S = h0.shape[0], step_tab.shape[0]
     dual = alt_mask is not None
     ps = _check_params(params, dual, dev)
@@ -322,6 +407,9 @@ def enc_fwd(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot
     return latent, g_out, y1s
 
 
+enc_fwd = torch.library.custom_op("trajsde::enc_fwd", _enc_fwd_impl, mutates_args=(), device_types="cuda")
+
+
 @enc_fwd.register_fake
 def _(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset, save_y1):
     rows, S = h0.shape[0], step_tab.shape[0]
@@ -331,13 +419,13 @@ def _(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, se
 _GRU_NAMES = ('u1', 'ub1', 'u2', 'ub2', 'r1', 'rb1', 'r2', 'rb2', 'n1', 'nb1', 'n2', 'nb2')
 
 
-@torch.library.custom_op("trajsde::enc_bwd", mutates_args=(), device_types="cuda")
-def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], latent: torch.Tensor, y1s: torch.Tensor,
+def _enc_bwd_impl(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], latent: torch.Tensor, y1s: torch.Tensor,
             h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor, slot: torch.Tensor, params: List[torch.Tensor],
             gru_params: List[torch.Tensor], step_tab: torch.Tensor, dw: Optional[torch.Tensor],
             alt_mask: Optional[torch.Tensor], seed: int, row_offset: int, step_offset: int) -> List[torch.Tensor]:
     """[grad_h0, grad_aa_out] + gradients of ``params`` + gradients of ``gru_params`` (same order / shapes)."""
     dev = latent.device
+    _monitor(dev).poll()
     S, rows = latent.shape[0], latent.shape[1]
     dual = alt_mask is not None
     ps = _check_params(params, dual, dev)
@@ -387,10 +475,15 @@ def enc_bwd(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Tensor],
     a.workspace, a.workspace_bytes = ws.data_ptr(), need
     with torch.cuda.device(dev):
         _lib.check(L.trajsde_enc_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_enc_bwd")
+        if rows > 0:
+            _monitor(dev).snapshot()
     if rows > 0:
         # tables + absmax x2 + pack per net + per iteration (GRU backward + one fused SDE backward per net) + two reduces
         LAUNCHES['n'] += 3 + (2 if dual else 1) + S * 2 + 2 + int(grad_latent is not None and rows * S >= (1 << 16))
     return [grad_h0, grad_aa] + gparams + ggru
+
+
+enc_bwd = torch.library.custom_op("trajsde::enc_bwd", _enc_bwd_impl, mutates_args=(), device_types="cuda")
 
 
 @enc_bwd.register_fake
@@ -454,8 +547,7 @@ def _gru_args(h_cur, x, mask, gru_params):
     return a, keep, L
 
 
-@torch.library.custom_op("trajsde::gru_fwd", mutates_args=(), device_types="cuda")
-def gru_fwd(h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor, gru_params: List[torch.Tensor]) -> torch.Tensor:
+def _gru_fwd_impl(h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor, gru_params: List[torch.Tensor]) -> torch.Tensor:
     """GRU_Unit.forward (models/utils/ode_utils.py:136-152) as one tensor-core launch: h_next[rows,64]."""
     a, keep, L = _gru_args(h_cur, x, mask, gru_params)
     out = torch.empty_like(keep[0])
@@ -467,13 +559,15 @@ def gru_fwd(h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor, gru_params
     return out
 
 
+gru_fwd = torch.library.custom_op("trajsde::gru_fwd", _gru_fwd_impl, mutates_args=(), device_types="cuda")
+
+
 @gru_fwd.register_fake
 def _(h_cur, x, mask, gru_params):
     return torch.empty_like(h_cur)
 
 
-@torch.library.custom_op("trajsde::gru_bwd", mutates_args=(), device_types="cuda")
-def gru_bwd(grad_out: torch.Tensor, h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor,
+def _gru_bwd_impl(grad_out: torch.Tensor, h_cur: torch.Tensor, x: torch.Tensor, mask: torch.Tensor,
             gru_params: List[torch.Tensor]) -> List[torch.Tensor]:
     """[grad_h_cur, grad_x] + gradients of the 12 GRU tensors."""
     a, keep, L = _gru_args(h_cur, x, mask, gru_params)
@@ -488,6 +582,9 @@ def gru_bwd(grad_out: torch.Tensor, h_cur: torch.Tensor, x: torch.Tensor, mask: 
     if h_cur.shape[0] > 0:
         LAUNCHES['n'] += 4
     return [gh, gx] + gg
+
+
+gru_bwd = torch.library.custom_op("trajsde::gru_bwd", _gru_bwd_impl, mutates_args=(), device_types="cuda")
 
 
 @gru_bwd.register_fake
@@ -513,16 +610,11 @@ gru_fwd.register_autograd(_gru_backward, setup_context=_gru_setup_context)
 # eager fast path
 # ---------------------------------------------------------------------------------------------------------------------
 # The torch.library operators above are the registered ops (dispatcher, fake tensors, torch.compile).  Eager callers — solver.py,
-# encoder.py, i.e. the drop-in functions — go through thin autograd.Function wrappers over the SAME implementations: that skips
+# encoder.py, i.e. the drop-in functions — go through thin autograd.Function wrappers over the SAME implementation functions
+# (`_*_impl`, the plain Python callables the operators were registered from): that skips
 # ~0.2 ms of dispatcher / pytree work per call, which is what the reference's 21-iteration encoder loop is made of.
 # TRAJSDE_USE_DISPATCHER=1 routes everything through the registered ops instead.
-import os as _os
-
 USE_DISPATCHER = _os.environ.get('TRAJSDE_USE_DISPATCHER', '0') == '1'
-
-
-def _raw(op):
-    return getattr(op, '_init_fn', op)
 
 
 def _needs_grad(*tensors) -> bool:
@@ -532,7 +624,7 @@ def _needs_grad(*tensors) -> bool:
 class _EulerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y0, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, rows_major, *params):
-        ys, g_last, states = _raw(euler_fwd)(y0, list(params), step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset,
+        ys, g_last, states = _euler_fwd_impl(y0, list(params), step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset,
                                              step_offset, mode, True, rows_major)
         ctx.save_for_backward(states, step_tab, out_begin, out_w, *params)
         ctx.dw, ctx.alt_mask = dw, alt_mask
@@ -544,7 +636,7 @@ class _EulerFn(torch.autograd.Function):
     def backward(ctx, grad_ys, grad_g):
         states, step_tab, out_begin, out_w, *params = ctx.saved_tensors
         n_outputs, seed, row_offset, step_offset, mode = ctx.meta
-        grads = _raw(euler_bwd)(grad_ys, grad_g, states, list(params), step_tab, out_begin, out_w, n_outputs, ctx.dw, ctx.alt_mask,
+        grads = _euler_bwd_impl(grad_ys, grad_g, states, list(params), step_tab, out_begin, out_w, n_outputs, ctx.dw, ctx.alt_mask,
                                 seed, row_offset, step_offset, mode)
         return (grads[0],) + (None,) * 11 + tuple(grads[1:])
 
@@ -559,7 +651,7 @@ def euler_call(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, 
     if save_states and _needs_grad(y0, *params):
         return _EulerFn.apply(y0, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode, rows_major,
                               *params)
-    ys, g_last, _ = _raw(euler_fwd)(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
+    ys, g_last, _ = _euler_fwd_impl(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset, step_offset, mode,
                                     False, rows_major)
     return ys, g_last
 
@@ -568,12 +660,12 @@ class _GruFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h_cur, x, mask, *gru_params):
         ctx.save_for_backward(h_cur, x, mask, *gru_params)
-        return _raw(gru_fwd)(h_cur, x, mask, list(gru_params))
+        return _gru_fwd_impl(h_cur, x, mask, list(gru_params))
 
     @staticmethod
     def backward(ctx, grad_out):
         h_cur, x, mask, *gru_params = ctx.saved_tensors
-        grads = _raw(gru_bwd)(grad_out, h_cur, x, mask, list(gru_params))
+        grads = _gru_bwd_impl(grad_out, h_cur, x, mask, list(gru_params))
         return (grads[0], grads[1], None) + tuple(grads[2:])
 
 
@@ -582,14 +674,14 @@ def gru_call(h_cur, x, mask, gru_params):
         return gru_fwd(h_cur, x, mask, gru_params)
     if _needs_grad(h_cur, x, *gru_params):
         return _GruFn.apply(h_cur, x, mask, *gru_params)
-    return _raw(gru_fwd)(h_cur, x, mask, gru_params)
+    return _gru_fwd_impl(h_cur, x, mask, gru_params)
 
 
 class _EncFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h0, aa_out, obs_mask, slot, step_tab, dw, alt_mask, seed, row_offset, step_offset, n_p, *all_params):
         params, gru_params = list(all_params[:n_p]), list(all_params[n_p:])
-        latent, g, y1s = _raw(enc_fwd)(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset,
+        latent, g, y1s = _enc_fwd_impl(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset,
                                        step_offset, True)
         ctx.save_for_backward(latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *all_params)
         ctx.dw, ctx.alt_mask = dw, alt_mask
@@ -601,7 +693,7 @@ class _EncFn(torch.autograd.Function):
     def backward(ctx, grad_latent, grad_g):
         latent, y1s, h0, aa_out, obs_mask, slot, step_tab, *all_params = ctx.saved_tensors
         seed, row_offset, step_offset, n_p = ctx.meta
-        grads = _raw(enc_bwd)(grad_latent, grad_g, latent, y1s, h0, aa_out, obs_mask, slot, list(all_params[:n_p]), list(all_params[n_p:]),
+        grads = _enc_bwd_impl(grad_latent, grad_g, latent, y1s, h0, aa_out, obs_mask, slot, list(all_params[:n_p]), list(all_params[n_p:]),
                               step_tab, ctx.dw, ctx.alt_mask, seed, row_offset, step_offset)
         return (grads[0], grads[1]) + (None,) * 9 + tuple(grads[2:])
 
@@ -615,7 +707,7 @@ def enc_call(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_m
     if need_grad:
         return _EncFn.apply(h0, aa_out, obs_mask, slot, step_tab, dw, alt_mask, seed, row_offset, step_offset, len(params),
                             *params, *gru_params)
-    latent, g, _ = _raw(enc_fwd)(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset,
+    latent, g, _ = _enc_fwd_impl(h0, aa_out, obs_mask, slot, params, gru_params, step_tab, dw, alt_mask, seed, row_offset, step_offset,
                                  False)
     return latent, g
 

@@ -32,7 +32,7 @@ def _sdeint_rows_major(sde, y0, ts, *args, **kwargs):
 
 def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True, fuse_heads: bool = True) -> dict:
     """Rebind ``sdeint`` (decoder module) and ``sdeint_dual`` (encoder module).  Pass the LightningModule-style ``model``
-    (with ``.decoder`` / ``.encoder``) or the stage modules directly.  With ``fuse_gru`` the encoder's ``GRU_unit`` instance
+    (with ``.decoder`` / ``.encoder``) or the stage modules directly.  With ``fuse_gru`` the encoder's ``gru_unit`` instance
     (the jump between SDE steps, enc…sep2.py:165-169) also gets its ``forward`` bound to the fused ``gru_jump`` — an instance
     attribute, the reference class is untouched — when the default mode is 'tc_f16' and its layers are 64 wide.  With
     ``fuse_heads`` the decoder's ``self.decoder`` / ``self.scale`` heads run as one fused launch under ``no_grad``.
@@ -61,7 +61,11 @@ def install(model=None, decoder=None, encoder=None, fuse_gru: bool = True, fuse_
             raise KeyError("encoder module has no global `sdeint_dual`")
         saved['encoder'] = (g, 'sdeint_dual', g['sdeint_dual'])
         g['sdeint_dual'] = sdeint_dual
-        gru = getattr(encoder, 'GRU_unit', None)
+        # the reference encoder's attribute is `gru_unit` (enc…sep2.py:49, used :169/:294; state_dict key `encoder.gru_unit.*`);
+        # `GRU_unit` is accepted for hosts that named it after the class
+        gru = getattr(encoder, 'gru_unit', None)
+        if gru is None:
+            gru = getattr(encoder, 'GRU_unit', None)
         if fuse_gru and gru is not None and get_default_mode() == 'tc_f16' and _is_64_wide_gru(gru):
             from .encoder import gru_jump
 

@@ -17,9 +17,9 @@ import torch.nn as nn
 from . import _lib, ops
 from .schedule import EulerSchedule, euler_schedule
 
-_state = threading.local()
-_defaults = {'mode': 'tc_f16', 'seed': 0x5DE0B200, 'calls': 0}
+_defaults = {'mode': 'tc_f16', 'seed': None, 'torch_seed': None, 'calls': 0}
 _seed_lock = threading.Lock()
+_MASK63 = 2**63 - 1
 
 
 def set_default_mode(mode: str) -> None:
@@ -34,17 +34,39 @@ def get_default_mode() -> str:
 
 
 def manual_seed(seed: int) -> None:
-    """Seed of the in-kernel Philox Brownian increments used when ``bm`` is None.  The op never touches torch's global
-    RNG; every solver call draws an independent stream derived from (seed, call index)."""
+    """Pin the base seed of the in-kernel Philox Brownian increments used when ``bm`` is None (every solver call draws an
+    independent stream derived from (base seed, call index); the call index restarts at 0 here).
+
+    Without this call the base seed follows torch: it is derived from ``torch.initial_seed()`` — so ``torch.manual_seed`` /
+    ``pl.seed_everything`` make runs reproducible, and an unseeded process draws fresh noise every run like the reference's
+    ``BrownianInterval(entropy=None)`` (models/utils/sdeint.py:983-984) — and, under ``torch.distributed``, from the rank, so
+    data-parallel ranks do not replay each other's increments.  The op itself never consumes torch's global RNG."""
     with _seed_lock:
-        _defaults['seed'], _defaults['calls'] = int(seed) & (2**63 - 1), 0
+        _defaults['seed'], _defaults['torch_seed'], _defaults['calls'] = int(seed) & _MASK63, None, 0
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+    return x ^ (x >> 31)
+
+
+def _rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
 def _next_call_seed() -> int:
     with _seed_lock:
+        if _defaults['seed'] is None or _defaults['torch_seed'] is not None:
+            ts = int(torch.initial_seed())                 # follows torch.manual_seed / seed_everything; re-derived when it changes
+            if ts != _defaults['torch_seed']:
+                _defaults['seed'] = _splitmix64(_splitmix64(ts & (2**64 - 1)) ^ (0xB200 + _rank())) & _MASK63
+                _defaults['torch_seed'], _defaults['calls'] = ts, 0
         k = _defaults['calls']
         _defaults['calls'] = k + 1
-        return (_defaults['seed'] + 0x9E3779B97F4A7C15 * (k + 1)) & (2**63 - 1)
+        return (_defaults['seed'] + 0x9E3779B97F4A7C15 * (k + 1)) & _MASK63
 
 
 # ---------------------------------------------------------------------------------------------------------------------
