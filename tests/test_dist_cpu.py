@@ -45,7 +45,10 @@ def _worker(rank, world, port, out):
     bucket.zero_()
     net(x_all[s:e]).sum().div(e - s).backward()
     assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())   # grads accumulated into the bucket
-    bucket.all_reduce_mean()
+    if rank == 0:
+        bucket.all_reduce_mean()
+    else:
+        bucket.all_reduce_mean_async().wait()                      # same collective through the async entry point
     # reference: gradient of the mean over per-rank means, computed in one process
     ref = torch.nn.Sequential(torch.nn.Linear(66, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1))
     ref.load_state_dict(net.state_dict())

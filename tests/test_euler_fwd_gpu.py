@@ -17,7 +17,8 @@ DEV = 'cuda:0'
 # Tolerances (max-abs over all steps/rows/channels; latents are O(1..20)):
 #   exact : fp32 FFMA with a different summation order than MKL sgemm, libm-accurate tanh -> rounding-level only
 #   tc_f16: fp16 operands (2^-11 relative, = TF32 operand precision) + MUFU tanh.approx, compounded over 61 steps
-TOL = {'exact': dict(atol=2e-4, rtol=2e-5), 'tc_f16': dict(atol=6e-2, rtol=2e-2)}
+#           measured 6.4e-3 (reference fixture) / 7e-3 (204,800 rows) max-abs on latents up to ~16 -> tolerance 2e-2 (<= 3x measured)
+TOL = {'exact': dict(atol=2e-4, rtol=2e-5), 'tc_f16': dict(atol=2e-2, rtol=0)}
 
 
 def modes():
@@ -47,10 +48,9 @@ def test_decoder_golden_fixture(mode, golden_decoder):
     print(f"[{mode}] decoder golden: max-abs {err:.3e}  max-rel {rel:.3e}")
     assert torch.allclose(ys, ref, **TOL[mode])
     assert sde.fnfe == 61 and sde.gnfe == 61
-    if mode == 'exact':
-        # ADE/FDE agreement through the unchanged heads
-        loc = so.decoder_loc_head_ref(sub(d, 'head', DEV), ys[1:].permute(1, 0, 2))
-        assert (loc - torch.from_numpy(d['loc']).to(DEV)).abs().max() < 1e-3
+    # decoded trajectories through the unchanged heads; the ADE/FDE pins live in tests/test_stage_gpu.py
+    loc = so.decoder_loc_head_ref(sub(d, 'head', DEV), ys[1:].permute(1, 0, 2))
+    assert (loc - torch.from_numpy(d['loc']).to(DEV)).abs().max() < (1e-3 if mode == 'exact' else 1e-2)
 
 
 @pytest.mark.parametrize('mode', modes())

@@ -4,7 +4,7 @@ rows are independent (any row range solved alone, keyed by its global row offset
 result is deterministic, `ys[0] == y0`, both storage layouts agree, weight gradients are additive over row ranges — plus
 spot checks of scattered row blocks against the CPU oracle under the increments the kernels actually drew.
 
-Tolerances as in the small-size tests (tc_f16: atol 6e-2 / rtol 2e-2 on latents; 3e-2 of the max-norm on gradients)."""
+Tolerances as in the small-size tests (tc_f16: atol 2e-2 on latents up to ~16 — measured 7e-3; 3e-2 of the max-norm on gradients — measured <= 6e-3)."""
 import pytest
 import torch
 
@@ -19,7 +19,7 @@ from trajsde_b200.schedule import euler_schedule
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 SCENES, AGENTS = 1024, 20
-TOL = dict(atol=6e-2, rtol=2e-2)
+TOL = dict(atol=2e-2, rtol=0)
 
 
 @pytest.fixture(scope='module')
@@ -86,6 +86,21 @@ def test_decoder_full_size_gradients_are_additive_over_row_ranges(batch):
         assert torch.isfinite(full).all()
         assert (full - parts).abs().max() <= 3e-2 * full.abs().max() + 1e-12, name
     assert ops.backward_status(torch.device(DEV)) == 0         # adjoint stayed inside the fp16 operand range
+    # oracle spot checks of dL/dy0 at full size: fp64 autograd through the oracle solve of 8-row blocks under the increments the
+    # kernel drew for exactly those rows (rows are independent, so dL/dy0 of a block needs only that block)
+    from trajsde_b200.schedule import euler_schedule
+    dsched = ops.DeviceSchedule.get(euler_schedule(ts, 0.1), torch.device(DEV))
+    pf = {k: v.double() for k, v in net_params(sde.f_func).items()}
+    pg = {k: v.double() for k, v in net_params(sde.g_func).items()}
+    scale, worst = float(gy_full.abs().max()), 0.0
+    for a in torch.linspace(0, M - 8, 8).long().tolist():
+        dW = ops.philox_dw(dsched, 8, 123, torch.device(DEV), row_offset=a).cpu().double()
+        y = y0[a:a + 8].cpu().double().requires_grad_(True)
+        ref_ys, _ = so.euler_solve_ref(pf, pg, y, ts, 0.1, dW)
+        (ref_ys * cot[:, a:a + 8].cpu().double()).sum().backward()
+        worst = max(worst, float((gy_full[a:a + 8].cpu().double() - y.grad).abs().max()) / scale)
+    print(f"full-size dL/dy0 vs fp64 oracle autograd: worst block error {worst:.2e} of the max-norm")
+    assert worst < 3e-2
 
 
 def test_encoder_full_size_properties_and_oracle_spot_checks(batch):

@@ -34,6 +34,7 @@ class FlatGradBucket:
         dev = self.params[0].device
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._side = None
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
@@ -49,7 +50,11 @@ class FlatGradBucket:
             off += p.numel()
 
     def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
-        """SUM all-reduce of the flat bucket followed by division by the world size (DDP's gradient averaging)."""
+        """SUM all-reduce of the flat bucket followed by division by the world size (DDP's gradient averaging).  Also the once-per-step
+        place where pending tensor-core backward status snapshots are looked at (non-blocking; see ops.poll_status)."""
+        if self.flat.is_cuda:
+            from . import ops
+            ops.poll_status(self.flat.device)
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world = dist.get_world_size(group)
@@ -57,6 +62,39 @@ class FlatGradBucket:
             return None
         self.flat.div_(world)
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+    def all_reduce_mean_async(self, group: Optional[dist.ProcessGroup] = None) -> "PendingReduce":
+        """The same reduction enqueued on a SIDE stream behind everything the current stream has produced so far (start
+        the all-reduce as soon as the fused backward has written the bucket, so that it overlaps the backward work that follows on
+        the main stream).  ``.wait()`` on the result makes the current stream wait for the reduced bucket; the host never blocks."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return PendingReduce(None, None)
+        world = dist.get_world_size(group)
+        if not self.flat.is_cuda:                                   # gloo / CPU tests: no streams
+            self.flat.div_(world)
+            return PendingReduce(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True), None)
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.flat.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.flat.device))
+        with torch.cuda.stream(self._side):
+            self.flat.div_(world)
+            work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return PendingReduce(work, self._side)
+
+
+class PendingReduce:
+    def __init__(self, work, side_stream):
+        self.work, self.side = work, side_stream
+
+    def wait(self) -> None:
+        if self.work is None:
+            return
+        if self.side is None:
+            self.work.wait()
+            return
+        with torch.cuda.stream(self.side):
+            self.work.wait()                                        # orders the side stream after NCCL's stream (no host block)
+        torch.cuda.current_stream(self.side.device).wait_stream(self.side)
 
 
 def bind_host_to_gpu(local_rank: int) -> Optional[int]:
