@@ -100,7 +100,7 @@ def test_decoder_full_size_gradients_are_additive_over_row_ranges(batch):
         (ref_ys * cot[:, a:a + 8].cpu().double()).sum().backward()
         worst = max(worst, float((gy_full[a:a + 8].cpu().double() - y.grad).abs().max()) / scale)
     print(f"full-size dL/dy0 vs fp64 oracle autograd: worst block error {worst:.2e} of the max-norm")
-    assert worst < 3e-2
+    assert worst < 2e-3                                     # measured 4.2e-4
 
 
 def test_encoder_full_size_properties_and_oracle_spot_checks(batch):

@@ -5,9 +5,9 @@ the non-silent adjoint-range status, fused heads under torch.inference_mode(), t
 
 Tolerances (tc_f16 = fp16 operands + MUFU tanh over 61 steps; measured values are printed by the tests):
     latents          atol 2e-2                      (measured 7e-3)
-    loc / scale      atol 1.5e-2                    (measured ~4e-3)
-    L2 loss, ADE_T, FDE_T   |delta| <= 1e-3 (metres)   north_star's ADE/FDE agreement
-    gradients        3e-2 of the max-norm           (measured <= 6e-3)
+    loc / scale      atol 9e-3 .. 1.1e-2            (measured 2.9e-3 fixture, 3.6e-3 at 204,800 rows)
+    L2 loss, ADE_T, FDE_T   |delta| <= 5e-4 .. 1e-3 (metres; measured <= 3.4e-4)   north_star's ADE/FDE agreement
+    gradients        3e-2 of the max-norm           (measured 1.8e-2 through the whole stage, 4e-4 for dL/dy0 of the solve alone)
 """
 import warnings
 
@@ -67,7 +67,7 @@ def test_stage_forward_interop_vs_reference_fixture(mode, ctx, golden_stage):
     assert loc.shape == (10, 12, 60, 4)
     err = (loc - ref).abs().max().item()
     print(f"[{mode}/{ctx}] stage forward: loc|scale max-abs {err:.3e}")
-    assert err < (2e-4 if mode == 'exact' else 1.5e-2)
+    assert err < (2e-4 if mode == 'exact' else 9e-3)                # measured 1.5e-6 / 2.9e-3
     assert torch.allclose(out['pi'].cpu(), torch.from_numpy(d['pi']), atol=1e-5, rtol=1e-5)
     assert torch.equal(out['reg_mask'].cpu(), torch.from_numpy(d['reg_mask']))
     y, rm, src = torch.from_numpy(d['y']), torch.from_numpy(d['reg_mask']), torch.from_numpy(d['source'])
@@ -75,7 +75,7 @@ def test_stage_forward_interop_vs_reference_fixture(mode, ctx, golden_stage):
     dade = abs(so.ade_t_ref(loc[..., :2], y, rm) - float(d['ade']))
     dfde = abs(so.fde_t_ref(loc[..., :2], y, rm, src) - float(d['fde']))
     print(f"[{mode}/{ctx}] |L2 - ref| {dl2:.2e}  |ADE - ref| {dade:.2e}  |FDE - ref| {dfde:.2e}")
-    assert max(dl2, dade, dfde) < (1e-5 if mode == 'exact' else 1e-3)
+    assert max(dl2, dade, dfde) < (1e-5 if mode == 'exact' else 5e-4)   # measured 5e-7 / 1.4e-4 (north_star bound: 1e-3 m)
 
 
 @pytest.mark.parametrize('mode', ['exact', 'tc_f16'])
@@ -150,7 +150,7 @@ def test_ade_fde_pin_at_full_size_tc_f16():
         e_fde = abs(so.fde_t_ref(got, target, rm, src) - so.fde_t_ref(ref_loc, target, rm, src))
         worst = (max(worst[0], e_loc), max(worst[1], e_ade), max(worst[2], e_fde))
     print(f"full-size tc_f16 chain vs oracle: loc max-abs {worst[0]:.2e}, |dADE| {worst[1]:.2e}, |dFDE| {worst[2]:.2e}")
-    assert worst[0] < 1.5e-2 and worst[1] < 1e-3 and worst[2] < 1e-3
+    assert worst[0] < 1.1e-2 and worst[1] < 2e-4 and worst[2] < 1e-3     # measured 3.6e-3, 5.9e-5, 3.4e-4
 
 
 def test_forward_ood_vs_oracle_replay():
@@ -175,7 +175,7 @@ def test_forward_ood_vs_oracle_replay():
     ref_mean, ref_std = outs.mean(0), outs.std(0).mean(-1)
     e_m, e_s = float((mean.cpu() - ref_mean).abs().max()), float((std.cpu() - ref_std).abs().max())
     print(f"forward_ood vs oracle replay: mean max-abs {e_m:.2e}, std max-abs {e_s:.2e} (std range {float(ref_std.min()):.3f}..{float(ref_std.max()):.3f})")
-    assert e_m < 1e-2 and e_s < 3e-3
+    assert e_m < 2e-3 and e_s < 2e-4                                 # measured 5.4e-4, 4.2e-5
     # the stepwise exact path (10 separate passes, per-pass seeds) is a different Monte-Carlo sample of the same distribution
     mean_e, std_e = enc_mod.encoder_recurrence_ood(sde, gru, aa.to(DEV), am.to(DEV), nm.to(DEV), bos.to(DEV), eval_iter=k, seed=5, mode='exact')
     assert mean_e.shape == mean.shape and (std_e > 0).all()

@@ -212,7 +212,9 @@ int trajsde_enc_bwd(const TrajsdeEncBwdArgs* a, void* cuda_stream) {
     // an empty shard still owes its caller defined parameter gradients (they are accumulated into .grad and all-reduced): zeros
     if ((rc = check_device()) != 0) return rc;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
-    for (int i = 0; i < (a->alt_mask ? 3 : 2); ++i) {
+    for (int i = 0; i < 3; ++i) {
+      // an empty mask tensor has a NULL data pointer: the alt net's gradients are zeroed whenever the caller passed buffers for them
+      if (i == 2 && (!mg[i]->w1 || !mg[i]->b1 || !mg[i]->w2 || !mg[i]->b2 || !mg[i]->w3 || !mg[i]->b3)) break;
       const size_t n3 = i == 0 ? 64 * 64 : 64, nb3 = i == 0 ? 64 : 1;
       TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->w1, 0, sizeof(float) * 64 * 66, s));
       TS_CUDA_CHECK(cudaMemsetAsync(mg[i]->b1, 0, sizeof(float) * 64, s));
