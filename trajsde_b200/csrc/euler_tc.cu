@@ -47,6 +47,11 @@ constexpr uint32_t IMG_V2A = 40960;
 constexpr uint32_t IMG_W3 = 49152;
 constexpr uint32_t IMG_VEC = 57344;       // fp32 vectors
 constexpr uint32_t IMG_BYTES = 59392;     // 58 KB
+// single-diffusion variants (no alt net): the alt tiles make room for a BIAS tile whose K=16 slices carry every bias of the step
+// through the tensor core (see "biases through the MMA" below)
+constexpr uint32_t SIMG_B1 = 0;           // [128 rows][64] f16 SW128: W1y | V1y
+constexpr uint32_t SIMG_BIAS = 16384;     // [128 rows][64] f16 SW128: slice 0 layer-1 bias + time columns, slice 1 b2 | c2, slice 2 b3
+constexpr uint32_t SIMG_W2 = 32768, SIMG_V2 = 40960, SIMG_W3 = 49152;
 // fp32 vector slots (float index inside IMG_VEC)
 constexpr int VEC_B2 = 0, VEC_C2 = 64, VEC_C2A = 128, VEC_B3 = 192, VEC_W3G = 256, VEC_W3GA = 320, VEC_C3 = 384, VEC_C3A = 385;
 constexpr int BIAS1_LD = 192;             // per-step layer-1 bias row: b1f | c1 | c1_alt (time features folded in)
@@ -77,18 +82,39 @@ struct TcParams {
 __global__ void tc_pack_kernel(TrajsdeEulerFwdArgs a, uint8_t* __restrict__ img, float* __restrict__ bias1, int dual) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   __half* b1 = reinterpret_cast<__half*>(img + IMG_B1);
-  for (int idx = tid; idx < 192 * 64; idx += nth) {
+  for (int idx = tid; idx < (dual ? 192 : 128) * 64; idx += nth) {
     const int n = idx >> 6, k = idx & 63, net = n >> 6, r = n & 63;
-    const float* w = net == 0 ? a.drift.w1 : net == 1 ? a.diffusion.w1 : (dual ? a.diffusion_alt.w1 : nullptr);
-    const float v = w ? w[r * TS_IN1 + k] : 0.f;
-    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(b1) + sw128_off_h(n, k)) = __float2half_rn(v);
+    const float* w = net == 0 ? a.drift.w1 : net == 1 ? a.diffusion.w1 : a.diffusion_alt.w1;
+    *reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(b1) + sw128_off_h(n, k)) = __float2half_rn(w[r * TS_IN1 + k]);
   }
   for (int idx = tid; idx < 4 * 64 * 64; idx += nth) {
     const int m = idx >> 12, n = (idx >> 6) & 63, k = idx & 63;
-    const float* w = m == 0 ? a.drift.w2 : m == 1 ? a.diffusion.w2 : m == 2 ? (dual ? a.diffusion_alt.w2 : nullptr) : a.drift.w3;
-    const uint32_t off = m == 0 ? IMG_W2 : m == 1 ? IMG_V2 : m == 2 ? IMG_V2A : IMG_W3;
-    const float v = w ? w[n * 64 + k] : 0.f;
-    *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(v);
+    if (m == 2 && !dual) continue;
+    const float* w = m == 0 ? a.drift.w2 : m == 1 ? a.diffusion.w2 : m == 2 ? a.diffusion_alt.w2 : a.drift.w3;
+    const uint32_t off = dual ? (m == 0 ? IMG_W2 : m == 1 ? IMG_V2 : m == 2 ? IMG_V2A : IMG_W3) : (m == 0 ? SIMG_W2 : m == 1 ? SIMG_V2 : SIMG_W3);
+    *reinterpret_cast<__half*>(img + off + sw128_off_h(n, k)) = __float2half_rn(w[n * 64 + k]);
+  }
+  if (!dual) {
+    // BIAS tile: B operand rows n = output channel (0..63 drift, 64..127 diffusion), K slices of 16; the matching A slice holds, for
+    // every row of the tile, (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi, 0...) with s = sin t0, c = cos t0 split into an fp16 head and
+    // an fp16 remainder — so slice 0 adds b1 + W1[:,64] sin t0 + W1[:,65] cos t0 to ~2^-22, slices 1 / 2 add b2 | c2 and b3
+    for (int idx = tid; idx < 128 * 64; idx += nth) {
+      const int n = idx >> 6, k = idx & 63, slice = k >> 4, j = k & 15, net = n >> 6, r = n & 63;
+      const TrajsdeMlp& m = net == 0 ? a.drift : a.diffusion;
+      float v = 0.f;
+      auto hi = [](float x) { return __half2float(__float2half_rn(x)); };
+      if (slice == 0 && j < 8) {
+        const float b = m.b1[r], ws = m.w1[r * TS_IN1 + 64], wc = m.w1[r * TS_IN1 + 65];
+        v = j == 0 ? hi(b) : j == 1 ? b - hi(b) : (j == 2 || j == 3) ? hi(ws) : j == 4 ? ws - hi(ws) : (j == 5 || j == 6) ? hi(wc) : wc - hi(wc);
+      } else if (slice == 1 && j < 2) {
+        const float b = m.b2[r];
+        v = j == 0 ? hi(b) : b - hi(b);
+      } else if (slice == 2 && j < 2 && net == 0) {
+        const float b = a.drift.b3[r];
+        v = j == 0 ? hi(b) : b - hi(b);
+      }
+      *reinterpret_cast<__half*>(img + SIMG_BIAS + sw128_off_h(n, k)) = __float2half_rn(v);
+    }
   }
   float* vec = reinterpret_cast<float*>(img + IMG_VEC);
   for (int i = tid; i < 512; i += nth) {
@@ -157,6 +183,15 @@ __device__ __forceinline__ void act32_to_tmem(const uint32_t (&v)[32], const Bia
   tc_wait_st();
 }
 
+// Bias-free variant: the MMA chain already added the bias (BIAS tile), so the burst is LDTM -> 32 x MUFU.TANH -> 16 x F2FP -> STTM.
+__device__ __forceinline__ void tanh32_to_tmem(const uint32_t (&v)[32], uint32_t taddr) {
+  uint32_t p[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) p[e] = pack_f16x2(ts_tanh_approx(__uint_as_float(v[2 * e])), ts_tanh_approx(__uint_as_float(v[2 * e + 1])));
+  tmem_st_32x32b_x16(taddr, p);
+  tc_wait_st();
+}
+
 // This row's diffusion-net column block -> registers.  In a warp whose rows use both diffusion nets the alt block is fetched
 // too and selected per lane (tcgen05.ld is warp-collective: its address must be warp-uniform).
 template <bool DUAL>
@@ -206,13 +241,17 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c) {
   for (int q = 0; q < 8; ++q) {
     float4* xp = reinterpret_cast<float4*>(c.x_row + ((q ^ (c.row & 7u)) << 4));
     const float4 dw = *xp;
-    const float4 b3 = *reinterpret_cast<const float4*>(c.b3 + 4 * q);
+    float f0 = __uint_as_float(fv[4 * q]), f1 = __uint_as_float(fv[4 * q + 1]), f2 = __uint_as_float(fv[4 * q + 2]), f3 = __uint_as_float(fv[4 * q + 3]);
+    if (!TMEM_A) {                                           // TMEM_A variants: b3 came through the MMA (BIAS tile, slice 2)
+      const float4 b3 = *reinterpret_cast<const float4*>(c.b3 + 4 * q);
+      f0 += b3.x; f1 += b3.y; f2 += b3.z; f3 += b3.w;
+    }
     const float y0 = __uint_as_float(yv[4 * q]), y1 = __uint_as_float(yv[4 * q + 1]);
     const float y2 = __uint_as_float(yv[4 * q + 2]), y3 = __uint_as_float(yv[4 * q + 3]);
-    const float n0 = fmaf(c.g, dw.x, fmaf(__uint_as_float(fv[4 * q]) + b3.x, c.h, y0));
-    const float n1 = fmaf(c.g, dw.y, fmaf(__uint_as_float(fv[4 * q + 1]) + b3.y, c.h, y1));
-    const float n2 = fmaf(c.g, dw.z, fmaf(__uint_as_float(fv[4 * q + 2]) + b3.z, c.h, y2));
-    const float n3 = fmaf(c.g, dw.w, fmaf(__uint_as_float(fv[4 * q + 3]) + b3.w, c.h, y3));
+    const float n0 = fmaf(c.g, dw.x, fmaf(f0, c.h, y0));
+    const float n1 = fmaf(c.g, dw.y, fmaf(f1, c.h, y1));
+    const float n2 = fmaf(c.g, dw.z, fmaf(f2, c.h, y2));
+    const float n3 = fmaf(c.g, dw.w, fmaf(f3, c.h, y3));
     if (c.has_out)
       *xp = make_float4(fmaf(c.w1, n0, c.w0 * y0), fmaf(c.w1, n1, c.w0 * y1), fmaf(c.w1, n2, c.w0 * y2), fmaf(c.w1, n3, c.w0 * y3));
     if (MULTI) {  // rare: one step completes several outputs (zero-step intervals) -> direct global stores
@@ -345,6 +384,13 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     c3.out_w = a.sched.out_w;
     c3.ys_t_stride = a.ys_t_stride;
 
+    if (TMEM_A) {
+      // biases through the MMA: the A0 tile (unused as an operand tile here: y / h1f / h2f live in tensor memory) holds the bias
+      // operand rows.  K slice (gstep & 1) of every row = (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi, 0 x 8) for the step's sin t0 /
+      // cos t0; the fifth MMA of every phase multiplies it with the BIAS tile's slice for that layer.  Zero everything once.
+#pragma unroll
+      for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(a0_row + (((hh * 4 + q) ^ (row & 7u)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
     mbar_wait(bar_w, 0);
 
     for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
@@ -389,117 +435,228 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         }
         tc_wait_st();
       }
+      if (TMEM_A) {                                        // bias operand slice of this tile's first step (its ring entry is published)
+        mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);
+        if (hh == 0)
+          *reinterpret_cast<uint4*>(a0_row + (((2u * (gstep & 1u)) ^ (row & 7u)) << 4)) =
+              *reinterpret_cast<const uint4*>(ring + (gstep % 3u) * RING_LD);
+      }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_opnd(slot, 0));                      // A0 ready -> P1 of step 0
       mbar_arrive(bar_xfull(slot));                        // y0 consumed: IO may store X as ys[0] and then refill it
 
       for (int k = 0; k < S; ++k, ++gstep) {
-        if (save_states && !TMEM_A) {                      // previous step's states store must have drained A1f|A1g before epilogue 1
-          mbar_wait(bar_xfree(slot), par_xfree);           // writes h1f there (the TMEM-operand variants write that staging area only
-          par_xfree ^= 1;                                  // in epilogue 3 and wait there)
-        }
-        mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's bias row + scalars are in the ring
-        const float* ent = ring + (gstep % 3u) * RING_LD;
-        const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
-        const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
+        if constexpr (TMEM_A) {
+          // ===================== single-diffusion variants: operands in tensor memory, biases through the MMA =====================
+          mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's scalars are in the ring
+          const float* ent = ring + (gstep % 3u) * RING_LD;
+          const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
+          const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
+          // In-kernel noise: the step's 8 Philox calls of this thread are spread over the three gaps in which the thread would
+          // otherwise only wait for the tensor core (after epilogue 1, inside epilogue 2, before epilogue 3), so the draw never
+          // forms one 500-instruction block in front of the P3 wait.
+          auto draw = [&](int q0, int q1) {
+#pragma unroll
+            for (int q = q0; q < q1; ++q)
+              *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
+                  philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
+          };
 
-        // ---- epilogue 1: h1f = tanh(z1f + b1f(t)) -> A1f (P2f may start), h1g = tanh(z1g + c1(t)) -> A1g -------------------
-        mbar_wait(bar_acc(slot, 0), par_accA);
-        par_accA ^= 1;
-        tc_fence_after();
-        {
-          uint32_t v[32];
-          Bias32 bf = ld_bias32(ent + hh * 32);
-          tmem_ld_32x32b_x32(tm_lane, v);
-          tc_wait_ld();
-          if (TMEM_A) {
-            act32_to_tmem(v, bf, tm_oa);
-          } else {
-            act32_to_operand(v, bf, a1f_row, row, hh * 4);
-            fence_proxy_async();
-          }
-          tc_fence_before();
-          mbar_arrive(bar_opnd(slot, 1));                  // A1f ready -> P2f
-          bf = ld_bias32(ent + gcol + hh * 32);
-          ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
-          if (TMEM_A) {
-            act32_to_tmem(v, bf, tm_ob);
-          } else {
-            act32_to_operand(v, bf, a1g_row, row, hh * 4);
-            fence_proxy_async();
-          }
-          tc_fence_before();
-          mbar_arrive(bar_opnd(slot, 0));                  // A1g ready -> P2g
-        }
-
-        // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 (P3 may start) ; partial of w3 . tanh(z2g + c2) ----------------------------
-        mbar_wait(bar_acc(slot, 1), par_accB);
-        par_accB ^= 1;
-        tc_fence_after();
-        {
-          uint32_t v[32];
-          const Bias32 b2 = ld_bias32(vec + VEC_B2 + hh * 32);
-          tmem_ld_32x32b_x32(tm_lane, v);
-          tc_wait_ld();
-          if (TMEM_A) {
-            act32_to_tmem(v, b2, tm_oa);
-          } else {
-            act32_to_operand(v, b2, a0_row, row, hh * 4);
-            fence_proxy_async();
-          }
-          tc_fence_before();
-          mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
+          // ---- epilogue 1: h1f = tanh(z1f) -> OA (P2f may start), h1g = tanh(z1g) -> OB (biases are in the accumulators) ----------
           mbar_wait(bar_acc(slot, 0), par_accA);
           par_accA ^= 1;
           tc_fence_after();
-          ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
-          float gd = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(c2v + j);
-            const float4 w = *reinterpret_cast<const float4*>(w3v + j);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
-            gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
+          {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tm_lane, v);
+            tc_wait_ld();
+            tanh32_to_tmem(v, tm_oa);
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 1));                  // h1f ready -> P2f
+            tmem_ld_32x32b_x32(tm_lane + 64, v);
+            tc_wait_ld();
+            tanh32_to_tmem(v, tm_ob);
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
           }
-          gpart[hh * TILE_M + row] = gd;
-        }
+          if (!HAS_DW) {
+            mbar_wait(bar_xfree(slot), par_xfree);           // stores of the previous step have finished reading X / the states staging
+            par_xfree ^= 1;
+            draw(0, 3);
+          }
 
-        // ---- epilogue 3 -----------------------------------------------------------------------------------------------------
-        if (!save_states || TMEM_A) {                        // stores of the previous step have finished reading X (and the states staging)
-          mbar_wait(bar_xfree(slot), par_xfree);
-          par_xfree ^= 1;
+          // ---- epilogue 2: h2f = tanh(z2f) -> OA (P3 may start) ; partial of w3 . tanh(z2g) -----------------------------------------
+          mbar_wait(bar_acc(slot, 1), par_accB);
+          par_accB ^= 1;
+          tc_fence_after();
+          {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tm_lane, v);
+            tc_wait_ld();
+            tanh32_to_tmem(v, tm_oa);
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
+            if (!HAS_DW) draw(3, 5);
+            mbar_wait(bar_acc(slot, 0), par_accA);
+            par_accA ^= 1;
+            tc_fence_after();
+            tmem_ld_32x32b_x32(tm_lane + 64, v);
+            tc_wait_ld();
+            float gd = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w = *reinterpret_cast<const float4*>(w3v + j);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j])), w.x, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1])), w.y, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2])), w.z, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3])), w.w, gd);
+            }
+            gpart[hh * TILE_M + row] = gd;
+          }
+
+          // ---- epilogue 3 ---------------------------------------------------------------------------------------------------------
+          if (HAS_DW) {
+            mbar_wait(bar_xfree(slot), par_xfree);
+            par_xfree ^= 1;
+            mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
+            par_tma ^= 1;
+          } else {
+            draw(5, 8);
+          }
+          mbar_wait(bar_acc(slot, 1), par_accB);
+          par_accB ^= 1;
+          tc_fence_after();
+          named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
+          const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
+          c3.h = sc.x;
+          c3.g = g;
+          c3.w0 = sc.z;
+          c3.w1 = sc.w;
+          c3.ob = so.x;
+          c3.nout = so.y;
+          c3.has_out = so.y > 0;
+          if (so.y > 1) epi3_update<true, true>(c3);
+          else epi3_update<false, true>(c3);
+          if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
+          if (k + 1 < S) {                                     // bias operand slice of the next step (other parity: nobody reads it now)
+            mbar_wait(bar_ring(slot, (gstep + 1) & 1), ((gstep + 1) >> 1) & 1);
+            if (hh == 0)
+              *reinterpret_cast<uint4*>(a0_row + (((2u * ((gstep + 1) & 1u)) ^ (row & 7u)) << 4)) =
+                  *reinterpret_cast<const uint4*>(ring + ((gstep + 1) % 3u) * RING_LD);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          if (k + 1 < S) mbar_arrive(bar_opnd(slot, 0));     // y' (tensor memory) + bias slice ready -> P1 of step k+1
+          mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
+        } else {
+          // ===================== dual-diffusion variants: operands through swizzled shared memory =====================================
+          if (save_states && !TMEM_A) {                      // previous step's states store must have drained A1f|A1g before epilogue 1
+            mbar_wait(bar_xfree(slot), par_xfree);           // writes h1f there (the TMEM-operand variants write that staging area only
+            par_xfree ^= 1;                                  // in epilogue 3 and wait there)
+          }
+          mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's bias row + scalars are in the ring
+          const float* ent = ring + (gstep % 3u) * RING_LD;
+          const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
+          const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
+
+          // ---- epilogue 1: h1f = tanh(z1f + b1f(t)) -> A1f (P2f may start), h1g = tanh(z1g + c1(t)) -> A1g -------------------
+          mbar_wait(bar_acc(slot, 0), par_accA);
+          par_accA ^= 1;
+          tc_fence_after();
+          {
+            uint32_t v[32];
+            Bias32 bf = ld_bias32(ent + hh * 32);
+            tmem_ld_32x32b_x32(tm_lane, v);
+            tc_wait_ld();
+            if (TMEM_A) {
+              act32_to_tmem(v, bf, tm_oa);
+            } else {
+              act32_to_operand(v, bf, a1f_row, row, hh * 4);
+              fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 1));                  // A1f ready -> P2f
+            bf = ld_bias32(ent + gcol + hh * 32);
+            ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
+            if (TMEM_A) {
+              act32_to_tmem(v, bf, tm_ob);
+            } else {
+              act32_to_operand(v, bf, a1g_row, row, hh * 4);
+              fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 0));                  // A1g ready -> P2g
+          }
+
+          // ---- epilogue 2: h2f = tanh(z2f + b2) -> A0 (P3 may start) ; partial of w3 . tanh(z2g + c2) ----------------------------
+          mbar_wait(bar_acc(slot, 1), par_accB);
+          par_accB ^= 1;
+          tc_fence_after();
+          {
+            uint32_t v[32];
+            const Bias32 b2 = ld_bias32(vec + VEC_B2 + hh * 32);
+            tmem_ld_32x32b_x32(tm_lane, v);
+            tc_wait_ld();
+            if (TMEM_A) {
+              act32_to_tmem(v, b2, tm_oa);
+            } else {
+              act32_to_operand(v, b2, a0_row, row, hh * 4);
+              fence_proxy_async();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
+            mbar_wait(bar_acc(slot, 0), par_accA);
+            par_accA ^= 1;
+            tc_fence_after();
+            ld_g<DUAL>(tm_lane + ucol, tm_lane + 128, w_mixed, use_alt, v);
+            float gd = 0.f;
+  #pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(c2v + j);
+              const float4 w = *reinterpret_cast<const float4*>(w3v + j);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j]) + b.x), w.x, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1]) + b.y), w.y, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2]) + b.z), w.z, gd);
+              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3]) + b.w), w.w, gd);
+            }
+            gpart[hh * TILE_M + row] = gd;
+          }
+
+          // ---- epilogue 3 -----------------------------------------------------------------------------------------------------
+          if (!save_states || TMEM_A) {                        // stores of the previous step have finished reading X (and the states staging)
+            mbar_wait(bar_xfree(slot), par_xfree);
+            par_xfree ^= 1;
+          }
+          if (HAS_DW) {
+            mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
+            par_tma ^= 1;
+          } else {                                             // draw this thread's 32 increments into X while P3 runs
+  #pragma unroll 2
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
+                  philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
+          }
+          mbar_wait(bar_acc(slot, 1), par_accB);
+          par_accB ^= 1;
+          tc_fence_after();
+          named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
+          const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
+          c3.h = sc.x;
+          c3.g = g;
+          c3.w0 = sc.z;
+          c3.w1 = sc.w;
+          c3.ob = so.x;
+          c3.nout = so.y;
+          c3.has_out = so.y > 0;
+          if (so.y > 1) epi3_update<true, TMEM_A>(c3);
+          else epi3_update<false, TMEM_A>(c3);
+          if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
+          fence_proxy_async();
+          tc_fence_before();
+          if (k + 1 < S) mbar_arrive(bar_opnd(slot, 0));     // A0 = y' ready -> P1 of step k+1
+          mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
         }
-        if (HAS_DW) {
-          mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
-          par_tma ^= 1;
-        } else {                                             // draw this thread's 32 increments into X while P3 runs
-#pragma unroll 2
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
-                philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
-        }
-        mbar_wait(bar_acc(slot, 1), par_accB);
-        par_accB ^= 1;
-        tc_fence_after();
-        named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
-        const float g = __fdividef(1.0f, 1.0f + __expf(-((gpart[row] + gpart[TILE_M + row]) + c3b)));
-        c3.h = sc.x;
-        c3.g = g;
-        c3.w0 = sc.z;
-        c3.w1 = sc.w;
-        c3.ob = so.x;
-        c3.nout = so.y;
-        c3.has_out = so.y > 0;
-        if (so.y > 1) epi3_update<true, TMEM_A>(c3);
-        else epi3_update<false, TMEM_A>(c3);
-        if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
-        fence_proxy_async();
-        tc_fence_before();
-        if (k + 1 < S) mbar_arrive(bar_opnd(slot, 0));     // A0 = y' ready -> P1 of step k+1
-        mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
       }
     }
   } else if (warp < WARP_IO0) {
@@ -519,11 +676,17 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       const uint32_t aA0 = slot_u32 + OFF_A0, aA1f = slot_u32 + OFF_A1F, aA1g = slot_u32 + OFF_A1G;
       constexpr bool TMEM_A = !DUAL;
       const uint32_t t_oa = d_base + 128, t_ob = d_base + 160;   // TMEM operand columns (lane field 0: all 128 rows)
-      const uint32_t aB1 = base + IMG_B1, aW2 = base + IMG_W2, aV2 = base + IMG_V2, aV2a = base + IMG_V2A, aW3 = base + IMG_W3;
+      const uint32_t aB1 = base + (TMEM_A ? SIMG_B1 : IMG_B1), aW2 = base + (TMEM_A ? SIMG_W2 : IMG_W2), aV2 = base + (TMEM_A ? SIMG_V2 : IMG_V2),
+                     aV2a = base + IMG_V2A, aW3 = base + (TMEM_A ? SIMG_W3 : IMG_W3);
+      // biases through the MMA (TMEM_A variants): fifth K=16 block of every phase = bias operand slice (A0 tile, slice gstep & 1)
+      // x BIAS tile slice of the layer (slice 0: layer 1 incl. time columns; slice 1: b2 | c2 at rows 0 / 64; slice 2: b3)
+      const uint32_t aBias = base + SIMG_BIAS;
       uint32_t par_op0 = 0, par_op1 = 0;
+      uint32_t gstep = 0;
       mbar_wait(bar_w, 0);
       for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
-        for (int k = 0; k < S; ++k) {
+        for (int k = 0; k < S; ++k, ++gstep) {
+          const uint64_t dAb = D(aA0 + 32u * (gstep & 1u));
           // P1: [z1f | z1g (| z1g_alt)] = y . [W1y ; V1y (; V1y_alt)]^T
           mbar_wait(bar_opnd(slot, 0), par_op0);
           par_op0 ^= 1;
@@ -534,6 +697,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aB1 + 32 * kk), idesc_p1, kk > 0);
               else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
             }
+            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias), idesc_p1, 1);
             tc_commit(bar_acc(slot, 0));
           }
           __syncwarp();
@@ -547,6 +711,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW2 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
             }
+            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias + 32), idesc_64, 1);
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
@@ -560,6 +725,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base + 64, t_ob + 8 * kk, D(aV2 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
             }
+            if (TMEM_A) tc_mma_f16(d_base + 64, dAb, D(aBias + 64 * 128 + 32), idesc_64, 1);
             if (DUAL) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
@@ -577,6 +743,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW3 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
             }
+            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias + 64), idesc_64, 1);
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
@@ -598,14 +765,21 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     // Ring entry of global step g -> ring[g % 3], announced on bar_ring[g & 1].  Entry g+1 is published at the start of IO
     // iteration g, i.e. once the epilogue has finished step g-1: its slot (last read in step g-2) is free and its barrier's
     // previous phase (entry g-1) has been consumed, so every barrier has at most one outstanding phase.
-    struct Ent { float2 b[3]; float4 sc; int2 so; };
+    struct Ent { float2 b[3]; float4 sc; int2 so; uint4 aw; };
+    constexpr bool TMEM_A = !DUAL;
     auto ent_fetch = [&](uint32_t g, Ent& e) {
       const int k = (int)(g % (uint32_t)S);
-      const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)k * BIAS1_LD);
+      if (!TMEM_A) {
+        const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)k * BIAS1_LD);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) e.b[i] = __ldg(src + lane + 32 * i);
+        for (int i = 0; i < 3; ++i) e.b[i] = __ldg(src + lane + 32 * i);
+      }
       if (lane == 0) {
         const float4 st = __ldg(reinterpret_cast<const float4*>(a.sched.step_tab) + k);
+        if (TMEM_A) {   // bias operand row of the step: (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi) as fp16 (head + remainder of sin t0, cos t0)
+          const float sh = __half2float(__float2half_rn(st.z)), ch = __half2float(__float2half_rn(st.w));
+          e.aw = make_uint4(pack_f16x2(1.f, 1.f), pack_f16x2(sh, st.z - sh), pack_f16x2(sh, ch), pack_f16x2(st.w - ch, ch));
+        }
         const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
         float w0 = 0.f, w1 = 1.f;
         if (oe > ob) {
@@ -618,9 +792,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     };
     auto ent_publish = [&](uint32_t g, const Ent& e) {
       float* dst = ring + (g % 3u) * RING_LD;
+      if (!TMEM_A) {
 #pragma unroll
-      for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(dst)[lane + 32 * i] = e.b[i];
+        for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(dst)[lane + 32 * i] = e.b[i];
+      }
       if (lane == 0) {
+        if (TMEM_A) *reinterpret_cast<uint4*>(dst) = e.aw;
         *reinterpret_cast<float4*>(dst + BIAS1_LD) = e.sc;
         *reinterpret_cast<int2*>(dst + BIAS1_LD + 4) = e.so;
       }
