@@ -226,10 +226,11 @@ struct Epi3Ctx {
 };
 
 // Epilogue 3: f = z3 + b3 ; y' = y + f h + g dW (dW already in this thread's X chunks) ; outputs in place ; Y, A0 <- y'.
-template <bool MULTI, bool TMEM_A>
-__device__ __forceinline__ void epi3_update(const Epi3Ctx& c) {
-  uint32_t yv[32], fv[32];
-  tmem_ld_32x32b_x32(c.tm_y, yv);
+// Y_LOADED: the caller issued the tcgen05.ld of the state columns into `yv` before it waited for P3 (the read runs under that wait).
+template <bool MULTI, bool TMEM_A, bool Y_LOADED = false>
+__device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]) {
+  uint32_t fv[32];
+  if (!Y_LOADED) tmem_ld_32x32b_x32(c.tm_y, yv);
   tmem_ld_32x32b_x32(c.tm_f, fv);
   tc_wait_ld();
   if (c.save_states) {  // Y[k] -> states staging (aliases A1f|A1g: both consumed by P2 already)
@@ -468,6 +469,18 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           par_accA ^= 1;
           tc_fence_after();
           {
+#ifdef TRAJSDE_FWD_E1_PREFETCH
+            uint32_t v[32], vg[32];
+            tmem_ld_32x32b_x32(tm_lane, v);                  // both layer-1 accumulator blocks in flight at once: the second read's
+            tmem_ld_32x32b_x32(tm_lane + 64, vg);            // latency hides behind the first block's tanh burst
+            tc_wait_ld();
+            tanh32_to_tmem(v, tm_oa);
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 1));                  // h1f ready -> P2f
+            tanh32_to_tmem(vg, tm_ob);
+            tc_fence_before();
+            mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
+#else
             uint32_t v[32];
             tmem_ld_32x32b_x32(tm_lane, v);
             tc_wait_ld();
@@ -479,6 +492,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             tanh32_to_tmem(v, tm_ob);
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
+#endif
           }
           if (!HAS_DW) {
             mbar_wait(bar_xfree(slot), par_xfree);           // stores of the previous step have finished reading X / the states staging
@@ -524,6 +538,13 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           } else {
             draw(5, 8);
           }
+          uint32_t yv[32];
+#ifdef TRAJSDE_FWD_Y_PREFETCH
+          tmem_ld_32x32b_x32(c3.tm_y, yv);                     // the state read runs under the P3 wait
+          constexpr bool YPRE = true;
+#else
+          constexpr bool YPRE = false;
+#endif
           mbar_wait(bar_acc(slot, 1), par_accB);
           par_accB ^= 1;
           tc_fence_after();
@@ -536,8 +557,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           c3.ob = so.x;
           c3.nout = so.y;
           c3.has_out = so.y > 0;
-          if (so.y > 1) epi3_update<true, true>(c3);
-          else epi3_update<false, true>(c3);
+          if (so.y > 1) epi3_update<true, true, YPRE>(c3, yv);
+          else epi3_update<false, true, YPRE>(c3, yv);
           if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
           if (k + 1 < S) {                                     // bias operand slice of the next step (other parity: nobody reads it now)
             mbar_wait(bar_ring(slot, (gstep + 1) & 1), ((gstep + 1) >> 1) & 1);
@@ -649,8 +670,11 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           c3.ob = so.x;
           c3.nout = so.y;
           c3.has_out = so.y > 0;
-          if (so.y > 1) epi3_update<true, TMEM_A>(c3);
-          else epi3_update<false, TMEM_A>(c3);
+          {
+            uint32_t yv[32];
+            if (so.y > 1) epi3_update<true, TMEM_A>(c3, yv);
+            else epi3_update<false, TMEM_A>(c3, yv);
+          }
           if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
           fence_proxy_async();
           tc_fence_before();
