@@ -133,6 +133,11 @@ typedef struct {
 
 /* TrajsdeEulerBwdArgs.flags */
 #define TRAJSDE_BWD_FLAG_EXACT_KERNELS 1 /* run the fp32 CUDA-core backward even in TC_F16 mode (A/B validation) */
+/* Skip the rows whose incoming gradients (grad_ys, grad_g_last) are all zero: their adjoint is zero at every step, so they contribute
+ * exactly nothing to grad_y0 (written as 0) or to any weight gradient.  One extra scan of grad_ys finds them on the device (no host
+ * synchronisation); pays off under a winner-takes-all loss such as the reference's L2 (losses/L2.py:17-20: one of the 10 modes of an actor
+ * receives a gradient).  Honoured by the tensor-core kernels with a single diffusion net; ignored otherwise. */
+#define TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS 2
 
 /* Backward kernels by mode: EXACT_F32 -> fp32 CUDA-core dgrad sweep + wgrad (euler_bwd_exact.cu).  TC_F16 with a single
  * diffusion net -> fused tensor-core dgrad+wgrad (euler_bwd_tc.cu; fp16 operands, fp32 accumulation, adjoint carried with a

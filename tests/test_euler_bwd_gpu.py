@@ -255,3 +255,52 @@ def test_rows_major_storage_gives_the_same_gradients(mode):
         out.append([y.grad.clone()] + [p.grad.clone() for p in sde.parameters()])
     for a, b in zip(*out):
         assert torch.allclose(a, b, atol=1e-6 * float(b.abs().max()) + 1e-12, rtol=1e-5)
+
+
+@pytest.mark.parametrize('rows,frac,rows_major', [(3000, 0.1, True), (5000, 0.0, False), (2500, 1.0, True), (70_000, 0.1, True)])
+def test_zero_row_skipping_is_exact(rows, frac, rows_major):
+    """TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS: rows with an all-zero incoming gradient (90 % of the decoder rows under the reference's
+    winner-takes-all L2 loss) are left out of the reverse sweep.  Same gradients as the full sweep for sparse, empty and dense cotangents
+    and both output layouts — up to the fp16 rounding of the delta operands: the two paths derive the power-of-two loss scale from a
+    full and from a sampled scan of max|grad|, which may differ by a binade, and partition the partial sums differently; in-kernel Philox
+    noise is regenerated for the compacted rows by their ORIGINAL row ids."""
+    sde = init_like_reference(DecoderSDE(), seed=rows, bias_std=0.2).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    g = torch.Generator().manual_seed(rows)
+    y0 = torch.relu(torch.randn(rows, 64, generator=g)).to(DEV)
+    active = torch.rand(rows, generator=g) < frac
+    cot = torch.randn(61, rows, 64, generator=g) * 1e-4
+    cot[0].zero_()
+    cot[5:, ~active] = 0                                         # inactive rows: nothing at all
+    cot[1:5, ~active] = 0
+    cot[0, active] = torch.randn(int(active.sum()), 64, generator=g) * 1e-4 if frac > 0 else 0     # ys[0] = y0 cotangent on active rows
+    if rows == 3000:
+        cot[:, 7] = 0
+        cot[0, 7, 3] = 1e-4                                       # a row that is active through its slab-0 gradient only
+    cot = cot.to(DEV)
+
+    def run(skip):
+        ops.SKIP_ZERO_ROWS = skip
+        for p_ in sde.parameters():
+            p_.grad = None
+        y = y0.clone().requires_grad_(True)
+        ys = tb.sdeint(sde, y, ts, dt=0.1, method='euler', mode='tc_f16', seed=31, row_offset=12345, rows_major=rows_major)
+        ys.backward(cot)
+        return y.grad.clone(), [p_.grad.clone() for p_ in sde.parameters()]
+
+    try:
+        gy_a, gw_a = run(False)
+        gy_b, gw_b = run(True)
+    finally:
+        ops.SKIP_ZERO_ROWS = True
+    scale = float(gy_a.abs().max())
+    if frac == 0.0:
+        assert scale == 0.0 and float(gy_b.abs().max()) == 0.0
+        assert all(float(w.abs().max()) == 0.0 for w in gw_a + gw_b)
+        return
+    assert float((gy_a - gy_b).abs().max()) <= 3e-3 * scale
+    assert torch.equal(gy_b[~active.to(DEV)] if rows != 3000 else gy_b[(~active).to(DEV) & (torch.arange(rows, device=DEV) != 7)],
+                       torch.zeros_like(gy_b[~active.to(DEV)] if rows != 3000 else gy_b[(~active).to(DEV) & (torch.arange(rows, device=DEV) != 7)]))
+    for name, a_, b_ in zip([n for n, _ in sde.named_parameters()], gw_a, gw_b):
+        assert float((a_ - b_).abs().max()) <= 3e-3 * float(a_.abs().max()) + 1e-12, name
+    assert ops.backward_status(torch.device(DEV)) == 0

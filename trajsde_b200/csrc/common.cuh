@@ -121,7 +121,7 @@ int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s);
 int bwd_tc_absmax(const float* x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride, uint32_t* amax_bits, cudaStream_t s);
 int bwd_tc_grid(int64_t rows, bool dual = false);
 int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
-                int accumulate, cudaStream_t s, bool pdl = false);
+                int accumulate, cudaStream_t s, bool pdl = false, const int32_t* row_map = nullptr, const int32_t* n_active = nullptr);
 int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int n1, const TrajsdeMlpGrad& gf, const TrajsdeMlpGrad& gg,
                             const TrajsdeMlpGrad& ga, cudaStream_t s);
 // GRU jump backward (gru_bwd.cu) and the encoder-recurrence backward driver (enc_bwd.cu)

@@ -85,6 +85,10 @@ struct BwdTcParams {
   float* partial[2];           // [gridDim.x][G_PAD] of the pass
   int filter[2];               // 0: all rows; 1: only rows with alt_mask != 0; 2: only rows with alt_mask == 0
   const uint32_t* amax_bits;   // max |grad| as float bits (absmax pre-pass)
+  // zero-row skipping (TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS): rows whose incoming gradients are all zero have a zero adjoint at every step and
+  // contribute exactly nothing to any result, so the sweep runs over the compacted list row_map[0 .. *n_active) of the other rows
+  const int32_t* row_map;      // device [rows] or NULL (identity)
+  const int32_t* n_active;     // device scalar or NULL (all rows)
   int num_tiles;
   int accumulate;              // add into the CTA's partial vector instead of overwriting it (multi-launch accumulation)
 };
@@ -158,6 +162,80 @@ __global__ void bwd_tc_absmax_kernel(const float* __restrict__ x, int slabs, int
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
 }
 
+// Zero-row skipping, pass 1: a scan of grad_ys (every slab) that yields BOTH max |grad| (for the loss scale) and a per-row flag "some
+// incoming gradient of this row is non-zero".  16 threads per row (one float4 each), 16 rows per 256-thread block and iteration: whole
+// 256-byte rows per slab, coalesced in either storage layout.  `grad_g` (sdeint_dual's second output) marks its rows too.
+//   sample == 1: only every 8th block of 32 rows is scanned; counts[0] += active sampled rows, counts[1] += sampled rows (0.06 ms at
+//                204,800 rows x 61 slabs);
+//   sample == 0: the full scan — unless the sample found more than half of its rows active: then the cotangent is (close to) dense,
+//                skipping would save little, and every row is flagged without reading the gradient again (the sampled maximum is good
+//                enough for the power-of-two loss scale, see bwd_tc_absmax_kernel).
+__global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride,
+                                        const float* __restrict__ grad_g, uint32_t* __restrict__ amax_bits, uint8_t* __restrict__ flags,
+                                        uint32_t* __restrict__ counts, int sample) {
+  const int sub = threadIdx.x & 15;
+  const bool dense = !sample && 2u * reinterpret_cast<volatile uint32_t*>(counts)[0] > reinterpret_cast<volatile uint32_t*>(counts)[1];
+  const int64_t n_items = sample ? ((rows + 255) / 256) * 32 : rows;       // sampled: 32 rows out of every 256
+  float bm = 0.f;
+  uint32_t n_act = 0, n_seen = 0;
+  for (int64_t it = (int64_t)blockIdx.x * 16 + (threadIdx.x >> 4); it < n_items; it += (int64_t)gridDim.x * 16) {   // uniform per 16-lane group
+    const int64_t r = sample ? (it >> 5) * 256 + (it & 31) : it;
+    if (r >= rows) continue;
+    if (dense) {
+      if (sub == 0) flags[r] = 1;
+      continue;
+    }
+    float m = 0.f;
+    const float* px = x + r * row_stride + 4 * sub;
+    for (int t = 0; t < slabs; ++t) {
+      const float4 v = ld_nc_f4(px + (int64_t)t * slab_stride);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (grad_g && sub == 0) m = fmaxf(m, fabsf(grad_g[r]));
+    if (!(m <= 3.0e38f)) m = 3.0e38f;
+#pragma unroll
+    for (int off = 8; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off, 16));
+    if (sub == 0) {
+      if (!sample) flags[r] = m > 0.f ? 1 : 0;
+      n_act += m > 0.f ? 1u : 0u;
+      n_seen += 1u;
+    }
+    bm = fmaxf(bm, m);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+  if ((threadIdx.x & 31) == 0 && bm > 0.f) atomicMax(amax_bits, __float_as_uint(bm));
+  if (sample) {
+    n_act += __shfl_xor_sync(0xffffffffu, n_act, 16);
+    n_seen += __shfl_xor_sync(0xffffffffu, n_seen, 16);
+    if ((threadIdx.x & 31) == 0 && n_seen) {
+      atomicAdd(counts, n_act);
+      atomicAdd(counts + 1, n_seen);
+    }
+  }
+}
+
+// pass 2: order-preserving compaction of the flagged rows (one 1024-thread block: count per contiguous chunk, block scan, write)
+__global__ void __launch_bounds__(1024, 1) bwd_compact_rows_kernel(const uint8_t* __restrict__ flags, int64_t rows, int32_t* __restrict__ row_map,
+                                                                    int32_t* __restrict__ n_active) {
+  __shared__ int32_t part[1024];
+  const int64_t chunk = (rows + 1023) / 1024, lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < rows ? lo + chunk : rows;
+  int32_t c = 0;
+  for (int64_t r = lo; r < hi; ++r) c += flags[r];
+  part[threadIdx.x] = c;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {          // Hillis–Steele inclusive scan
+    const int32_t v = (int)threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int32_t pos = part[threadIdx.x] - c;
+  for (int64_t r = lo; r < hi; ++r)
+    if (flags[r]) row_map[pos++] = (int32_t)r;
+  if (threadIdx.x == 1023) *n_active = part[1023];
+}
+
 #ifdef TRAJSDE_BWD_TIMELINE
 }  // namespace (anonymous)
 __device__ long long g_bwd_tl[16];
@@ -181,9 +259,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int pass = blockIdx.y;
   const int S = a.sched.n_steps;
-  const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
-  const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
-  const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
 
   const uint32_t bar_w = base + OFF_BARS, bar_opnd = bar_w + 8, bar_acc = bar_w + 16, bar_wg = bar_w + 24;
   const uint32_t bar_dwfull = bar_w + 32, bar_dwempty = bar_w + 40;
@@ -205,6 +280,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   for (uint32_t i = threadIdx.x; i < TILE_BYTES / 16 && threadIdx.x < NUM_EPI_THREADS; i += NUM_EPI_THREADS)   // epilogue threads: they fence.proxy.async later
     reinterpret_cast<uint4*>(sm + OFF_TILES + T_TIME * TILE_BYTES)[i] = make_uint4(0u, 0u, 0u, 0u);
   pdl_wait();   // nothing above touches global memory; everything below may depend on the previous kernel of the stream
+  // rows of this sweep: all of them, or the compacted list of rows with a non-zero incoming gradient (count known on the device only)
+  const int32_t* __restrict__ rmap = p.row_map;
+  const int64_t n_rows = p.n_active ? (int64_t)*p.n_active : a.rows;
+  const int num_tiles = (int)((n_rows + TILE_M - 1) / TILE_M);
+  const int tiles_q = num_tiles / (int)gridDim.x, tiles_r = num_tiles % (int)gridDim.x;
+  const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
+  const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
   // schedule tables -> shared memory (every step reads them; three dependent global round trips otherwise)
   const bool sched_in_smem = S <= SCHED_MAX && a.sched.n_outputs <= SCHED_MAX;
   const float4* stab = reinterpret_cast<const float4*>(a.sched.step_tab);
@@ -271,8 +353,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     TL_MARK(13);  // kernel prologue: barriers, TMEM, tables, weight image
 
     for (int tile = tile_lo; tile < tile_hi; ++tile) {
-      const int64_t grow = (int64_t)tile * TILE_M + row;
-      bool valid = grow < a.rows;
+      const int64_t srow = (int64_t)tile * TILE_M + row;       // position in the (possibly compacted) row list
+      bool valid = srow < n_rows;
+      const int64_t grow = valid && rmap ? (int64_t)rmap[srow] : srow;   // row of the tensors
       if (valid && p.filter[pass]) valid = (a.alt_mask[grow] != 0) == (p.filter[pass] == 1);   // other net's rows: adjoint stays zero
       // Row prefetch, coalesced: lane L of this warp loads, for i = 0..7, the 16-byte chunk (L & 7) of tile row 32 quad + 4 i + (L >> 3)
       // of its 32-channel half (one instruction = four full 128-byte row segments instead of 32 scattered 16-byte pieces); the
@@ -280,12 +363,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       float4 py[8], pdw[8], pgy[8];
       const int64_t lrow0 = (int64_t)tile * TILE_M + quad * 32 + (lane >> 3);     // + 4 i
       const int lcol = hh * 32 + (lane & 7) * 4;
+      int32_t lmap[8];                                         // tensor rows behind the eight list positions this lane fetches (-1: none)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t r = lrow0 + 4 * i;
+        lmap[i] = r < n_rows ? (rmap ? rmap[r] : (int32_t)r) : -1;
+      }
       auto load_rows = [&](const float* slab, int64_t row_stride, float4 (&dst)[8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t r = lrow0 + 4 * i;
-          dst[i] = r < a.rows ? ld_nc_f4(slab + r * row_stride + lcol) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < 8; ++i)
+          dst[i] = lmap[i] >= 0 ? ld_nc_f4(slab + (int64_t)lmap[i] * row_stride + lcol) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       uint8_t* stage = sm + OFF_TILES + T_H1F * TILE_BYTES + (uint32_t)warp * 4096;   // h1f|h1g tiles are idle at step start
       auto to_own_row = [&](float4 (&v)[8]) {
@@ -585,6 +672,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
     float* out = p.partial[pass] + (size_t)blockIdx.x * G_PAD;
     const bool acc_out = p.accumulate != 0;
     auto put = [&](int idx, float v) { out[idx] = acc_out ? out[idx] + v : v; };
+    if (tile_lo == tile_hi) {                                  // no tile for this CTA (the tile count is a device value): a zero partial vector
+      if (!acc_out)
+        for (int i = eid; i < G_PAD; i += NUM_EPI_THREADS) out[i] = 0.f;
+    } else {
     const bool lo = quad < 2;                                    // TMEM lanes 0..63: drift net, 64..127: diffusion net
     const int m = (int)row & 63;
     {
@@ -635,6 +726,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
         put(G_GB3, ((red[256] + red[257]) + (red[258] + red[259])) * inv_sigma);
       }
     }
+    }
     TL_MARK(14);  // weight-gradient flush
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
@@ -646,17 +738,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
       const uint32_t t = (uint32_t)(warp - NUM_EPI_WARPS - 1) * 32u + (uint32_t)lane;      // 0..95
       uint32_t n = 0;                                                                    // tiles-steps produced: dwempty parity
       for (int tile = tile_lo; tile < tile_hi; ++tile) {
-        const uint64_t grow0 = (uint64_t)tile * TILE_M + a.noise.row_offset;
+        const int64_t srow0 = (int64_t)tile * TILE_M;
         for (int k = S - 1; k >= 0; --k, ++n) {
           const float sqrt_h = sqrtf(stab[k].y);
           if (n > 0) mbar_wait(bar_dwempty, (n - 1) & 1);                                // every epilogue thread has read the previous tile
           for (uint32_t item = t; item < 2u * TILE_M; item += NUM_DW_THREADS) {
             const uint32_t r = item & (TILE_M - 1), h2 = item >> 7;
             uint8_t* tr = sm + OFF_DWT + r * 128;
+            const int64_t sr = srow0 + r;
+            const uint64_t grow_r = (uint64_t)(rmap && sr < n_rows ? (int64_t)rmap[sr] : sr) + a.noise.row_offset;
 #pragma unroll 1
             for (uint32_t c = 0; c < 4; ++c) {                                           // 16-byte chunk = 8 channels = two Philox calls
-              const float4 n0 = philox_dw4(a.noise.seed, grow0 + r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c, sqrt_h);
-              const float4 n1 = philox_dw4(a.noise.seed, grow0 + r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c + 1, sqrt_h);
+              const float4 n0 = philox_dw4(a.noise.seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c, sqrt_h);
+              const float4 n1 = philox_dw4(a.noise.seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c + 1, sqrt_h);
               *reinterpret_cast<uint4*>(tr + (((h2 * 4 + c) ^ (r & 7u)) << 4)) =
                   make_uint4(pack_f16x2(n0.x, n0.y), pack_f16x2(n0.z, n0.w), pack_f16x2(n1.x, n1.y), pack_f16x2(n1.z, n1.w));
             }
@@ -801,7 +895,7 @@ int bwd_tc_grid(int64_t rows, bool dual) {
 // img1 != NULL: dual diffusion — pass 0 (img0, part0) takes the rows with alt_mask != 0, pass 1 (img1 packed with a.diffusion_alt,
 // part1) the rows with alt_mask == 0; both passes run in the same launch (gridDim.y = 2).
 int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t* img1, const uint32_t* amax_bits, float* part0, float* part1,
-                int accumulate, cudaStream_t s, bool pdl) {
+                int accumulate, cudaStream_t s, bool pdl, const int32_t* row_map, const int32_t* n_active) {
   if ((reinterpret_cast<uintptr_t>(img0) & 15u) != 0 || (reinterpret_cast<uintptr_t>(img1) & 15u) != 0)
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
   if (a.rows >= (int64_t)1 << 31) return set_error(TRAJSDE_ERR_UNSUPPORTED, "rows >= 2^31 unsupported in TC mode");
@@ -815,6 +909,8 @@ int bwd_tc_main(const TrajsdeEulerBwdArgs& a, const uint8_t* img0, const uint8_t
   p.filter[0] = dual ? 1 : 0;
   p.filter[1] = 2;
   p.amax_bits = amax_bits;
+  p.row_map = row_map;
+  p.n_active = n_active;
   p.num_tiles = (int)((a.rows + TILE_M - 1) / TILE_M);
   p.accumulate = accumulate;
   const int grid = bwd_tc_grid(a.rows, dual);
@@ -845,13 +941,14 @@ int launch_euler_bwd_reduce(const float* part0, const float* part1, int n0, int 
   return TRAJSDE_OK;
 }
 
+static int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
 int64_t euler_bwd_tc_workspace_bytes(int64_t rows, int32_t n_steps) {
-  (void)rows;
   (void)n_steps;
-  return 2 * (int64_t)BWD_TC_IMG_BYTES + 256 + 2 * (int64_t)MAX_PARTIALS * G_PAD * 4 + 256;
+  return 2 * (int64_t)BWD_TC_IMG_BYTES + 256 + align256(2 * (int64_t)MAX_PARTIALS * G_PAD * 4) + 256 + align256(rows) + align256(4 * rows);
 }
 
-// workspace: img0 | img1 | amax (256 B) | partial0 | partial1
+// workspace: img0 | img1 | amax (256 B) | partial0 | partial1 | n_active (256 B) | row flags [rows] | row_map [rows] (zero-row skipping)
 int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(a.workspace) & 255u) != 0) return set_error(TRAJSDE_ERR_UNSUPPORTED, "workspace must be 256-byte aligned");
   uint8_t* ws = static_cast<uint8_t*>(a.workspace);
@@ -862,18 +959,44 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
   float* part1 = part0 + (size_t)MAX_PARTIALS * G_PAD;
   const bool dual = a.alt_mask != nullptr;
   const int grid = bwd_tc_grid(a.rows, dual);
+  // zero-row skipping: a winner-takes-all loss (losses/L2.py:17-20: only the best of the 10 modes of an actor receives a gradient) leaves
+  // ~90 % of the decoder rows with an all-zero incoming gradient; their adjoint is zero at every step, so the sweep visits the others only
+  const bool skip_zero = (a.flags & TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS) != 0 && !dual && a.grad_ys != nullptr;
+  uint8_t* tail = reinterpret_cast<uint8_t*>(part0) + align256(2 * (int64_t)MAX_PARTIALS * G_PAD * 4);
+  int32_t* n_active = reinterpret_cast<int32_t*>(tail);
+  uint8_t* row_flags = tail + 256;
+  int32_t* row_map = reinterpret_cast<int32_t*>(row_flags + align256(a.rows));
   int rc;
   if (grid > 0) {
     TS_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, s));
-    if (a.grad_ys && (rc = bwd_tc_absmax(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride, a.grad_ys_row_stride, amax, s)) != 0) return rc;
-    if (a.grad_g_last && (rc = bwd_tc_absmax(a.grad_g_last, 1, a.rows, 0, 0, amax, s)) != 0) return rc;
+    if (skip_zero) {
+      int dev = 0, sms = 0;
+      TS_CUDA_CHECK(cudaGetDevice(&dev));
+      TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      uint32_t* counts = reinterpret_cast<uint32_t*>(n_active) + 2;        // {active, seen} sampled rows
+      TS_CUDA_CHECK(cudaMemsetAsync(counts, 0, 8, s));
+      for (int sample = 1; sample >= 0; --sample) {
+        const int64_t want = ((sample ? ((a.rows + 255) / 256) * 32 : a.rows) + 15) / 16;
+        bwd_row_activity_kernel<<<(int)(want < 8 * sms ? want : 8 * sms), 256, 0, s>>>(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride,
+                                                                                     a.grad_ys_row_stride, a.grad_g_last, amax, row_flags, counts, sample);
+        TS_CUDA_CHECK(cudaGetLastError());
+      }
+      bwd_compact_rows_kernel<<<1, 1024, 0, s>>>(row_flags, a.rows, row_map, n_active);
+      TS_CUDA_CHECK(cudaGetLastError());
+      TS_CUDA_CHECK(cudaMemsetAsync(a.grad_y0, 0, sizeof(float) * 64 * (size_t)a.rows, s));   // skipped rows: dL/dy0 = 0
+    } else {
+      if (a.grad_ys && (rc = bwd_tc_absmax(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride, a.grad_ys_row_stride, amax, s)) != 0) return rc;
+      if (a.grad_g_last && (rc = bwd_tc_absmax(a.grad_g_last, 1, a.rows, 0, 0, amax, s)) != 0) return rc;
+    }
     if ((rc = bwd_tc_pack(a, img0, s)) != 0) return rc;
     if (dual) {   // second pass: the rows of the other diffusion net (rows are independent; the drift gradients of both passes add up)
       TrajsdeEulerBwdArgs b = a;
       b.diffusion = a.diffusion_alt;
       if ((rc = bwd_tc_pack(b, img1, s)) != 0) return rc;
     }
-    if ((rc = bwd_tc_main(a, img0, dual ? img1 : nullptr, amax, part0, part1, 0, s, false)) != 0) return rc;
+    if ((rc = bwd_tc_main(a, img0, dual ? img1 : nullptr, amax, part0, part1, 0, s, false, skip_zero ? row_map : nullptr,
+                          skip_zero ? n_active : nullptr)) != 0)
+      return rc;
   }
   euler_bwd_reduce_kernel<<<(G_TOTAL + 255) / 256, 256, 0, s>>>(part0, dual ? part1 : nullptr, grid, dual ? grid : 0, a.grad_drift,
                                                               a.grad_diffusion, a.grad_diffusion_alt, 0);

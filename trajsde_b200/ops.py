@@ -24,6 +24,11 @@ _KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-
 
 # A/B switch (tests, bench): run the fp32 CUDA-core backward kernels even in 'tc_f16' mode (TRAJSDE_BWD_FLAG_EXACT_KERNELS)
 BWD_EXACT_KERNELS = False
+# TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS: the tensor-core backward of a single-diffusion solve (the decoder) first finds the rows whose incoming
+# gradient is all zero (one scan of grad_ys on the device, no host sync) and sweeps only the others.  Exact (those rows contribute
+# nothing), and worth ~8x under the reference's winner-takes-all L2 loss (losses/L2.py:17-20: 1 of 10 modes per actor gets a gradient);
+# a sampled pre-scan recognises (nearly) dense cotangents and then skips the full scan.
+SKIP_ZERO_ROWS = True
 
 # per-device int32 status word the tensor-core backward kernels OR their TRAJSDE_STATUS_* bits into.  The word is never read on the
 # hot path: after every tensor-core backward call a snapshot is copied to pinned host memory on the same stream (4 bytes, no sync)
@@ -265,7 +270,8 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
     gparams = [torch.empty_like(p) for p in ps]       # the fixed-order reduce writes every element
     a = _lib.EulerBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EulerBwdArgs)
-    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0)
+    skip_zero = bool(SKIP_ZERO_ROWS) and not dual and mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS and grad_ys is not None and rows >= 2048
+    a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0) | (2 if skip_zero else 0)
     a.sched.n_steps, a.sched.n_outputs = S, n_outputs
     a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
     a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
@@ -302,7 +308,10 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
         tc = mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS
         # TC: pack + absmax + fused dgrad/wgrad + reduce; exact: (dgrad + wgrad) per diffusion net + reduce
         sampled = tc and grad_ys is not None and rows * grad_ys.shape[0] >= (1 << 16)   # sampled absmax + its conditional full scan
-        LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
+        if skip_zero:
+            LAUNCHES['n'] += 6            # row activity (sampled, full) + compaction + pack + fused dgrad/wgrad + reduce
+        else:
+            LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
     return [grad_y0] + gparams
 
 
