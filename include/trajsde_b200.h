@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 4
+#define TRAJSDE_ABI_VERSION 5
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -339,6 +339,41 @@ typedef struct {
 
 int64_t trajsde_heads_workspace_bytes(int32_t mode);
 int trajsde_heads_fwd(const TrajsdeHeadsArgs* args, void* cuda_stream);
+
+/* Backward of the fused decoder heads (training): what autograd computes through the two nn.Sequential heads of SDEDecoder.forward
+ * (dec_hivt_nusargo_sde.py:50-61, 96, 98) — dL/dx summed over the heads and the gradients of every head parameter, from
+ * dL/dout_h [rows, n_t, 2].  Only the (point, head) pairs with a non-zero dL/dout are processed (the reference's winner-takes-all L2
+ * loss, losses/L2.py:12-20, leaves ~5 % of them): grad_x must be ZERO-FILLED by the caller, rows of active points are accumulated into.
+ * fp32 arithmetic on CUDA cores in every mode (the validation-grade twin of the tensor-core forward). */
+typedef struct {
+  float* w1; float* b1; float* ln_g; float* ln_b; float* w2; float* b2;   /* written, not accumulated */
+} TrajsdeHeadGrad;
+
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t mode;              /* any TrajsdeMode (the arithmetic is fp32) */
+  int64_t rows;
+  int32_t dim;               /* 64 */
+  int32_t flags;
+  int32_t n_t;
+  int32_t n_heads;           /* 1 or 2 */
+  TrajsdeHead head[2];
+  float ln_eps;
+  float reserved;
+  const float* x;            /* as in TrajsdeHeadsArgs */
+  int64_t x_row_stride;
+  int64_t x_t_stride;
+  const float* grad_out[2];  /* per head dL/dout [rows, n_t, 2] contiguous, or NULL (no gradient reaches that head) */
+  float* grad_x;             /* element (t, row, c) at grad_x + t * gx_t_stride + row * gx_row_stride + c; zero-filled by the caller */
+  int64_t gx_row_stride;
+  int64_t gx_t_stride;
+  TrajsdeHeadGrad grad_head[2];
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeHeadsBwdArgs;
+
+int64_t trajsde_heads_bwd_workspace_bytes(int32_t mode);
+int trajsde_heads_bwd(const TrajsdeHeadsBwdArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

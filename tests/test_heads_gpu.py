@@ -77,15 +77,16 @@ def test_single_head_and_errors():
         loc, none = hd.decoder_heads(loc_h, None, x)
     assert none is None
     assert torch.allclose(loc.cpu(), so.decoder_loc_head_ref(params_of(loc_h), x.cpu()), **TOL)
-    with pytest.raises(NotImplementedError):                  # autograd requested: no silent fallback
-        hd.decoder_heads(loc_h, None, x.clone().requires_grad_(True))
+    xg = x.clone().requires_grad_(True)                       # autograd requested: the fused backward serves it (single head too)
+    out, _ = hd.decoder_heads(loc_h, None, xg)
+    out.sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all() and loc_h[0].weight.grad is not None
     with pytest.raises(RuntimeError):
         hd.decoder_heads(loc_h.cpu(), None, x.cpu())
 
 
 def test_install_heads_drop_in_pair():
-    """The reference forward calls self.decoder(sol_y) then self.scale(sol_y): one fused launch serves both; training goes to
-    the original nn.Sequential."""
+    """The reference forward calls self.decoder(sol_y) then self.scale(sol_y): one fused launch serves both, with and without autograd."""
     class Dec(nn.Module):
         def __init__(self):
             super().__init__()
@@ -103,10 +104,14 @@ def test_install_heads_drop_in_pair():
         sc = dec.scale(x)
     assert ops.LAUNCHES['n'] - n0 == 2                         # pack + one fused kernel for both heads
     assert torch.allclose(loc, want_loc, **TOL) and torch.allclose(sc, want_sc, **TOL)
-    xg = x.clone().requires_grad_(True)                        # autograd -> reference PyTorch heads
-    out = dec.decoder(xg)
-    out.sum().backward()
-    assert xg.grad is not None and torch.allclose(out, want_loc, atol=1e-5, rtol=1e-5)
+    xg = x.clone().requires_grad_(True)                        # autograd: one differentiable fused node serves both calls
+    n0 = ops.LAUNCHES['n']
+    out, out_sc = dec.decoder(xg), dec.scale(xg)
+    assert ops.LAUNCHES['n'] - n0 == 2 and torch.allclose(out, want_loc, **TOL) and torch.allclose(out_sc, want_sc, **TOL)
+    (out.sum() + 0.5 * out_sc.sum()).backward()
+    ref = x.clone().requires_grad_(True)
+    (torch.nn.Sequential.forward(dec.decoder, ref).sum() + 0.5 * torch.nn.Sequential.forward(dec.scale, ref).sum()).backward()
+    assert (xg.grad - ref.grad).abs().max() <= 1e-4 * ref.grad.abs().max()
     hd.uninstall_heads(saved)
     assert 'forward' not in dec.decoder.__dict__
     with torch.no_grad():
@@ -124,3 +129,65 @@ def test_heads_on_solver_output_rows_major():
         sol_y = ys[1:].permute(1, 0, 2)
         loc, sc = hd.decoder_heads(loc_h, sc_h, sol_y)
         assert torch.allclose(loc, loc_h(sol_y), **TOL) and torch.allclose(sc, sc_h(sol_y), **TOL)
+
+
+def _fp64_head_grads(heads, x, cots):
+    """fp64 autograd through the oracle's restatement of the heads: dL/dx and dL/dparam for L = sum_h <out_h, cot_h>."""
+    xd = x.double().clone().requires_grad_(True)
+    P = [{k: v.double().clone().requires_grad_(True) for k, v in params_of(h).items()} for h in heads]
+    loss = sum((so.decoder_loc_head_ref(p, xd) * c.double()).sum() for p, c in zip(P, cots) if c is not None)
+    leaves = [xd] + [t for p in P for t in p.values()]
+    g = torch.autograd.grad(loss, leaves, allow_unused=True)
+    return g[0], [dict(zip(p.keys(), g[1 + 6 * i:7 + 6 * i])) for i, p in enumerate(P)]
+
+
+@pytest.mark.parametrize('rows,T,frac,which', [(50, 7, 1.0, 'both'), (300, 60, 0.1, 'both'), (300, 60, 0.1, 'loc'), (2000, 60, 0.03, 'both'),
+                                               (130, 5, 0.0, 'both')])
+def test_heads_backward_vs_fp64_autograd(rows, T, frac, which):
+    """trajsde_heads_bwd (fp32, active points only) against fp64 autograd of the oracle heads: dL/dsol_y and every head parameter,
+    for dense, sparse (winner-takes-all shaped), single-head and empty cotangents.  The forward values that autograd differentiates
+    are the tensor-core ones; the backward recomputes the activations in fp32 from the same inputs."""
+    loc_h, sc_h = make_head(21).to(DEV), make_head(22).to(DEV)
+    g = torch.Generator().manual_seed(rows + T)
+    x = torch.randn(rows, T, 64, generator=g) * 2.0
+    act = torch.rand(rows, T, generator=g) < frac
+    c0 = torch.randn(rows, T, 2, generator=g) * act.unsqueeze(-1)
+    c1 = torch.randn(rows, T, 2, generator=g) * (torch.rand(rows, T, generator=g) < frac).unsqueeze(-1) if which == 'both' else None
+    gx_ref, gp_ref = _fp64_head_grads([loc_h, sc_h], x, [c0, c1])
+    xg = x.to(DEV).requires_grad_(True)
+    o0, o1 = hd.decoder_heads(loc_h, sc_h, xg)
+    loss = (o0 * c0.to(DEV)).sum() + ((o1 * c1.to(DEV)).sum() if c1 is not None else 0.0)
+    loss.backward()
+    if frac == 0.0:
+        assert float(xg.grad.abs().max()) == 0.0 and all(float(p_.grad.abs().max()) == 0.0 for p_ in loc_h.parameters())
+        return
+    assert float((xg.grad.double().cpu() - gx_ref).abs().max()) <= 1e-4 * float(gx_ref.abs().max())
+    for h, head in enumerate((loc_h, sc_h)):
+        for k, p_ in head.state_dict(keep_vars=True).items():
+            r = gp_ref[h][k]
+            if r is None or float(r.abs().max()) == 0.0:
+                assert p_.grad is None or float(p_.grad.abs().max()) == 0.0, (h, k)
+                continue
+            e = float((p_.grad.double().cpu() - r).abs().max() / r.abs().max())
+            assert e < 1e-4, (h, k, e)
+
+
+@pytest.mark.parametrize('rows_major', [True, False])
+def test_heads_from_solution_gradient_reaches_the_solver_in_place(rows_major):
+    """decoder_heads_from_solution: heads on the solver's full ys; dL/dys comes back in ys's own layout (slab 0 zero) and the chain
+    solver -> heads trains end to end (gradients of the SDE nets and of y0 are finite and non-zero)."""
+    sde = init_like_reference(DecoderSDE(), seed=2).to(DEV)
+    loc_h, sc_h = make_head(11).to(DEV), make_head(12).to(DEV)
+    y0 = torch.relu(torch.randn(2100, 64, generator=torch.Generator().manual_seed(3))).to(DEV).requires_grad_(True)
+    ts = torch.linspace(0, 6, 61)
+    ys = tb.sdeint(sde, y0, ts, dt=0.1, method='euler', mode='tc_f16', seed=5, rows_major=rows_major)
+    loc, sc = hd.decoder_heads_from_solution(loc_h, sc_h, ys)
+    with torch.no_grad():
+        want, _ = hd.decoder_heads(loc_h, sc_h, ys.detach()[1:].permute(1, 0, 2))
+    assert torch.equal(loc.detach(), want)
+    best = torch.zeros(2100, dtype=torch.bool, device=DEV)
+    best[::10] = True                                          # one "mode" in ten receives a gradient
+    (loc[best, :30].square().sum()).backward()
+    assert float(y0.grad[best].abs().max()) > 0 and float(y0.grad[~best].abs().max()) == 0.0
+    assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in sde.parameters())
+    assert sc_h[0].weight.grad is None or float(sc_h[0].weight.grad.abs().max()) == 0.0     # no gradient reached the scale head

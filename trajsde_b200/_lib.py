@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -19,7 +19,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_philox_dw', 'trajsde_enc_fwd_workspace_bytes', 'trajsde_enc_fwd',
     'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
     'trajsde_gru_workspace_bytes', 'trajsde_gru_fwd', 'trajsde_gru_bwd',
-    'trajsde_heads_workspace_bytes', 'trajsde_heads_fwd',
+    'trajsde_heads_workspace_bytes', 'trajsde_heads_fwd', 'trajsde_heads_bwd_workspace_bytes', 'trajsde_heads_bwd',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -96,6 +96,14 @@ class HeadsArgs(C.Structure):
                 ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
+class HeadsBwdArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
+                ('flags', C.c_int32), ('n_t', C.c_int32), ('n_heads', C.c_int32), ('head', Head * 2), ('ln_eps', C.c_float),
+                ('reserved', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('grad_out', _fp * 2),
+                ('grad_x', _fp), ('gx_row_stride', C.c_int64), ('gx_t_stride', C.c_int64), ('grad_head', Head * 2),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -146,6 +154,10 @@ def lib():
         L.trajsde_heads_workspace_bytes.argtypes = [C.c_int32]
         L.trajsde_heads_fwd.restype = C.c_int
         L.trajsde_heads_fwd.argtypes = [C.POINTER(HeadsArgs), C.c_void_p]
+        L.trajsde_heads_bwd_workspace_bytes.restype = C.c_int64
+        L.trajsde_heads_bwd_workspace_bytes.argtypes = [C.c_int32]
+        L.trajsde_heads_bwd.restype = C.c_int
+        L.trajsde_heads_bwd.argtypes = [C.POINTER(HeadsBwdArgs), C.c_void_p]
         v = L.trajsde_abi_version()
         if v != ABI_VERSION:
             raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")

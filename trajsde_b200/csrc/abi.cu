@@ -316,6 +316,43 @@ int trajsde_heads_fwd(const TrajsdeHeadsArgs* a, void* cuda_stream) {
   return launch_heads_fwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
+int64_t trajsde_heads_bwd_workspace_bytes(int32_t mode) {
+  (void)mode;
+  return heads_bwd_workspace_bytes();
+}
+
+int trajsde_heads_bwd(const TrajsdeHeadsBwdArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeHeadsBwdArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeHeadsBwdArgs));
+  if (a->dim != TRAJSDE_DIM) return set_error(TRAJSDE_ERR_UNSUPPORTED, "dim %d unsupported (only 64)", a->dim);
+  if (a->rows < 0 || a->n_t < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "rows / n_t < 0");
+  if (a->n_heads != 1 && a->n_heads != 2) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_heads %d (1 or 2)", a->n_heads);
+  for (int h = 0; h < a->n_heads; ++h) {
+    const TrajsdeHead& hd = a->head[h];
+    const TrajsdeHeadGrad& g = a->grad_head[h];
+    if (!hd.w1 || !hd.b1 || !hd.ln_g || !hd.ln_b || !hd.w2 || !hd.b2)
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "head[%d]: null parameter pointer", h);
+    if (!g.w1 || !g.b1 || !g.ln_g || !g.ln_b || !g.w2 || !g.b2)
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_head[%d]: null pointer", h);
+    if (a->grad_out[h] && (reinterpret_cast<uintptr_t>(a->grad_out[h]) & 7u))
+      return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_out[%d] must be 8-byte aligned", h);
+  }
+  const bool empty = a->rows == 0 || a->n_t == 0;
+  if (!empty) {
+    if (!a->x || !aligned16(a->x) || (a->x_row_stride & 3) != 0 || (a->x_t_stride & 3) != 0)
+      return set_error(TRAJSDE_ERR_UNSUPPORTED, "x must be 16-byte aligned with row / t strides that are multiples of 4 elements");
+    if (!a->grad_x || !aligned16(a->grad_x) || (a->gx_row_stride & 3) != 0 || (a->gx_t_stride & 3) != 0)
+      return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_x must be 16-byte aligned with row / t strides that are multiples of 4 elements");
+  }
+  const int64_t need = heads_bwd_workspace_bytes();
+  if (a->workspace_bytes < need || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_heads_bwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));     // rows == 0: the reduce still writes zero gradients
+}
+
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
   if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
   int rc;

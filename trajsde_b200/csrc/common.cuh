@@ -140,6 +140,8 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s);
 int64_t enc_bwd_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s);
 int64_t heads_workspace_bytes();
+int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s);
+int64_t heads_bwd_workspace_bytes();
 int launch_philox_dw(const TrajsdeSchedule& sched, const TrajsdeNoise& noise, int64_t rows, float* out, cudaStream_t s);
 
 }  // namespace trajsde

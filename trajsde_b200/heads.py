@@ -4,8 +4,10 @@
     loc, scale_raw = decoder_heads(dec.decoder, dec.scale, sol_y)        # sol_y [rows, T, 64], any row / time strides
     scale = F.elu_(scale_raw, alpha=1.0) + 1.0 + min_scale               # :98-99 stays with the caller
 
-Forward only: inference / ``torch.no_grad()``.  Under autograd the reference's own ``nn.Sequential`` heads run (they are outside
-the solver path and stay on the reference PyTorch path); ``decoder_heads`` itself raises instead of falling back silently.
+Forward: tensor-core kernel (csrc/heads.cu).  Under autograd the call is differentiable: the backward (csrc/heads_bwd.cu) processes only
+the (point, head) pairs that received a gradient — the reference's winner-takes-all L2 loss (losses/L2.py:12-20) reaches ~5 % of them —
+and returns dL/dsol_y plus the gradients of all head parameters.  ``decoder_heads_from_solution`` takes the solver's full ``ys``
+(slab 0 = y0 included) so that no slice-backward copy of the 3 GB gradient is needed.
 """
 import ctypes as C
 from typing import List, Optional, Tuple
@@ -27,8 +29,7 @@ def head_params(head: torch.nn.Module) -> List[torch.Tensor]:
     return ps
 
 
-@torch.library.custom_op("trajsde::heads_fwd", mutates_args=(), device_types="cuda")
-def heads_fwd(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+def _heads_fwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
     """x[rows, T, 64] (last dim unit-stride) -> (out0[rows, T, 2], out1[rows, T, 2]); out1 is empty when n_heads == 1."""
     if x.dim() != 3 or x.shape[2] != 64 or x.dtype != torch.float32 or (x.numel() > 0 and x.stride(2) != 1):
         raise ValueError("`sol_y` must be float32 of shape (rows, T, 64) with a unit-stride last dimension")
@@ -63,38 +64,124 @@ def heads_fwd(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps:
     return outs[0], outs[1]
 
 
+heads_fwd = torch.library.custom_op("trajsde::heads_fwd", _heads_fwd_impl, mutates_args=(), device_types="cuda")
+
+
 @heads_fwd.register_fake
 def _(x, params, n_heads, ln_eps):
     rows, T = x.shape[0], x.shape[1]
     return x.new_empty((rows, T, 2)), x.new_empty((rows, T, 2) if n_heads == 2 else (0, T, 2))
 
 
-def _fusable(x: torch.Tensor, heads) -> bool:
-    need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for h in heads for p in h.parameters()))
-    return x.is_cuda and not need_grad
+def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float, grad0: Optional[torch.Tensor],
+                    grad1: Optional[torch.Tensor], grad_x: torch.Tensor) -> List[torch.Tensor]:
+    """Gradients of the 6 * n_heads head tensors; dL/dx is ACCUMULATED into the zero-filled ``grad_x`` (same shape as x, any row / t
+    strides, unit channel stride) for the points that carry a non-zero dL/dout.  ``grad_h`` [rows, T, 2] or None per head."""
+    rows, T = x.shape[0], x.shape[1]
+    dev = x.device
+    ps = [p.detach().contiguous() for p in params]
+    gps = [torch.empty_like(p) for p in ps]
+    a = _lib.HeadsBwdArgs()
+    a.struct_bytes = C.sizeof(_lib.HeadsBwdArgs)
+    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, 0, T, n_heads
+    for h in range(n_heads):
+        for name, t, g in zip(('w1', 'b1', 'ln_g', 'ln_b', 'w2', 'b2'), ps[6 * h:6 * h + 6], gps[6 * h:6 * h + 6]):
+            setattr(a.head[h], name, t.data_ptr())
+            setattr(a.grad_head[h], name, g.data_ptr())
+    a.ln_eps = ln_eps
+    xd = x.detach()
+    if rows > 0 and T > 0 and (xd.data_ptr() % 16 != 0 or xd.stride(0) % 4 != 0 or xd.stride(1) % 4 != 0 or xd.stride(2) != 1):
+        xd = xd.contiguous()
+    a.x, a.x_row_stride, a.x_t_stride = xd.data_ptr(), max(xd.stride(0), 64), max(xd.stride(1), 64)
+    keep = []
+    for h, g in enumerate((grad0, grad1)[:n_heads]):
+        if g is not None:
+            g = g.contiguous()
+            keep.append(g)
+            a.grad_out[h] = g.data_ptr()
+    if grad_x.stride(2) != 1 or grad_x.stride(0) % 4 or grad_x.stride(1) % 4 or (grad_x.numel() and grad_x.data_ptr() % 16):
+        raise ValueError("grad_x: unit channel stride, 16-byte aligned, row / t strides multiples of 4 elements")
+    a.grad_x, a.gx_row_stride, a.gx_t_stride = grad_x.data_ptr(), max(grad_x.stride(0), 64), max(grad_x.stride(1), 64)
+    L = _lib.lib()
+    need = _lib.check(L.trajsde_heads_bwd_workspace_bytes(_lib.MODE_TC_F16), "trajsde_heads_bwd_workspace_bytes")
+    ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), need
+    with torch.cuda.device(dev):
+        _lib.check(L.trajsde_heads_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_heads_bwd")
+    LAUNCHES['n'] += 2
+    return gps
 
 
-def decoder_heads(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], sol_y: torch.Tensor):
-    """(loc[rows,T,2], scale_raw[rows,T,2] or None) = (loc_head(sol_y), scale_head(sol_y)) in one fused launch."""
+class _HeadsFn(torch.autograd.Function):
+    """Both heads on ``sol_y`` [rows, T, 64] (a view is fine).  ``full``: the first argument is the solver's whole ``ys`` [T+1, rows, 64]
+    and the heads read ``ys[1:].permute(1, 0, 2)`` — the gradient is then produced directly in ``ys``'s shape and layout (slab 0 zero),
+    so autograd has no slice-backward copy to make."""
+
+    @staticmethod
+    def forward(ctx, x, full, n_heads, ln_eps, *params):
+        sol = x[1:].permute(1, 0, 2) if full else x
+        o0, o1 = _heads_fwd_impl(sol, list(params), n_heads, ln_eps)
+        ctx.save_for_backward(x, *params)
+        ctx.meta = (full, n_heads, ln_eps)
+        ctx.set_materialize_grads(False)
+        return o0, o1
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        x, *params = ctx.saved_tensors
+        full, n_heads, ln_eps = ctx.meta
+        if full:        # ys is dense in one of the two storage layouts: the gradient takes the same strides (slab 0 stays zero)
+            gfull = torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device).zero_()
+        else:
+            gfull = torch.zeros(x.shape, dtype=x.dtype, device=x.device)
+        sol = x[1:].permute(1, 0, 2) if full else x
+        gsol = gfull[1:].permute(1, 0, 2) if full else gfull
+        gps = _heads_bwd_impl(sol, list(params), n_heads, ln_eps, g0, g1 if n_heads == 2 else None, gsol)
+        return (gfull, None, None, None) + tuple(gps)
+
+
+def _needs_grad(x: torch.Tensor, heads) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for h in heads for p in h.parameters()))
+
+
+def _head_args(loc_head, scale_head):
     heads = [loc_head] + ([scale_head] if scale_head is not None else [])
-    if not sol_y.is_cuda:
-        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
-    if not _fusable(sol_y, heads):
-        raise NotImplementedError("the fused decoder heads are forward-only: call them under torch.no_grad() / with frozen inputs, "
-                                  "or use the reference nn.Sequential heads for training")
     eps = {float(h[1].eps) for h in heads}
     if len(eps) != 1:
         raise NotImplementedError("both heads must share the LayerNorm eps")
-    params = [p for h in heads for p in head_params(h)]
-    o0, o1 = heads_fwd(sol_y, params, len(heads), eps.pop())
+    return heads, [p for h in heads for p in head_params(h)], eps.pop()
+
+
+def decoder_heads(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], sol_y: torch.Tensor):
+    """(loc[rows,T,2], scale_raw[rows,T,2] or None) = (loc_head(sol_y), scale_head(sol_y)) in one fused launch; differentiable."""
+    if not sol_y.is_cuda:
+        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    heads, params, eps = _head_args(loc_head, scale_head)
+    if _needs_grad(sol_y, heads):
+        o0, o1 = _HeadsFn.apply(sol_y, False, len(heads), eps, *params)
+    else:
+        o0, o1 = _heads_fwd_impl(sol_y, params, len(heads), eps)
+    return o0, (o1 if scale_head is not None else None)
+
+
+def decoder_heads_from_solution(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], ys: torch.Tensor):
+    """The same on the solver's full output ``ys`` [T+1, rows, 64] (``sdeint``'s return value, either storage layout): the heads read
+    ``ys[1:].permute(1, 0, 2)`` (dec…sde.py:88) and, in training, hand dL/dys back in ``ys``'s own layout — no slice-backward copy."""
+    if not ys.is_cuda:
+        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    heads, params, eps = _head_args(loc_head, scale_head)
+    if _needs_grad(ys, heads):
+        o0, o1 = _HeadsFn.apply(ys, True, len(heads), eps, *params)
+    else:
+        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), params, len(heads), eps)
     return o0, (o1 if scale_head is not None else None)
 
 
 class FusedHeadPair:
     """No-edit drop-in for ``SDEDecoder.forward``'s two head calls: ``install_heads`` binds ``loc_forward`` / ``scale_forward`` as the
     ``forward`` of the decoder's ``self.decoder`` / ``self.scale`` instances.  The first call on a given ``sol_y`` runs the fused
-    launch and keeps the other head's result for the call that follows (dec…sde.py:96 then :98).  Calls that need autograd go to
-    the original ``nn.Sequential.forward`` — the reference PyTorch path."""
+    launch for BOTH heads and keeps the other head's result for the call that follows (dec…sde.py:96 then :98); under autograd both
+    results are outputs of one differentiable node.  Inputs the kernels do not serve (non-CUDA, not 3-D) go to ``nn.Sequential.forward``."""
 
     def __init__(self, loc_head, scale_head):
         self.loc_head, self.scale_head = loc_head, scale_head
@@ -104,13 +191,17 @@ class FusedHeadPair:
     def _key_of(x):
         # inference tensors (torch.inference_mode(): Lightning's validate / test / predict loops) do not track a version counter
         version = None if x.is_inference() else x._version
-        return (x.data_ptr(), version, tuple(x.shape), tuple(x.stride()))
+        return (x.data_ptr(), version, tuple(x.shape), tuple(x.stride()), torch.is_grad_enabled())
+
+    @staticmethod
+    def _served(x):
+        return x.is_cuda and x.dim() == 3 and x.shape[2] == 64 and x.dtype == torch.float32
 
     def _both(self, x):
         return decoder_heads(self.loc_head, self.scale_head, x)
 
     def loc_forward(self, x):
-        if not (_fusable(x, [self.loc_head, self.scale_head]) and x.dim() == 3):
+        if not self._served(x):
             return torch.nn.Sequential.forward(self.loc_head, x)
         if self._key == self._key_of(x) and self._pending is not None and self._pending[0] == 'loc':
             out, self._key, self._pending = self._pending[1], None, None
@@ -120,7 +211,7 @@ class FusedHeadPair:
         return loc
 
     def scale_forward(self, x):
-        if not (_fusable(x, [self.loc_head, self.scale_head]) and x.dim() == 3):
+        if not self._served(x):
             return torch.nn.Sequential.forward(self.scale_head, x)
         if self._key == self._key_of(x) and self._pending is not None and self._pending[0] == 'scale':
             out, self._key, self._pending = self._pending[1], None, None
