@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 5
+#define TRAJSDE_ABI_VERSION 6
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -374,6 +374,85 @@ typedef struct {
 
 int64_t trajsde_heads_bwd_workspace_bytes(int32_t mode);
 int trajsde_heads_bwd(const TrajsdeHeadsBwdArgs* args, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The decoder stage's prologue and the two training losses around the solve; fp32, fused, one call each.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* aggr_embed: hidden_0[m * N + n] = ReLU(LayerNorm(W [global_embed[m, n] ; local_embed[n]] + b))
+ * replaces `self.aggr_embed(torch.cat((global_embed, local_embed.expand(num_modes, ...)), dim=-1))` + the view to [modes * N, 64]
+ * (models/decoders/dec_hivt_nusargo_sde.py:26-29, 82-85).  Forward writes `out`; backward (what autograd computes through it) reads
+ * grad_out and writes grad_global, grad_local (summed over the modes) and the parameter gradients (written, not accumulated). */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t n_modes;
+  int64_t n_actors;
+  const float* global_embed; /* [n_modes, n_actors, 64] contiguous */
+  const float* local_embed;  /* [n_actors, 64] contiguous */
+  const float* w;            /* [64, 128] aggr_embed[0].weight: columns 0..63 multiply global_embed, 64..127 local_embed */
+  const float* b;            /* [64] */
+  const float* ln_g;         /* [64] aggr_embed[1].weight */
+  const float* ln_b;         /* [64] aggr_embed[1].bias */
+  float ln_eps;
+  float reserved;
+  float* out;                /* forward: [n_modes * n_actors, 64] */
+  const float* grad_out;     /* backward: dL/dout */
+  float* grad_global;        /* backward out [n_modes, n_actors, 64] */
+  float* grad_local;         /* backward out [n_actors, 64] */
+  float* grad_w; float* grad_b; float* grad_ln_g; float* grad_ln_b;
+  void* workspace;           /* backward only */
+  int64_t workspace_bytes;
+} TrajsdeAggrArgs;
+
+int64_t trajsde_aggr_embed_workspace_bytes(int64_t n_modes, int64_t n_actors);
+int trajsde_aggr_embed_fwd(const TrajsdeAggrArgs* args, void* cuda_stream);
+int trajsde_aggr_embed_bwd(const TrajsdeAggrArgs* args, void* cuda_stream);
+
+/* L2 (losses/L2.py:10-27): per actor the mode with the smallest masked mean displacement wins; loss = mean over the valid
+ * (actor, slot) pairs of that mode's ||y - loc||; 0 when nothing is valid.  Forward writes loss, count (= reg_mask.sum()) and
+ * best_mode; backward writes dL/dloc for the winning mode's valid slots into the ZERO-FILLED grad_loc. */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t n_modes;
+  int64_t n_actors;
+  int32_t n_t;
+  int32_t reserved;
+  const float* loc;          /* element (m, n, t, c) at loc + ((m * n_actors + n) * n_t + t) * loc_stride + c, c = 0, 1 */
+  int64_t loc_stride;        /* 4 for the reference's cat(loc, scale) output, 2 for a plain loc tensor */
+  const float* target;       /* [n_actors, n_t, 2] data['y'] */
+  const uint8_t* reg_mask;   /* [n_actors, n_t] bool */
+  float* loss;               /* [1] */
+  float* count;              /* [1] number of valid (actor, slot) pairs, as float */
+  int32_t* best_mode;        /* [n_actors] */
+  const float* grad_loss;    /* backward: [1] dL/dloss */
+  float* grad_loc;           /* backward: same indexing as loc with grad_loc_stride; zero-filled by the caller */
+  int64_t grad_loc_stride;
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeL2Args;
+
+int64_t trajsde_l2_loss_workspace_bytes(int64_t n_actors);
+int trajsde_l2_loss_fwd(const TrajsdeL2Args* args, void* cuda_stream);
+int trajsde_l2_loss_bwd(const TrajsdeL2Args* args, void* cuda_stream);
+
+/* DiffBCE (losses/diff_BCE.py:11-16 with the labels of enc…sep2.py:194-195): loss = BCE(diff_in, 0) + BCE(diff_out, 1), mean
+ * reduction, log terms clamped at -100 like nn.BCELoss; grad_in / grad_out (optional) receive dloss/d diff_*. */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t reserved;
+  int64_t n_in;
+  int64_t n_out;
+  const float* diff_in;
+  const float* diff_out;
+  float* loss;               /* [1] */
+  float* grad_in;            /* [n_in] or NULL */
+  float* grad_out;           /* [n_out] or NULL */
+  void* workspace;
+  int64_t workspace_bytes;
+} TrajsdeBceArgs;
+
+int64_t trajsde_diff_bce_workspace_bytes(void);
+int trajsde_diff_bce(const TrajsdeBceArgs* args, void* cuda_stream);
 
 /* Materialise the in-kernel Brownian increments: dw_out[n_steps, rows, 64] = exactly what trajsde_euler_fwd would draw
  * with the same TrajsdeNoise (dw field ignored) and schedule.  Lets parity tests replay Philox runs through the oracle. */

@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -20,6 +20,8 @@ EXPORTED_SYMBOLS = (
     'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
     'trajsde_gru_workspace_bytes', 'trajsde_gru_fwd', 'trajsde_gru_bwd',
     'trajsde_heads_workspace_bytes', 'trajsde_heads_fwd', 'trajsde_heads_bwd_workspace_bytes', 'trajsde_heads_bwd',
+    'trajsde_aggr_embed_workspace_bytes', 'trajsde_aggr_embed_fwd', 'trajsde_aggr_embed_bwd',
+    'trajsde_l2_loss_workspace_bytes', 'trajsde_l2_loss_fwd', 'trajsde_l2_loss_bwd', 'trajsde_diff_bce_workspace_bytes', 'trajsde_diff_bce',
 )
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -104,6 +106,24 @@ class HeadsBwdArgs(C.Structure):
                 ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
+class AggrArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('n_modes', C.c_int32), ('n_actors', C.c_int64), ('global_embed', _fp), ('local_embed', _fp),
+                ('w', _fp), ('b', _fp), ('ln_g', _fp), ('ln_b', _fp), ('ln_eps', C.c_float), ('reserved', C.c_float), ('out', _fp),
+                ('grad_out', _fp), ('grad_global', _fp), ('grad_local', _fp), ('grad_w', _fp), ('grad_b', _fp), ('grad_ln_g', _fp),
+                ('grad_ln_b', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class L2Args(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('n_modes', C.c_int32), ('n_actors', C.c_int64), ('n_t', C.c_int32), ('reserved', C.c_int32),
+                ('loc', _fp), ('loc_stride', C.c_int64), ('target', _fp), ('reg_mask', _fp), ('loss', _fp), ('count', _fp), ('best_mode', _fp),
+                ('grad_loss', _fp), ('grad_loc', _fp), ('grad_loc_stride', C.c_int64), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class BceArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('reserved', C.c_int32), ('n_in', C.c_int64), ('n_out', C.c_int64), ('diff_in', _fp),
+                ('diff_out', _fp), ('loss', _fp), ('grad_in', _fp), ('grad_out', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
 _lock = threading.Lock()
 _lib = None
 
@@ -158,6 +178,20 @@ def lib():
         L.trajsde_heads_bwd_workspace_bytes.argtypes = [C.c_int32]
         L.trajsde_heads_bwd.restype = C.c_int
         L.trajsde_heads_bwd.argtypes = [C.POINTER(HeadsBwdArgs), C.c_void_p]
+        L.trajsde_aggr_embed_workspace_bytes.restype = C.c_int64
+        L.trajsde_aggr_embed_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+        for f in (L.trajsde_aggr_embed_fwd, L.trajsde_aggr_embed_bwd):
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(AggrArgs), C.c_void_p]
+        L.trajsde_l2_loss_workspace_bytes.restype = C.c_int64
+        L.trajsde_l2_loss_workspace_bytes.argtypes = [C.c_int64]
+        for f in (L.trajsde_l2_loss_fwd, L.trajsde_l2_loss_bwd):
+            f.restype = C.c_int
+            f.argtypes = [C.POINTER(L2Args), C.c_void_p]
+        L.trajsde_diff_bce_workspace_bytes.restype = C.c_int64
+        L.trajsde_diff_bce_workspace_bytes.argtypes = []
+        L.trajsde_diff_bce.restype = C.c_int
+        L.trajsde_diff_bce.argtypes = [C.POINTER(BceArgs), C.c_void_p]
         v = L.trajsde_abi_version()
         if v != ABI_VERSION:
             raise TrajsdeError(f"ABI version mismatch: library {v}, binding {ABI_VERSION}")

@@ -353,6 +353,81 @@ int trajsde_heads_bwd(const TrajsdeHeadsBwdArgs* a, void* cuda_stream) {
   return launch_heads_bwd(*a, reinterpret_cast<cudaStream_t>(cuda_stream));     // rows == 0: the reduce still writes zero gradients
 }
 
+int64_t trajsde_aggr_embed_workspace_bytes(int64_t n_modes, int64_t n_actors) {
+  if (n_modes < 0 || n_actors < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_modes / n_actors < 0");
+  return aggr_workspace_bytes(n_modes, n_actors);
+}
+
+static int aggr_call(const TrajsdeAggrArgs* a, void* cuda_stream, bool backward) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeAggrArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeAggrArgs));
+  if (a->n_modes < 0 || a->n_actors < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_modes / n_actors < 0");
+  if (!a->w || !a->b || !a->ln_g || !a->ln_b) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null parameter pointer");
+  const bool empty = a->n_modes == 0 || a->n_actors == 0;
+  if (!empty && (!a->global_embed || !a->local_embed || !aligned16(a->global_embed) || !aligned16(a->local_embed)))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "global_embed / local_embed null or misaligned");
+  if (!backward) {
+    if (!empty && (!a->out || !aligned16(a->out))) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "out null or misaligned");
+  } else {
+    if (!a->grad_w || !a->grad_b || !a->grad_ln_g || !a->grad_ln_b) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null gradient pointer");
+    if (!empty && (!a->grad_out || !a->grad_global || !a->grad_local || !aligned16(a->grad_out) || !aligned16(a->grad_global) || !aligned16(a->grad_local)))
+      return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_out / grad_global / grad_local null or misaligned");
+    const int64_t need = aggr_workspace_bytes(a->n_modes, a->n_actors);
+    if (a->workspace_bytes < need || !a->workspace || (reinterpret_cast<uintptr_t>(a->workspace) & 255u))
+      return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes (256-byte aligned)", (long long)a->workspace_bytes, (long long)need);
+  }
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_aggr_embed(*a, backward, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+int trajsde_aggr_embed_fwd(const TrajsdeAggrArgs* a, void* cuda_stream) { return aggr_call(a, cuda_stream, false); }
+int trajsde_aggr_embed_bwd(const TrajsdeAggrArgs* a, void* cuda_stream) { return aggr_call(a, cuda_stream, true); }
+
+int64_t trajsde_l2_loss_workspace_bytes(int64_t n_actors) {
+  if (n_actors < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_actors < 0");
+  return l2_workspace_bytes(n_actors);
+}
+
+static int l2_call(const TrajsdeL2Args* a, void* cuda_stream, bool backward) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeL2Args))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeL2Args));
+  if (a->n_modes <= 0 || a->n_actors < 0 || a->n_t < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_modes <= 0 or n_actors / n_t < 0");
+  if (a->loc_stride < 2) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "loc_stride < 2");
+  if (!a->count || !a->best_mode) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "count / best_mode null");
+  const bool empty = a->n_actors == 0 || a->n_t == 0;
+  if (!empty && (!a->loc || !a->target || !a->reg_mask)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "loc / target / reg_mask null");
+  if (!backward) {
+    if (!a->loss) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "loss null");
+    const int64_t need = l2_workspace_bytes(a->n_actors);
+    if (a->workspace_bytes < need || !a->workspace)
+      return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
+  } else if (!a->grad_loss || (!empty && !a->grad_loc) || a->grad_loc_stride < 2) {
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "grad_loss / grad_loc null or grad_loc_stride < 2");
+  }
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_l2_loss(*a, backward, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+int trajsde_l2_loss_fwd(const TrajsdeL2Args* a, void* cuda_stream) { return l2_call(a, cuda_stream, false); }
+int trajsde_l2_loss_bwd(const TrajsdeL2Args* a, void* cuda_stream) { return l2_call(a, cuda_stream, true); }
+
+int64_t trajsde_diff_bce_workspace_bytes(void) { return bce_workspace_bytes(); }
+
+int trajsde_diff_bce(const TrajsdeBceArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdeBceArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdeBceArgs));
+  if (a->n_in < 0 || a->n_out < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_in / n_out < 0");
+  if ((a->n_in > 0 && !a->diff_in) || (a->n_out > 0 && !a->diff_out) || !a->loss) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "diff_in / diff_out / loss null");
+  if (a->workspace_bytes < bce_workspace_bytes() || !a->workspace)
+    return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)bce_workspace_bytes());
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_diff_bce(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
 int trajsde_philox_dw(const TrajsdeSchedule* sched, const TrajsdeNoise* noise, int64_t rows, float* dw_out, void* cuda_stream) {
   if (!sched || !noise) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "sched/noise null");
   int rc;

@@ -140,6 +140,12 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s);
 int64_t enc_bwd_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s);
 int64_t heads_workspace_bytes();
+int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s);
+int64_t aggr_workspace_bytes(int64_t n_modes, int64_t n_actors);
+int launch_l2_loss(const TrajsdeL2Args& a, bool backward, cudaStream_t s);
+int64_t l2_workspace_bytes(int64_t n_actors);
+int launch_diff_bce(const TrajsdeBceArgs& a, cudaStream_t s);
+int64_t bce_workspace_bytes();
 int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s);
 int64_t heads_bwd_workspace_bytes();
 int launch_philox_dw(const TrajsdeSchedule& sched, const TrajsdeNoise& noise, int64_t rows, float* out, cudaStream_t s);
