@@ -1,0 +1,139 @@
+"""The fused stage classes (trajsde_b200/stages.py mixins — what trajsde_b200/plugins/* put on top of the reference's stage classes) on
+the GPU, over reference-SHAPED stand-ins for the parts that need the reference tree / PyG (tests/ref_shaped.py):
+
+  decoder  : fused prologue + solve + heads vs the fixture the REAL reference SDEDecoder produced (outputs, L2 loss, training gradients);
+  encoder  : one fused recurrence launch vs the reference's 21-iteration loop (run through install()'s drop-in ops on the same
+             increments) — outputs of the stage, the DiffBCE inputs, gradients into the AA stand-in; forward_ood shapes."""
+import pytest
+import torch
+
+import ref_shaped
+import trajsde_b200 as tb
+from oracle import sde_oracle as so
+from trajsde_b200 import ops, patch, stage, synthetic as syn
+from trajsde_b200.schedule import encoder_schedule
+from trajsde_b200.stages import FusedDecoderMixin, FusedEncoderMixin
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+class StandInDecoderFused(FusedDecoderMixin, ref_shaped.RefShapedDecoder):
+    pass
+
+
+class StandInEncoderFused(FusedEncoderMixin, ref_shaped.RefShapedEncoder):
+    noise = None
+
+    def _prepare(self, data, ood):
+        if ood:
+            aa_out = self.aa_encoder(data['x'].transpose(0, 1).reshape(-1, 2)).view(self.historical_steps, data['x'].shape[0], -1)
+            nus = torch.isin(data['batch'], torch.where(data['source'] == 0)[0])
+            return {'aa_out': aa_out, 'actors_mask': ~data['padding_mask'][:, :self.ref_time + 1], 'nus_mask': nus,
+                    'agent_index': data['agent_index'], 'n_fake': 0}
+        aa_out, actors_mask, nus_mask, _ = self.prepare(data, self.noise)
+        return {'aa_out': aa_out, 'actors_mask': actors_mask, 'nus_mask': nus_mask, 'agent_index': data['agent_index'],
+                'n_fake': data['agent_index'].numel()}
+
+    def _finish(self, data, prep, out):
+        return self.al_encoder(out)
+
+
+def _t(d, k):
+    return torch.from_numpy(d[k]).to(DEV)
+
+
+@pytest.mark.parametrize('mode', ['exact', 'tc_f16'])
+def test_fused_decoder_stage_vs_reference_fixture(mode, golden_stage):
+    d = golden_stage
+    sd = {k[len('param/'):]: torch.from_numpy(d[k]) for k in d if k.startswith('param/')}
+    dec = StandInDecoderFused().load_reference_state_dict(sd).to(DEV)
+    dec.solver_kwargs = {'bm': _t(d, 'dW'), 'mode': mode}
+    le, ge = _t(d, 'local_embed').requires_grad_(True), _t(d, 'global_embed').requires_grad_(True)
+    n0 = ops.LAUNCHES['n']
+    out = dec({'padding_mask': _t(d, 'padding_mask')}, le, ge)
+    assert ops.LAUNCHES['n'] - n0 == (5 if mode == 'tc_f16' else 4)        # aggr_embed + (pack +) solve + pack + heads
+    err = float((out['loc'].detach().cpu() - torch.from_numpy(d['loc'])).abs().max())
+    print(f"[{mode}] fused decoder stage: loc|scale max-abs {err:.3e}")
+    assert err < (4e-3 if mode == 'exact' else 9e-3)                         # exact solve + tensor-core heads (3e-3) / tc solve + heads
+    assert torch.allclose(out['pi'].detach().cpu(), torch.from_numpy(d['pi']), atol=1e-5, rtol=1e-5)
+    loss = stage.l2_loss(out['loc'], _t(d, 'y'), out['reg_mask'])
+    assert abs(float(loss) - float(d['loss_l2'])) < 5e-4
+    loss.backward()
+    ops.poll_status(DEV, block=True)
+    worst = 0.0
+    pairs = [('local_embed', le.grad, d['grad_local_embed']), ('global_embed', ge.grad, d['grad_global_embed'])]
+    pairs += [(k, p.grad, d['grad/' + k]) for k, p in dec.named_parameters() if k != 'hidden']
+    for name, got, ref in pairs:
+        ref = torch.from_numpy(ref)
+        if float(ref.abs().max()) == 0.0:
+            assert got is None or float(got.abs().max()) == 0.0, name
+            continue
+        e = float((got.cpu() - ref).abs().max() / ref.abs().max())
+        worst = max(worst, e)
+        assert e < 3e-2, (name, e)
+    print(f"[{mode}] fused decoder stage training step: worst relative gradient error {worst:.2e}")
+
+
+def _encoder_data(scenes=6, agents=9, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    n = scenes * agents
+    source = (torch.arange(scenes) % 2).long()                             # nuScenes and Argoverse scenes alternate: both diffusion nets are used
+    batch = torch.arange(scenes).repeat_interleave(agents)
+    pad = torch.rand(n, 81, generator=g) < 0.2
+    pad[:, 20] = False                                                    # every actor is observed at the reference time
+    first = torch.argmax((~pad[:, :21]).float(), dim=1)
+    bos = torch.zeros(n, 21, dtype=torch.bool)
+    bos[torch.arange(n), first] = True
+    data = {'x': torch.randn(n, 21, 2, generator=g), 'padding_mask': pad, 'bos_mask': bos, 'agent_index': torch.arange(scenes) * agents,
+            'batch': batch, 'source': source}
+    return {k: v.to(DEV) for k, v in data.items()}, torch.randn(scenes, 21, 2, generator=g).to(DEV) * 2
+
+
+def test_fused_encoder_stage_vs_the_reference_loop():
+    data, noise = _encoder_data()
+    torch.manual_seed(0)
+    ref_enc = ref_shaped.RefShapedEncoder()
+    syn.init_reference_style(ref_enc.gru_unit, 5, bias_std=0.1)
+    ref_enc = ref_enc.to(DEV)
+    fused = StandInEncoderFused().to(DEV)
+    fused.load_state_dict(ref_enc.state_dict())
+    fused.noise = noise
+    rows = data['x'].shape[0] + data['agent_index'].numel()
+    hs = torch.from_numpy(encoder_schedule().h).to(DEV)
+    dW = torch.randn(21, rows, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4)) * torch.sqrt(hs).view(-1, 1, 1)
+    # reference loop through install()'s drop-in ops, fed the same increments call by call
+    saved = patch.install(encoder=ref_enc)
+    glob = type(ref_enc).forward.__globals__
+    installed, calls = glob['sdeint_dual'], {'n': 0}
+
+    def with_dw(sde, y0, ts, nus_mask, **kw):
+        k = calls['n']
+        calls['n'] += 1
+        return installed(sde, y0, ts, nus_mask, bm=dW[k:k + 1], **kw)
+
+    glob['sdeint_dual'] = with_dw
+    try:
+        want = ref_enc(data, noise)
+    finally:
+        glob['sdeint_dual'] = installed
+        patch.uninstall(saved)
+    assert calls['n'] == 21
+    fused.recurrence_kwargs = {'dW': dW}
+    n0 = ops.LAUNCHES['n']
+    got = fused(data)
+    assert ops.LAUNCHES['n'] - n0 == 2                                    # pack + ONE fused recurrence launch
+    for name, a_, b_ in zip(('out', 'diff_in', 'diff_out', 'label_in', 'label_out'), got, want):
+        assert a_.shape == b_.shape, name
+        assert float((a_ - b_).abs().max()) < 2e-2, (name, float((a_ - b_).abs().max()))
+    assert got[1].shape == (6, 64) and float(got[3].max()) == 0 and float(got[4].min()) == 1
+    # training: gradients reach the AA stand-in, the GRU and the SDE nets through the fused backward
+    loss = got[0].square().mean() + stage.diff_bce_loss(got[1], got[2])
+    loss.backward()
+    for name in ('aa_encoder.net.0.weight', 'gru_unit.update_gate.0.weight', 'lsde_func.f_func.net.0.weight', 'lsde_func.g_nus.net.4.weight', 'hidden'):
+        gr = fused.get_parameter(name).grad
+        assert gr is not None and torch.isfinite(gr).all() and float(gr.abs().max()) > 0, name
+    # forward_ood: 10 Monte-Carlo passes in one launch
+    with torch.no_grad():
+        mean, std = fused.forward_ood(data)
+    assert mean.shape == (54, 64) and std.shape == (54,) and (std > 0).all()
