@@ -189,6 +189,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--strong-scenes', type=int, default=8192, help='total scenes of the strong-scaling training entry (0 = skip)')
     ap.add_argument('--no-heads', action='store_true')
     ap.add_argument('--e2e-chunks', type=int, default=2, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
     args = ap.parse_args()
@@ -290,33 +291,62 @@ def main():
     dec_ms_philox = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
     dec_events.clear()
 
-    # ---- e2e: public API with HOST buffers: every step copies all inputs from pinned host memory, runs bm=None (in-kernel Philox, like
-    # the reference's default BrownianInterval) and copies the final latents back; the batch arrives as `e2e_chunks` micro-batches whose
-    # copies overlap the kernels (trajsde_b200.pipeline.HostFedSdePath) ---------------------------------------------------------------------
+    # ---- e2e: public API with HOST buffers: every step copies all inputs from pinned host memory (the AA-encoder output as fp16: the
+    # kernel rounds it to fp16 MMA operands anyway), runs bm=None (in-kernel Philox, like the reference's default BrownianInterval), the
+    # fused heads on the device, and copies the decoder's RESULT out['loc'] = cat(loc, scale) [10 N, 60, 4] (dec…sde.py:95-100) plus the
+    # encoder's final latents back; the batch arrives as `e2e_chunks` decoder slices whose copies overlap the kernels
+    # (trajsde_b200.pipeline.HostFedSdePath) ---------------------------------------------------------------------------------------
+    import torch.nn as nn
     from trajsde_b200.pipeline import HostFedSdePath
+    mk_head = lambda sd: syn.init_reference_style(nn.Sequential(nn.Linear(64, 64), nn.LayerNorm(64), nn.ReLU(inplace=True),  # noqa: E731
+                                                                nn.Linear(64, 2)), sd).to(dev)
+    loc_h, sc_h = mk_head(7), mk_head(8)
     n_chunks = args.e2e_chunks
+    aa_half = host.aa_out.half().pin_memory()
     out_enc = torch.empty((E, 64), dtype=torch.float32).pin_memory()
-    out_dec = torch.empty((M, 64), dtype=torch.float32).pin_memory()
-    h2d = sum(getattr(host, k).numel() * getattr(host, k).element_size() for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0'))
+    out_dec = torch.empty((M, sched_d.n_outputs, 4), dtype=torch.float32).pin_memory()
+    h2d = sum(getattr(host, k).numel() * getattr(host, k).element_size() for k in ('enc_h0', 'actors_mask', 'nus_mask', 'dec_y0')) + aa_half.numel() * 2
     d2h = (out_enc.numel() + out_dec.numel()) * 4
     pipe = HostFedSdePath(enc_sde, gru, dec_sde, dev, ts_dec, mode=mode)
     e2e_work = work
 
     def e2e_step(i):
-        pipe.run_batch(host, out_enc, out_dec, seed=20 + 10 * i, dec_chunks=n_chunks, enc_row_offset=rank * E, dec_row_offset=rank * M)
+        pipe.run_batch(host, out_enc, out_dec, seed=20 + 10 * i, dec_chunks=n_chunks, enc_row_offset=rank * E, dec_row_offset=rank * M,
+                       heads=(loc_h, sc_h), aa_out_half=aa_half)
 
     for i in range(2):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
+    # pinned-copy microbenchmark on the same box: what the host link gives this rank while every rank copies at once (the e2e floor)
+    link = {}
+    if mode == 'tc_f16':
+        src = torch.empty((256 << 20,), dtype=torch.uint8).pin_memory()
+        dst_d = torch.empty_like(src, device=dev)
+        dst_h = torch.empty_like(src).pin_memory()
+        s2 = torch.cuda.Stream(dev)
+        def h2d_only(i):
+            dst_d.copy_(src, non_blocking=True)
+        def both(i):
+            dst_d.copy_(src, non_blocking=True)
+            with torch.cuda.stream(s2):
+                dst_h.copy_(dst_d, non_blocking=True)
+        h2d_only(0); both(0); torch.cuda.synchronize()
+        t_h = timed(h2d_only, 4) / 4
+        def both_timed(i):
+            both(i)
+            torch.cuda.current_stream().wait_stream(s2)
+        t_b = timed(both_timed, 4) / 4
+        link = {"h2d_gbs_per_rank": src.numel() / (t_h * 1e-3) / 1e9, "h2d_plus_d2h_gbs_per_rank_each_way": src.numel() / (t_b * 1e-3) / 1e9,
+                "e2e_copy_floor_ms": max(h2d, d2h) / (src.numel() / (t_b * 1e-3)) * 1e3,
+                "note": "256 MiB pinned copies timed on every rank at once; floor = max(H2D, D2H bytes) at the duplex rate"}
+        del src, dst_d, dst_h
+        torch.cuda.empty_cache()
 
-    # ---- decoder heads on the solver output: fused launch vs the reference nn.Sequential heads, inference ----------------
+    # ---- decoder heads on the solver output: fused launch vs the reference nn.Sequential heads; forward (inference) and
+    # forward + backward under a winner-takes-all cotangent (one mode in ten, 30 valid slots: what losses/L2.py hands back) ---------------
     heads = None
     if not args.no_heads:
-        import torch.nn as nn
         from trajsde_b200 import heads as hd
-        mk = lambda sd: syn.init_reference_style(nn.Sequential(nn.Linear(64, 64), nn.LayerNorm(64), nn.ReLU(inplace=True),  # noqa: E731
-                                                               nn.Linear(64, 2)), sd).to(dev)
-        loc_h, sc_h = mk(7), mk(8)
         with torch.no_grad():
             ys_rm = tb.sdeint(dec_sde, res['dec_y0'], ts_dec, bm=dW_d, dt=0.1, method='euler', mode=mode, rows_major=True)
             sol_y = ys_rm[1:].permute(1, 0, 2)                                   # dec…sde.py:88: unit-stride rows here
@@ -327,68 +357,112 @@ def main():
             loc_h(sol_y[:128])
             ms_heads_eager = timed(lambda i: (loc_h(sol_y), sc_h(sol_y)), 2) / 2
             err = max(float((loc_f - loc_h(sol_y)).abs().max()), float((sc_f - sc_h(sol_y)).abs().max()))
+        cot = torch.zeros((M, sched_d.n_outputs, 2), device=dev)
+        cot[::10, :30] = 1e-6
+        ysg = ys_rm.detach().requires_grad_(True)
+
+        def heads_fb(i):
+            ysg.grad = None
+            loc_, _ = hd.decoder_heads_from_solution(loc_h, sc_h, ysg)
+            loc_.backward(cot)
+
+        for _ in range(2):
+            heads_fb(0)
+        ms_heads_fb = timed(heads_fb, args.steps) / args.steps
         hbytes = M * sched_d.n_outputs * (256 + 16)
         heads = {"kernel": "heads_fwd_kernel (self.decoder + self.scale of SDEDecoder.forward, one launch)", "ms": ms_heads,
                  "points_per_s": world * M * sched_d.n_outputs / (ms_heads * 1e-3), "reference_torch_ms": ms_heads_eager,
                  "roofline_frac_hbm": hbytes / (ms_heads * 1e-3) / 1e9 / peaks()[0], "algorithmic_bytes": hbytes,
-                 "max_abs_diff_vs_torch_fp32": err, "layout": "rows_major solver output"}
-        del ys_rm, sol_y, loc_f, sc_f
+                 "max_abs_diff_vs_torch_fp32": err, "layout": "rows_major solver output",
+                 "fwd_bwd_ms_sparse_cotangent": ms_heads_fb,
+                 "fwd_bwd_note": "heads_fwd_kernel + heads_bwd_kernel (fp32, active points only) + the zero-fill of dL/dys; cotangent on 1 row in 10, 30 slots"}
+        for p_ in list(loc_h.parameters()) + list(sc_h.parameters()):
+            p_.grad = None
+        del ys_rm, sol_y, loc_f, sc_f, cot, ysg
         torch.cuda.empty_cache()
 
-    # ---- training step (BASELINE configs[2]/[3]): fwd + bwd through both solvers, one all-reduce of the flat gradient bucket, AdamW ----------
+    # ---- training step (BASELINE configs[2]/[3]): the SDE path and its direct consumers, for real: fused encoder recurrence -> eos
+    # gather -> fused aggr_embed -> decoder solve -> fused heads -> out['loc'] -> L2 (winner-takes-all) + DiffBCE on the agents'
+    # diffusion -> backward through all of it (heads_bwd, zero-row-skipping solver backward, aggr_embed_bwd, encoder backward) ->
+    # all-reduce of the flat gradient buckets (decoder side launched on a side stream as soon as its gradients exist, under the encoder
+    # backward) -> AdamW.  The HiVT stages that feed it (AA encoder -> aa_out, global interactor -> global_embed) are out of scope:
+    # their outputs are inputs here and receive gradients. ------------------------------------------------------------------------------
     train = None
     if not args.no_train:
+        from trajsde_b200 import stage as stg
         from trajsde_b200.dist import FlatGradBucket
-        tparams = list(enc_sde.parameters()) + list(dec_sde.parameters()) + list(gru.parameters())
+        from trajsde_b200.stages import FusedDecoderMixin
 
-        def measure_train(scenes_per_gpu):
-            tb_host = syn.make_batch(scenes_per_gpu, args.agents, seed=2000 + rank, mixed_sources=True)
-            tr = {k: getattr(tb_host, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'dec_y0')}
-            bucket = FlatGradBucket(tparams)
-            opt = torch.optim.AdamW(tparams, lr=1e-3, weight_decay=7e-4)          # yml:2-3
-            Et, Mt = tb_host.enc_rows, tb_host.dec_rows
+        class DecStage(FusedDecoderMixin, syn.DecoderStage):
+            pass
 
-            # dL/d(outputs) as the (out-of-scope, reference PyTorch) decoder heads and losses would deliver them: dense tensors
-            # of mean-reduced-loss magnitude, fixed across steps so that the timed region holds only the SDE path itself
-            T_out = sched_d.n_outputs + 1
-            cot_ys = torch.randn(T_out, Mt, 64, device=dev, generator=gen) * (1.0 / (Mt * 60))
-            cot_ys[0].zero_()                                                     # the reference drops ys[0] (dec…sde.py:88)
-            cot_lat = torch.randn(ENC_STEPS, Et, 64, device=dev, generator=gen) * (1.0 / Et)
-            cot_g = torch.randn(ENC_STEPS, Et, device=dev, generator=gen) * (1.0 / Et)
+        dstage = syn.init_reference_style(DecStage(), 11).to(dev)
+        hidden = torch.nn.Parameter(torch.randn(64, device=dev) * 0.02)                 # enc…sep2.py:61-62
+        dec_params = list(dstage.parameters())
+        enc_params = list(enc_sde.parameters()) + list(gru.parameters()) + [hidden]
+
+        def measure_train(scenes_per_gpu, global_scenes=None):
+            tbatch = syn.make_train_batch(scenes_per_gpu, args.agents, seed=2000 + rank, device=dev)
+            b = tbatch.base
+            Et, Mt, Nt = b.enc_rows, b.dec_rows, scenes_per_gpu * args.agents
+            bk_dec, bk_enc = FlatGradBucket(dec_params), FlatGradBucket(enc_params)
+            opt = torch.optim.AdamW(dec_params + enc_params, lr=1e-3, weight_decay=7e-4)          # yml:2-3
+            eos = 20 - torch.argmax(b.bos_mask.float(), dim=1)                                # enc…sep2.py:187
+            ar = torch.arange(Nt, device=dev)
+            new_agent_index = torch.cat((tbatch.agent_index, torch.arange(Nt, Et, device=dev)))   # :101
+            agent_eos = eos[tbatch.agent_index].repeat(2)                                     # :190
+            data = {'padding_mask': tbatch.padding_mask}
+            pending = {}
 
             def train_step(i):
-                bucket.zero_()
-                y0 = tr['dec_y0'].detach().requires_grad_(True)                   # upstream (aggr_embed / AA encoder) needs
-                aa = tr['aa_out'].detach().requires_grad_(True)                   # dL/dy0 and dL/daa_out too
-                lat, g = enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], aa, tr['actors_mask'], tr['nus_mask'],
-                                                    seed=300 + i, mode=mode, row_offset=rank * Et)
-                ys = tb.sdeint(dec_sde, y0, ts_dec, dt=0.1, dt_min=0.1, rtol=1e-3, atol=1e-3, method='euler', mode=mode, seed=400 + i,
-                               row_offset=rank * Mt)
-                torch.autograd.backward([ys, lat, g], [cot_ys, cot_lat, cot_g])
-                bucket.all_reduce_mean()
+                bk_dec.zero_(); bk_enc.zero_()
+                aa = b.aa_out.detach().requires_grad_(True)                    # the AA encoder upstream needs dL/daa_out
+                ge = tbatch.global_embed.detach().requires_grad_(True)         # the global interactor upstream needs dL/dglobal_embed
+                h0 = hidden.unsqueeze(0).repeat(Et, 1)                         # :78
+                lat, g = enc_mod.encoder_recurrence(enc_sde, gru, h0, aa, b.actors_mask, b.nus_mask, seed=300 + i, mode=mode, row_offset=rank * Et)
+                local_embed = lat[eos, ar]                                     # :184-188 (the AL encoder after it is out of scope)
+                if world > 1:       # decoder-side gradients are complete when dL/dlocal_embed arrives: reduce them under the encoder backward
+                    local_embed.register_hook(lambda gr: pending.__setitem__('dec', bk_dec.all_reduce_mean_async()))
+                dstage.solver_kwargs = {'seed': 400 + i, 'row_offset': rank * Mt, 'mode': mode}
+                out = dstage(data, local_embed, ge)
+                diff_in, diff_out = torch.chunk(g[agent_eos, new_agent_index], 2, 0)          # :171, :190-194
+                loss = stg.l2_loss(out['loc'], tbatch.y, out['reg_mask']) + stg.diff_bce_loss(diff_in, diff_out)   # loss_weights [1, 1]
+                loss.backward()
+                if world > 1:
+                    pe = bk_enc.all_reduce_mean_async()
+                    pending.pop('dec').wait()
+                    pe.wait()
+                else:
+                    bk_enc.all_reduce_mean()                                   # single rank: only polls the backward status words
                 opt.step()
+                return loss
 
             for i in range(3):
                 train_step(i)
             k_train = max(3, min(args.steps, 10))
             n0 = ops.LAUNCHES['n']
             ms = timed(train_step, k_train) / k_train
+            nl = (ops.LAUNCHES['n'] - n0) // k_train
+            loss_v = float(train_step(99))
             twork = Et * ENC_STEPS + Mt * DEC_STEPS
-            out = {"scenes_per_gpu": scenes_per_gpu, "ms_per_step": ms, "steps": k_train,
+            gs = global_scenes or world * scenes_per_gpu
+            out = {"scenes_per_gpu": scenes_per_gpu, "global_scenes": gs, "ms_per_step": ms, "steps": k_train,
                    "agent_steps_per_s_fwd_bwd": world * twork / (ms * 1e-3), "scenes_per_s_fwd_bwd": world * scenes_per_gpu / (ms * 1e-3),
-                   "allreduce_floats": bucket.numel if world > 1 else 0, "gpu_launches_per_step": (ops.LAUNCHES['n'] - n0) // k_train}
-            for p_ in tparams:
+                   "allreduce_floats": (bk_dec.numel + bk_enc.numel) if world > 1 else 0, "gpu_launches_per_step": nl, "loss": loss_v}
+            for p_ in dec_params + enc_params:
                 p_.grad = None
-            del bucket, opt, tr, cot_ys, cot_lat, cot_g
+            del bk_dec, bk_enc, opt, tbatch, b
             torch.cuda.empty_cache()
             return out
 
-        train = {"note": "fwd+bwd through the fused encoder recurrence (enc_fwd_tc_kernel / trajsde_enc_bwd) and the decoder solve "
-                         "(euler_fwd_tc_kernel / fused tensor-core dgrad+wgrad euler_bwd_tc_kernel), in-kernel Philox noise, mixed "
-                         "nuScenes/Argoverse rows, output cotangents supplied as fixed dense tensors (what the heads/losses deliver), flat-bucket "
-                         "NCCL all-reduce, AdamW on the SDE+GRU parameters",
+        train = {"note": "real step of the SDE path and its direct consumers: fused encoder recurrence (enc_fwd_tc_kernel / trajsde_enc_bwd), eos gather, "
+                         "fused aggr_embed, decoder solve (euler_fwd_tc_kernel / euler_bwd_tc_kernel with zero-row skipping), fused heads fwd + bwd, "
+                         "L2 (winner-takes-all) + DiffBCE kernels, in-kernel Philox noise, mixed nuScenes/Argoverse scenes, NCCL all-reduce of two flat "
+                         "gradient buckets launched asynchronously on a side stream (the decoder's under the encoder backward), AdamW",
                  "cfg2_reference_batch": measure_train(args.train_scenes),          # BASELINE configs[2]: yml:106 batch 128
-                 "cfg3_scene_sharded": measure_train(args.scenes)}                  # BASELINE configs[3]: 8192 scenes / 8 GPUs
+                 "cfg3_scene_sharded": measure_train(args.scenes)}                  # BASELINE configs[3] weak: 1024 scenes per GPU (8192 at N=8)
+        if args.strong_scenes and args.strong_scenes % world == 0:                    # BASELINE configs[3] strong: 8192 scenes in total at every N
+            train["cfg3_strong_8192"] = measure_train(args.strong_scenes // world, global_scenes=args.strong_scenes)
 
     # parity is NOT checked here: the oracle is test infrastructure (tests/test_full_size_gpu.py checks this very workload against it);
     # in this file only the cpu_baseline / reference-arm legs execute oracle code, as the thing being timed on the host cores
@@ -401,14 +475,15 @@ def main():
 
     hbm_gbs, bf16_tf, peak_src = peaks()
     traffic = None
-    try:                                            # ncu-measured DRAM bytes per launch of the dominant kernel, if captured for this workload
-        for name in ('r1e_traffic.json', 'r1b_traffic.json'):       # latest capture first
-            fp = os.path.join(ROOT, 'profiles', name)
-            if not os.path.isfile(fp):
-                continue
-            t = json.load(open(fp))['euler_fwd_tc_kernel<1,0>']
-            if t['rows'] == M and t['steps'] == DEC_STEPS:
-                traffic = t['dram_bytes']
+    # ncu-measured DRAM bytes per launch of the dominant kernel: the newest profiles/*_traffic.json captured for this workload (written by
+    # tools/gpu_visit.sh from an `ncu --set full` capture of the same source tree; its "commit" field says which)
+    traffic_src = None
+    try:
+        import glob
+        for fp in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')), key=os.path.getmtime, reverse=True):
+            t = json.load(open(fp)).get('euler_fwd_tc_kernel<1,0>')
+            if t and t['rows'] == M and t['steps'] == DEC_STEPS:
+                traffic, traffic_src = t['dram_bytes'], os.path.basename(fp)
                 break
     except (OSError, KeyError, ValueError):
         pass
@@ -429,7 +504,8 @@ def main():
                    "cache": "inputs larger than L2 (dW 3.2 GB + ys 3.2 GB per step vs 126 MB L2)",
                    "e2e_note": "e2e uses bm=None (in-kernel Philox, like the reference's BrownianInterval default); every step copies all "
                                "inputs from pinned host memory (decoder y0 first, in row slices solved as they land; encoder inputs behind "
-                               "them) and copies the final encoder/decoder latents back (HostFedSdePath.run_batch)"},
+                               "them, the AA-encoder output as fp16), runs the fused heads on the device and copies the decoder's RESULT "
+                               "out['loc'] = cat(loc, scale) [10 N, 60, 4] and the encoder's final latents back (HostFedSdePath.run_batch)"},
         "scenes_per_s": world * args.scenes / (ms_fixed / args.steps * 1e-3),
         "philox": {"value": world * work / (ms_philox / args.steps * 1e-3), "ms_per_step": ms_philox / args.steps,
                    "decoder_ms": dec_ms_philox, "decoder_agent_steps_per_s": M * DEC_STEPS / (dec_ms_philox * 1e-3),
@@ -439,13 +515,15 @@ def main():
                     "agent_steps_per_s": E * ENC_STEPS / ((ms_fixed / args.steps - dec_ms_avg) * 1e-3),
                     "note": "one fused kernel: 21 x [Euler step of the dual-diffusion SDE + GRU jump] (enc_fwd_tc_kernel)"},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "kernel": "euler_fwd_tc_kernel (decoder solve)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dec_bytes_fixed,
                      "tensor_frac_of_bf16_peak": flops / (dec_ms_avg * 1e-3) / 1e12 / bf16_tf,
                      "sfu_note": "informational third ceiling: 257 MUFU ops per agent-step at the measured 16/clk/SM"},
         "e2e": {"value": world * e2e_work / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps, "micro_batches": n_chunks,
-                "host_cores_bound_per_rank": cores_bound},
+                "host_cores_bound_per_rank": cores_bound, "result": "decoder out['loc'] [M,60,4] fp32 + encoder final latents [N',64]",
+                "host_link": link},
         "heads": heads,
         "train": train,
         "gpu_launches": launches,

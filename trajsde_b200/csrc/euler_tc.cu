@@ -52,6 +52,9 @@ constexpr uint32_t IMG_BYTES = 59392;     // 58 KB
 constexpr uint32_t SIMG_B1 = 0;           // [128 rows][64] f16 SW128: W1y | V1y
 constexpr uint32_t SIMG_BIAS = 16384;     // [128 rows][64] f16 SW128: slice 0 layer-1 bias + time columns, slice 1 b2 | c2, slice 2 b3
 constexpr uint32_t SIMG_W2 = 32768, SIMG_V2 = 40960, SIMG_W3 = 49152;
+#ifndef TRAJSDE_FWD_BIAS_MMA
+#define TRAJSDE_FWD_BIAS_MMA 1          // in-kernel-noise variants only (see BIAS_MMA); 0 adds the biases in the epilogues everywhere (A/B)
+#endif
 // fp32 vector slots (float index inside IMG_VEC)
 constexpr int VEC_B2 = 0, VEC_C2 = 64, VEC_C2A = 128, VEC_B3 = 192, VEC_W3G = 256, VEC_W3GA = 320, VEC_C3 = 384, VEC_C3A = 385;
 constexpr int BIAS1_LD = 192;             // per-step layer-1 bias row: b1f | c1 | c1_alt (time features folded in)
@@ -227,7 +230,7 @@ struct Epi3Ctx {
 
 // Epilogue 3: f = z3 + b3 ; y' = y + f h + g dW (dW already in this thread's X chunks) ; outputs in place ; Y, A0 <- y'.
 // Y_LOADED: the caller issued the tcgen05.ld of the state columns into `yv` before it waited for P3 (the read runs under that wait).
-template <bool MULTI, bool TMEM_A, bool Y_LOADED = false>
+template <bool MULTI, bool TMEM_A, bool Y_LOADED = false, bool BIAS_IN_MMA = TMEM_A>
 __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]) {
   uint32_t fv[32];
   if (!Y_LOADED) tmem_ld_32x32b_x32(c.tm_y, yv);
@@ -243,7 +246,7 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
     float4* xp = reinterpret_cast<float4*>(c.x_row + ((q ^ (c.row & 7u)) << 4));
     const float4 dw = *xp;
     float f0 = __uint_as_float(fv[4 * q]), f1 = __uint_as_float(fv[4 * q + 1]), f2 = __uint_as_float(fv[4 * q + 2]), f3 = __uint_as_float(fv[4 * q + 3]);
-    if (!TMEM_A) {                                           // TMEM_A variants: b3 came through the MMA (BIAS tile, slice 2)
+    if (!BIAS_IN_MMA) {                                      // otherwise b3 came through the MMA (BIAS tile, slice 2)
       const float4 b3 = *reinterpret_cast<const float4*>(c.b3 + 4 * q);
       f0 += b3.x; f1 += b3.y; f2 += b3.z; f3 += b3.w;
     }
@@ -367,6 +370,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     // single-diffusion variants keep the MMA A operands in the TMEM columns the dual variant needs for its second diffusion net:
     // OA = [128,160): y -> h1f -> h2f -> y' (each written after the MMA that read the previous content has completed), OB = [160,192): h1g
     constexpr bool TMEM_A = !DUAL;
+    constexpr bool BIAS_MMA = TMEM_A && !HAS_DW && (TRAJSDE_FWD_BIAS_MMA != 0);   // measured: +2 % with in-kernel noise, -2 % with supplied dW
     const uint32_t tm_oa = tmem_base + ((uint32_t)(quad * 32) << 16) + slot * 256 + 128 + hh * 16, tm_ob = tm_oa + 32;
     const uint32_t pair_bar = 1 + slot * 4 + quad;         // named barrier shared by the two warps that own the same rows
     uint32_t par_accA = 0, par_accB = 0, par_tma = 0, par_xfree = 0;
@@ -385,7 +389,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     c3.out_w = a.sched.out_w;
     c3.ys_t_stride = a.ys_t_stride;
 
-    if (TMEM_A) {
+    if (BIAS_MMA) {
       // biases through the MMA: the A0 tile (unused as an operand tile here: y / h1f / h2f live in tensor memory) holds the bias
       // operand rows.  K slice (gstep & 1) of every row = (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi, 0 x 8) for the step's sin t0 /
       // cos t0; the fifth MMA of every phase multiplies it with the BIAS tile's slice for that layer.  Zero everything once.
@@ -436,7 +440,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         }
         tc_wait_st();
       }
-      if (TMEM_A) {                                        // bias operand slice of this tile's first step (its ring entry is published)
+      if (BIAS_MMA) {                                      // bias operand slice of this tile's first step (its ring entry is published)
         mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);
         if (hh == 0)
           *reinterpret_cast<uint4*>(a0_row + (((2u * (gstep & 1u)) ^ (row & 7u)) << 4)) =
@@ -482,14 +486,19 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
 #else
             uint32_t v[32];
+            Bias32 bf;
+            if (!BIAS_MMA) bf = ld_bias32(ent + hh * 32);
             tmem_ld_32x32b_x32(tm_lane, v);
             tc_wait_ld();
-            tanh32_to_tmem(v, tm_oa);
+            if (BIAS_MMA) tanh32_to_tmem(v, tm_oa);
+            else act32_to_tmem(v, bf, tm_oa);
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 1));                  // h1f ready -> P2f
+            if (!BIAS_MMA) bf = ld_bias32(ent + 64 + hh * 32);
             tmem_ld_32x32b_x32(tm_lane + 64, v);
             tc_wait_ld();
-            tanh32_to_tmem(v, tm_ob);
+            if (BIAS_MMA) tanh32_to_tmem(v, tm_ob);
+            else act32_to_tmem(v, bf, tm_ob);
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
 #endif
@@ -506,9 +515,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tc_fence_after();
           {
             uint32_t v[32];
+            Bias32 b2;
+            if (!BIAS_MMA) b2 = ld_bias32(vec + VEC_B2 + hh * 32);
             tmem_ld_32x32b_x32(tm_lane, v);
             tc_wait_ld();
-            tanh32_to_tmem(v, tm_oa);
+            if (BIAS_MMA) tanh32_to_tmem(v, tm_oa);
+            else act32_to_tmem(v, b2, tm_oa);
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
             if (!HAS_DW) draw(3, 5);
@@ -521,10 +533,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 w = *reinterpret_cast<const float4*>(w3v + j);
-              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j])), w.x, gd);
-              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 1])), w.y, gd);
-              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 2])), w.z, gd);
-              gd = fmaf(ts_tanh_approx(__uint_as_float(v[j + 3])), w.w, gd);
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!BIAS_MMA) b = *reinterpret_cast<const float4*>(c2v + j);
+              gd = fmaf(ts_tanh_approx(BIAS_MMA ? __uint_as_float(v[j]) : __uint_as_float(v[j]) + b.x), w.x, gd);
+              gd = fmaf(ts_tanh_approx(BIAS_MMA ? __uint_as_float(v[j + 1]) : __uint_as_float(v[j + 1]) + b.y), w.y, gd);
+              gd = fmaf(ts_tanh_approx(BIAS_MMA ? __uint_as_float(v[j + 2]) : __uint_as_float(v[j + 2]) + b.z), w.z, gd);
+              gd = fmaf(ts_tanh_approx(BIAS_MMA ? __uint_as_float(v[j + 3]) : __uint_as_float(v[j + 3]) + b.w), w.w, gd);
             }
             gpart[hh * TILE_M + row] = gd;
           }
@@ -557,10 +571,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           c3.ob = so.x;
           c3.nout = so.y;
           c3.has_out = so.y > 0;
-          if (so.y > 1) epi3_update<true, true, YPRE>(c3, yv);
-          else epi3_update<false, true, YPRE>(c3, yv);
+          if (so.y > 1) epi3_update<true, true, YPRE, BIAS_MMA>(c3, yv);
+          else epi3_update<false, true, YPRE, BIAS_MMA>(c3, yv);
           if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
-          if (k + 1 < S) {                                     // bias operand slice of the next step (other parity: nobody reads it now)
+          if (BIAS_MMA && k + 1 < S) {                         // bias operand slice of the next step (other parity: nobody reads it now)
             mbar_wait(bar_ring(slot, (gstep + 1) & 1), ((gstep + 1) >> 1) & 1);
             if (hh == 0)
               *reinterpret_cast<uint4*>(a0_row + (((2u * ((gstep + 1) & 1u)) ^ (row & 7u)) << 4)) =
@@ -699,6 +713,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       auto D = [&](uint32_t addr) { return dhi | (uint64_t)((addr & 0x3FFFFu) >> 4); };
       const uint32_t aA0 = slot_u32 + OFF_A0, aA1f = slot_u32 + OFF_A1F, aA1g = slot_u32 + OFF_A1G;
       constexpr bool TMEM_A = !DUAL;
+      constexpr bool BIAS_MMA = TMEM_A && !HAS_DW && (TRAJSDE_FWD_BIAS_MMA != 0);
       const uint32_t t_oa = d_base + 128, t_ob = d_base + 160;   // TMEM operand columns (lane field 0: all 128 rows)
       const uint32_t aB1 = base + (TMEM_A ? SIMG_B1 : IMG_B1), aW2 = base + (TMEM_A ? SIMG_W2 : IMG_W2), aV2 = base + (TMEM_A ? SIMG_V2 : IMG_V2),
                      aV2a = base + IMG_V2A, aW3 = base + (TMEM_A ? SIMG_W3 : IMG_W3);
@@ -721,7 +736,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aB1 + 32 * kk), idesc_p1, kk > 0);
               else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aB1 + 32 * kk), idesc_p1, kk > 0);
             }
-            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias), idesc_p1, 1);
+            if (BIAS_MMA) tc_mma_f16(d_base, dAb, D(aBias), idesc_p1, 1);
             tc_commit(bar_acc(slot, 0));
           }
           __syncwarp();
@@ -735,7 +750,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW2 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base, D(aA1f + 32 * kk), D(aW2 + 32 * kk), idesc_64, kk > 0);
             }
-            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias + 32), idesc_64, 1);
+            if (BIAS_MMA) tc_mma_f16(d_base, dAb, D(aBias + 32), idesc_64, 1);
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
@@ -749,7 +764,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base + 64, t_ob + 8 * kk, D(aV2 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base + 64, D(aA1g + 32 * kk), D(aV2 + 32 * kk), idesc_64, kk > 0);
             }
-            if (TMEM_A) tc_mma_f16(d_base + 64, dAb, D(aBias + 64 * 128 + 32), idesc_64, 1);
+            if (BIAS_MMA) tc_mma_f16(d_base + 64, dAb, D(aBias + 64 * 128 + 32), idesc_64, 1);
             if (DUAL) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) tc_mma_f16(d_base + 128, D(aA1g + 32 * kk), D(aV2a + 32 * kk), idesc_64, kk > 0);
@@ -767,7 +782,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               if (TMEM_A) tc_mma_f16_ts(d_base, t_oa + 8 * kk, D(aW3 + 32 * kk), idesc_64, kk > 0);
               else tc_mma_f16(d_base, D(aA0 + 32 * kk), D(aW3 + 32 * kk), idesc_64, kk > 0);
             }
-            if (TMEM_A) tc_mma_f16(d_base, dAb, D(aBias + 64), idesc_64, 1);
+            if (BIAS_MMA) tc_mma_f16(d_base, dAb, D(aBias + 64), idesc_64, 1);
             tc_commit(bar_acc(slot, 1));
           }
           __syncwarp();
@@ -790,17 +805,17 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     // iteration g, i.e. once the epilogue has finished step g-1: its slot (last read in step g-2) is free and its barrier's
     // previous phase (entry g-1) has been consumed, so every barrier has at most one outstanding phase.
     struct Ent { float2 b[3]; float4 sc; int2 so; uint4 aw; };
-    constexpr bool TMEM_A = !DUAL;
+    constexpr bool BIAS_MMA = !DUAL && !HAS_DW && (TRAJSDE_FWD_BIAS_MMA != 0);
     auto ent_fetch = [&](uint32_t g, Ent& e) {
       const int k = (int)(g % (uint32_t)S);
-      if (!TMEM_A) {
+      if (!BIAS_MMA) {
         const float2* src = reinterpret_cast<const float2*>(p.bias1 + (size_t)k * BIAS1_LD);
 #pragma unroll
         for (int i = 0; i < 3; ++i) e.b[i] = __ldg(src + lane + 32 * i);
       }
       if (lane == 0) {
         const float4 st = __ldg(reinterpret_cast<const float4*>(a.sched.step_tab) + k);
-        if (TMEM_A) {   // bias operand row of the step: (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi) as fp16 (head + remainder of sin t0, cos t0)
+        if (BIAS_MMA) { // bias operand row of the step: (1, 1, s_hi, s_lo, s_hi, c_hi, c_lo, c_hi) as fp16 (head + remainder of sin t0, cos t0)
           const float sh = __half2float(__float2half_rn(st.z)), ch = __half2float(__float2half_rn(st.w));
           e.aw = make_uint4(pack_f16x2(1.f, 1.f), pack_f16x2(sh, st.z - sh), pack_f16x2(sh, ch), pack_f16x2(st.w - ch, ch));
         }
@@ -816,12 +831,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     };
     auto ent_publish = [&](uint32_t g, const Ent& e) {
       float* dst = ring + (g % 3u) * RING_LD;
-      if (!TMEM_A) {
+      if (!BIAS_MMA) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(dst)[lane + 32 * i] = e.b[i];
       }
       if (lane == 0) {
-        if (TMEM_A) *reinterpret_cast<uint4*>(dst) = e.aw;
+        if (BIAS_MMA) *reinterpret_cast<uint4*>(dst) = e.aw;
         *reinterpret_cast<float4*>(dst + BIAS1_LD) = e.sc;
         *reinterpret_cast<int2*>(dst + BIAS1_LD + 4) = e.so;
       }

@@ -68,16 +68,24 @@ class HostFedSdePath:
         del keep
 
     def run_batch(self, hb: SdeBatch, out_enc: torch.Tensor, out_dec: torch.Tensor, seed: int = 0, dec_chunks: int = 4,
-                  enc_row_offset: int = 0, dec_row_offset: int = 0) -> None:
+                  enc_row_offset: int = 0, dec_row_offset: int = 0, heads=None, min_scale: float = 0.001,
+                  aa_out_half: Optional[torch.Tensor] = None) -> None:
         """One pinned host batch, copies ordered by what the kernels can start on first: the decoder's `dec_y0` goes over
         in `dec_chunks` row slices, each solved as soon as it lands (Philox streams are keyed by global row, so the slices
         reproduce the unsliced solve exactly); the encoder's inputs (two thirds of the bytes) stream in behind them while
-        those solves run, and the latency-bound recurrence kernel then runs once over all rows.  Final decoder latents are
-        copied back per slice, final encoder latents at the end; returns when the host can read both."""
+        those solves run, and the latency-bound recurrence kernel then runs once over all rows.
+
+        What comes back to the host is the stage's RESULT, not an internal state: with ``heads=(loc_head, scale_head)`` every
+        decoder slice goes through the fused heads on the device and ``out_dec`` [M, 60, 4] receives ``cat(loc, elu(scale) + 1 +
+        min_scale)`` — the decoder's ``out['loc']`` (dec…sde.py:95-100), 16 B per (row, t) instead of the 256 B latent; without heads
+        the final decoder latents [M, 64] (round-1 behaviour).  ``out_enc`` [N', 64] receives the encoder's final latents.
+        ``aa_out_half``: the AA-encoder output as fp16 on the host (the kernel rounds it to fp16 MMA operands anyway): one third fewer
+        H2D bytes; converted to fp32 on the device."""
         dev, cur = self.device, torch.cuda.current_stream(self.device)
         M = hb.dec_y0.shape[0]
         if not self._dev or self._dev[0]['dec_y0'].shape != hb.dec_y0.shape or self._dev[0]['aa_out'].shape != hb.aa_out.shape:
             self._dev = [{k: torch.empty_like(getattr(hb, k), device=dev) for k in _KEYS}]
+            self._dev[0]['aa_half'] = torch.empty(hb.aa_out.shape, dtype=torch.float16, device=dev)
             self._done = [torch.cuda.Event()]
             self._done[0].record(cur)
         d = self._dev[0]
@@ -88,8 +96,12 @@ class HostFedSdePath:
             for c in range(dec_chunks):
                 d['dec_y0'][bounds[c]:bounds[c + 1]].copy_(hb.dec_y0[bounds[c]:bounds[c + 1]], non_blocking=True)
                 ready[c].record(self.copy_in)
-            for k in ('enc_h0', 'actors_mask', 'nus_mask', 'aa_out'):
+            for k in ('enc_h0', 'actors_mask', 'nus_mask'):
                 d[k].copy_(getattr(hb, k), non_blocking=True)
+            if aa_out_half is not None:
+                d['aa_half'].copy_(aa_out_half, non_blocking=True)
+            else:
+                d['aa_out'].copy_(hb.aa_out, non_blocking=True)
             ready[dec_chunks].record(self.copy_in)
         keep = []
         with torch.no_grad():
@@ -97,15 +109,22 @@ class HostFedSdePath:
                 cur.wait_event(ready[c])
                 lo, hi = bounds[c], bounds[c + 1]
                 ys = sdeint(self.dec_sde, d['dec_y0'][lo:hi], self.ts_dec, dt=self.dt, dt_min=self.dt, rtol=1e-3, atol=1e-3,
-                            method='euler', mode=self.mode, seed=seed + 1, row_offset=dec_row_offset + lo)
+                            method='euler', mode=self.mode, seed=seed + 1, row_offset=dec_row_offset + lo, rows_major=heads is not None)
+                if heads is not None:
+                    from .heads import decoder_heads_from_solution
+                    loc, scale_raw = decoder_heads_from_solution(heads[0], heads[1], ys)
+                    res = torch.cat((loc, torch.nn.functional.elu(scale_raw, alpha=1.0) + (1.0 + min_scale)), dim=-1)   # dec…sde.py:98-100
+                else:
+                    res = ys[-1]
                 ev = torch.cuda.Event()
                 ev.record(cur)
-                keep.append(ys)
+                keep.append((ys, res))
                 with torch.cuda.stream(self.copy_out):
                     self.copy_out.wait_event(ev)
-                    out_dec[lo:hi].copy_(ys[-1], non_blocking=True)
+                    out_dec[lo:hi].copy_(res, non_blocking=True)
             cur.wait_event(ready[dec_chunks])
-            lat, _ = enc_mod.encoder_recurrence(self.enc_sde, self.gru, d['enc_h0'], d['aa_out'], d['actors_mask'], d['nus_mask'],
+            aa = d['aa_half'].float() if aa_out_half is not None else d['aa_out']
+            lat, _ = enc_mod.encoder_recurrence(self.enc_sde, self.gru, d['enc_h0'], aa, d['actors_mask'], d['nus_mask'],
                                                 dt=self.dt, seed=seed, mode=self.mode, row_offset=enc_row_offset)
             self._done[0].record(cur)
             keep.append(lat)
@@ -114,4 +133,3 @@ class HostFedSdePath:
                 out_enc.copy_(lat[-1], non_blocking=True)
         self.copy_out.synchronize()                                   # the host reads the results now
         del keep
-

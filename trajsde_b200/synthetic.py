@@ -120,3 +120,52 @@ def make_batch(scenes: int, agents_per_scene: int = 20, seed: int = 0, mixed_sou
         for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'bos_mask', 'dec_y0'):
             setattr(out, k, getattr(out, k).pin_memory())
     return out
+
+
+def _head(out_dim: int, in_dim: int = DIM) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(in_dim, DIM), nn.LayerNorm(DIM), nn.ReLU(inplace=True), nn.Linear(DIM, out_dim))
+
+
+class DecoderStage(nn.Module):
+    """Parameter containers of the decoder stage around the solve, with the reference's names and shapes (dec_hivt_nusargo_sde.py:26-29,
+    46-67): ``aggr_embed``, ``lsde_func``, ``decoder``, ``scale``, ``pi``.  Forward = trajsde_b200.stages.FusedDecoderMixin."""
+
+    def __init__(self, num_modes: int = MODES, future_steps: int = FUT, min_scale: float = 0.001):
+        super().__init__()
+        self.num_modes, self.future_steps, self.min_scale, self.uncertain = num_modes, future_steps, min_scale, True
+        self.min_stepsize, self.rtol, self.atol, self.method = 0.1, 0.001, 0.001, 'euler'
+        self.aggr_embed = nn.Sequential(nn.Linear(2 * DIM, DIM), nn.LayerNorm(DIM), nn.ReLU(inplace=True))
+        self.lsde_func = DecoderSDEFunc()
+        self.decoder, self.scale, self.pi = _head(2), _head(2), _head(1, 2 * DIM)
+        self.ts_pred = torch.linspace(0, 6, future_steps + 1)
+
+
+@dataclass
+class TrainBatch:
+    """Device-resident inputs of one training step of the SDE path and its direct consumers (the HiVT stages that produce them are out
+    of scope: ``aa_out`` is the AA encoder's output, ``global_embed`` the global interactor's)."""
+    base: SdeBatch
+    global_embed: torch.Tensor     # [10, N, 64]
+    y: torch.Tensor                # [N, 60, 2] ground-truth displacements
+    padding_mask: torch.Tensor     # [N, 81] bool
+    agent_index: torch.Tensor      # [scenes] long: the target agent of every scene
+
+
+def make_train_batch(scenes: int, agents_per_scene: int = 20, seed: int = 0, device='cpu') -> TrainBatch:
+    """Mixed nuScenes / Argoverse-shaped scenes (BASELINE configs[2]/[3]): past / future validity patterns of
+    dataset/nuScenes_Argoerse/nuScenes_Argoverse.py:92-103 plus 10 % random padding."""
+    b = make_batch(scenes, agents_per_scene, seed=seed, mixed_sources=True)
+    g = torch.Generator().manual_seed(seed + 17)
+    n = scenes * agents_per_scene
+    nus = b.nus_mask[:n]
+    fut_argo = torch.zeros(FUT, dtype=torch.bool); fut_argo[:30] = True
+    fut_nusc = torch.zeros(FUT, dtype=torch.bool); fut_nusc[4::5] = True
+    fut_valid = torch.where(nus.unsqueeze(1), fut_nusc.unsqueeze(0), fut_argo.unsqueeze(0)) & (torch.rand(n, FUT, generator=g) > 0.1)
+    padding_mask = torch.cat((~b.actors_mask[:n], ~fut_valid), dim=1)
+    tb_ = TrainBatch(b, torch.randn(MODES, n, DIM, generator=g), torch.randn(n, FUT, 2, generator=g).cumsum(1) * 0.5, padding_mask,
+                     torch.arange(scenes) * agents_per_scene)
+    if str(device) != 'cpu':
+        for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask', 'bos_mask', 'dec_y0'):
+            setattr(b, k, getattr(b, k).to(device))
+        tb_.global_embed, tb_.y, tb_.padding_mask, tb_.agent_index = (t.to(device) for t in (tb_.global_embed, tb_.y, tb_.padding_mask, tb_.agent_index))
+    return tb_
