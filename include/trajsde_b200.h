@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 6
+#define TRAJSDE_ABI_VERSION 7
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -164,6 +164,9 @@ typedef struct {
   TrajsdeMlpGrad grad_diffusion;
   TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
   int32_t* status;           /* device int32 or NULL: the TC kernels OR in TRAJSDE_STATUS_* bits (never cleared by the library) */
+  const uint8_t* row_flags;  /* device [rows] or NULL.  With TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS: row_flags[r] == 0 PROMISES that every incoming
+                                gradient of row r is zero (its grad_ys entries are then never read and may be uninitialised), so the call
+                                skips its own activity scan — trajsde_heads_bwd produces exactly these flags */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeEulerBwdArgs;
@@ -343,7 +346,8 @@ int trajsde_heads_fwd(const TrajsdeHeadsArgs* args, void* cuda_stream);
 /* Backward of the fused decoder heads (training): what autograd computes through the two nn.Sequential heads of SDEDecoder.forward
  * (dec_hivt_nusargo_sde.py:50-61, 96, 98) — dL/dx summed over the heads and the gradients of every head parameter, from
  * dL/dout_h [rows, n_t, 2].  Only the (point, head) pairs with a non-zero dL/dout are processed (the reference's winner-takes-all L2
- * loss, losses/L2.py:12-20, leaves ~5 % of them): grad_x must be ZERO-FILLED by the caller, rows of active points are accumulated into.
+ * loss, losses/L2.py:12-20, leaves ~5 % of them): grad_x must be ZERO-FILLED by the caller (or see row_flags), rows of active points are
+ * accumulated into.
  * fp32 arithmetic on CUDA cores in every mode (the validation-grade twin of the tensor-core forward). */
 typedef struct {
   float* w1; float* b1; float* ln_g; float* ln_b; float* w2; float* b2;   /* written, not accumulated */
@@ -368,6 +372,9 @@ typedef struct {
   int64_t gx_row_stride;
   int64_t gx_t_stride;
   TrajsdeHeadGrad grad_head[2];
+  uint8_t* row_flags;        /* device [rows] or NULL.  Non-NULL: grad_x may be UNINITIALISED on entry; the call writes row_flags[r] = "some
+                                point of row r carries a gradient", zero-fills the n_t entries of exactly those rows and accumulates into
+                                them — rows with flag 0 are left untouched (hand the flags to trajsde_euler_bwd, which then never reads them) */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeHeadsBwdArgs;

@@ -191,3 +191,36 @@ def test_heads_from_solution_gradient_reaches_the_solver_in_place(rows_major):
     assert float(y0.grad[best].abs().max()) > 0 and float(y0.grad[~best].abs().max()) == 0.0
     assert all(p_.grad is not None and torch.isfinite(p_.grad).all() for p_ in sde.parameters())
     assert sc_h[0].weight.grad is None or float(sc_h[0].weight.grad.abs().max()) == 0.0     # no gradient reached the scale head
+
+
+def test_solve_and_heads_single_node_equals_the_composition():
+    """solve_and_heads (one autograd node: the solution's gradient is an internal, only partly written buffer; the heads backward tells
+    the solver backward which rows carry a gradient) against sdeint -> decoder_heads_from_solution on the same Philox seed."""
+    from trajsde_b200 import ops
+    sde = init_like_reference(DecoderSDE(), seed=2, bias_std=0.1).to(DEV)
+    loc_h, sc_h = make_head(11).to(DEV), make_head(12).to(DEV)
+    y_init = torch.relu(torch.randn(4100, 64, generator=torch.Generator().manual_seed(3))).to(DEV)
+    ts = torch.linspace(0, 6, 61)
+    cot = torch.zeros(4100, 60, 2, device=DEV)
+    cot[3::10, :30] = torch.randn(410, 30, 2, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-3
+
+    def grads(fn):
+        for p_ in list(sde.parameters()) + list(loc_h.parameters()) + list(sc_h.parameters()):
+            p_.grad = None
+        y0 = y_init.clone().requires_grad_(True)
+        loc, sc = fn(y0)
+        (loc * cot).sum().backward()
+        return loc.detach(), y0.grad, [p_.grad.clone() for p_ in list(sde.parameters()) + list(loc_h.parameters())]
+
+    n0 = ops.LAUNCHES['n']
+    loc_a, gy_a, gp_a = grads(lambda y0: hd.solve_and_heads(sde, loc_h, sc_h, y0, ts, 0.1, seed=77, row_offset=5))
+    assert ops.LAUNCHES['n'] - n0 == 4 + 4 + 5         # fwd: pack + solve + pack + heads; bwd: heads (flags, zero rows, main, reduce) + solver (5)
+    loc_b, gy_b, gp_b = grads(lambda y0: hd.decoder_heads_from_solution(
+        loc_h, sc_h, tb.sdeint(sde, y0, ts, dt=0.1, method='euler', seed=77, row_offset=5, rows_major=True)))
+    assert torch.equal(loc_a, loc_b)
+    assert float((gy_a - gy_b).abs().max()) <= 3e-3 * float(gy_b.abs().max())
+    assert float(gy_a[0::10].abs().max()) == 0.0 and float(gy_a[3::10].abs().max()) > 0
+    for a_, b_ in zip(gp_a, gp_b):
+        assert float((a_ - b_).abs().max()) <= 3e-3 * float(b_.abs().max()) + 1e-12
+    assert sc_h[0].weight.grad is None or float(sc_h[0].weight.grad.abs().max()) == 0.0
+    assert ops.backward_status(torch.device(DEV)) == 0

@@ -172,9 +172,11 @@ __global__ void bwd_tc_absmax_kernel(const float* __restrict__ x, int slabs, int
 //                enough for the power-of-two loss scale, see bwd_tc_absmax_kernel).
 __global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, int64_t rows, int64_t slab_stride, int64_t row_stride,
                                         const float* __restrict__ grad_g, uint32_t* __restrict__ amax_bits, uint8_t* __restrict__ flags,
-                                        uint32_t* __restrict__ counts, int sample) {
+                                        uint32_t* __restrict__ counts, int sample, const uint8_t* __restrict__ given) {
+  // `given`: the caller's row flags (TrajsdeEulerBwdArgs.row_flags): rows with given[r] == 0 are not even read; the others are scanned
+  // for max |grad| only
   const int sub = threadIdx.x & 15;
-  const bool dense = !sample && 2u * reinterpret_cast<volatile uint32_t*>(counts)[0] > reinterpret_cast<volatile uint32_t*>(counts)[1];
+  const bool dense = !given && !sample && 2u * reinterpret_cast<volatile uint32_t*>(counts)[0] > reinterpret_cast<volatile uint32_t*>(counts)[1];
   const int64_t n_items = sample ? ((rows + 255) / 256) * 32 : rows;       // sampled: 32 rows out of every 256
   float bm = 0.f;
   uint32_t n_act = 0, n_seen = 0;
@@ -183,6 +185,10 @@ __global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, 
     if (r >= rows) continue;
     if (dense) {
       if (sub == 0) flags[r] = 1;
+      continue;
+    }
+    if (given && !given[r]) {
+      if (sub == 0) flags[r] = 0;
       continue;
     }
     float m = 0.f;
@@ -196,7 +202,7 @@ __global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, 
 #pragma unroll
     for (int off = 8; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off, 16));
     if (sub == 0) {
-      if (!sample) flags[r] = m > 0.f ? 1 : 0;
+      if (!sample) flags[r] = (given || m > 0.f) ? 1 : 0;
       n_act += m > 0.f ? 1u : 0u;
       n_seen += 1u;
     }
@@ -975,10 +981,11 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
       TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       uint32_t* counts = reinterpret_cast<uint32_t*>(n_active) + 2;        // {active, seen} sampled rows
       TS_CUDA_CHECK(cudaMemsetAsync(counts, 0, 8, s));
-      for (int sample = 1; sample >= 0; --sample) {
+      for (int sample = a.row_flags ? 0 : 1; sample >= 0; --sample) {          // caller's flags: no sampling pass, flagged rows only
         const int64_t want = ((sample ? ((a.rows + 255) / 256) * 32 : a.rows) + 15) / 16;
         bwd_row_activity_kernel<<<(int)(want < 8 * sms ? want : 8 * sms), 256, 0, s>>>(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride,
-                                                                                     a.grad_ys_row_stride, a.grad_g_last, amax, row_flags, counts, sample);
+                                                                                     a.grad_ys_row_stride, a.grad_g_last, amax, row_flags, counts, sample,
+                                                                                     a.row_flags);
         TS_CUDA_CHECK(cudaGetLastError());
       }
       bwd_compact_rows_kernel<<<1, 1024, 0, s>>>(row_flags, a.rows, row_map, n_active);

@@ -315,6 +315,32 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
   }
 }
 
+// row_flags mode, pass 1: flags[r] = 1 if any point of row r carries a gradient in any head (flags zeroed by a memset before)
+__global__ void heads_row_flags_kernel(const TrajsdeHeadsBwdArgs a, int64_t n_points) {
+  for (int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid < n_points; pid += (int64_t)gridDim.x * blockDim.x) {
+    bool act = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (h < a.n_heads && a.grad_out[h]) {
+        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * 2);
+        act = act || d.x != 0.f || d.y != 0.f;
+      }
+    if (act) a.row_flags[pid / a.n_t] = 1;                     // benign race: every writer stores the same value
+  }
+}
+
+// pass 2: zero the n_t x 64 gradient entries of the flagged rows (one warp per row; the other rows stay untouched)
+__global__ void heads_zero_rows_kernel(const TrajsdeHeadsBwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < a.rows; r += nwarps) {
+    if (!a.row_flags[r]) continue;
+    float* base = a.grad_x + r * a.gx_row_stride;
+    for (int i = lane; i < a.n_t * 16; i += 32)
+      *reinterpret_cast<float4*>(base + (int64_t)(i >> 4) * a.gx_t_stride + 4 * (i & 15)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // fixed-order sum over the blocks' partial vectors -> the caller's gradient tensors (written, not accumulated)
 __global__ void heads_bwd_reduce_kernel(const float* __restrict__ partial, int n_blocks, TrajsdeHeadsBwdArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,6 +380,15 @@ int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s) {
   if (grid <= 0) return set_error(TRAJSDE_ERR_CUDA, "device attributes unavailable");
   const int64_t chunks = (p.n_points + HB_THREADS - 1) / HB_THREADS;
   if (chunks < grid) grid = (int)(chunks > 0 ? chunks : 1);
+  if (a.row_flags && a.rows > 0) {
+    TS_CUDA_CHECK(cudaMemsetAsync(a.row_flags, 0, (size_t)a.rows, s));
+    if (p.n_points > 0) {
+      heads_row_flags_kernel<<<grid, HB_THREADS, 0, s>>>(a, p.n_points);
+      TS_CUDA_CHECK(cudaGetLastError());
+      heads_zero_rows_kernel<<<grid, HB_THREADS, 0, s>>>(a);
+      TS_CUDA_CHECK(cudaGetLastError());
+    }
+  }
   TS_CUDA_CHECK(cudaFuncSetAttribute(heads_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB_SMEM));
   heads_bwd_kernel<<<grid, HB_THREADS, HB_SMEM, s>>>(p);
   TS_CUDA_CHECK(cudaGetLastError());

@@ -310,15 +310,29 @@ __global__ void __launch_bounds__(256) l2_loss_fwd_kernel(const TrajsdeL2Args a,
   }
 }
 
-__global__ void l2_loss_finish_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ loss, float* __restrict__ count) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// fixed-order two-level sum of the per-block partials: thread i adds entries i, i + 256, ... ; then a shared-memory tree
+__global__ void __launch_bounds__(256) l2_loss_finish_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ loss,
+                                                             float* __restrict__ count) {
+  __shared__ double sl[256], sc[256];
   double l = 0.0, c = 0.0;
-  for (int i = 0; i < n_blocks; ++i) {
+  for (int i = threadIdx.x; i < n_blocks; i += 256) {
     l += partial[2 * i];
     c += partial[2 * i + 1];
   }
-  *count = (float)c;
-  *loss = c > 0.0 ? (float)(l / c) : 0.f;                                             // reg_mask.sum() == 0 -> 0   (:22-27)
+  sl[threadIdx.x] = l;
+  sc[threadIdx.x] = c;
+  __syncthreads();
+  for (int off = 128; off >= 1; off >>= 1) {
+    if ((int)threadIdx.x < off) {
+      sl[threadIdx.x] += sl[threadIdx.x + off];
+      sc[threadIdx.x] += sc[threadIdx.x + off];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    *count = (float)sc[0];
+    *loss = sc[0] > 0.0 ? (float)(sl[0] / sc[0]) : 0.f;                               // reg_mask.sum() == 0 -> 0   (:22-27)
+  }
 }
 
 // dL/dloc of the best mode: (loc - y) / ||loc - y|| * grad_loss / count on valid slots; every other entry stays zero (caller zero-fills)
@@ -425,7 +439,7 @@ int launch_l2_loss(const TrajsdeL2Args& a, bool backward, cudaStream_t s) {
       l2_loss_fwd_kernel<<<blocks, 256, 0, s>>>(a, partial);
       TS_CUDA_CHECK(cudaGetLastError());
     }
-    l2_loss_finish_kernel<<<1, 32, 0, s>>>(partial, blocks, a.loss, a.count);
+    l2_loss_finish_kernel<<<1, 256, 0, s>>>(partial, blocks, a.loss, a.count);
     TS_CUDA_CHECK(cudaGetLastError());
     return TRAJSDE_OK;
   }

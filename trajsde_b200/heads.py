@@ -74,7 +74,7 @@ def _(x, params, n_heads, ln_eps):
 
 
 def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float, grad0: Optional[torch.Tensor],
-                    grad1: Optional[torch.Tensor], grad_x: torch.Tensor) -> List[torch.Tensor]:
+                    grad1: Optional[torch.Tensor], grad_x: torch.Tensor, row_flags: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """Gradients of the 6 * n_heads head tensors; dL/dx is ACCUMULATED into the zero-filled ``grad_x`` (same shape as x, any row / t
     strides, unit channel stride) for the points that carry a non-zero dL/dout.  ``grad_h`` [rows, T, 2] or None per head."""
     rows, T = x.shape[0], x.shape[1]
@@ -102,13 +102,15 @@ def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, l
     if grad_x.stride(2) != 1 or grad_x.stride(0) % 4 or grad_x.stride(1) % 4 or (grad_x.numel() and grad_x.data_ptr() % 16):
         raise ValueError("grad_x: unit channel stride, 16-byte aligned, row / t strides multiples of 4 elements")
     a.grad_x, a.gx_row_stride, a.gx_t_stride = grad_x.data_ptr(), max(grad_x.stride(0), 64), max(grad_x.stride(1), 64)
+    if row_flags is not None:      # grad_x may be uninitialised: the call flags the rows that carry a gradient and zero-fills only those
+        a.row_flags = row_flags.data_ptr()
     L = _lib.lib()
     need = _lib.check(L.trajsde_heads_bwd_workspace_bytes(_lib.MODE_TC_F16), "trajsde_heads_bwd_workspace_bytes")
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), need
     with torch.cuda.device(dev):
         _lib.check(L.trajsde_heads_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_heads_bwd")
-    LAUNCHES['n'] += 2
+    LAUNCHES['n'] += 4 if row_flags is not None else 2
     return gps
 
 
@@ -138,6 +140,73 @@ class _HeadsFn(torch.autograd.Function):
         gsol = gfull[1:].permute(1, 0, 2) if full else gfull
         gps = _heads_bwd_impl(sol, list(params), n_heads, ln_eps, g0, g1 if n_heads == 2 else None, gsol)
         return (gfull, None, None, None) + tuple(gps)
+
+
+class _SolveHeadsFn(torch.autograd.Function):
+    """The decoder's solve and both heads as ONE autograd node (what "heads as an epilogue of the solver" means for training): the
+    solution ``ys`` never becomes an autograd tensor, so its 3 GB gradient is an internal buffer — the heads backward writes only the
+    rows that carry a gradient (a winner-takes-all loss reaches one mode in ten) and hands the solver backward the list of those rows;
+    no zero-fill of the rest, no scan for it, no slice / permute copies."""
+
+    @staticmethod
+    def forward(ctx, y0, step_tab, out_begin, out_w, n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde, *params):
+        from . import ops
+        sde_params, head_params_ = list(params[:n_sde]), list(params[n_sde:])
+        ys, _, states = ops._euler_fwd_impl(y0, sde_params, step_tab, out_begin, out_w, n_outputs, None, None, seed, row_offset, 0, mode, True, True)
+        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps)
+        ctx.save_for_backward(ys, states, step_tab, out_begin, out_w, *params)
+        ctx.meta = (n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde)
+        ctx.set_materialize_grads(False)
+        return o0, o1
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        from . import ops
+        ys, states, step_tab, out_begin, out_w, *params = ctx.saved_tensors
+        n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde = ctx.meta
+        sde_params, head_params_ = list(params[:n_sde]), list(params[n_sde:])
+        rows = ys.shape[1]
+        sparse = ops.row_flags_supported(mode, False) and bool(ops.SKIP_ZERO_ROWS) and rows > 0
+        if sparse:          # uninitialised gradient buffer in ys's layout: only flagged rows are ever written or read
+            gys = torch.empty_strided(ys.size(), ys.stride(), dtype=ys.dtype, device=ys.device)
+            gys[0].zero_()                                  # dL/dys[0] = 0 (the heads read ys[1:]); 256 B per row
+            flags = torch.empty((rows,), dtype=torch.uint8, device=ys.device)
+        else:
+            gys = torch.empty_strided(ys.size(), ys.stride(), dtype=ys.dtype, device=ys.device).zero_()
+            flags = None
+        gps = _heads_bwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps, g0, g1 if n_heads == 2 else None,
+                              gys[1:].permute(1, 0, 2), flags)
+        grads = ops._euler_bwd_impl(gys, None, states, sde_params, step_tab, out_begin, out_w, n_outputs, None, None, seed, row_offset, 0,
+                                    mode, flags)
+        return (grads[0],) + (None,) * 10 + tuple(grads[1:]) + tuple(gps)
+
+
+def solve_and_heads(sde, loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], y0: torch.Tensor, ts, dt: float, *,
+                    mode: Optional[str] = None, seed: Optional[int] = None, row_offset: int = 0, bm=None):
+    """``loc, scale_raw = heads(sdeint(sde, y0, ts, dt=dt, method='euler')[1:].permute(1, 0, 2))`` — dec_hivt_nusargo_sde.py:88, 95, 98 —
+    as one differentiable node (in-kernel Philox noise).  With ``bm`` (caller-supplied increments: validation) or without autograd it
+    is the plain composition of ``sdeint`` and ``decoder_heads_from_solution``."""
+    from . import ops, solver
+    from .schedule import euler_schedule
+    heads, hparams, eps = _head_args(loc_head, scale_head)
+    sde_params = solver._mlp_params(sde.f_func, 64, 'f_func') + solver._mlp_params(sde.g_func, 1, 'g_func')
+    need_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in sde_params + hparams))
+    if bm is not None or not need_grad:
+        ys = solver.sdeint(sde, y0, ts, bm=bm, dt=dt, method='euler', mode=mode, seed=seed, row_offset=row_offset, rows_major=True)
+        return decoder_heads_from_solution(loc_head, scale_head, ys)
+    solver._check_sde_types(sde)
+    if not y0.is_cuda or y0.dim() != 2 or y0.shape[1] != 64:
+        raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only, y0 [rows, 64]; there is no CPU fallback")
+    sched = euler_schedule(solver._as_ts(ts, y0), float(dt))
+    ds = ops.DeviceSchedule.get(sched, y0.device)
+    mode_id = _lib.MODES[mode or solver.get_default_mode()]
+    seed = solver._next_call_seed() if seed is None else int(seed)
+    o0, o1 = _SolveHeadsFn.apply(y0, ds.step_tab, ds.out_begin, ds.out_w, sched.n_outputs, seed, int(row_offset), mode_id, len(heads), eps,
+                                 len(sde_params), *sde_params, *hparams)
+    for name in ('fnfe', 'gnfe'):
+        if hasattr(sde, name):
+            setattr(sde, name, getattr(sde, name) + sched.n_steps)
+    return o0, (o1 if scale_head is not None else None)
 
 
 def _needs_grad(x: torch.Tensor, heads) -> bool:

@@ -155,6 +155,11 @@ class DeviceSchedule:
         return hit
 
 
+def row_flags_supported(mode: int, dual: bool) -> bool:
+    """Can ``euler_bwd`` take the heads backward's row flags (and leave unflagged ``grad_ys`` rows unread)?"""
+    return mode == _lib.MODE_TC_F16 and not dual and not BWD_EXACT_KERNELS
+
+
 def _mlp_struct(ts: Sequence[torch.Tensor]) -> _lib.Mlp:
     m = _lib.Mlp()
     m.w1, m.b1, m.w2, m.b2, m.w3, m.b3 = (t.data_ptr() for t in ts)
@@ -259,8 +264,10 @@ def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row
 def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], states: torch.Tensor,
               params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor, out_w: torch.Tensor,
               n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor], seed: int, row_offset: int,
-              step_offset: int, mode: int) -> List[torch.Tensor]:
-    """[grad_y0] + gradients of every tensor in ``params`` (same order/shapes)."""
+              step_offset: int, mode: int, row_flags: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    """[grad_y0] + gradients of every tensor in ``params`` (same order/shapes).  ``row_flags`` (uint8 [rows], from
+    ``trajsde_heads_bwd``): rows flagged 0 have no incoming gradient and their ``grad_ys`` entries may be uninitialised — honoured by
+    the tensor-core kernels of a single-diffusion solve only (the caller checks ``row_flags_supported``)."""
     dev = states.device
     _monitor(dev).poll()
     S, rows = states.shape[0], states.shape[1]
@@ -271,6 +278,11 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
     a = _lib.EulerBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EulerBwdArgs)
     skip_zero = bool(SKIP_ZERO_ROWS) and not dual and mode == _lib.MODE_TC_F16 and not BWD_EXACT_KERNELS and grad_ys is not None and rows >= 2048
+    if row_flags is not None:
+        if not row_flags_supported(mode, dual) or grad_ys is None:
+            raise ValueError("row_flags need the tensor-core backward of a single-diffusion solve")
+        skip_zero = True
+        a.row_flags = row_flags.data_ptr()
     a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0) | (2 if skip_zero else 0)
     a.sched.n_steps, a.sched.n_outputs = S, n_outputs
     a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
@@ -309,7 +321,8 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
         # TC: pack + absmax + fused dgrad/wgrad + reduce; exact: (dgrad + wgrad) per diffusion net + reduce
         sampled = tc and grad_ys is not None and rows * grad_ys.shape[0] >= (1 << 16)   # sampled absmax + its conditional full scan
         if skip_zero:
-            LAUNCHES['n'] += 6            # row activity (sampled, full) + compaction + pack + fused dgrad/wgrad + reduce
+            # row activity (sampled + full, or flagged rows only) + compaction + pack + fused dgrad/wgrad + reduce
+            LAUNCHES['n'] += 5 if row_flags is not None else 6
         else:
             LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
     return [grad_y0] + gparams
@@ -320,7 +333,7 @@ euler_bwd = torch.library.custom_op("trajsde::euler_bwd", _euler_bwd_impl, mutat
 
 @euler_bwd.register_fake
 def _(grad_ys, grad_g, states, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row_offset,
-      step_offset, mode):
+      step_offset, mode, row_flags=None):
     return [states.new_empty((states.shape[1], 64))] + [torch.empty_like(p) for p in params]
 
 

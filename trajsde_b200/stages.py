@@ -22,8 +22,7 @@ import torch.nn.functional as F
 
 from . import stage
 from .encoder import encoder_recurrence, encoder_recurrence_ood, eos_gather
-from .heads import decoder_heads_from_solution
-from .solver import sdeint
+from .heads import solve_and_heads
 
 
 class FusedDecoderMixin:
@@ -36,11 +35,12 @@ class FusedDecoderMixin:
     def forward(self, data, local_embed: torch.Tensor, global_embed: torch.Tensor):
         num_actors = local_embed.shape[0]
         hidden_0 = stage.aggr_embed(self.aggr_embed, local_embed, global_embed)                                   # :82-85
-        ys = sdeint(self.lsde_func, hidden_0, self.ts_pred, dt=self.min_stepsize, dt_min=self.min_stepsize, rtol=self.rtol, atol=self.atol,
-                    method=self.method, rows_major=True, **self.solver_kwargs)                                    # :88 (the [1:] stays inside the heads)
+        if self.method != 'euler':
+            raise NotImplementedError(f"fused solve implements method='euler' only (reference yml:76), got {self.method!r}")
+        loc, scale_raw = solve_and_heads(self.lsde_func, self.decoder, self.scale if self.uncertain else None, hidden_0, self.ts_pred,
+                                         self.min_stepsize, **self.solver_kwargs)                                 # :88, :95, :98 as one node
         expanded = local_embed.expand(self.num_modes, *local_embed.shape)
         pi = self.pi(torch.cat((expanded, global_embed), dim=-1)).squeeze(-1).t()                                 # :92-94 (reference path)
-        loc, scale_raw = decoder_heads_from_solution(self.decoder, self.scale if self.uncertain else None, ys)    # :95, :98
         loc = loc.view(self.num_modes, num_actors, self.future_steps, 2)
         if self.uncertain:
             scale = F.elu(scale_raw, alpha=1.0).view(self.num_modes, -1, self.future_steps, 2) + 1.0 + self.min_scale   # :98-99
