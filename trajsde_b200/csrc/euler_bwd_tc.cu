@@ -861,6 +861,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
 
 }  // namespace
 
+// order-preserving compaction of flagged rows (shared with the aggr_embed backward, stage_ops.cu)
+int launch_compact_rows(const uint8_t* flags, int64_t rows, int32_t* row_map, int32_t* n_active, cudaStream_t s) {
+  bwd_compact_rows_kernel<<<1, 1024, 0, s>>>(flags, rows, row_map, n_active);
+  TS_CUDA_CHECK(cudaGetLastError());
+  return TRAJSDE_OK;
+}
+
 // ---- internal launch API (also used by enc_bwd.cu) ---------------------------------------------------------------------------------
 int bwd_tc_pack(const TrajsdeEulerBwdArgs& a, uint8_t* img, cudaStream_t s) {
   bwd_tc_pack_kernel<<<16, 256, 0, s>>>(a, img);

@@ -26,11 +26,12 @@ constexpr int AG_W = 0, AG_B = 8192, AG_G = 8256, AG_BETA = 8320, AG_N = 8384, A
 
 __device__ __forceinline__ float4 ld4s(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// X tile [64 rows][128]: columns 0..63 = global_embed[row], 64..127 = local_embed[row % n_actors]  (cat order of dec…sde.py:82)
-__device__ __forceinline__ void aggr_load_x(const TrajsdeAggrArgs& a, int64_t row0, int64_t rows, float* xs, int tid) {
+// X tile [64 rows][128]: columns 0..63 = global_embed[row], 64..127 = local_embed[row % n_actors]  (cat order of dec…sde.py:82);
+// `rmap` (backward): the tile's rows are entries row0 .. row0 + 63 of a compacted row list
+__device__ __forceinline__ void aggr_load_x(const TrajsdeAggrArgs& a, int64_t row0, int64_t rows, float* xs, int tid, const int32_t* rmap = nullptr) {
   const int pt = tid >> 2, qq = tid & 3;                     // 4 threads per row, 32 columns each
-  const int64_t r = row0 + pt;
-  const bool ok = r < rows;
+  const bool ok = row0 + pt < rows;
+  const int64_t r = ok && rmap ? (int64_t)rmap[row0 + pt] : row0 + pt;
   const float* src = qq < 2 ? a.global_embed + r * 64 + 32 * qq : a.local_embed + (r % a.n_actors) * 64 + 32 * (qq - 2);
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -131,8 +132,26 @@ __global__ void __launch_bounds__(SO_THREADS, 2) aggr_embed_fwd_kernel(const Tra
 
 // backward: recompute z, LayerNorm / ReLU backward, dX = dZ W (global half -> grad_global rows, local half -> per-row scratch that
 // aggr_reduce_modes_kernel sums over the modes), dW += dZ^T X, column sums for db / dgamma / dbeta; one partial vector per block
+// flags[r] = dL/dout[r] has a non-zero entry (4 threads per row).  The rows of a decoder batch that received no gradient — nine modes in
+// ten under the reference's winner-takes-all L2 — contribute nothing to any result of the backward and are left out of it.
+__global__ void aggr_row_flags_kernel(const float* __restrict__ grad_out, int64_t rows, uint8_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = i >> 2;
+  bool nz = false;
+  if (r < rows) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = ld4s(grad_out + r * 64 + 16 * (i & 3) + 4 * q);
+      nz = nz || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, nz);
+  if (r < rows && (i & 3) == 0) flags[r] = ((m >> (threadIdx.x & 28)) & 0xFu) ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(SO_THREADS, 1) aggr_embed_bwd_kernel(const TrajsdeAggrArgs a, float* __restrict__ local_rows,
-                                                                        float* __restrict__ partial) {
+                                                                        float* __restrict__ partial, const int32_t* __restrict__ rmap,
+                                                                        const int32_t* __restrict__ n_active) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* ws = reinterpret_cast<float*>(smem);
   float* xs = ws + 64 * LDX;
@@ -141,7 +160,7 @@ __global__ void __launch_bounds__(SO_THREADS, 1) aggr_embed_bwd_kernel(const Tra
   float* dz = dr + SO_TILE * LDZ;
   float* vecs = dz + SO_TILE * LDZ;
   const int tid = threadIdx.x;
-  const int64_t rows = (int64_t)a.n_modes * a.n_actors;
+  const int64_t rows = (int64_t)*n_active;             // length of the compacted list rmap[0 .. rows): the rows with a gradient
   aggr_stage_weights(a, ws, vecs, tid);
   const int pt = tid >> 2, qq = tid & 3, pm = tid >> 4, kq = tid & 15;
   float gw[4][8];                                  // dW[pm + 16 jj][4 kq .. +3] and [64 + 4 kq .. +3]
@@ -152,7 +171,7 @@ __global__ void __launch_bounds__(SO_THREADS, 1) aggr_embed_bwd_kernel(const Tra
   float gcol = 0.f;                                // threads 0..191: db | dgamma | dbeta of channel tid % 64
   for (int64_t row0 = (int64_t)blockIdx.x * SO_TILE; row0 < rows; row0 += (int64_t)gridDim.x * SO_TILE) {
     __syncthreads();
-    aggr_load_x(a, row0, rows, xs, tid);
+    aggr_load_x(a, row0, rows, xs, tid, rmap);
     __syncthreads();
     aggr_gemm_z(xs, ws, vecs, zh, tid);
     __syncthreads();
@@ -168,7 +187,7 @@ __global__ void __launch_bounds__(SO_THREADS, 1) aggr_embed_bwd_kernel(const Tra
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int c = 16 * qq + i;
-        const float go = ok ? a.grad_out[(row0 + pt) * 64 + c] : 0.f;
+        const float go = ok ? a.grad_out[(int64_t)rmap[row0 + pt] * 64 + c] : 0.f;
         const float pre = fmaf(vecs[64 + c], z[i], vecs[128 + c]);
         const float drv = pre > 0.f ? go : 0.f;
         dzh[i] = drv * vecs[64 + c];
@@ -204,8 +223,8 @@ __global__ void __launch_bounds__(SO_THREADS, 1) aggr_embed_bwd_kernel(const Tra
       }
 #pragma unroll
       for (int pp = 0; pp < 4; ++pp) {
-        const int64_t r = row0 + 4 * pm + pp;
-        if (r < rows) {
+        if (row0 + 4 * pm + pp < rows) {
+          const int64_t r = rmap[row0 + 4 * pm + pp];
           *reinterpret_cast<float4*>(a.grad_global + r * 64 + 4 * kq) = ag[pp];
           *reinterpret_cast<float4*>(local_rows + r * 64 + 4 * kq) = al[pp];
         }
@@ -398,8 +417,12 @@ int sm_count() {
 
 }  // namespace
 
+static int64_t a256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+// partials | per-row local halves [rows][64] | n_active (256 B) | row flags [rows] | row map [rows]
 int64_t aggr_workspace_bytes(int64_t n_modes, int64_t n_actors) {
-  return (int64_t)sm_count() * AG_PAD * 4 + 256 + n_modes * n_actors * 64 * 4 + 256;
+  const int64_t rows = n_modes * n_actors;
+  return a256((int64_t)sm_count() * AG_PAD * 4) + a256(rows * 64 * 4) + 256 + a256(rows) + a256(rows * 4) + 256;
 }
 
 int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s) {
@@ -414,11 +437,25 @@ int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s) {
     TS_CUDA_CHECK(cudaGetLastError());
     return TRAJSDE_OK;
   }
-  float* partial = static_cast<float*>(a.workspace);
-  float* local_rows = reinterpret_cast<float*>(static_cast<uint8_t*>(a.workspace) + (((int64_t)sms * AG_PAD * 4 + 255) & ~(int64_t)255));
+  uint8_t* wsb = static_cast<uint8_t*>(a.workspace);
+  float* partial = reinterpret_cast<float*>(wsb);
+  float* local_rows = reinterpret_cast<float*>(wsb + a256((int64_t)sms * AG_PAD * 4));
+  int32_t* n_active = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(local_rows) + a256(rows * 64 * 4));
+  uint8_t* flags = reinterpret_cast<uint8_t*>(n_active) + 256;
+  int32_t* rmap = reinterpret_cast<int32_t*>(flags + a256(rows));
   const int grid = (int)(tiles < sms ? (tiles > 0 ? tiles : 1) : sms);
+  TS_CUDA_CHECK(cudaMemsetAsync(n_active, 0, 4, s));
+  if (rows > 0) {
+    // rows without a gradient: dL/dglobal = 0, no contribution to dL/dlocal or to the parameter gradients -> only the others are visited
+    TS_CUDA_CHECK(cudaMemsetAsync(a.grad_global, 0, sizeof(float) * 64 * (size_t)rows, s));
+    TS_CUDA_CHECK(cudaMemsetAsync(local_rows, 0, sizeof(float) * 64 * (size_t)rows, s));
+    aggr_row_flags_kernel<<<(int)((rows * 4 + 255) / 256), 256, 0, s>>>(a.grad_out, rows, flags);
+    TS_CUDA_CHECK(cudaGetLastError());
+    int rc = launch_compact_rows(flags, rows, rmap, n_active, s);
+    if (rc != 0) return rc;
+  }
   TS_CUDA_CHECK(cudaFuncSetAttribute(aggr_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGGR_BWD_SMEM));
-  aggr_embed_bwd_kernel<<<grid, SO_THREADS, AGGR_BWD_SMEM, s>>>(a, local_rows, partial);
+  aggr_embed_bwd_kernel<<<grid, SO_THREADS, AGGR_BWD_SMEM, s>>>(a, local_rows, partial, rmap, n_active);
   TS_CUDA_CHECK(cudaGetLastError());
   aggr_reduce_kernel<<<(AG_N + 255) / 256, 256, 0, s>>>(partial, grid, a);
   TS_CUDA_CHECK(cudaGetLastError());

@@ -73,7 +73,7 @@ class _AggrFn(torch.autograd.Function):
         a.workspace, a.workspace_bytes = base, need
         with torch.cuda.device(dev):
             _lib.check(L.trajsde_aggr_embed_bwd(C.byref(a), _stream_ptr(dev)), "trajsde_aggr_embed_bwd")
-        LAUNCHES['n'] += 3
+        LAUNCHES['n'] += 5            # row flags + compaction + backward over the rows with a gradient + two reduces
         return gl, gg, gw, gb, gga, gbe, None
 
 
