@@ -191,7 +191,7 @@ def main():
     ap.add_argument('--no-train', action='store_true')
     ap.add_argument('--strong-scenes', type=int, default=8192, help='total scenes of the strong-scaling training entry (0 = skip)')
     ap.add_argument('--no-heads', action='store_true')
-    ap.add_argument('--e2e-chunks', type=int, default=2, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
+    ap.add_argument('--e2e-chunks', type=int, default=8, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     out = _claim_stdout()
