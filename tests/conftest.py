@@ -55,3 +55,8 @@ def golden_schedule():
 @pytest.fixture(scope='session')
 def golden_stage():
     return load_golden('decoder_stage.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_encoder_stage():
+    return load_golden('encoder_stage.npz')

@@ -9,6 +9,10 @@ Fixtures (all float32 unless noted, seeds fixed):
   decoder_stage.npz   the reference's whole `SDEDecoder.forward` (dec…sde.py:77-105: aggr_embed -> sdeint -> heads -> elu -> cat, pi) on
                       seeded embeddings with supplied dW, its `L2` / `DiffBCE` losses (losses/L2.py, losses/diff_BCE.py) with their
                       gradients through the reference solver, and `ADE_T` / `FDE_T` (metrics/ade_t.py, metrics/fde_t.py) of the result.
+  encoder_stage.npz   the reference's whole `LocalEncoderSDESepPara2.forward` (enc…sep2.py:66-202: AA encoder -> 21 x [sdeint_dual + GRU jump] ->
+                      gathers -> AL encoder) on a small synthetic graph batch, through the functional PyG stand-in of oracle/shims, eval
+                      mode, supplied dW: what the SDE recurrence receives (aa_out, masks), what it hands on (latents at eos, agents'
+                      diffusion), the stage outputs, and the gradients of a loss on them.
   schedule.npz        step schedules for the grids of SURVEY App. A (F = 10,20,30,50,60,100,200 and the encoder pairs),
                       from the literal torch replay + the (ta,tb) the reference solver actually queried.
 Cannot run on the GPU box (/root/reference absent there) — the outputs are committed.
@@ -172,9 +176,105 @@ def stage_fixture():
     print('decoder_stage: loc', tuple(out['loc'].shape), 'L2', l2.item(), 'BCE', bce.item(), 'ADE', float(ade.compute()), 'FDE', float(fde.compute()))
 
 
+def synthetic_graph_batch(scenes=4, agents=6, lanes=9, seed=11):
+    """A small TemporalData-shaped batch (models/utils/util.py:20-75) with the fields LocalEncoderSDESepPara2.forward reads."""
+    from models.utils.util import TemporalData
+    g = torch.Generator().manual_seed(seed)
+    n = scenes * agents
+    x = torch.randn(n, 21, 2, generator=g)
+    positions = torch.randn(n, 81, 2, generator=g).cumsum(1)
+    pad = torch.rand(n, 81, generator=g) < 0.2
+    pad[:, 20] = False                                          # every actor is observed at the reference time
+    bos = torch.zeros(n, 21, dtype=torch.bool)
+    bos[torch.arange(n), torch.argmax((~pad[:, :21]).float(), 1)] = True
+    ei = torch.tensor([[i, j] for s in range(scenes) for i in range(s * agents, (s + 1) * agents)
+                       for j in range(s * agents, (s + 1) * agents) if i != j]).t()
+    la = torch.stack((torch.randint(0, lanes, (5 * n,), generator=g), torch.arange(n).repeat(5)))
+    data = TemporalData(x=x, positions=positions, edge_index=ei, y=torch.randn(n, 60, 2, generator=g), num_nodes=n, padding_mask=pad,
+                        bos_mask=bos, rotate_angles=torch.rand(n, generator=g) * 6.28, lane_positions=torch.randn(lanes, 10, 2, generator=g),
+                        lane_vectors=torch.randn(lanes, 2, generator=g), lane_paddings=torch.zeros(lanes, 10),
+                        lane_actor_index=la, lane_actor_vectors=torch.randn(5 * n, 2, generator=g))
+    data['agent_index'] = torch.arange(scenes) * agents
+    data.batch = torch.arange(scenes).repeat_interleave(agents)
+    data.source = torch.arange(scenes) % 2                      # nuScenes and Argoverse scenes alternate
+    ang = data['rotate_angles']
+    rot = torch.empty(n, 2, 2)                                  # model_base_mix_sde.py:76-83
+    rot[:, 0, 0], rot[:, 0, 1], rot[:, 1, 0], rot[:, 1, 1] = torch.cos(ang), -torch.sin(ang), torch.sin(ang), torch.cos(ang)
+    data['rotate_mat'] = rot
+    return data
+
+
+ENC_KW = dict(historical_steps=21, node_dim=2, edge_dim=2, embed_dim=64, num_heads=8, dropout=0.1, parallel=True, local_radius=50,
+              sde_layers=2, ref_time=20, max_past_t=2, run_backwards=True, minimum_step=0.1, rtol=0.001, atol=0.001, method='euler')
+
+
+def encoder_stage_fixture():
+    from importlib.machinery import SourceFileLoader
+    m = rr.load_reference()
+    DiffBCE = SourceFileLoader('DiffBCE', os.path.join(rr.REFERENCE_ROOT, 'losses/diff_BCE.py')).load_module('DiffBCE').DiffBCE
+    torch.manual_seed(21)
+    enc = m['enc'].LocalEncoderSDESepPara2(**ENC_KW).eval()     # eval: no dropout in the HiVT blocks
+    rr._perturb_biases(enc.gru_unit, 0.1, torch.Generator().manual_seed(22))
+    rr._perturb_biases(enc.lsde_func, 0.1, torch.Generator().manual_seed(23))
+    data = synthetic_graph_batch()
+    n, n_fake = data.x.shape[0], data['agent_index'].numel()
+    rows = n + n_fake
+    pairs = so.encoder_time_pairs_ref(2.0, 21)
+    hs = torch.stack([so.euler_schedule_ref(torch.tensor([a, b]), 0.1)['h'][0] for a, b, _ in pairs])
+    dW = torch.randn(21, rows, 64, generator=torch.Generator().manual_seed(24)) * torch.sqrt(hs).view(21, 1, 1)
+    glob = type(enc).forward.__globals__
+    orig, calls, cap = glob['sdeint_dual'], {'n': 0}, {'x': [], 'mask': [], 'slot': []}
+
+    def with_dw(sde, y0, ts, nus_mask, **kw):
+        k = calls['n']
+        calls['n'] += 1
+        cap['nus_mask'] = nus_mask.clone()
+        return orig(sde, y0, ts, nus_mask, bm=m['torchsde'].FixedIncrements(dW[k:k + 1]), **kw)
+
+    def gru_pre(mod, args, kwargs):
+        kwargs['input_tensor'].retain_grad()
+        cap['x'].append(kwargs['input_tensor'])
+        cap['mask'].append(kwargs['mask'].clone())
+
+    def al_pre(mod, args, kwargs):
+        kwargs['x'][1].retain_grad()
+        cap['pre_al'] = kwargs['x'][1]
+
+    h1 = enc.gru_unit.register_forward_pre_hook(gru_pre, with_kwargs=True)
+    h2 = enc.al_encoder.register_forward_pre_hook(al_pre, with_kwargs=True)
+    glob['sdeint_dual'] = with_dw
+    torch.manual_seed(25)                                       # the perturbed target copies draw from the global RNG (enc…sep2.py:95)
+    try:
+        out, d_in, d_out, l_in, l_out = enc(data)
+    finally:
+        glob['sdeint_dual'] = orig
+        h1.remove(); h2.remove()
+    assert calls['n'] == 21
+    loss = out.square().mean() + DiffBCE(reduction='mean')(data, {'diff_in': d_in, 'diff_out': d_out, 'label_in': l_in, 'label_out': l_out})
+    loss.backward()
+    slots = [t for _, _, t in pairs]                            # iteration k consumed aa_out[slots[k]]
+    aa_out = torch.zeros(21, rows, 64)
+    g_aa = torch.zeros(21, rows, 64)
+    actors_mask = torch.zeros(rows, 21, dtype=torch.bool)
+    for k, t in enumerate(slots):
+        aa_out[t], actors_mask[:, t] = cap['x'][k].detach(), cap['mask'][k]
+        g_aa[t] = cap['x'][k].grad if cap['x'][k].grad is not None else 0
+    d = dict(aa_out=aa_out.numpy(), actors_mask=actors_mask.numpy(), nus_mask=cap['nus_mask'].numpy(), dW=dW.numpy(),
+             bos_mask=data['bos_mask'].numpy(), agent_index=data['agent_index'].numpy(), pre_al=cap['pre_al'].detach().numpy(),
+             out=out.detach().numpy(), diff_in=d_in.detach().numpy(), diff_out=d_out.detach().numpy(), label_in=l_in.numpy(),
+             label_out=l_out.numpy(), loss=np.float64(loss.item()), grad_aa_out=g_aa.numpy(), grad_pre_al=cap['pre_al'].grad.numpy(),
+             torch_seed_fake_agents=np.int64(25), init_seed=np.int64(21))
+    keep = ('gru_unit.', 'lsde_func.f_func', 'lsde_func.g_nus', 'lsde_func.g_argo', 'hidden')
+    d.update({f'param/{k}': v.detach().numpy() for k, v in enc.state_dict().items() if k.startswith(keep)})
+    d.update({f'grad/{k}': p.grad.numpy() for k, p in enc.named_parameters() if k.startswith(keep) and p.grad is not None})
+    np.savez_compressed(os.path.join(OUT, 'encoder_stage.npz'), **d)
+    print('encoder_stage: out', tuple(out.shape), 'diff_in', tuple(d_in.shape), 'rows', rows, 'loss', loss.item())
+
+
 if __name__ == '__main__':
     torch.set_num_threads(1)       # fixture bytes must not depend on the thread count of the generating host
     decoder_fixture()
     encoder_fixture()
     schedule_fixture()
     stage_fixture()
+    encoder_stage_fixture()

@@ -137,3 +137,55 @@ def test_training_gradients_through_the_stage_vs_golden(golden_stage):
         close(p[k].grad, d['grad/' + k], k)
     # the scale head and pi do not reach L2 (loc only, losses/L2.py:12,15): their reference gradients are exactly zero
     assert not d['grad/scale.0.weight'].any() and not d['grad/pi.0.weight'].any()
+
+
+# ---- encoder stage (enc…sep2.py:66-202 run verbatim through the functional PyG stand-in): what the SDE recurrence receives and hands on ----
+def _enc_stage_params(d, dtype=torch.float32):
+    p = {k[len('param/'):]: torch.from_numpy(d[k]).to(dtype) for k in d if k.startswith('param/')}
+    sub_ = lambda pre: {k[len(pre) + 1:]: v for k, v in p.items() if k.startswith(pre + '.')}  # noqa: E731
+    return p, sub_('lsde_func.f_func.net'), sub_('lsde_func.g_nus.net'), sub_('lsde_func.g_argo.net'), sub_('gru_unit')
+
+
+def encoder_stage_ref(d, dtype=torch.float32, leaves=False):
+    """Oracle restatement of the SDE part of LocalEncoderSDESepPara2.forward on the fixture's captured inputs: recurrence, eos gather
+    (:184-188), agents' diffusion read-out (:171, :190-194)."""
+    p, pf, pgn, pga, pgru = _enc_stage_params(d, dtype)
+    aa = torch.from_numpy(d['aa_out']).to(dtype)
+    if leaves:
+        for t in [aa] + list(p.values()):
+            t.requires_grad_(True)
+    rows, n = aa.shape[1], d['bos_mask'].shape[0]
+    h0 = p['hidden'].unsqueeze(0).repeat(rows, 1)
+    lat, g = so.encoder_recurrence_ref(pf, pgn, pga, pgru, h0, aa, torch.from_numpy(d['actors_mask']), torch.from_numpy(d['nus_mask']),
+                                       torch.from_numpy(d['dW']).to(dtype))
+    bos, ai = torch.from_numpy(d['bos_mask']), torch.from_numpy(d['agent_index'])
+    eos = 20 - torch.argmax(bos.float(), dim=1)
+    pre_al = lat[:, :n][eos, torch.arange(n)]
+    new_ai = torch.cat((ai, torch.arange(n, rows)))
+    diff = g[eos[ai].repeat(2), new_ai, 0]
+    return pre_al, diff, aa, p
+
+
+def test_encoder_stage_recurrence_vs_golden(golden_encoder_stage):
+    d = golden_encoder_stage
+    pre_al, diff, _, _ = encoder_stage_ref(d)
+    assert torch.allclose(pre_al, torch.from_numpy(d['pre_al']), atol=3e-6, rtol=1e-5)
+    ref_diff = torch.cat((torch.from_numpy(d['diff_in']), torch.from_numpy(d['diff_out'])))
+    assert torch.allclose(diff.unsqueeze(-1).expand(-1, 64), ref_diff, atol=1e-6, rtol=1e-5)
+    assert float(d['label_in'].max()) == 0 and float(d['label_out'].min()) == 1
+
+
+def test_encoder_stage_gradients_vs_golden(golden_encoder_stage):
+    """fp64 autograd of the oracle recurrence under the cotangents the reference's own backward delivered to it (dL/d pre_al from the
+    AL encoder + out.square().mean(), DiffBCE on the agents' diffusion) reproduces the reference's gradients of aa_out, hidden, GRU, SDE."""
+    d = golden_encoder_stage
+    pre_al, diff, aa, p = encoder_stage_ref(d, torch.float64, leaves=True)
+    d_in, d_out = torch.chunk(diff, 2, 0)
+    loss = (pre_al * torch.from_numpy(d['grad_pre_al']).double()).sum() + so.diff_bce_ref(d_in.unsqueeze(-1).expand(-1, 64), d_out.unsqueeze(-1).expand(-1, 64))
+    loss.backward()
+    ga = torch.from_numpy(d['grad_aa_out']).double()
+    assert (aa.grad - ga).abs().max() <= 2e-4 * ga.abs().max()
+    for k in d:
+        if k.startswith('grad/'):
+            r = torch.from_numpy(d[k]).double()
+            assert (p[k[5:]].grad - r).abs().max() <= 3e-4 * r.abs().max() + 1e-10, k

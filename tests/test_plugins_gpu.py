@@ -137,3 +137,47 @@ def test_fused_encoder_stage_vs_the_reference_loop():
     with torch.no_grad():
         mean, std = fused.forward_ood(data)
     assert mean.shape == (54, 64) and std.shape == (54,) and (std > 0).all()
+
+
+@pytest.mark.parametrize('mode', ['tc_f16'])
+def test_fused_encoder_stage_vs_the_reference_forward_fixture(mode, golden_encoder_stage):
+    """tests/golden/encoder_stage.npz was captured from the REAL reference LocalEncoderSDESepPara2.forward (AA encoder, 21 x
+    [sdeint_dual + GRU_Unit], gathers, AL encoder; functional PyG stand-in): the fused mixin gets what its recurrence received there
+    (aa_out, masks, increments) and must hand on what it handed on (latents at eos = the AL encoder's input, the agents' diffusion),
+    forward and — under the cotangents the reference's backward delivered — backward."""
+    d = golden_encoder_stage
+
+    class FixtureEncoder(FusedEncoderMixin, ref_shaped.RefShapedEncoder):
+        def _prepare(self, data, ood):
+            return {'aa_out': data['aa_out'], 'actors_mask': data['actors_mask'], 'nus_mask': data['nus_mask'],
+                    'agent_index': data['agent_index'], 'n_fake': data['agent_index'].numel()}
+
+        def _finish(self, data, prep, out):
+            return out
+
+    enc = FixtureEncoder()
+    sd = {k[len('param/'):]: torch.from_numpy(d[k]) for k in d if k.startswith('param/')}
+    own = enc.state_dict()
+    own.update(sd)
+    enc.load_state_dict(own)
+    enc = enc.to(DEV)
+    aa = _t(d, 'aa_out').requires_grad_(True)
+    data = {'aa_out': aa, 'actors_mask': _t(d, 'actors_mask'), 'nus_mask': _t(d, 'nus_mask'), 'agent_index': _t(d, 'agent_index'),
+            'bos_mask': _t(d, 'bos_mask')}
+    enc.recurrence_kwargs = {'dW': _t(d, 'dW'), 'mode': mode}
+    out, d_in, d_out, l_in, l_out = enc(data)
+    e_out = float((out.detach().cpu() - torch.from_numpy(d['pre_al'])).abs().max())
+    e_diff = max(float((d_in.detach().cpu() - torch.from_numpy(d['diff_in'])).abs().max()), float((d_out.detach().cpu() - torch.from_numpy(d['diff_out'])).abs().max()))
+    print(f"fused encoder stage vs reference forward: latents at eos max-abs {e_out:.2e}, agents' diffusion max-abs {e_diff:.2e}")
+    assert e_out < 1e-2 and e_diff < 2e-3
+    assert torch.equal(l_in.cpu(), torch.from_numpy(d['label_in'])) and torch.equal(l_out.cpu(), torch.from_numpy(d['label_out']))
+    ((out * _t(d, 'grad_pre_al')).sum() + stage.diff_bce_loss(d_in, d_out)).backward()
+    worst = float((aa.grad.cpu() - torch.from_numpy(d['grad_aa_out'])).abs().max() / torch.from_numpy(d['grad_aa_out']).abs().max())
+    assert worst < 3e-2, ('aa_out', worst)
+    for k in d:
+        if k.startswith('grad/'):
+            r = torch.from_numpy(d[k])
+            e = float((enc.get_parameter(k[5:]).grad.cpu() - r).abs().max() / (r.abs().max() + 1e-12))
+            worst = max(worst, e)
+            assert e < 3e-2, (k, e)
+    print(f"fused encoder stage training gradients vs the reference's own: worst relative error {worst:.2e}")
