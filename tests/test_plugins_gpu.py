@@ -169,11 +169,11 @@ def test_fused_encoder_stage_vs_the_reference_forward_fixture(mode, golden_encod
     e_out = float((out.detach().cpu() - torch.from_numpy(d['pre_al'])).abs().max())
     e_diff = max(float((d_in.detach().cpu() - torch.from_numpy(d['diff_in'])).abs().max()), float((d_out.detach().cpu() - torch.from_numpy(d['diff_out'])).abs().max()))
     print(f"fused encoder stage vs reference forward: latents at eos max-abs {e_out:.2e}, agents' diffusion max-abs {e_diff:.2e}")
-    assert e_out < 1e-2 and e_diff < 2e-3
+    assert e_out < 2.5e-3 and e_diff < 6e-4                         # measured 7.1e-4, 1.7e-4
     assert torch.equal(l_in.cpu(), torch.from_numpy(d['label_in'])) and torch.equal(l_out.cpu(), torch.from_numpy(d['label_out']))
     ((out * _t(d, 'grad_pre_al')).sum() + stage.diff_bce_loss(d_in, d_out)).backward()
     worst = float((aa.grad.cpu() - torch.from_numpy(d['grad_aa_out'])).abs().max() / torch.from_numpy(d['grad_aa_out']).abs().max())
-    assert worst < 3e-2, ('aa_out', worst)
+    assert worst < 2e-2, ("aa_out", worst)                       # measured 5e-3 over all gradients
     for k in d:
         if k.startswith('grad/'):
             r = torch.from_numpy(d[k])
