@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 7
+#define TRAJSDE_ABI_VERSION 8
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -101,6 +101,8 @@ typedef struct {
   uint64_t row_offset;
   uint32_t step_offset;
   uint32_t reserved;
+  const uint64_t* seed_dev; /* device pointer or NULL: the effective key is seed + *seed_dev — a seed that lives in device memory lets
+                               a captured CUDA graph draw fresh noise on every replay (bump the word between replays) */
 } TrajsdeNoise;
 
 typedef struct {

@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -37,7 +37,7 @@ class Schedule(C.Structure):
 
 class Noise(C.Structure):
     _fields_ = [('dw', _fp), ('seed', C.c_uint64), ('row_offset', C.c_uint64), ('step_offset', C.c_uint32),
-                ('reserved', C.c_uint32)]
+                ('reserved', C.c_uint32), ('seed_dev', _fp)]
 
 
 class EulerFwdArgs(C.Structure):

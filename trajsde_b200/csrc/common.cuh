@@ -73,6 +73,10 @@ __device__ __forceinline__ void ts_sincos_approx(float x, float& s, float& c) {
   asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(x));
   asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(x));
 }
+// Effective Philox key of a call: the host-side seed plus, when the caller keeps its seed in device memory (TrajsdeNoise.seed_dev: CUDA-graph
+// replays draw fresh noise by bumping that word between replays), the device word.
+__device__ __forceinline__ uint64_t ts_noise_seed(const TrajsdeNoise& n) { return n.seed + (n.seed_dev ? *n.seed_dev : 0ull); }
+
 __device__ __forceinline__ float4 philox_dw4(uint64_t seed, uint64_t grow, uint32_t step, uint32_t chunk, float sqrt_h) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), step, chunk),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
   const TrajsdeEncFwdArgs& a = p.a;
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = a.sched.n_steps;
+  const uint64_t noise_seed = HAS_DW ? 0ull : ts_noise_seed(a.noise);
 
   const uint32_t bar_w = base + OFF_BARS;
   auto bar_opnd = [&](int i) { return base + OFF_BARS + 8u + 8u * i; };
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           const float sqrt_h = sqrtf(h);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            dwv[q] = philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
+            dwv[q] = philox_dw4(noise_seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)it,
                                 (uint32_t)(hh * 8 + q), sqrt_h);
           }
         }

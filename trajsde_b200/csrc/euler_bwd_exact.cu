@@ -84,7 +84,7 @@ __device__ __forceinline__ void fill(float (&acc)[2][4], const float* vec, int t
 
 __device__ __forceinline__ float noise_elem(const TrajsdeNoise& nz, int64_t rows, int k, int64_t r, int c, float sqrt_h) {
   if (nz.dw) return nz.dw[((int64_t)k * rows + r) * 64 + c];
-  const float4 n4 = philox_dw4(nz.seed, (uint64_t)r + nz.row_offset, nz.step_offset + (uint32_t)k, (uint32_t)(c >> 2), sqrt_h);
+  const float4 n4 = philox_dw4(ts_noise_seed(nz), (uint64_t)r + nz.row_offset, nz.step_offset + (uint32_t)k, (uint32_t)(c >> 2), sqrt_h);
   return (c & 3) == 0 ? n4.x : (c & 3) == 1 ? n4.y : (c & 3) == 2 ? n4.z : n4.w;
 }
 

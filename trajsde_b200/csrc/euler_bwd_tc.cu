@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
   // rows of this sweep: all of them, or the compacted list of rows with a non-zero incoming gradient (count known on the device only)
   const int32_t* __restrict__ rmap = p.row_map;
   const int64_t n_rows = p.n_active ? (int64_t)*p.n_active : a.rows;
+  const uint64_t noise_seed = HAS_DW ? 0ull : ts_noise_seed(a.noise);
   const int num_tiles = (int)((n_rows + TILE_M - 1) / TILE_M);
   const int tiles_q = num_tiles / (int)gridDim.x, tiles_r = num_tiles % (int)gridDim.x;
   const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
@@ -755,8 +756,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) euler_bwd_tc_kernel(const BwdT
             const uint64_t grow_r = (uint64_t)(rmap && sr < n_rows ? (int64_t)rmap[sr] : sr) + a.noise.row_offset;
 #pragma unroll 1
             for (uint32_t c = 0; c < 4; ++c) {                                           // 16-byte chunk = 8 channels = two Philox calls
-              const float4 n0 = philox_dw4(a.noise.seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c, sqrt_h);
-              const float4 n1 = philox_dw4(a.noise.seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c + 1, sqrt_h);
+              const float4 n0 = philox_dw4(noise_seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c, sqrt_h);
+              const float4 n1 = philox_dw4(noise_seed, grow_r, a.noise.step_offset + (uint32_t)k, h2 * 8 + 2 * c + 1, sqrt_h);
               *reinterpret_cast<uint4*>(tr + (((h2 * 4 + c) ^ (r & 7u)) << 4)) =
                   make_uint4(pack_f16x2(n0.x, n0.y), pack_f16x2(n0.z, n0.w), pack_f16x2(n1.x, n1.y), pack_f16x2(n1.z, n1.w));
             }

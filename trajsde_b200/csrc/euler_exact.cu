@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) euler_fwd_exact_kernel(const Ex
   float* act2 = smem + L::act2;
   float* grow = smem + L::grow;
   const int S = a.sched.n_steps;
+  const uint64_t noise_seed = a.noise.dw ? 0ull : ts_noise_seed(a.noise);
 
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * EX_ROWS;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(EX_THREADS, 1) euler_fwd_exact_kernel(const Ex
             dw = valid[i] ? a.noise.dw[((int64_t)k * a.rows + r[i]) * 64 + tx + 16 * j] : 0.f;
           } else {
             const int c = tx + 16 * j;
-            const float4 n4 = philox_dw4(a.noise.seed, (uint64_t)r[i] + a.noise.row_offset,
+            const float4 n4 = philox_dw4(noise_seed, (uint64_t)r[i] + a.noise.row_offset,
                                          a.noise.step_offset + (uint32_t)k, (uint32_t)(c >> 2), sqrt_h);
             dw = (c & 3) == 0 ? n4.x : (c & 3) == 1 ? n4.y : (c & 3) == 2 ? n4.z : n4.w;
           }
@@ -285,7 +286,7 @@ __global__ void philox_dw_kernel(TrajsdeSchedule sched, TrajsdeNoise noise, int6
     const int k = (int)(rk / rows);
     const float sqrt_h = sqrtf(sched.step_tab[4 * k + 1]);
     *reinterpret_cast<float4*>(out + idx * 4) =
-        philox_dw4(noise.seed, (uint64_t)row + noise.row_offset, noise.step_offset + (uint32_t)k, chunk, sqrt_h);
+        philox_dw4(ts_noise_seed(noise), (uint64_t)row + noise.row_offset, noise.step_offset + (uint32_t)k, chunk, sqrt_h);
   }
 }
 

@@ -305,6 +305,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
   const int tile_hi = tile_lo + tiles_q + ((int)blockIdx.x < tiles_r ? 1 : 0);
   const bool save_states = a.states != nullptr;
+  const uint64_t noise_seed = HAS_DW ? 0ull : ts_noise_seed(a.noise);
 
   // mbarriers.  [0] weights; per slot s (stride 80 B): opnd[2] (256 epilogue arrivals each), acc[2] (tcgen05.commit), tma
   // (TMA tx), xfull (256: staging written / y0 consumed), xfree (IO: stores have read the staging buffers), ring[2] (IO:
@@ -465,7 +466,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 #pragma unroll
             for (int q = q0; q < q1; ++q)
               *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
-                  philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
+                  philox_dw4(noise_seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
           };
 
           // ---- epilogue 1: h1f = tanh(z1f) -> OA (P2f may start), h1g = tanh(z1g) -> OB (biases are in the accumulators) ----------
@@ -670,7 +671,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   #pragma unroll 2
             for (int q = 0; q < 8; ++q)
               *reinterpret_cast<float4*>(x_row + ((q ^ (row & 7u)) << 4)) =
-                  philox_dw4(a.noise.seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
+                  philox_dw4(noise_seed, (uint64_t)grow + a.noise.row_offset, a.noise.step_offset + (uint32_t)k, (uint32_t)(hh * 8 + q), sc.y);
           }
           mbar_wait(bar_acc(slot, 1), par_accB);
           par_accB ^= 1;

@@ -52,7 +52,7 @@ class FlatGradBucket:
     def all_reduce_mean(self, group: Optional[dist.ProcessGroup] = None, async_op: bool = False):
         """SUM all-reduce of the flat bucket followed by division by the world size (DDP's gradient averaging).  Also the once-per-step
         place where pending tensor-core backward status snapshots are looked at (non-blocking; see ops.poll_status)."""
-        if self.flat.is_cuda:
+        if self.flat.is_cuda and not torch.cuda.is_current_stream_capturing():
             from . import ops
             ops.poll_status(self.flat.device)
         if not (dist.is_available() and dist.is_initialized()):

@@ -58,14 +58,14 @@ class _StatusMonitor:
 
     def snapshot(self):
         """Enqueue a 4-byte D2H copy of the status word behind the backward kernels just launched (if none is pending)."""
-        if _POLICY['adjoint_range'] == 'ignore' or self.event is not None:
-            return
+        if _POLICY['adjoint_range'] == 'ignore' or self.event is not None or torch.cuda.is_current_stream_capturing():
+            return      # inside a CUDA-graph capture the word still accumulates; poll it with backward_status() between replays
         self.host.copy_(self.word, non_blocking=True)
         self.event = torch.cuda.Event()
         self.event.record(torch.cuda.current_stream(self.word.device))
 
     def poll(self, block: bool = False):
-        if self.event is None or not (block or self.event.query()):
+        if self.event is None or torch.cuda.is_current_stream_capturing() or not (block or self.event.query()):
             return
         if block:
             self.event.synchronize()
@@ -155,6 +155,22 @@ class DeviceSchedule:
         return hit
 
 
+# Device-resident noise seed (TrajsdeNoise.seed_dev): {device string: int64 tensor [1]}.  When set for a device every solver / encoder
+# call on it keys its Philox stream by (host seed + that word): a captured CUDA graph then draws fresh noise on every replay once the
+# word is bumped between replays (the host seed of each call is baked into the graph as an offset).  See solver.set_device_seed.
+SEED_DEV = {}
+
+
+def _apply_seed_dev(noise, dev) -> None:
+    t = SEED_DEV.get(str(dev))
+    if t is not None:
+        noise.seed_dev = t.data_ptr()
+
+
+def _capturing() -> bool:
+    return torch.cuda.is_current_stream_capturing()
+
+
 def row_flags_supported(mode: int, dual: bool) -> bool:
     """Can ``euler_bwd`` take the heads backward's row flags (and leave unflagged ``grad_ys`` rows unread)?"""
     return mode == _lib.MODE_TC_F16 and not dual and not BWD_EXACT_KERNELS
@@ -231,6 +247,7 @@ def _euler_fwd_impl(y0: torch.Tensor, params: List[torch.Tensor], step_tab: torc
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
     a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    _apply_seed_dev(a.noise, dev)
     a.y0, a.y0_row_stride = y0c.data_ptr(), y0c.stride(0)
     a.ys, a.ys_t_stride, a.ys_row_stride = ys.data_ptr(), ys.stride(0), ys.stride(1)
     a.g_last = g_last.data_ptr()
@@ -297,6 +314,7 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
     a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    _apply_seed_dev(a.noise, dev)
     states = states.contiguous()
     a.states = states.data_ptr()
     if grad_ys is not None:
@@ -413,6 +431,7 @@ def _enc_fwd_impl(h0: torch.Tensor, aa_out: torch.Tensor, obs_mask: torch.Tensor
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
     a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    _apply_seed_dev(a.noise, dev)
     a.h0, a.h0_row_stride = h0c.data_ptr(), h0c.stride(0)
     a.aa_out, a.slot = aa.data_ptr(), slot.data_ptr()
     a.obs_mask, a.obs_mask_row_stride = om.data_ptr(), om.stride(0)
@@ -476,6 +495,7 @@ def _enc_bwd_impl(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Te
         dw = dw.contiguous()
         a.noise.dw = dw.data_ptr()
     a.noise.seed, a.noise.row_offset, a.noise.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    _apply_seed_dev(a.noise, dev)
     h0c = h0.detach().contiguous()
     aa = aa_out.detach().contiguous()
     om = obs_mask.contiguous().view(torch.uint8)
@@ -744,6 +764,7 @@ def philox_dw(dsched: DeviceSchedule, rows: int, seed: int, device, row_offset: 
     s.step_tab, s.out_begin, s.out_w = dsched.step_tab.data_ptr(), dsched.out_begin.data_ptr(), dsched.out_w.data_ptr()
     n = _lib.Noise()
     n.seed, n.row_offset, n.step_offset = seed & (2**63 - 1), row_offset, step_offset
+    _apply_seed_dev(n, torch.device(device))
     with torch.cuda.device(device):
         _lib.check(_lib.lib().trajsde_philox_dw(C.byref(s), C.byref(n), rows, out.data_ptr(), _stream_ptr(device)),
                    "trajsde_philox_dw")

@@ -45,6 +45,21 @@ def manual_seed(seed: int) -> None:
         _defaults['seed'], _defaults['torch_seed'], _defaults['calls'] = int(seed) & _MASK63, None, 0
 
 
+def set_device_seed(word: Optional[torch.Tensor]) -> None:
+    """Keep (part of) the Philox key in device memory: ``word`` = int64 CUDA tensor with one element, or None to go back to host
+    seeds (for the word's device).  Every call on that device then draws its stream from (host seed of the call + word[0]).  This is
+    what makes the path CUDA-graph friendly: capture a whole step once (the per-call host seeds become constants of the graph), then
+    ``word += 1`` between replays gives every replay fresh Brownian increments.  Forward and backward of a step must see the same value:
+    bump it after the backward."""
+    from . import ops
+    if word is None:
+        ops.SEED_DEV.clear()
+        return
+    if not (torch.is_tensor(word) and word.is_cuda and word.dtype == torch.int64 and word.numel() == 1):
+        raise ValueError("device seed: an int64 CUDA tensor with one element")
+    ops.SEED_DEV[str(word.device)] = word
+
+
 def _splitmix64(x: int) -> int:
     x = (x + 0x9E3779B97F4A7C15) & (2**64 - 1)
     x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
