@@ -505,12 +505,12 @@ def main():
 
     hbm_gbs, bf16_tf, peak_src = peaks()
     traffic = None
-    # ncu-measured DRAM bytes per launch of the dominant kernel: the newest profiles/*_traffic.json captured for this workload (written by
+    # ncu-measured DRAM bytes per launch of the dominant kernel: the latest (by round tag) profiles/r*_traffic.json captured for this workload (written by
     # tools/gpu_visit.sh from an `ncu --set full` capture of the same source tree; its "commit" field says which)
     traffic_src = None
     try:
         import glob
-        for fp in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')), key=os.path.getmtime, reverse=True):
+        for fp in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_traffic.json')), reverse=True):
             t = json.load(open(fp)).get('euler_fwd_tc_kernel<1,0>')
             if t and t['rows'] == M and t['steps'] == DEC_STEPS:
                 traffic, traffic_src = t['dram_bytes'], os.path.basename(fp)
