@@ -132,6 +132,10 @@ typedef struct {
  * are exact to 2^-11 (it grew by more than ~2^17 over max|incoming gradient|): gradients of this call may be clipped — rerun with
  * TRAJSDE_BWD_FLAG_EXACT_KERNELS or TRAJSDE_MODE_EXACT_F32. */
 #define TRAJSDE_STATUS_ADJOINT_RANGE 1
+/* trajsde_enc_bwd only: a CTA of the single-launch sweep waited ~2 s for a tile another CTA of the same launch had to hand over (the
+ * launch was not fully co-resident, e.g. the device is shared through MPS); the call's results are invalid — rerun with
+ * TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES. */
+#define TRAJSDE_STATUS_SWEEP_TIMEOUT 2
 
 /* TrajsdeEulerBwdArgs.flags */
 #define TRAJSDE_BWD_FLAG_EXACT_KERNELS 1 /* run the fp32 CUDA-core backward even in TC_F16 mode (A/B validation) */
@@ -140,6 +144,10 @@ typedef struct {
  * synchronisation); pays off under a winner-takes-all loss such as the reference's L2 (losses/L2.py:17-20: one of the 10 modes of an actor
  * receives a gradient).  Honoured by the tensor-core kernels with a single diffusion net; ignored otherwise. */
 #define TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS 2
+/* trajsde_enc_bwd: run the reverse sweep as 2 launches per iteration of the recurrence (GRU backward, SDE-step backward) instead of ONE
+ * persistent launch whose CTAs take the GRU / SDE roles and hand tiles to each other through global progress counters (A/B validation;
+ * also the path for devices where the launch cannot be fully co-resident). */
+#define TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES 4
 
 /* Backward kernels by mode: EXACT_F32 -> fp32 CUDA-core dgrad sweep + wgrad (euler_bwd_exact.cu).  TC_F16 with a single
  * diffusion net -> fused tensor-core dgrad+wgrad (euler_bwd_tc.cu; fp16 operands, fp32 accumulation, adjoint carried with a

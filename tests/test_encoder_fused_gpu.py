@@ -164,6 +164,52 @@ def test_fused_encoder_gradients_vs_fp64_autograd(rows, mixed):
         assert e < 3e-2, (n, e)
 
 
+@pytest.mark.parametrize('rows,mixed,philox', [(90, True, False), (700, True, True), (6500, True, False), (8000, False, True), (21504, True, True)])
+def test_single_launch_sweep_matches_per_step_launches(rows, mixed, philox):
+    """trajsde_enc_bwd's default form (ONE persistent launch, CTAs in GRU / SDE-step roles handing tiles over through progress counters,
+    enc_bwd_sweep.cu) against the per-iteration form (TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES): the per-row results (dL/dh0, dL/daa_out) are
+    the same arithmetic on the same tiles -> bit-identical; the weight gradients differ only in how the per-CTA partial sums are grouped.
+    Row counts cover one tile, fewer tiles than CTAs per role, and several tiles per CTA (the pipelined case); run twice for the
+    stale-counter / reuse-of-workspace case."""
+    from trajsde_b200 import ops
+    sde = init_like_reference(EncoderSDE(), seed=rows, bias_std=0.2).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), rows + 1, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(rows)
+    h0 = (torch.randn(rows, 64, generator=g) * 0.3).to(DEV)
+    aa = torch.randn(21, rows, 64, generator=g).to(DEV)
+    am = (torch.rand(rows, 21, generator=g) > 0.3).to(DEV)
+    nm = ((torch.rand(rows, generator=g) > 0.5) if mixed else torch.ones(rows, dtype=torch.bool)).to(DEV)
+    dW = None if philox else (torch.randn(21, rows, 64, generator=g) * 0.3).to(DEV)
+    cot = torch.randn(21, rows, 64, generator=g).to(DEV)
+    cot_g = torch.randn(21, rows, generator=g).to(DEV)
+    params = [p_ for net in (sde.f_func, sde.g_nus, sde.g_argo) for _, p_ in net.net.named_parameters()] + list(gru.parameters())
+
+    def run(per_step):
+        ops.ENC_BWD_PER_STEP = per_step
+        try:
+            h, a = h0.clone().requires_grad_(True), aa.clone().requires_grad_(True)
+            for p_ in params:
+                p_.grad = None
+            lat, gg = enc.encoder_recurrence(sde, gru, h, a, am, nm, dW=dW, mode='tc_f16', fused=True, seed=5)
+            ((lat * cot).sum() + (gg * cot_g).sum()).backward()
+            torch.cuda.synchronize()
+            return [h.grad, a.grad] + [None if p_.grad is None else p_.grad.clone() for p_ in params]
+        finally:
+            ops.ENC_BWD_PER_STEP = False
+
+    ref = run(True)
+    for rep in range(2):
+        got = run(False)
+        assert ops.backward_status(DEV) == 0
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), rep
+        for i, (x, r) in enumerate(zip(got[2:], ref[2:])):
+            if r is None or float(r.abs().max()) == 0.0:
+                assert x is None or float(x.abs().max()) == 0.0, i
+                continue
+            e = float((x - r).abs().max() / r.abs().max())
+            assert e < 2e-5, (i, e)
+
+
 @pytest.mark.parametrize('rows', [1, 130, 700])
 def test_gru_jump_forward_and_gradients(rows):
     """Stand-alone fused GRU_Unit jump (trajsde_gru_fwd / trajsde_gru_bwd) against the oracle's gru_ref and fp64 autograd."""

@@ -11,6 +11,7 @@ MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
 STATUS_ADJOINT_RANGE = 1
+STATUS_SWEEP_TIMEOUT = 2
 
 EXPORTED_SYMBOLS = (
     'trajsde_abi_version', 'trajsde_last_error_string', 'trajsde_device_sm_count',

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libtrajsde_b200.so')
-SOURCES = ['abi.cu', 'euler_exact.cu', 'euler_bwd_exact.cu', 'euler_bwd_tc.cu', 'gru_bwd.cu', 'gru_bwd_tc.cu', 'enc_bwd.cu', 'euler_tc.cu', 'enc_tc.cu', 'heads.cu', 'heads_bwd.cu', 'stage_ops.cu']
+SOURCES = ['abi.cu', 'euler_exact.cu', 'euler_bwd_exact.cu', 'euler_bwd_tc.cu', 'gru_bwd.cu', 'gru_bwd_tc.cu', 'enc_bwd.cu', 'enc_bwd_sweep.cu', 'euler_tc.cu', 'enc_tc.cu', 'heads.cu', 'heads_bwd.cu', 'stage_ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

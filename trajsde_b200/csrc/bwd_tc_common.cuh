@@ -77,6 +77,96 @@ __device__ __forceinline__ void to_own_row(uint8_t* stage4k, int lane, float4 (&
   __syncwarp();
 }
 
+// Same loads through L2 only (ld.global.cg): for rows another CTA of the SAME launch has written (the single-launch encoder sweep), where
+// the non-coherent path of ld_nc_f4 could return a stale line.
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void load_rows_coalesced_cg(const float* slab, int64_t row_stride, int64_t first_row, int64_t n_rows, int col,
+                                                       int lane, float4 (&dst)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = first_row + 4 * i + (lane >> 3);
+    dst[i] = r < n_rows ? ld_cg_f4(slab + r * row_stride + col + (lane & 7) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ---- single-launch encoder sweep (enc_bwd_sweep.cu): per-tile progress counters in global memory -------------------------------------
+// The GRU role and the SDE role(s) of the merged kernel hand a 128-row tile back and forth once per iteration of the recurrence:
+//   gru_done[tile]      = number of iterations whose GRU backward has written dL/dy1 of the tile       (S - i after iteration i)
+//   sde_done[pass][tile] = number of iterations whose SDE-step backward has written the carried adjoint of the tile (that pass's rows)
+// Writers: every epilogue thread stores its rows, CTA-local named barrier, then ONE thread publishes with st.release.gpu (the release is
+// cumulative over the stores ordered before it by the barrier — the split-K semaphore pattern; a __threadfence() per thread in front of the
+// barrier cost 2.5 us per GRU tile).
+// Readers: every thread polls with ld.acquire.gpu and then reads the rows with ld.global.cg.  All CTAs of the launch are co-resident (grid
+// <= SM count, one CTA per SM), so the polls cannot starve the producers; a bounded spin (about 2 s) plus a launch-wide abort word turns a
+// scheduling accident into a status bit instead of a hung GPU.
+struct SweepCtl {
+  int S;                       // iterations of the recurrence (0: not a sweep)
+  int32_t* gru_done;           // [num_tiles]
+  int32_t* sde_done[2];        // [num_tiles] per pass (sde_done[1] == NULL: single diffusion net)
+  int32_t* abort_word;         // launch-wide: set by the first wait that timed out
+  int32_t* status;             // TrajsdeEncBwdArgs.status or NULL
+  // SDE role: where iteration i finds its state and writes its result
+  const float* h0;             // state of iteration 0
+  const float* latent;         // [S][rows][64]: state of iteration i > 0 = latent[i-1]
+  float* carry;                // [rows][64]: dL/dy0 of iteration i > 0
+  float* grad_h0;              // dL/dy0 of iteration 0
+  int64_t slab;                // rows * 64
+};
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int32_t v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+#ifdef TRAJSDE_SWEEP_TIMELINE
+// debug build only (bench_micro/enc_bwd_ab.py --timeline): per CTA, thread 0: [0] kernel clocks, [1] clocks inside sweep_wait, [2] inside sweep_publish, [3] waits that blocked
+static __device__ long long g_sweep_tl[160 * 4];
+#define SWEEP_TL_ADD(slot, v) do { if (threadIdx.x == 0) g_sweep_tl[blockIdx.x * 4 + (slot)] += (v); } while (0)
+#else
+#define SWEEP_TL_ADD(slot, v) do { } while (0)
+#endif
+__device__ __forceinline__ void sweep_wait_(const SweepCtl& sw, const int32_t* counter, int32_t target) {
+  if (ld_acquire_gpu(counter) >= target) return;
+  SWEEP_TL_ADD(3, 1);
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(counter) < target) {
+    __nanosleep(40);
+    if ((++spins & 63u) == 0) {
+      if (*reinterpret_cast<volatile int32_t*>(sw.abort_word) != 0) return;
+      if (clock64() - t0 > (1ll << 32)) {                      // ~2 s at 1.9 GHz: give up, flag the call
+        atomicExch(sw.abort_word, 1);
+        if (sw.status) atomicOr(sw.status, TRAJSDE_STATUS_SWEEP_TIMEOUT);
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void sweep_wait(const SweepCtl& sw, const int32_t* counter, int32_t target) {
+#ifdef TRAJSDE_SWEEP_TIMELINE
+  const long long t0 = clock64();
+#endif
+  sweep_wait_(sw, counter, target);
+#ifdef TRAJSDE_SWEEP_TIMELINE
+  SWEEP_TL_ADD(1, clock64() - t0);
+#endif
+}
+// all `nthreads` callers have stored their rows of the tile: publish `value` on `counter`
+__device__ __forceinline__ void sweep_publish(int32_t* counter, int32_t value, uint32_t bar_id, uint32_t nthreads, bool leader) {
+#ifdef TRAJSDE_SWEEP_TIMELINE
+  const long long t0 = clock64();
+#endif
+  named_bar_sync(bar_id, nthreads);
+  if (leader) st_release_gpu(counter, value);
+#ifdef TRAJSDE_SWEEP_TIMELINE
+  SWEEP_TL_ADD(2, clock64() - t0);
+#endif
+}
+
 // Column sums over the warp's 32 rows: on return lane L holds sum over lanes of v[L] (butterfly transpose-reduce, 31 shuffles).
 __device__ __forceinline__ float colsum32(const float (&v)[32], int lane) {
   float a16[16], a8[8], a4[4], a2[2];

@@ -141,6 +141,12 @@ int launch_gru_standalone(const TrajsdeGruArgs& a, bool backward, cudaStream_t s
 int64_t gru_standalone_workspace_bytes(int64_t rows);
 int launch_gru_bwd_reduce(const float* partial, int n, const TrajsdeGruGrad& g, cudaStream_t s);
 int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s);
+// single-launch form of the sweep (enc_bwd_sweep.cu)
+int enc_bwd_sweep_grid(int64_t rows, bool dual, int* gg, int* gs);
+int64_t enc_bwd_sweep_counter_bytes(int64_t rows);
+int launch_enc_bwd_sweep(const TrajsdeEncBwdArgs& a, const TrajsdeEulerBwdArgs& b, const uint8_t* img0, const uint8_t* img1, const uint8_t* gru_img,
+                         const uint32_t* amax_bits, float* part0, float* part1, float* gru_part, float* gbuf, float* carry, int32_t* counters,
+                         int Gg, int Gs, cudaStream_t s);
 int64_t enc_bwd_workspace_bytes(int64_t rows, int32_t n_steps, int32_t dual);
 int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s);
 int64_t heads_workspace_bytes();

@@ -2,7 +2,9 @@
 // LocalEncoderSDESepPara2.forward (models/encoders/enc_hivt_nusargo_sde_sep2.py:128-182): n_steps x [sdeint_dual one Euler step
 // (models/utils/sdeint.py:110-197) + GRU_Unit jump (models/utils/ode_utils.py:136-152)].
 //
-// One C-ABI call = one reverse sweep over the iterations, enqueued from the host without any synchronisation:
+// One C-ABI call = one reverse sweep over the iterations.  Default: ONE persistent launch whose CTAs take the GRU / SDE-step roles and
+// hand tiles to each other (enc_bwd_sweep.cu).  With TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES / _EXACT_KERNELS, or more than 128 iterations, the
+// same sweep enqueued from the host without any synchronisation, two launches per iteration:
 //   for i = S-1 .. 0:   a_h   = carry (dL/dy0 of iteration i+1's SDE step) + dL/d latent[i]
 //                       GRU backward (gru_bwd_tc.cu; gru_bwd.cu = fp32 validation kernel):  a_h -> a_y1, dL/d aa_out[slot_i], GRU partials
 //                       SDE step backward (euler_bwd_tc.cu):  a_y1, dL/dg[i] -> carry, SDE weight-gradient partials (one pass per diffusion net, same launch)
@@ -34,10 +36,12 @@ struct Ws {
   float* part0;
   float* part1;
   float* gru_part;
+  int32_t* counters;   // per-tile progress counters of the single-launch sweep
   int64_t bytes;
 };
 
 int64_t align256(int64_t x) { return (x + 255) & ~255ll; }
+constexpr int64_t SWEEP_MAX_ROWS = 40960;   // measured: 2,688 rows 1.35 -> 0.98 ms, 21,504 rows 2.44 -> 2.03 ms, 86,016 rows 6.3 -> 7.0 ms (bench_micro/enc_bwd_ab.py)
 
 Ws carve(void* base, int64_t rows) {
   Ws w;
@@ -55,6 +59,7 @@ Ws carve(void* base, int64_t rows) {
   w.part0 = reinterpret_cast<float*>(take((int64_t)MAX_PARTIALS * G_PAD * 4));
   w.part1 = reinterpret_cast<float*>(take((int64_t)MAX_PARTIALS * G_PAD * 4));
   w.gru_part = reinterpret_cast<float*>(take((int64_t)MAX_PARTIALS * GRU_G_PAD * 4));
+  w.counters = reinterpret_cast<int32_t*>(take(enc_bwd_sweep_counter_bytes(rows)));
   w.bytes = off;
   return w;
 }
@@ -74,7 +79,12 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
   const int64_t slab = a.rows * 64;
   const bool dual = a.alt_mask != nullptr;
   const bool gru_tc = !(a.flags & TRAJSDE_BWD_FLAG_EXACT_KERNELS);   // fp32 GRU kernel kept for A/B validation
-  const int grid = bwd_tc_grid(a.rows, dual), ggrid = gru_tc ? bwd_tc_grid(a.rows) : gru_bwd_grid(a.rows);
+  // single launch: up to SWEEP_MAX_ROWS (beyond it every per-iteration kernel fills the device for long enough that the launches cost
+  // nothing, and the sweep's fixed split of the SMs between the roles can only lose); 128: step-table rows staged in shared memory
+  const bool sweep = gru_tc && !(a.flags & TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES) && S <= 128 && a.rows <= SWEEP_MAX_ROWS;
+  int Gg = 0, Gs = 0;
+  if (sweep && enc_bwd_sweep_grid(a.rows, dual, &Gg, &Gs) != 0) return set_error(TRAJSDE_ERR_CUDA, "cudaGetDevice failed");
+  const int grid = sweep ? Gs : bwd_tc_grid(a.rows, dual), ggrid = sweep ? Gg : gru_tc ? bwd_tc_grid(a.rows) : gru_bwd_grid(a.rows);
   int rc;
 
   enc_bwd_tables_kernel<<<1, 1, 0, s>>>(w.out_begin, w.out_w);
@@ -116,7 +126,14 @@ int launch_enc_bwd(const TrajsdeEncBwdArgs& a, cudaStream_t s) {
     if ((rc = bwd_tc_pack(b2, w.img1, s)) != 0) return rc;
   }
 
-  for (int i = S - 1; i >= 0; --i) {
+  if (sweep) {
+    b.sched.step_tab = a.sched.step_tab;
+    b.grad_g_last = a.grad_g;
+    if ((rc = launch_enc_bwd_sweep(a, b, w.img0, dual ? w.img1 : nullptr, w.gru_img, w.amax, w.part0, w.part1, w.gru_part, w.gbuf, w.carry,
+                                   w.counters, Gg, Gs, s)) != 0)
+      return rc;
+  }
+  for (int i = S - 1; i >= 0 && !sweep; --i) {
     const float* carry_in = i == S - 1 ? nullptr : w.carry;
     const float* glat = a.grad_latent ? a.grad_latent + (int64_t)i * slab : nullptr;
     rc = gru_tc ? launch_gru_bwd_tc(a.rows, a.y1 + (int64_t)i * slab, a.aa_out, slab, a.obs_mask, a.obs_mask_row_stride, a.slot, i, carry_in,

@@ -24,6 +24,9 @@ _KERNELS_PER_FWD = {_lib.MODE_EXACT_F32: 1, _lib.MODE_TC_F16: 2}   # TC: weight-
 
 # A/B switch (tests, bench): run the fp32 CUDA-core backward kernels even in 'tc_f16' mode (TRAJSDE_BWD_FLAG_EXACT_KERNELS)
 BWD_EXACT_KERNELS = False
+# A/B switch: run the encoder-recurrence backward as 2 launches per iteration instead of the single persistent launch
+# (TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES; also the escape hatch when the status word reports TRAJSDE_STATUS_SWEEP_TIMEOUT)
+ENC_BWD_PER_STEP = False
 # TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS: the tensor-core backward of a single-diffusion solve (the decoder) first finds the rows whose incoming
 # gradient is all zero (one scan of grad_ys on the device, no host sync) and sweeps only the others.  Exact (those rows contribute
 # nothing), and worth ~8x under the reference's winner-takes-all L2 loss (losses/L2.py:17-20: 1 of 10 modes per actor gets a gradient);
@@ -73,6 +76,12 @@ class _StatusMonitor:
         v = int(self.host[0])
         new_bits = v & ~self.seen
         self.seen |= v
+        if new_bits & _lib.STATUS_SWEEP_TIMEOUT:            # results of that call are invalid, whatever the policy
+            self.word.zero_()
+            self.seen = 0
+            raise RuntimeError("trajsde_b200: trajsde_enc_bwd reported TRAJSDE_STATUS_SWEEP_TIMEOUT — the single-launch encoder backward was "
+                               "not fully co-resident on the device (shared GPU?) and gave up after ~2 s; the gradients of that step are "
+                               "invalid.  Set trajsde_b200.ops.ENC_BWD_PER_STEP = True and rerun the step.")
         if new_bits & _lib.STATUS_ADJOINT_RANGE:
             pol = _POLICY['adjoint_range']
             if pol == 'raise':
@@ -478,7 +487,8 @@ def _enc_bwd_impl(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Te
     ggru = [torch.empty_like(p) for p in gs]
     a = _lib.EncBwdArgs()
     a.struct_bytes = C.sizeof(_lib.EncBwdArgs)
-    a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, 0
+    per_step = bool(ENC_BWD_PER_STEP) or S > 128 or rows > 40960      # mirrors enc_bwd.cu (launch accounting only)
+    a.mode, a.rows, a.dim, a.flags = _lib.MODE_TC_F16, rows, 64, (4 if per_step else 0)
     a.sched.n_steps, a.sched.n_outputs = S, 0
     a.sched.step_tab = step_tab.data_ptr()
     a.drift, a.diffusion = _mlp_struct(ps[0:6]), _mlp_struct(ps[6:12])
@@ -520,8 +530,9 @@ def _enc_bwd_impl(grad_latent: Optional[torch.Tensor], grad_g: Optional[torch.Te
         if rows > 0:
             _monitor(dev).snapshot()
     if rows > 0:
-        # tables + absmax x2 + pack per net + per iteration (GRU backward + one fused SDE backward per net) + two reduces
-        LAUNCHES['n'] += 3 + (2 if dual else 1) + S * 2 + 2 + int(grad_latent is not None and rows * S >= (1 << 16))
+        # tables + absmax x2 + GRU pack + pack per net + the sweep (one persistent launch, or per iteration a GRU backward + a fused SDE
+        # backward) + two reduces
+        LAUNCHES['n'] += 3 + (2 if dual else 1) + (S * 2 if per_step else 1) + 2 + int(grad_latent is not None and rows * S >= (1 << 16))
     return [grad_h0, grad_aa] + gparams + ggru
 
 
