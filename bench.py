@@ -189,7 +189,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--train-scenes', type=int, default=128, help='scenes per GPU of the fwd+bwd training step (reference batch 128, yml:106)')
     ap.add_argument('--no-train', action='store_true')
-    ap.add_argument('--no-graph', action='store_true', help='skip the CUDA-graph replay of the training step (single rank)')
+    ap.add_argument('--no-graph', action='store_true', help='skip the CUDA-graph replay of the training step')
+    ap.add_argument('--no-graph-ddp', action='store_true', help='N > 1: do not capture the training step (with its NCCL all-reduces) into a CUDA graph')
     ap.add_argument('--strong-scenes', type=int, default=8192, help='total scenes of the strong-scaling training entry (0 = skip)')
     ap.add_argument('--no-heads', action='store_true')
     ap.add_argument('--e2e-chunks', type=int, default=8, help='decoder row slices per e2e step (H2D / kernels / D2H overlap)')
@@ -450,7 +451,7 @@ def main():
             out = {"scenes_per_gpu": scenes_per_gpu, "global_scenes": gs, "ms_per_step": ms, "steps": k_train,
                    "agent_steps_per_s_fwd_bwd": world * twork / (ms * 1e-3), "scenes_per_s_fwd_bwd": world * scenes_per_gpu / (ms * 1e-3),
                    "allreduce_floats": (bk_dec.numel + bk_enc.numel) if world > 1 else 0, "gpu_launches_per_step": nl, "loss": loss_v}
-            if world == 1 and not args.no_graph:
+            if not args.no_graph and (world == 1 or not args.no_graph_ddp):
                 # the same step captured ONCE into a CUDA graph (~75 launches + the Python between them become one replay): the Philox key
                 # lives in device memory (trajsde_b200.set_device_seed) and is bumped inside the graph, so every replay draws fresh noise
                 word = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -462,22 +463,27 @@ def main():
                     word.add_(1)
                     return l_
 
-                side = torch.cuda.Stream(dev)
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    for _ in range(3):
-                        graph_body()
-                torch.cuda.current_stream(dev).wait_stream(side)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    loss_static = graph_body()
-                for _ in range(2):
-                    graph.replay()
-                ms_g = timed(lambda i: graph.replay(), k_train) / k_train
-                out.update(ms_per_step_cuda_graph=ms_g, scenes_per_s_fwd_bwd_cuda_graph=scenes_per_gpu / (ms_g * 1e-3),
-                           loss_cuda_graph=float(loss_static.detach()))
+                try:
+                    side = torch.cuda.Stream(dev)
+                    side.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            graph_body()
+                    torch.cuda.current_stream(dev).wait_stream(side)
+                    graph = torch.cuda.CUDAGraph()
+                    # thread_local: NCCL's watchdog thread may query its events while this thread captures (N > 1: the two bucket
+                    # all-reduces and their side-stream fork/join are captured with the step)
+                    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                        loss_static = graph_body()
+                    for _ in range(2):
+                        graph.replay()
+                    ms_g = timed(lambda i: graph.replay(), k_train) / k_train
+                    out.update(ms_per_step_cuda_graph=ms_g, scenes_per_s_fwd_bwd_cuda_graph=world * scenes_per_gpu / (ms_g * 1e-3),
+                               loss_cuda_graph=float(loss_static.detach()))
+                    del graph, loss_static
+                except RuntimeError as e:                      # the eager numbers above stand; say why the replay is missing
+                    out.update(ms_per_step_cuda_graph=None, cuda_graph_error=str(e).splitlines()[0][:200])
                 tb.set_device_seed(None)
-                del graph, loss_static
                 opt = opt_eager
             for p_ in dec_params + enc_params:
                 p_.grad = None
