@@ -331,21 +331,26 @@ typedef struct {
   const float* b2;   /* [2]     net[3].bias */
 } TrajsdeHead;
 
+/* TrajsdeHeadsArgs.flags / TrajsdeHeadsBwdArgs.flags: write (read the gradient of) the decoder's RESULT tensor instead of the two raw
+ * head outputs — out['loc'] = cat(loc, elu(scale) + 1.0 + min_scale) of dec_hivt_nusargo_sde.py:98-100, [rows, n_t, 4] contiguous at
+ * out[0] (grad_out[0]); needs n_heads == 2.  Deletes the ELU, the two adds and the cat (and their backward) from the caller's graph. */
+#define TRAJSDE_HEADS_FLAG_CAT4 1
+
 typedef struct {
   uint32_t struct_bytes;
   int32_t mode;              /* TRAJSDE_MODE_TC_F16 */
   int64_t rows;
   int32_t dim;               /* 64 */
-  int32_t flags;
+  int32_t flags;             /* TRAJSDE_HEADS_FLAG_* */
   int32_t n_t;               /* time slabs of x (60 for the reference decoder) */
   int32_t n_heads;           /* 1 (uncertain = False) or 2 */
   TrajsdeHead head[2];
   float ln_eps;              /* nn.LayerNorm eps (1e-5) */
-  float reserved;
+  float min_scale;           /* TRAJSDE_HEADS_FLAG_CAT4: self.min_scale of the decoder (yml: 1e-3) */
   const float* x;            /* element (t, row, c) at x + t * x_t_stride + row * x_row_stride + c; 16-byte aligned, strides % 4 == 0 */
   int64_t x_row_stride;
   int64_t x_t_stride;
-  float* out[2];             /* per head [rows, n_t, 2] contiguous */
+  float* out[2];             /* per head [rows, n_t, 2] contiguous; CAT4: out[0] = [rows, n_t, 4], out[1] unused */
   void* workspace;
   int64_t workspace_bytes;
 } TrajsdeHeadsArgs;
@@ -368,16 +373,17 @@ typedef struct {
   int32_t mode;              /* any TrajsdeMode (the arithmetic is fp32) */
   int64_t rows;
   int32_t dim;               /* 64 */
-  int32_t flags;
+  int32_t flags;             /* TRAJSDE_HEADS_FLAG_* */
   int32_t n_t;
   int32_t n_heads;           /* 1 or 2 */
   TrajsdeHead head[2];
   float ln_eps;
-  float reserved;
+  float min_scale;           /* unused (the ELU derivative needs only the recomputed raw scale) */
   const float* x;            /* as in TrajsdeHeadsArgs */
   int64_t x_row_stride;
   int64_t x_t_stride;
-  const float* grad_out[2];  /* per head dL/dout [rows, n_t, 2] contiguous, or NULL (no gradient reaches that head) */
+  const float* grad_out[2];  /* per head dL/dout [rows, n_t, 2] contiguous, or NULL (no gradient reaches that head); CAT4: grad_out[0] =
+                                dL/d out['loc'] [rows, n_t, 4] (channels 2..3 go through the ELU derivative), grad_out[1] unused */
   float* grad_x;             /* element (t, row, c) at grad_x + t * gx_t_stride + row * gx_row_stride + c; zero-filled by the caller */
   int64_t gx_row_stride;
   int64_t gx_t_stride;
@@ -420,6 +426,28 @@ typedef struct {
   void* workspace;           /* backward only */
   int64_t workspace_bytes;
 } TrajsdeAggrArgs;
+
+/* pi head: pi[n, m] = w2 . ReLU(LayerNorm(W1 [local_embed[n] ; global_embed[m, n]] + b1)) + b2
+ * replaces `self.pi(torch.cat((local_embed.expand(num_modes, ...), global_embed), dim=-1)).squeeze(-1).t()`
+ * (models/decoders/dec_hivt_nusargo_sde.py:63-67, 92-94).  Forward only: no loss of the reference configuration reads pi. */
+typedef struct {
+  uint32_t struct_bytes;
+  int32_t n_modes;
+  int64_t n_actors;
+  const float* global_embed; /* [n_modes, n_actors, 64] contiguous */
+  const float* local_embed;  /* [n_actors, 64] contiguous */
+  const float* w1;           /* [64, 128] pi[0].weight: columns 0..63 multiply local_embed, 64..127 global_embed */
+  const float* b1;           /* [64] */
+  const float* ln_g;         /* [64] pi[1].weight */
+  const float* ln_b;         /* [64] pi[1].bias */
+  const float* w2;           /* [64] pi[3].weight */
+  const float* b2;           /* [1]  pi[3].bias */
+  float ln_eps;
+  float reserved;
+  float* out;                /* [n_actors, n_modes] */
+} TrajsdePiArgs;
+
+int trajsde_pi_head_fwd(const TrajsdePiArgs* args, void* cuda_stream);
 
 int64_t trajsde_aggr_embed_workspace_bytes(int64_t n_modes, int64_t n_actors);
 int trajsde_aggr_embed_fwd(const TrajsdeAggrArgs* args, void* cuda_stream);

@@ -29,17 +29,19 @@ def test_struct_sizes_match_header(tmp_path):
     """ctypes mirrors must have the C sizes (compiled with gcc from the header)."""
     import subprocess
     src = tmp_path / 'sz.c'
-    src.write_text('#include "trajsde_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include "trajsde_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(TrajsdeEulerFwdArgs),sizeof(TrajsdeEulerBwdArgs),sizeof(TrajsdeSchedule),sizeof(TrajsdeNoise),'
                    'sizeof(TrajsdeMlp),sizeof(TrajsdeEncFwdArgs),sizeof(TrajsdeGru),sizeof(TrajsdeEncBwdArgs),'
-                   'sizeof(TrajsdeGruGrad),sizeof(TrajsdeGruArgs),sizeof(TrajsdeHead),sizeof(TrajsdeHeadsArgs),sizeof(TrajsdeHeadsBwdArgs));return 0;}\n')
+                   'sizeof(TrajsdeGruGrad),sizeof(TrajsdeGruArgs),sizeof(TrajsdeHead),sizeof(TrajsdeHeadsArgs),sizeof(TrajsdeHeadsBwdArgs),'
+                   'sizeof(TrajsdeAggrArgs),sizeof(TrajsdePiArgs),sizeof(TrajsdeL2Args),sizeof(TrajsdeBceArgs));return 0;}\n')
     exe = tmp_path / 'sz'
     subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)])
     sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     assert sizes == [C.sizeof(_lib.EulerFwdArgs), C.sizeof(_lib.EulerBwdArgs), C.sizeof(_lib.Schedule),
                      C.sizeof(_lib.Noise), C.sizeof(_lib.Mlp), C.sizeof(_lib.EncFwdArgs), C.sizeof(_lib.Gru),
                      C.sizeof(_lib.EncBwdArgs), C.sizeof(_lib.Gru), C.sizeof(_lib.GruArgs), C.sizeof(_lib.Head),
-                     C.sizeof(_lib.HeadsArgs), C.sizeof(_lib.HeadsBwdArgs)]
+                     C.sizeof(_lib.HeadsArgs), C.sizeof(_lib.HeadsBwdArgs), C.sizeof(_lib.AggrArgs), C.sizeof(_lib.PiArgs),
+                     C.sizeof(_lib.L2Args), C.sizeof(_lib.BceArgs)]
 
 
 def test_invalid_arguments_return_status_and_message():

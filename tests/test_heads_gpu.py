@@ -172,6 +172,47 @@ def test_heads_backward_vs_fp64_autograd(rows, T, frac, which):
             assert e < 1e-4, (h, k, e)
 
 
+@pytest.mark.parametrize('rows,T,frac', [(50, 7, 1.0), (300, 60, 0.1), (2000, 60, 0.03), (129, 1, 1.0)])
+def test_fused_result_cat4_forward_and_backward(rows, T, frac):
+    """TRAJSDE_HEADS_FLAG_CAT4: the heads kernel writes the stage's result out['loc'] = cat(loc, elu(scale) + 1 + min_scale) [rows, T, 4]
+    (dec…sde.py:98-100) and the heads backward takes dL/d out['loc'] (scale channels through the ELU derivative).  Forward: the loc
+    channels are bit-identical to the two-output launch, the scale channels equal torch's elu / add / add on its raw scale.  Backward:
+    fp64 autograd through the oracle heads + elu + cat (the kernel recomputes the raw scale in fp32, so its ELU derivative is the exact
+    one, not the derivative at the tensor-core forward value)."""
+    import torch.nn.functional as F
+    loc_h, sc_h = make_head(31).to(DEV), make_head(32).to(DEV)
+    with torch.no_grad():
+        sc_h[3].bias.sub_(0.5)                                  # both ELU branches populated
+    min_scale = 1e-3
+    g = torch.Generator().manual_seed(rows * 7 + T)
+    x = torch.randn(rows, T, 64, generator=g) * 2.0
+    cot = torch.randn(rows, T, 4, generator=g) * (torch.rand(rows, T, 1, generator=g) < frac)
+    cot[..., 2:] *= (torch.rand(rows, T, 1, generator=g) < 0.5)               # points active in loc only / in both
+
+    xd = x.double().clone().requires_grad_(True)
+    P = [{k: v.double().clone().requires_grad_(True) for k, v in params_of(h).items()} for h in (loc_h, sc_h)]
+    out_ref = torch.cat((so.decoder_loc_head_ref(P[0], xd), F.elu(so.decoder_loc_head_ref(P[1], xd)) + 1.0 + min_scale), dim=-1)
+    leaves = [xd] + [t for p in P for t in p.values()]
+    g_ref = torch.autograd.grad((out_ref * cot.double()).sum(), leaves)
+
+    xg = x.to(DEV).requires_grad_(True)
+    out, none = hd.decoder_heads(loc_h, sc_h, xg, cat_min_scale=min_scale)
+    assert none is None and out.shape == (rows, T, 4)
+    (out * cot.to(DEV)).sum().backward()
+    with torch.no_grad():
+        loc2, raw2 = hd.decoder_heads(loc_h, sc_h, xg.detach())
+        o_i, _ = hd.decoder_heads(loc_h, sc_h, xg.detach(), cat_min_scale=min_scale)       # inference path (no autograd node)
+    assert torch.equal(out.detach()[..., :2], loc2) and torch.equal(o_i, out.detach())
+    assert torch.allclose(out.detach()[..., 2:], F.elu(raw2) + 1.0 + min_scale, atol=2e-6, rtol=2e-6)
+    assert torch.allclose(out.detach().cpu().double(), out_ref.detach(), **TOL)
+    sc = out.detach()[..., 2:]
+    assert float((sc < 1.0 + min_scale).float().mean()) > 0.05 and float((sc > 1.0 + min_scale).float().mean()) > 0.05
+    got = [xg.grad] + [p_.grad for h in (loc_h, sc_h) for p_ in h.state_dict(keep_vars=True).values()]
+    for i, (a_, r_) in enumerate(zip(got, g_ref)):
+        e = float((a_.double().cpu() - r_).abs().max() / r_.abs().max())
+        assert e < 1e-4, (i, e)
+
+
 @pytest.mark.parametrize('rows_major', [True, False])
 def test_heads_from_solution_gradient_reaches_the_solver_in_place(rows_major):
     """decoder_heads_from_solution: heads on the solver's full ys; dL/dys comes back in ys's own layout (slab 0 zero) and the chain

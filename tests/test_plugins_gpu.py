@@ -52,7 +52,7 @@ def test_fused_decoder_stage_vs_reference_fixture(mode, golden_stage):
     le, ge = _t(d, 'local_embed').requires_grad_(True), _t(d, 'global_embed').requires_grad_(True)
     n0 = ops.LAUNCHES['n']
     out = dec({'padding_mask': _t(d, 'padding_mask')}, le, ge)
-    assert ops.LAUNCHES['n'] - n0 == (5 if mode == 'tc_f16' else 4)        # aggr_embed + (pack +) solve + pack + heads
+    assert ops.LAUNCHES['n'] - n0 == (6 if mode == 'tc_f16' else 5)        # aggr_embed + (pack +) solve + pack + heads + pi head
     err = float((out['loc'].detach().cpu() - torch.from_numpy(d['loc'])).abs().max())
     print(f"[{mode}] fused decoder stage: loc|scale max-abs {err:.3e}")
     assert err < (4e-3 if mode == 'exact' else 9e-3)                         # exact solve + tensor-core heads (3e-3) / tc solve + heads

@@ -47,6 +47,44 @@ def test_aggr_embed_shapes_vs_torch(modes, n):
     assert got.shape == want.shape and torch.allclose(got, want, atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize('modes,n', [(10, 1), (10, 777), (6, 20480), (10, 0)])
+def test_pi_head_vs_torch_module(modes, n):
+    """trajsde_pi_head_fwd (dec…sde.py:63-67, 92-94: the 4-layer pi head on cat(local.expand, global), squeezed and transposed) against
+    the nn.Sequential it replaces; then its autograd path (cold: torch recompute) against autograd through the module."""
+    mod = nn.Sequential(nn.Linear(128, 64), nn.LayerNorm(64), nn.ReLU(inplace=True), nn.Linear(64, 1)).to(DEV)
+    with torch.no_grad():
+        mod[1].weight.add_(0.1 * torch.randn(64, device=DEV)); mod[1].bias.add_(0.1 * torch.randn(64, device=DEV))
+        mod[3].bias.add_(0.3)
+    le, ge = torch.randn(n, 64, device=DEV), torch.randn(modes, n, 64, device=DEV)
+
+    def ref(le_, ge_):
+        return mod(torch.cat((le_.expand(modes, *le_.shape), ge_), dim=-1)).squeeze(-1).t()
+
+    with torch.no_grad():
+        got = stage.pi_head(mod, le, ge)
+        want = ref(le, ge)
+    assert got.shape == want.shape == (n, modes) and torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+    if n == 0:
+        return
+    cot = torch.randn(n, modes, device=DEV)
+    res = []
+    for fn in (lambda a, b: stage.pi_head(mod, a, b), ref):
+        for p_ in mod.parameters():
+            p_.grad = None
+        a, b = le.clone().requires_grad_(True), ge.clone().requires_grad_(True)
+        (fn(a, b) * cot).sum().backward()
+        res.append([a.grad, b.grad] + [p_.grad.clone() for p_ in mod.parameters()])
+    for x, r in zip(*res):
+        assert torch.allclose(x, r, atol=1e-5 * float(r.abs().max()) + 1e-7, rtol=1e-4)
+    # unused pi (the reference's training configuration): backward returns without touching the head
+    for p_ in mod.parameters():
+        p_.grad = None
+    a = le.clone().requires_grad_(True)
+    out = stage.pi_head(mod, a, ge)
+    (a.sum() + 0.0 * out.detach().sum()).backward()
+    assert all(p_.grad is None for p_ in mod.parameters())
+
+
 def test_l2_and_bce_vs_reference_fixture(golden_stage):
     d = golden_stage
     loc = _t(d, 'loc').requires_grad_(True)

@@ -12,6 +12,7 @@ MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
 STATUS_ADJOINT_RANGE = 1
 STATUS_SWEEP_TIMEOUT = 2
+HEADS_FLAG_CAT4 = 1
 
 EXPORTED_SYMBOLS = (
     'trajsde_abi_version', 'trajsde_last_error_string', 'trajsde_device_sm_count',
@@ -21,7 +22,7 @@ EXPORTED_SYMBOLS = (
     'trajsde_enc_bwd_workspace_bytes', 'trajsde_enc_bwd',
     'trajsde_gru_workspace_bytes', 'trajsde_gru_fwd', 'trajsde_gru_bwd',
     'trajsde_heads_workspace_bytes', 'trajsde_heads_fwd', 'trajsde_heads_bwd_workspace_bytes', 'trajsde_heads_bwd',
-    'trajsde_aggr_embed_workspace_bytes', 'trajsde_aggr_embed_fwd', 'trajsde_aggr_embed_bwd',
+    'trajsde_aggr_embed_workspace_bytes', 'trajsde_aggr_embed_fwd', 'trajsde_aggr_embed_bwd', 'trajsde_pi_head_fwd',
     'trajsde_l2_loss_workspace_bytes', 'trajsde_l2_loss_fwd', 'trajsde_l2_loss_bwd', 'trajsde_diff_bce_workspace_bytes', 'trajsde_diff_bce',
 )
 
@@ -96,14 +97,14 @@ class Head(C.Structure):
 class HeadsArgs(C.Structure):
     _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
                 ('flags', C.c_int32), ('n_t', C.c_int32), ('n_heads', C.c_int32), ('head', Head * 2), ('ln_eps', C.c_float),
-                ('reserved', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('out', _fp * 2),
+                ('min_scale', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('out', _fp * 2),
                 ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 class HeadsBwdArgs(C.Structure):
     _fields_ = [('struct_bytes', C.c_uint32), ('mode', C.c_int32), ('rows', C.c_int64), ('dim', C.c_int32),
                 ('flags', C.c_int32), ('n_t', C.c_int32), ('n_heads', C.c_int32), ('head', Head * 2), ('ln_eps', C.c_float),
-                ('reserved', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('grad_out', _fp * 2),
+                ('min_scale', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('grad_out', _fp * 2),
                 ('grad_x', _fp), ('gx_row_stride', C.c_int64), ('gx_t_stride', C.c_int64), ('grad_head', Head * 2),
                 ('row_flags', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
@@ -113,6 +114,12 @@ class AggrArgs(C.Structure):
                 ('w', _fp), ('b', _fp), ('ln_g', _fp), ('ln_b', _fp), ('ln_eps', C.c_float), ('reserved', C.c_float), ('out', _fp),
                 ('grad_out', _fp), ('grad_global', _fp), ('grad_local', _fp), ('grad_w', _fp), ('grad_b', _fp), ('grad_ln_g', _fp),
                 ('grad_ln_b', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+
+
+class PiArgs(C.Structure):
+    _fields_ = [('struct_bytes', C.c_uint32), ('n_modes', C.c_int32), ('n_actors', C.c_int64), ('global_embed', _fp), ('local_embed', _fp),
+                ('w1', _fp), ('b1', _fp), ('ln_g', _fp), ('ln_b', _fp), ('w2', _fp), ('b2', _fp), ('ln_eps', C.c_float),
+                ('reserved', C.c_float), ('out', _fp)]
 
 
 class L2Args(C.Structure):
@@ -185,6 +192,8 @@ def lib():
         for f in (L.trajsde_aggr_embed_fwd, L.trajsde_aggr_embed_bwd):
             f.restype = C.c_int
             f.argtypes = [C.POINTER(AggrArgs), C.c_void_p]
+        L.trajsde_pi_head_fwd.restype = C.c_int
+        L.trajsde_pi_head_fwd.argtypes = [C.POINTER(PiArgs), C.c_void_p]
         L.trajsde_l2_loss_workspace_bytes.restype = C.c_int64
         L.trajsde_l2_loss_workspace_bytes.argtypes = [C.c_int64]
         for f in (L.trajsde_l2_loss_fwd, L.trajsde_l2_loss_bwd):

@@ -303,8 +303,13 @@ int trajsde_heads_fwd(const TrajsdeHeadsArgs* a, void* cuda_stream) {
     const TrajsdeHead& hd = a->head[h];
     if (!hd.w1 || !hd.b1 || !hd.ln_g || !hd.ln_b || !hd.w2 || !hd.b2)
       return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "head[%d]: null parameter pointer", h);
-    if (a->rows > 0 && a->n_t > 0 && !a->out[h]) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "out[%d] null", h);
+    const bool needs_out = h == 0 || !(a->flags & TRAJSDE_HEADS_FLAG_CAT4);
+    if (a->rows > 0 && a->n_t > 0 && needs_out && !a->out[h]) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "out[%d] null", h);
   }
+  if ((a->flags & TRAJSDE_HEADS_FLAG_CAT4) && a->n_heads != 2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "TRAJSDE_HEADS_FLAG_CAT4 needs n_heads == 2 (loc and scale)");
+  if ((a->flags & TRAJSDE_HEADS_FLAG_CAT4) && a->out[0] && (reinterpret_cast<uintptr_t>(a->out[0]) & 7u))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "out[0] must be 8-byte aligned");
   if (a->rows == 0 || a->n_t == 0) return TRAJSDE_OK;
   if (!a->x || !aligned16(a->x) || (a->x_row_stride & 3) != 0 || (a->x_t_stride & 3) != 0 || a->x_row_stride < 64 || a->x_t_stride < 64)
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "x must be 16-byte aligned with row / t strides that are multiples of 4 elements and >= 64");
@@ -338,6 +343,8 @@ int trajsde_heads_bwd(const TrajsdeHeadsBwdArgs* a, void* cuda_stream) {
     if (a->grad_out[h] && (reinterpret_cast<uintptr_t>(a->grad_out[h]) & 7u))
       return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_out[%d] must be 8-byte aligned", h);
   }
+  if ((a->flags & TRAJSDE_HEADS_FLAG_CAT4) && a->n_heads != 2)
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "TRAJSDE_HEADS_FLAG_CAT4 needs n_heads == 2 (loc and scale)");
   const bool empty = a->rows == 0 || a->n_t == 0;
   if (!empty) {
     if (!a->x || !aligned16(a->x) || (a->x_row_stride & 3) != 0 || (a->x_t_stride & 3) != 0)
@@ -383,6 +390,21 @@ static int aggr_call(const TrajsdeAggrArgs* a, void* cuda_stream, bool backward)
 }
 int trajsde_aggr_embed_fwd(const TrajsdeAggrArgs* a, void* cuda_stream) { return aggr_call(a, cuda_stream, false); }
 int trajsde_aggr_embed_bwd(const TrajsdeAggrArgs* a, void* cuda_stream) { return aggr_call(a, cuda_stream, true); }
+
+int trajsde_pi_head_fwd(const TrajsdePiArgs* a, void* cuda_stream) {
+  if (!a) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "args == NULL");
+  if (a->struct_bytes != sizeof(TrajsdePiArgs))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "struct_bytes %u != %zu (ABI mismatch)", a->struct_bytes, sizeof(TrajsdePiArgs));
+  if (a->n_modes < 0 || a->n_actors < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_modes / n_actors < 0");
+  if (!a->w1 || !a->b1 || !a->ln_g || !a->ln_b || !a->w2 || !a->b2) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null parameter pointer");
+  const bool empty = a->n_modes == 0 || a->n_actors == 0;
+  if (!empty && (!a->global_embed || !a->local_embed || !aligned16(a->global_embed) || !aligned16(a->local_embed)))
+    return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "global_embed / local_embed null or misaligned");
+  if (!empty && !a->out) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "out null");
+  int rc;
+  if ((rc = check_device()) != 0) return rc;
+  return launch_pi_head(*a, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
 
 int64_t trajsde_l2_loss_workspace_bytes(int64_t n_actors) {
   if (n_actors < 0) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "n_actors < 0");

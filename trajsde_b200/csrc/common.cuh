@@ -152,6 +152,7 @@ int launch_heads_fwd(const TrajsdeHeadsArgs& a, cudaStream_t s);
 int64_t heads_workspace_bytes();
 int launch_compact_rows(const uint8_t* flags, int64_t rows, int32_t* row_map, int32_t* n_active, cudaStream_t s);
 int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s);
+int launch_pi_head(const TrajsdePiArgs& a, cudaStream_t s);
 int64_t aggr_workspace_bytes(int64_t n_modes, int64_t n_actors);
 int launch_l2_loss(const TrajsdeL2Args& a, bool backward, cudaStream_t s);
 int64_t l2_workspace_bytes(int64_t n_actors);

@@ -152,7 +152,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
     const uint32_t row = quad * 32 + lane;
     const uint32_t tml = tmem_base + ((uint32_t)(quad * 32) << 16);
     const bool head_on = (int)hh < a.n_heads;
-    float* outp = head_on ? a.out[hh] : nullptr;
+    const bool cat4 = (a.flags & TRAJSDE_HEADS_FLAG_CAT4) != 0;   // both heads write one [rows, n_t, 4] result (dec…sde.py:98-100)
+    float* outp = head_on ? (cat4 ? a.out[0] + 2 * hh : a.out[hh]) : nullptr;
+    const int64_t ostride = cat4 ? 4 : 2;
     uint32_t par_acc = 0;
 
     // fp32 tile (this thread's 32 channels) -> fp16 pairs -> operand buffer `ab` in tensor memory; releases the smem buffer
@@ -234,9 +236,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) heads_fwd_kernel(const HeadsPa
           o0a = fmaf(r0, wa.x, o0a); o0b = fmaf(r1, wa.y, o0b); o0a = fmaf(r2, wa.z, o0a); o0b = fmaf(r3, wa.w, o0b);
           o1a = fmaf(r0, wb.x, o1a); o1b = fmaf(r1, wb.y, o1b); o1a = fmaf(r2, wb.z, o1a); o1b = fmaf(r3, wb.w, o1b);
         }
-        const float o0 = o0a + o0b, o1 = o1a + o1b;
+        float o0 = o0a + o0b, o1 = o1a + o1b;
+        if (cat4 && hh == 1) {                               // F.elu_(scale) + 1.0, then + min_scale (same order of the fp32 adds)
+          o0 = ((o0 > 0.f ? o0 : expf(o0) - 1.f) + 1.0f) + a.min_scale;
+          o1 = ((o1 > 0.f ? o1 : expf(o1) - 1.f) + 1.0f) + a.min_scale;
+        }
         const int64_t grow = (int64_t)rt * TILE_M + row;
-        if (grow < a.rows) *reinterpret_cast<float2*>(outp + (grow * a.n_t + t) * 2) = make_float2(o0, o1);
+        if (grow < a.rows) *reinterpret_cast<float2*>(outp + (grow * a.n_t + t) * ostride) = make_float2(o0, o1);
       }
     }
   } else if (warp == WARP_MMA) {

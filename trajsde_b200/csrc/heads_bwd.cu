@@ -30,6 +30,8 @@ struct HeadsBwdParams {
   TrajsdeHeadsBwdArgs a;
   float* partial;        // [grid][2][HG_PAD]
   int64_t n_points;      // rows * n_t
+  int gstride;           // floats between consecutive points of a.grad_out[h]: 2, or 4 in CAT4 mode (a.grad_out[1] = a.grad_out[0] + 2 then)
+  int elu_head1;         // CAT4: head 1's incoming gradient goes through the derivative of elu(raw) + 1 + min_scale first
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(xs + pt * HB_LD + 16 * qq + 4 * i) = ok ? ld4(src + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (qq == 0) {
-        const float2 d = ok ? *reinterpret_cast<const float2*>(a.grad_out[h] + pid * 2) : make_float2(0.f, 0.f);
+        const float2 d = ok ? *reinterpret_cast<const float2*>(a.grad_out[h] + pid * p.gstride) : make_float2(0.f, 0.f);
         dsc[2 * pt] = d.x;
         dsc[2 * pt + 1] = d.y;
       }
@@ -144,7 +146,30 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
       v2 += __shfl_xor_sync(0xffffffffu, v2, 1);
       v2 += __shfl_xor_sync(0xffffffffu, v2, 2);
       const float rstd = 1.0f / sqrtf(v2 * (1.0f / 64.0f) + a.ln_eps);
-      const float d0 = dsc[2 * pt], d1 = dsc[2 * pt + 1];
+      float d0 = dsc[2 * pt], d1 = dsc[2 * pt + 1];
+      if (p.elu_head1 && h == 1) {                             // block-uniform.  d/draw [elu(raw) + 1 + min_scale] = raw > 0 ? 1 : exp(raw)
+        float r0 = 0.f, r1 = 0.f;                              // raw = W2 relu(LayerNorm(z)) + b2, recomputed (4 threads per point)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = 16 * qq + i;
+          const float actv = fmaxf(fmaf(vg[c], z[i] * rstd, vbeta[c]), 0.f);
+          r0 = fmaf(vw2[c], actv, r0);
+          r1 = fmaf(vw2[64 + c], actv, r1);
+        }
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        r0 += a.head[1].b2[0];
+        r1 += a.head[1].b2[1];
+        d0 *= r0 > 0.f ? 1.f : expf(r0);
+        d1 *= r1 > 0.f ? 1.f : expf(r1);
+        __syncwarp();                                          // the point's four threads (same warp) have read the incoming gradient
+        if (qq == 0) {                                         // the dW2 / db2 sums below use dL/draw
+          dsc[2 * pt] = d0;
+          dsc[2 * pt + 1] = d1;
+        }
+      }
       float dzh[16], s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -243,7 +268,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
       if (h >= n_heads || !a.grad_out[h]) continue;
       bool act = false;
       if (pid < p_hi) {
-        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * 2);
+        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * p.gstride);
         act = d.x != 0.f || d.y != 0.f;
       }
       const unsigned m = __ballot_sync(0xffffffffu, act);
@@ -316,13 +341,13 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
 }
 
 // row_flags mode, pass 1: flags[r] = 1 if any point of row r carries a gradient in any head (flags zeroed by a memset before)
-__global__ void heads_row_flags_kernel(const TrajsdeHeadsBwdArgs a, int64_t n_points) {
+__global__ void heads_row_flags_kernel(const TrajsdeHeadsBwdArgs a, int64_t n_points, int gstride) {
   for (int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid < n_points; pid += (int64_t)gridDim.x * blockDim.x) {
     bool act = false;
 #pragma unroll
     for (int h = 0; h < 2; ++h)
       if (h < a.n_heads && a.grad_out[h]) {
-        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * 2);
+        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * gstride);
         act = act || d.x != 0.f || d.y != 0.f;
       }
     if (act) a.row_flags[pid / a.n_t] = 1;                     // benign race: every writer stores the same value
@@ -376,6 +401,10 @@ int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s) {
   p.a = a;
   p.partial = static_cast<float*>(a.workspace);
   p.n_points = a.rows * (int64_t)a.n_t;
+  const bool cat4 = (a.flags & TRAJSDE_HEADS_FLAG_CAT4) != 0;
+  p.gstride = cat4 ? 4 : 2;
+  p.elu_head1 = cat4 ? 1 : 0;
+  if (cat4) p.a.grad_out[1] = a.grad_out[0] ? a.grad_out[0] + 2 : nullptr;   // channels 2..3 of dL/d out['loc']
   int grid = heads_bwd_grid();
   if (grid <= 0) return set_error(TRAJSDE_ERR_CUDA, "device attributes unavailable");
   const int64_t chunks = (p.n_points + HB_THREADS - 1) / HB_THREADS;
@@ -383,7 +412,7 @@ int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s) {
   if (a.row_flags && a.rows > 0) {
     TS_CUDA_CHECK(cudaMemsetAsync(a.row_flags, 0, (size_t)a.rows, s));
     if (p.n_points > 0) {
-      heads_row_flags_kernel<<<grid, HB_THREADS, 0, s>>>(a, p.n_points);
+      heads_row_flags_kernel<<<grid, HB_THREADS, 0, s>>>(p.a, p.n_points, p.gstride);
       TS_CUDA_CHECK(cudaGetLastError());
       heads_zero_rows_kernel<<<grid, HB_THREADS, 0, s>>>(a);
       TS_CUDA_CHECK(cudaGetLastError());

@@ -4,6 +4,10 @@
 //                rows = modes x actors; the reference materialises cat(global, local.expand(modes, ...)) [modes, N, 128] and runs
 //                Linear / LayerNorm / ReLU as separate passes — here one pass reads both embeddings and writes y0 [modes*N, 64].
 //                Backward: dL/dglobal, dL/dlocal (summed over the modes in a fixed order), dL/dW, db, dgamma, dbeta.
+//   pi           mode scores pi[n, m] = w2 . ReLU(LayerNorm(W1 [local_embed[n] ; global_embed[m, n]] + b1)) + b2      dec…sde.py:63-67, 92-94
+//                same inputs and first layer shape as aggr_embed (the cat order is swapped): the forward kernel with a 64 -> 1 projection
+//                behind it instead of the store.  Forward only — no loss of the reference configuration reads pi (losses L2 + DiffBCE,
+//                yml:78-80; pi feeds the test-time metrics), so its rarely needed backward stays with autograd (trajsde_b200/stage.py).
 //   L2           winner-takes-all displacement loss                                          losses/L2.py:10-27
 //                per actor: best mode = argmin_m mean_t (masked) ||y - loc_m|| ; loss = mean over valid (actor, slot) of the best mode's
 //                displacement.  One warp per actor; the backward writes (loc - y) / ||loc - y|| / count for the best mode only.
@@ -87,12 +91,16 @@ __device__ __forceinline__ float ln_rows16(float (&z)[16], float eps) {
   return rstd;
 }
 
-__device__ __forceinline__ void aggr_stage_weights(const TrajsdeAggrArgs& a, float* ws, float* vecs, int tid) {
-  for (int i = tid; i < 64 * 128; i += SO_THREADS) ws[(i >> 7) * LDX + (i & 127)] = a.w[i];
+// swap_halves: the weight's input columns are [local | global] (pi head) while the X tile is always staged [global | local]
+__device__ __forceinline__ void aggr_stage_weights(const TrajsdeAggrArgs& a, float* ws, float* vecs, int tid, bool swap_halves = false) {
+  for (int i = tid; i < 64 * 128; i += SO_THREADS) ws[(i >> 7) * LDX + (swap_halves ? (i & 127) ^ 64 : (i & 127))] = a.w[i];
   for (int i = tid; i < 192; i += SO_THREADS) vecs[i] = i < 64 ? a.b[i] : i < 128 ? a.ln_g[i - 64] : a.ln_b[i - 128];
 }
 
-__global__ void __launch_bounds__(SO_THREADS, 2) aggr_embed_fwd_kernel(const TrajsdeAggrArgs a) {
+// PI: `a` carries the pi head's first layer; w2 [64], b2 [1] its projection; pi_out [n_actors, n_modes] (the .squeeze(-1).t() of :94)
+template <bool PI>
+__global__ void __launch_bounds__(SO_THREADS, 2) aggr_embed_fwd_kernel(const TrajsdeAggrArgs a, const float* __restrict__ w2,
+                                                                        const float* __restrict__ b2, float* __restrict__ pi_out) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* ws = reinterpret_cast<float*>(smem);      // [64][LDX]
   float* xs = ws + 64 * LDX;                       // [64][LDX]
@@ -100,8 +108,13 @@ __global__ void __launch_bounds__(SO_THREADS, 2) aggr_embed_fwd_kernel(const Tra
   float* vecs = zs + SO_TILE * LDZ;                // b | gamma | beta
   const int tid = threadIdx.x;
   const int64_t rows = (int64_t)a.n_modes * a.n_actors;
-  aggr_stage_weights(a, ws, vecs, tid);
+  aggr_stage_weights(a, ws, vecs, tid, PI);
   const int pt = tid >> 2, qq = tid & 3;
+  float w2r[16];
+  if (PI) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w2r[i] = w2[16 * qq + i];
+  }
   for (int64_t row0 = (int64_t)blockIdx.x * SO_TILE; row0 < rows; row0 += (int64_t)gridDim.x * SO_TILE) {
     __syncthreads();
     aggr_load_x(a, row0, rows, xs, tid);
@@ -115,6 +128,16 @@ __global__ void __launch_bounds__(SO_THREADS, 2) aggr_embed_fwd_kernel(const Tra
       z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w;
     }
     ln_rows16(z, a.ln_eps);
+    if (PI) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s = fmaf(fmaxf(fmaf(vecs[64 + 16 * qq + i], z[i], vecs[128 + 16 * qq + i]), 0.f), w2r[i], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const int64_t r = row0 + pt;
+      if (qq == 0 && r < rows) pi_out[(r % a.n_actors) * a.n_modes + r / a.n_actors] = s + b2[0];
+      continue;
+    }
     if (row0 + pt < rows) {
       float* dst = a.out + (row0 + pt) * 64 + 16 * qq;
 #pragma unroll
@@ -432,8 +455,8 @@ int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s) {
   const int64_t tiles = (rows + SO_TILE - 1) / SO_TILE;
   if (!backward) {
     if (rows == 0) return TRAJSDE_OK;
-    TS_CUDA_CHECK(cudaFuncSetAttribute(aggr_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGGR_FWD_SMEM));
-    aggr_embed_fwd_kernel<<<(int)(tiles < 2 * sms ? tiles : 2 * sms), SO_THREADS, AGGR_FWD_SMEM, s>>>(a);
+    TS_CUDA_CHECK(cudaFuncSetAttribute(aggr_embed_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGGR_FWD_SMEM));
+    aggr_embed_fwd_kernel<false><<<(int)(tiles < 2 * sms ? tiles : 2 * sms), SO_THREADS, AGGR_FWD_SMEM, s>>>(a, nullptr, nullptr, nullptr);
     TS_CUDA_CHECK(cudaGetLastError());
     return TRAJSDE_OK;
   }
@@ -463,6 +486,29 @@ int launch_aggr_embed(const TrajsdeAggrArgs& a, bool backward, cudaStream_t s) {
     aggr_reduce_modes_kernel<<<(int)((a.n_actors * 16 + 255) / 256), 256, 0, s>>>(local_rows, a.n_modes, a.n_actors, a.grad_local);
     TS_CUDA_CHECK(cudaGetLastError());
   }
+  return TRAJSDE_OK;
+}
+
+int launch_pi_head(const TrajsdePiArgs& p, cudaStream_t s) {
+  const int64_t rows = (int64_t)p.n_modes * p.n_actors;
+  if (rows == 0) return TRAJSDE_OK;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(TRAJSDE_ERR_CUDA, "device attributes unavailable");
+  TrajsdeAggrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_modes = p.n_modes;
+  a.n_actors = p.n_actors;
+  a.global_embed = p.global_embed;
+  a.local_embed = p.local_embed;
+  a.w = p.w1;
+  a.b = p.b1;
+  a.ln_g = p.ln_g;
+  a.ln_b = p.ln_b;
+  a.ln_eps = p.ln_eps;
+  const int64_t tiles = (rows + SO_TILE - 1) / SO_TILE;
+  TS_CUDA_CHECK(cudaFuncSetAttribute(aggr_embed_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AGGR_FWD_SMEM));
+  aggr_embed_fwd_kernel<true><<<(int)(tiles < 2 * sms ? tiles : 2 * sms), SO_THREADS, AGGR_FWD_SMEM, s>>>(a, p.w2, p.b2, p.out);
+  TS_CUDA_CHECK(cudaGetLastError());
   return TRAJSDE_OK;
 }
 

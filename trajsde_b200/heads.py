@@ -29,8 +29,11 @@ def head_params(head: torch.nn.Module) -> List[torch.Tensor]:
     return ps
 
 
-def _heads_fwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
-    """x[rows, T, 64] (last dim unit-stride) -> (out0[rows, T, 2], out1[rows, T, 2]); out1 is empty when n_heads == 1."""
+def _heads_fwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float,
+                    cat4: Optional[float] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x[rows, T, 64] (last dim unit-stride) -> (out0[rows, T, 2], out1[rows, T, 2]); out1 is empty when n_heads == 1.
+    ``cat4`` = the decoder's ``min_scale``: out0 is the stage's result ``cat(loc, elu(scale) + 1 + min_scale)`` [rows, T, 4]
+    (dec_hivt_nusargo_sde.py:98-100, TRAJSDE_HEADS_FLAG_CAT4) and out1 is empty."""
     if x.dim() != 3 or x.shape[2] != 64 or x.dtype != torch.float32 or (x.numel() > 0 and x.stride(2) != 1):
         raise ValueError("`sol_y` must be float32 of shape (rows, T, 64) with a unit-stride last dimension")
     if n_heads not in (1, 2) or len(params) != 6 * n_heads:
@@ -40,19 +43,26 @@ def _heads_fwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, l
     ps = [p.detach().contiguous() for p in params]
     a = _lib.HeadsArgs()
     a.struct_bytes = C.sizeof(_lib.HeadsArgs)
-    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, 0, T, n_heads
+    if cat4 is not None and n_heads != 2:
+        raise ValueError("the fused out['loc'] result needs both heads (uncertain=True)")
+    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, (_lib.HEADS_FLAG_CAT4 if cat4 is not None else 0), T, n_heads
     for h in range(n_heads):
         for name, t in zip(('w1', 'b1', 'ln_g', 'ln_b', 'w2', 'b2'), ps[6 * h:6 * h + 6]):
             setattr(a.head[h], name, t.data_ptr())
     a.ln_eps = ln_eps
+    a.min_scale = 0.0 if cat4 is None else float(cat4)
     xd = x.detach()
     if rows > 0 and T > 0 and (xd.data_ptr() % 16 != 0 or xd.stride(0) % 4 != 0 or xd.stride(1) % 4 != 0):
         xd = xd.contiguous()
     a.x, a.x_row_stride, a.x_t_stride = xd.data_ptr(), max(xd.stride(0), 64), max(xd.stride(1), 64)
-    outs = [torch.empty((rows, T, 2), dtype=torch.float32, device=dev),
-            torch.empty((rows, T, 2) if n_heads == 2 else (0, T, 2), dtype=torch.float32, device=dev)]
-    for h in range(n_heads):
-        a.out[h] = outs[h].data_ptr()
+    if cat4 is not None:
+        outs = [torch.empty((rows, T, 4), dtype=torch.float32, device=dev), torch.empty((0, T, 2), dtype=torch.float32, device=dev)]
+        a.out[0] = outs[0].data_ptr()
+    else:
+        outs = [torch.empty((rows, T, 2), dtype=torch.float32, device=dev),
+                torch.empty((rows, T, 2) if n_heads == 2 else (0, T, 2), dtype=torch.float32, device=dev)]
+        for h in range(n_heads):
+            a.out[h] = outs[h].data_ptr()
     L = _lib.lib()
     need = _lib.check(L.trajsde_heads_workspace_bytes(_lib.MODE_TC_F16), "trajsde_heads_workspace_bytes")
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
@@ -68,22 +78,26 @@ heads_fwd = torch.library.custom_op("trajsde::heads_fwd", _heads_fwd_impl, mutat
 
 
 @heads_fwd.register_fake
-def _(x, params, n_heads, ln_eps):
+def _(x, params, n_heads, ln_eps, cat4=None):
     rows, T = x.shape[0], x.shape[1]
+    if cat4 is not None:
+        return x.new_empty((rows, T, 4)), x.new_empty((0, T, 2))
     return x.new_empty((rows, T, 2)), x.new_empty((rows, T, 2) if n_heads == 2 else (0, T, 2))
 
 
 def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float, grad0: Optional[torch.Tensor],
-                    grad1: Optional[torch.Tensor], grad_x: torch.Tensor, row_flags: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                    grad1: Optional[torch.Tensor], grad_x: torch.Tensor, row_flags: Optional[torch.Tensor] = None,
+                    cat4: bool = False) -> List[torch.Tensor]:
     """Gradients of the 6 * n_heads head tensors; dL/dx is ACCUMULATED into the zero-filled ``grad_x`` (same shape as x, any row / t
-    strides, unit channel stride) for the points that carry a non-zero dL/dout.  ``grad_h`` [rows, T, 2] or None per head."""
+    strides, unit channel stride) for the points that carry a non-zero dL/dout.  ``grad_h`` [rows, T, 2] or None per head.
+    ``cat4``: ``grad0`` is dL/d out['loc'] [rows, T, 4] of the fused result (channels 2..3 pass through the ELU derivative)."""
     rows, T = x.shape[0], x.shape[1]
     dev = x.device
     ps = [p.detach().contiguous() for p in params]
     gps = [torch.empty_like(p) for p in ps]
     a = _lib.HeadsBwdArgs()
     a.struct_bytes = C.sizeof(_lib.HeadsBwdArgs)
-    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, 0, T, n_heads
+    a.mode, a.rows, a.dim, a.flags, a.n_t, a.n_heads = _lib.MODE_TC_F16, rows, 64, (_lib.HEADS_FLAG_CAT4 if cat4 else 0), T, n_heads
     for h in range(n_heads):
         for name, t, g in zip(('w1', 'b1', 'ln_g', 'ln_b', 'w2', 'b2'), ps[6 * h:6 * h + 6], gps[6 * h:6 * h + 6]):
             setattr(a.head[h], name, t.data_ptr())
@@ -120,26 +134,26 @@ class _HeadsFn(torch.autograd.Function):
     so autograd has no slice-backward copy to make."""
 
     @staticmethod
-    def forward(ctx, x, full, n_heads, ln_eps, *params):
+    def forward(ctx, x, full, n_heads, ln_eps, cat4, *params):
         sol = x[1:].permute(1, 0, 2) if full else x
-        o0, o1 = _heads_fwd_impl(sol, list(params), n_heads, ln_eps)
+        o0, o1 = _heads_fwd_impl(sol, list(params), n_heads, ln_eps, cat4)
         ctx.save_for_backward(x, *params)
-        ctx.meta = (full, n_heads, ln_eps)
+        ctx.meta = (full, n_heads, ln_eps, cat4 is not None)
         ctx.set_materialize_grads(False)
         return o0, o1
 
     @staticmethod
     def backward(ctx, g0, g1):
         x, *params = ctx.saved_tensors
-        full, n_heads, ln_eps = ctx.meta
+        full, n_heads, ln_eps, cat4 = ctx.meta
         if full:        # ys is dense in one of the two storage layouts: the gradient takes the same strides (slab 0 stays zero)
             gfull = torch.empty_strided(x.size(), x.stride(), dtype=x.dtype, device=x.device).zero_()
         else:
             gfull = torch.zeros(x.shape, dtype=x.dtype, device=x.device)
         sol = x[1:].permute(1, 0, 2) if full else x
         gsol = gfull[1:].permute(1, 0, 2) if full else gfull
-        gps = _heads_bwd_impl(sol, list(params), n_heads, ln_eps, g0, g1 if n_heads == 2 else None, gsol)
-        return (gfull, None, None, None) + tuple(gps)
+        gps = _heads_bwd_impl(sol, list(params), n_heads, ln_eps, g0, g1 if n_heads == 2 and not cat4 else None, gsol, cat4=cat4)
+        return (gfull, None, None, None, None) + tuple(gps)
 
 
 class _SolveHeadsFn(torch.autograd.Function):
@@ -149,13 +163,13 @@ class _SolveHeadsFn(torch.autograd.Function):
     no zero-fill of the rest, no scan for it, no slice / permute copies."""
 
     @staticmethod
-    def forward(ctx, y0, step_tab, out_begin, out_w, n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde, *params):
+    def forward(ctx, y0, step_tab, out_begin, out_w, n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde, cat4, *params):
         from . import ops
         sde_params, head_params_ = list(params[:n_sde]), list(params[n_sde:])
         ys, _, states = ops._euler_fwd_impl(y0, sde_params, step_tab, out_begin, out_w, n_outputs, None, None, seed, row_offset, 0, mode, True, True)
-        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps)
+        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps, cat4)
         ctx.save_for_backward(ys, states, step_tab, out_begin, out_w, *params)
-        ctx.meta = (n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde)
+        ctx.meta = (n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde, cat4 is not None)
         ctx.set_materialize_grads(False)
         return o0, o1
 
@@ -163,7 +177,7 @@ class _SolveHeadsFn(torch.autograd.Function):
     def backward(ctx, g0, g1):
         from . import ops
         ys, states, step_tab, out_begin, out_w, *params = ctx.saved_tensors
-        n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde = ctx.meta
+        n_outputs, seed, row_offset, mode, n_heads, ln_eps, n_sde, cat4 = ctx.meta
         sde_params, head_params_ = list(params[:n_sde]), list(params[n_sde:])
         rows = ys.shape[1]
         sparse = ops.row_flags_supported(mode, False) and bool(ops.SKIP_ZERO_ROWS) and rows > 0
@@ -174,26 +188,32 @@ class _SolveHeadsFn(torch.autograd.Function):
         else:
             gys = torch.empty_strided(ys.size(), ys.stride(), dtype=ys.dtype, device=ys.device).zero_()
             flags = None
-        gps = _heads_bwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps, g0, g1 if n_heads == 2 else None,
-                              gys[1:].permute(1, 0, 2), flags)
+        gps = _heads_bwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps, g0, g1 if n_heads == 2 and not cat4 else None,
+                              gys[1:].permute(1, 0, 2), flags, cat4=cat4)
         grads = ops._euler_bwd_impl(gys, None, states, sde_params, step_tab, out_begin, out_w, n_outputs, None, None, seed, row_offset, 0,
                                     mode, flags)
-        return (grads[0],) + (None,) * 10 + tuple(grads[1:]) + tuple(gps)
+        return (grads[0],) + (None,) * 11 + tuple(grads[1:]) + tuple(gps)
 
 
 def solve_and_heads(sde, loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], y0: torch.Tensor, ts, dt: float, *,
-                    mode: Optional[str] = None, seed: Optional[int] = None, row_offset: int = 0, bm=None):
+                    mode: Optional[str] = None, seed: Optional[int] = None, row_offset: int = 0, bm=None,
+                    cat_min_scale: Optional[float] = None):
     """``loc, scale_raw = heads(sdeint(sde, y0, ts, dt=dt, method='euler')[1:].permute(1, 0, 2))`` — dec_hivt_nusargo_sde.py:88, 95, 98 —
     as one differentiable node (in-kernel Philox noise).  With ``bm`` (caller-supplied increments: validation) or without autograd it
-    is the plain composition of ``sdeint`` and ``decoder_heads_from_solution``."""
+    is the plain composition of ``sdeint`` and ``decoder_heads_from_solution``.
+    ``cat_min_scale`` (the decoder's ``min_scale``; needs ``scale_head``): returns ``(out4, None)`` with
+    ``out4 = cat(loc, elu(scale_raw) + 1 + min_scale)`` [rows, T, 4] — lines :98-100 written by the heads kernel itself, their
+    backward folded into the heads backward."""
     from . import ops, solver
     from .schedule import euler_schedule
     heads, hparams, eps = _head_args(loc_head, scale_head)
     sde_params = solver._mlp_params(sde.f_func, 64, 'f_func') + solver._mlp_params(sde.g_func, 1, 'g_func')
     need_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in sde_params + hparams))
+    if cat_min_scale is not None and scale_head is None:
+        raise ValueError("cat_min_scale needs the scale head (uncertain=True)")
     if bm is not None or not need_grad:
         ys = solver.sdeint(sde, y0, ts, bm=bm, dt=dt, method='euler', mode=mode, seed=seed, row_offset=row_offset, rows_major=True)
-        return decoder_heads_from_solution(loc_head, scale_head, ys)
+        return decoder_heads_from_solution(loc_head, scale_head, ys, cat_min_scale=cat_min_scale)
     solver._check_sde_types(sde)
     if not y0.is_cuda or y0.dim() != 2 or y0.shape[1] != 64:
         raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only, y0 [rows, 64]; there is no CPU fallback")
@@ -202,11 +222,11 @@ def solve_and_heads(sde, loc_head: torch.nn.Module, scale_head: Optional[torch.n
     mode_id = _lib.MODES[mode or solver.get_default_mode()]
     seed = solver._next_call_seed() if seed is None else int(seed)
     o0, o1 = _SolveHeadsFn.apply(y0, ds.step_tab, ds.out_begin, ds.out_w, sched.n_outputs, seed, int(row_offset), mode_id, len(heads), eps,
-                                 len(sde_params), *sde_params, *hparams)
+                                 len(sde_params), None if cat_min_scale is None else float(cat_min_scale), *sde_params, *hparams)
     for name in ('fnfe', 'gnfe'):
         if hasattr(sde, name):
             setattr(sde, name, getattr(sde, name) + sched.n_steps)
-    return o0, (o1 if scale_head is not None else None)
+    return o0, (o1 if scale_head is not None and cat_min_scale is None else None)
 
 
 def _needs_grad(x: torch.Tensor, heads) -> bool:
@@ -221,29 +241,38 @@ def _head_args(loc_head, scale_head):
     return heads, [p for h in heads for p in head_params(h)], eps.pop()
 
 
-def decoder_heads(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], sol_y: torch.Tensor):
-    """(loc[rows,T,2], scale_raw[rows,T,2] or None) = (loc_head(sol_y), scale_head(sol_y)) in one fused launch; differentiable."""
+def decoder_heads(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], sol_y: torch.Tensor,
+                  cat_min_scale: Optional[float] = None):
+    """(loc[rows,T,2], scale_raw[rows,T,2] or None) = (loc_head(sol_y), scale_head(sol_y)) in one fused launch; differentiable.
+    ``cat_min_scale``: (``cat(loc, elu(scale_raw) + 1 + min_scale)`` [rows,T,4], None) instead — the stage's out['loc'] (dec…sde.py:98-100)."""
     if not sol_y.is_cuda:
         raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if cat_min_scale is not None and scale_head is None:
+        raise ValueError("cat_min_scale needs the scale head (uncertain=True)")
     heads, params, eps = _head_args(loc_head, scale_head)
+    cat4 = None if cat_min_scale is None else float(cat_min_scale)
     if _needs_grad(sol_y, heads):
-        o0, o1 = _HeadsFn.apply(sol_y, False, len(heads), eps, *params)
+        o0, o1 = _HeadsFn.apply(sol_y, False, len(heads), eps, cat4, *params)
     else:
-        o0, o1 = _heads_fwd_impl(sol_y, params, len(heads), eps)
-    return o0, (o1 if scale_head is not None else None)
+        o0, o1 = _heads_fwd_impl(sol_y, params, len(heads), eps, cat4)
+    return o0, (o1 if scale_head is not None and cat4 is None else None)
 
 
-def decoder_heads_from_solution(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], ys: torch.Tensor):
+def decoder_heads_from_solution(loc_head: torch.nn.Module, scale_head: Optional[torch.nn.Module], ys: torch.Tensor,
+                                cat_min_scale: Optional[float] = None):
     """The same on the solver's full output ``ys`` [T+1, rows, 64] (``sdeint``'s return value, either storage layout): the heads read
     ``ys[1:].permute(1, 0, 2)`` (dec…sde.py:88) and, in training, hand dL/dys back in ``ys``'s own layout — no slice-backward copy."""
     if not ys.is_cuda:
         raise RuntimeError("trajsde_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+    if cat_min_scale is not None and scale_head is None:
+        raise ValueError("cat_min_scale needs the scale head (uncertain=True)")
     heads, params, eps = _head_args(loc_head, scale_head)
+    cat4 = None if cat_min_scale is None else float(cat_min_scale)
     if _needs_grad(ys, heads):
-        o0, o1 = _HeadsFn.apply(ys, True, len(heads), eps, *params)
+        o0, o1 = _HeadsFn.apply(ys, True, len(heads), eps, cat4, *params)
     else:
-        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), params, len(heads), eps)
-    return o0, (o1 if scale_head is not None else None)
+        o0, o1 = _heads_fwd_impl(ys[1:].permute(1, 0, 2), params, len(heads), eps, cat4)
+    return o0, (o1 if scale_head is not None and cat4 is None else None)
 
 
 class FusedHeadPair:

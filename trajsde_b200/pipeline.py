@@ -112,8 +112,7 @@ class HostFedSdePath:
                             method='euler', mode=self.mode, seed=seed + 1, row_offset=dec_row_offset + lo, rows_major=heads is not None)
                 if heads is not None:
                     from .heads import decoder_heads_from_solution
-                    loc, scale_raw = decoder_heads_from_solution(heads[0], heads[1], ys)
-                    res = torch.cat((loc, torch.nn.functional.elu(scale_raw, alpha=1.0) + (1.0 + min_scale)), dim=-1)   # dec…sde.py:98-100
+                    res, _ = decoder_heads_from_solution(heads[0], heads[1], ys, cat_min_scale=min_scale)   # dec…sde.py:95-100 in one launch
                 else:
                     res = ys[-1]
                 ev = torch.cuda.Event()

@@ -2,6 +2,7 @@
 fused backward (csrc/stage_ops.cu):
 
     aggr_embed(module, local_embed, global_embed) -> hidden_0 [modes * N, 64]     dec_hivt_nusargo_sde.py:26-29, 82-85
+    pi_head(module, local_embed, global_embed)    -> pi [N, modes]                 dec_hivt_nusargo_sde.py:63-67, 92-94 (fused forward)
     l2_loss(loc, target, reg_mask)               -> scalar                        losses/L2.py:10-27
     diff_bce_loss(diff_in, diff_out)             -> scalar                        losses/diff_BCE.py:11-16 (labels of enc…sep2.py:194-195)
 
@@ -83,6 +84,66 @@ def aggr_embed(module: torch.nn.Module, local_embed: torch.Tensor, global_embed:
     _cuda_only(global_embed)
     lin, ln = module[0], module[1]
     return _AggrFn.apply(local_embed, global_embed, lin.weight, lin.bias, ln.weight, ln.bias, float(ln.eps))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# pi head
+# ---------------------------------------------------------------------------------------------------------------------
+def _pi_torch(local_embed, global_embed, w1, b1, g, beta, w2, b2, eps):
+    """dec_hivt_nusargo_sde.py:92-94 in torch ops (the backward of ``pi_head`` differentiates this)."""
+    x = torch.cat((local_embed.expand(global_embed.shape[0], *local_embed.shape), global_embed), dim=-1)
+    z = torch.relu(torch.nn.functional.layer_norm(torch.nn.functional.linear(x, w1, b1), (64,), g, beta, eps))
+    return torch.nn.functional.linear(z, w2.view(1, 64), b2).squeeze(-1).t()
+
+
+class _PiFn(torch.autograd.Function):
+    """Fused forward.  No loss of the reference configuration reads ``pi`` (yml:78-80: L2 + DiffBCE; pi feeds test-time metrics), so in
+    training its gradient is None and backward returns at once; if a loss DOES use pi, backward recomputes the 4-layer head with
+    torch ops under autograd (GPU, exact) — a cold path, not a fallback of the forward."""
+
+    @staticmethod
+    def forward(ctx, local_embed, global_embed, w1, b1, g, beta, w2, b2, eps):
+        modes, n = global_embed.shape[0], global_embed.shape[1]
+        if global_embed.dim() != 3 or global_embed.shape[2] != 64 or tuple(local_embed.shape) != (n, 64):
+            raise ValueError("global_embed [modes, N, 64] and local_embed [N, 64] expected")
+        keep = [t.detach().contiguous().float() for t in (global_embed, local_embed, w1, b1, g, beta, w2, b2)]
+        a = _lib.PiArgs()
+        a.struct_bytes = C.sizeof(_lib.PiArgs)
+        a.n_modes, a.n_actors = modes, n
+        a.global_embed, a.local_embed, a.w1, a.b1, a.ln_g, a.ln_b, a.w2, a.b2 = (t.data_ptr() for t in keep)
+        a.ln_eps = eps
+        out = torch.empty((n, modes), dtype=torch.float32, device=global_embed.device)
+        a.out = out.data_ptr()
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().trajsde_pi_head_fwd(C.byref(a), _stream_ptr(out.device)), "trajsde_pi_head_fwd")
+        if modes * n > 0:
+            LAUNCHES['n'] += 1
+        ctx.save_for_backward(local_embed, global_embed, w1, b1, g, beta, w2, b2)
+        ctx.eps = eps
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_pi):
+        if grad_pi is None:
+            return (None,) * 9
+        saved = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(need) for t, need in zip(saved, ctx.needs_input_grad[:8])]
+            pi = _pi_torch(*leaves, ctx.eps)
+            wanted = [t for t in leaves if t.requires_grad]
+            grads = iter(torch.autograd.grad(pi, wanted, grad_pi, allow_unused=True)) if wanted else iter(())
+        return tuple(next(grads) if t.requires_grad else None for t in leaves) + (None,)
+
+
+def pi_head(module: torch.nn.Module, local_embed: torch.Tensor, global_embed: torch.Tensor) -> torch.Tensor:
+    """``module`` = the decoder's ``pi`` Sequential(Linear(128, 64), LayerNorm(64), ReLU, Linear(64, 1)) (dec…sde.py:63-67): returns
+    ``pi`` [N, modes] = what :92-94 compute, in one launch without the [modes, N, 128] concatenation."""
+    _cuda_only(global_embed)
+    lin, ln, proj = module[0], module[1], module[3]
+    if tuple(lin.weight.shape) != (64, 128) or tuple(proj.weight.shape) != (1, 64) or tuple(ln.weight.shape) != (64,):
+        raise NotImplementedError("fused pi head supports Linear(128, 64) + LayerNorm(64) + ReLU + Linear(64, 1) only")
+    return _PiFn.apply(local_embed, global_embed, lin.weight, lin.bias, ln.weight, ln.bias, proj.weight.reshape(64), proj.bias, float(ln.eps))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -37,16 +37,11 @@ class FusedDecoderMixin:
         hidden_0 = stage.aggr_embed(self.aggr_embed, local_embed, global_embed)                                   # :82-85
         if self.method != 'euler':
             raise NotImplementedError(f"fused solve implements method='euler' only (reference yml:76), got {self.method!r}")
-        loc, scale_raw = solve_and_heads(self.lsde_func, self.decoder, self.scale if self.uncertain else None, hidden_0, self.ts_pred,
-                                         self.min_stepsize, **self.solver_kwargs)                                 # :88, :95, :98 as one node
-        expanded = local_embed.expand(self.num_modes, *local_embed.shape)
-        pi = self.pi(torch.cat((expanded, global_embed), dim=-1)).squeeze(-1).t()                                 # :92-94 (reference path)
-        loc = loc.view(self.num_modes, num_actors, self.future_steps, 2)
-        if self.uncertain:
-            scale = F.elu(scale_raw, alpha=1.0).view(self.num_modes, -1, self.future_steps, 2) + 1.0 + self.min_scale   # :98-99
-            out = {'loc': torch.cat((loc, scale), dim=-1), 'pi': pi}
-        else:
-            out = {'loc': loc, 'pi': pi}
+        # :88, :95-100 as one node: with the scale head the heads kernel writes out['loc'] = cat(loc, elu(scale) + 1 + min_scale) itself
+        loc, _ = solve_and_heads(self.lsde_func, self.decoder, self.scale if self.uncertain else None, hidden_0, self.ts_pred,
+                                 self.min_stepsize, cat_min_scale=float(self.min_scale) if self.uncertain else None, **self.solver_kwargs)
+        pi = stage.pi_head(self.pi, local_embed, global_embed)                                                    # :92-94
+        out = {'loc': loc.view(self.num_modes, num_actors, self.future_steps, 4 if self.uncertain else 2), 'pi': pi}
         out['reg_mask'] = ~data['padding_mask'][:, -self.future_steps:]                                           # :104
         return out
 
