@@ -163,9 +163,21 @@ __global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, 
 __global__ void __launch_bounds__(1024, 1) bwd_compact_rows_kernel(const uint8_t* __restrict__ flags, int64_t rows, int32_t* __restrict__ row_map,
                                                                     int32_t* __restrict__ n_active) {
   __shared__ int32_t part[1024];
-  const int64_t chunk = (rows + 1023) / 1024, lo = (int64_t)threadIdx.x * chunk, hi = lo + chunk < rows ? lo + chunk : rows;
+  // chunks are multiples of 16 rows so that the flags go through 16-byte loads when the array is 16-byte aligned (byte loads took 82 us
+  // at 204,800 rows — a latency chain of 200 dependent-address loads per thread)
+  const int64_t chunk = (((rows + 1023) / 1024) + 15) & ~(int64_t)15, lo = (int64_t)threadIdx.x * chunk;
+  const int64_t hi = lo >= rows ? lo : (lo + chunk < rows ? lo + chunk : rows);
+  const bool vec = (reinterpret_cast<uintptr_t>(flags) & 15u) == 0;
   int32_t c = 0;
-  for (int64_t r = lo; r < hi; ++r) c += flags[r];
+  {
+    int64_t r = lo;
+    if (vec)
+      for (; r + 16 <= hi; r += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(flags + r);
+        c += (__popc(__vcmpne4(v.x, 0u)) + __popc(__vcmpne4(v.y, 0u)) + __popc(__vcmpne4(v.z, 0u)) + __popc(__vcmpne4(v.w, 0u))) >> 3;
+      }
+    for (; r < hi; ++r) c += flags[r] != 0;
+  }
   part[threadIdx.x] = c;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {          // Hillis–Steele inclusive scan
@@ -175,8 +187,20 @@ __global__ void __launch_bounds__(1024, 1) bwd_compact_rows_kernel(const uint8_t
     __syncthreads();
   }
   int32_t pos = part[threadIdx.x] - c;
-  for (int64_t r = lo; r < hi; ++r)
-    if (flags[r]) row_map[pos++] = (int32_t)r;
+  {
+    int64_t r = lo;
+    if (vec)
+      for (; r + 16 <= hi; r += 16) {
+        const uint4 v = *reinterpret_cast<const uint4*>(flags + r);
+        if ((v.x | v.y | v.z | v.w) == 0u) continue;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if ((w[i >> 2] >> (8 * (i & 3))) & 0xffu) row_map[pos++] = (int32_t)(r + i);
+      }
+    for (; r < hi; ++r)
+      if (flags[r]) row_map[pos++] = (int32_t)r;
+  }
   if (threadIdx.x == 1023) *n_active = part[1023];
 }
 

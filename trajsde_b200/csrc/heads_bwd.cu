@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
   int64_t* qpt = reinterpret_cast<int64_t*>(dsc + 2 * HB_TILE);   // [2 heads][HB_TILE + HB_THREADS] queued active point ids
   int* qn = reinterpret_cast<int*>(qpt + 2 * (HB_TILE + HB_THREADS));   // [2] queue lengths
   int* wsum = qn + 2;                                          // [8] per-warp counts
+  int64_t* rlist = reinterpret_cast<int64_t*>(wsum + 14);      // [HB_THREADS] flagged rows of the current 256-row chunk (row_flags mode)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_heads = a.n_heads;
@@ -258,16 +259,14 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
     __syncthreads();                                           // tiles and queue entries are free again
   };
 
-  // ---- scan this block's contiguous range of points, compact the active ones per head, process full tiles as they form ----------------
-  const int64_t per = (p.n_points + gridDim.x - 1) / gridDim.x;
-  const int64_t p_lo = (int64_t)blockIdx.x * per, p_hi = p_lo + per < p.n_points ? p_lo + per : p.n_points;
-  for (int64_t base = p_lo; base < p_hi; base += HB_THREADS) {
-    const int64_t pid = base + tid;
+  // ---- scan this block's share of the points, compact the active ones per head, process full tiles as they form -----------------------------
+  // one step: 256 candidate points (has / pid per thread) -> per head: ballot-compact the active ones into the queue, drain full tiles
+  auto scan256 = [&](bool has, int64_t pid) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h >= n_heads || !a.grad_out[h]) continue;
       bool act = false;
-      if (pid < p_hi) {
+      if (has) {
         const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * p.gstride);
         act = d.x != 0.f || d.y != 0.f;
       }
@@ -309,6 +308,42 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
       if (tid == 0) qn[h] = n;
       __syncthreads();
     }
+  };
+  if (a.row_flags) {
+    // the caller's row flags are known (heads_row_flags_kernel ran before): walk this block's contiguous range of ROWS 256 at a time, compact
+    // the flagged ones and scan only their points — under a winner-takes-all loss nine rows in ten are skipped without reading a gradient
+    const int64_t rper = (a.rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r_lo = (int64_t)blockIdx.x * rper, r_hi = r_lo + rper < a.rows ? r_lo + rper : a.rows;
+    for (int64_t rc = r_lo; rc < r_hi; rc += HB_THREADS) {
+      const int64_t r = rc + tid;
+      const bool f = r < r_hi && a.row_flags[r] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      __syncthreads();                                         // previous chunk's row list / wsum are no longer read
+      if (lane == 0) wsum[warp] = __popc(m);
+      __syncthreads();
+      int off = 0, nr = 0;
+      for (int w = 0; w < HB_THREADS / 32; ++w) {
+        if (w < warp) off += wsum[w];
+        nr += wsum[w];
+      }
+      if (f) rlist[off + __popc(m & ((1u << lane) - 1u))] = r;
+      __syncthreads();
+      const int64_t nv = (int64_t)nr * a.n_t;
+      for (int64_t vb = 0; vb < nv; vb += HB_THREADS) {
+        const int64_t vp = vb + tid;
+        const bool has = vp < nv;
+        int64_t pid = 0;
+        if (has) {
+          const int64_t li = vp / a.n_t;
+          pid = rlist[li] * a.n_t + (vp - li * a.n_t);
+        }
+        scan256(has, pid);
+      }
+    }
+  } else {
+    const int64_t per = (p.n_points + gridDim.x - 1) / gridDim.x;
+    const int64_t p_lo = (int64_t)blockIdx.x * per, p_hi = p_lo + per < p.n_points ? p_lo + per : p.n_points;
+    for (int64_t base = p_lo; base < p_hi; base += HB_THREADS) scan256(base + tid < p_hi, base + tid);
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -341,16 +376,25 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
 }
 
 // row_flags mode, pass 1: flags[r] = 1 if any point of row r carries a gradient in any head (flags zeroed by a memset before)
+// Four independent points per thread and iteration: the scan is a pure stream over dL/dout (196 MB at BASELINE configs[1]) and needs the
+// loads in flight, not arithmetic (one point per iteration: 171 us; this form: HBM speed).
 __global__ void heads_row_flags_kernel(const TrajsdeHeadsBwdArgs a, int64_t n_points, int gstride) {
-  for (int64_t pid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid < n_points; pid += (int64_t)gridDim.x * blockDim.x) {
-    bool act = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pid0 < n_points; pid0 += 4 * stride) {
+    float2 d[4][2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
-      if (h < a.n_heads && a.grad_out[h]) {
-        const float2 d = *reinterpret_cast<const float2*>(a.grad_out[h] + pid * gstride);
-        act = act || d.x != 0.f || d.y != 0.f;
-      }
-    if (act) a.row_flags[pid / a.n_t] = 1;                     // benign race: every writer stores the same value
+    for (int k = 0; k < 4; ++k) {
+      const int64_t pid = pid0 + k * stride;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        d[k][h] = (pid < n_points && h < a.n_heads && a.grad_out[h]) ? *reinterpret_cast<const float2*>(a.grad_out[h] + pid * gstride)
+                                                                      : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool act = d[k][0].x != 0.f || d[k][0].y != 0.f || d[k][1].x != 0.f || d[k][1].y != 0.f;
+      if (act) a.row_flags[(pid0 + k * stride) / a.n_t] = 1;   // benign race: every writer stores the same value
+    }
   }
 }
 
@@ -384,7 +428,7 @@ __global__ void heads_bwd_reduce_kernel(const float* __restrict__ partial, int n
 }
 
 constexpr size_t HB_SMEM = (2 * 64 * HB_LD + 4 * HB_TILE * HB_LD + 2 * 320 + 2 * HB_TILE) * sizeof(float) + 2 * (HB_TILE + HB_THREADS) * sizeof(int64_t) +
-                           16 * sizeof(int);
+                           16 * sizeof(int) + HB_THREADS * sizeof(int64_t);
 
 int heads_bwd_grid() {
   int dev = 0, sms = 0;
