@@ -288,6 +288,15 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
   tc_wait_st();
 }
 
+#ifdef TRAJSDE_FWD_TIMELINE
+// debug build only (bench_micro/fwd_timeline.py): clocks of thread 0 of CTA 0 — [0] kernel, [1] waiting for X to be released (previous
+// step's output store), [2] waiting for the step's dW tile to land, [3] waiting for P3, [4] steps
+__device__ long long g_fwd_tl[8];
+#define FWD_TL(i, expr) do { const long long _t0 = clock64(); expr; if (threadIdx.x == 0 && blockIdx.x == 0) g_fwd_tl[i] += clock64() - _t0; } while (0)
+#else
+#define FWD_TL(i, expr) do { expr; } while (0)
+#endif
+
 template <bool HAS_DW, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_dw,
@@ -300,6 +309,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const TrajsdeEulerFwdArgs& a = p.a;
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int S = a.sched.n_steps;
+#ifdef TRAJSDE_FWD_TIMELINE
+  const long long tl_start = clock64();
+#endif
   // contiguous, balanced tile range of this CTA (sizes differ by at most one tile); its two slots take alternate tiles
   const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
   const int tile_lo = (int)blockIdx.x * tiles_q + min((int)blockIdx.x, tiles_r);
@@ -546,9 +558,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
           // ---- epilogue 3 ---------------------------------------------------------------------------------------------------------
           if (HAS_DW) {
-            mbar_wait(bar_xfree(slot), par_xfree);
+            FWD_TL(1, mbar_wait(bar_xfree(slot), par_xfree));
             par_xfree ^= 1;
-            mbar_wait(bar_tma(slot), par_tma);                 // dW tile of this step has landed in X
+            FWD_TL(2, mbar_wait(bar_tma(slot), par_tma));      // dW tile of this step has landed in X
             par_tma ^= 1;
           } else {
             draw(5, 8);
@@ -560,7 +572,10 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 #else
           constexpr bool YPRE = false;
 #endif
-          mbar_wait(bar_acc(slot, 1), par_accB);
+          FWD_TL(3, mbar_wait(bar_acc(slot, 1), par_accB));
+#ifdef TRAJSDE_FWD_TIMELINE
+          if (threadIdx.x == 0 && blockIdx.x == 0) g_fwd_tl[4] += 1;
+#endif
           par_accB ^= 1;
           tc_fence_after();
           named_bar_sync(pair_bar, 64);                        // partner warp's partial g dot is in smem
@@ -906,6 +921,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
   tc_fence_before();
   __syncthreads();
+#ifdef TRAJSDE_FWD_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x == 0) g_fwd_tl[0] += clock64() - tl_start;
+#endif
   if (warp == WARP_MMA0) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
@@ -1006,3 +1024,11 @@ int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s) {
 }
 
 }  // namespace trajsde
+
+#ifdef TRAJSDE_FWD_TIMELINE
+extern "C" int trajsde_debug_fwd_timeline(long long* out8) {
+  long long zero[8] = {0};
+  if (cudaMemcpyFromSymbol(out8, trajsde::g_fwd_tl, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::g_fwd_tl, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
