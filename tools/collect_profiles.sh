@@ -3,7 +3,7 @@
 #   bash tools/collect_profiles.sh <tag>
 tag=$1
 commit=$(git rev-parse --short HEAD)
-for k in fwd_dw fwd_philox enc_fwd bwd_tc heads_fwd; do
+for k in fwd_dw fwd_philox enc_fwd bwd_tc enc_bwd_sweep heads_fwd; do
   rep=gpurun_out/${tag}_$k.ncu-rep
   [ -f $rep ] || continue
   python profiles/summarize_ncu.py $rep > profiles/${tag}_$k.txt
@@ -12,7 +12,8 @@ python - "$tag" "$commit" <<'PY'
 import csv, io, json, os, subprocess, sys
 tag, commit = sys.argv[1], sys.argv[2]
 names = {'fwd_dw': ('euler_fwd_tc_kernel<1,0>', 204800, 61), 'fwd_philox': ('euler_fwd_tc_kernel<0,0>', 204800, 61),
-         'enc_fwd': ('enc_fwd_tc_kernel', 21504, 21), 'bwd_tc': ('euler_bwd_tc_kernel<0>', 204800, 61), 'heads_fwd': ('heads_fwd_kernel', 204800, 60)}
+         'enc_fwd': ('enc_fwd_tc_kernel', 21504, 21), 'bwd_tc': ('euler_bwd_tc_kernel<0>', 204800, 61),
+         'enc_bwd_sweep': ('enc_bwd_sweep_kernel<0>', 21504, 21), 'heads_fwd': ('heads_fwd_kernel', 204800, 60)}
 out = {"_comment": "DRAM traffic per launch from ncu --set full captures (dram__bytes_read.sum + dram__bytes_write.sum); bench.py copies the "
                    "matching entry into roofline.traffic", "commit": commit}
 for k, (name, rows, steps) in names.items():

@@ -20,7 +20,9 @@ for w in $what; do
                 python tools/bench_dec.py 204800 2 philox > /dev/null 2>&1
               timeout 300 ncu --set full --clock-control none --import-source on -k regex:enc_fwd_tc_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_enc_fwd \
                 python tools/bench_enc.py 1024 2 > /dev/null 2>&1
-              timeout 300 ncu --set full --clock-control none --import-source on -k regex:euler_bwd_tc_kernel -s 44 -c 1 -f -o gpurun_out/${tag}_bwd_tc \
+              timeout 300 ncu --set full --clock-control none --import-source on -k regex:euler_bwd_tc_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_bwd_tc \
+                python tools/train_prof.py 1024 1 > /dev/null 2>&1
+              timeout 300 ncu --set full --clock-control none --import-source on -k regex:enc_bwd_sweep_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_enc_bwd_sweep \
                 python tools/train_prof.py 1024 1 > /dev/null 2>&1
               timeout 300 ncu --set full --clock-control none --import-source on -k regex:heads_fwd_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_heads_fwd \
                 python tools/bench_heads.py 204800 2 > /dev/null 2>&1
