@@ -159,8 +159,20 @@ __device__ __forceinline__ void ld_g32(uint32_t tm_uniform, uint32_t tm_alt, boo
   }
 }
 
+#ifdef TRAJSDE_ENC_TIMELINE
+// debug build only (bench_micro/enc_fwd_timeline.py): thread 0 of CTA 0: [0] kernel clocks, [1] clocks waiting for the tensor core (all eight
+// accumulator barriers of an iteration), [2] iterations
+__device__ long long g_enc_tl[4];
+#define ENC_TL_WAIT(expr) do { const long long _t0 = clock64(); expr; if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_tl[1] += clock64() - _t0; } while (0)
+#else
+#define ENC_TL_WAIT(expr) do { expr; } while (0)
+#endif
+
 template <bool HAS_DW, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncParams p) {
+#ifdef TRAJSDE_ENC_TIMELINE
+  const long long tl_start = clock64();
+#endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -270,6 +282,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
       }
 
       for (int it = 0; it < S; ++it) {
+#ifdef TRAJSDE_ENC_TIMELINE
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_tl[2] += 1;
+#endif
         const float h = __shfl_sync(0xffffffffu, lane_h, it);                // step size / slot index of iteration `it`: held by lane `it`
         const int slot_next = __shfl_sync(0xffffffffu, lane_slot, (it + 1) & 31);
         const float* b1row = bias1_tab + it * 192;
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         }
 
         // ---- epilogue 1 ------------------------------------------------------------------------------------------------------
-        mbar_wait(bar_acc(0), par_accA);                   // P1
+        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // P1
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           mbar_arrive(bar_opnd(0));                        // h1g -> P2g
         }
         // ---- epilogue 2 ------------------------------------------------------------------------------------------------------
-        mbar_wait(bar_acc(1), par_accB);                   // P2f
+        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // P2f
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -316,7 +331,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_opnd(1));                        // h2f -> P3
-          mbar_wait(bar_acc(0), par_accA);                 // P2g
+          ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                 // P2g
           par_accA ^= 1;
           tc_fence_after();
           ld_g32<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
@@ -341,7 +356,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
                                 (uint32_t)(hh * 8 + q), sqrt_h);
           }
         }
-        mbar_wait(bar_acc(1), par_accB);                   // P3
+        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // P3
         par_accB ^= 1;
         tc_fence_after();
         named_bar_sync(pair_bar, 64);                      // both partial diffusion dots of every row are in smem
@@ -384,7 +399,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           for (int q = 0; q < 8; ++q) xn[q] = ld_nc_f4(xs + 4 * q);
         }
         // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
-        mbar_wait(bar_acc(0), par_accA);                   // G1
+        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // G1
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         mbar_arrive(bar_opnd(1));                          // tu, tr -> G2
         // ---- GRU epilogue 2: u = sigmoid(u' + ub2) (kept), r = sigmoid(r' + rb2), r * y1 -> AH ---------------------------------------------
         float u[32];
-        mbar_wait(bar_acc(1), par_accB);                   // G2
+        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // G2
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -423,7 +438,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         tc_fence_before();
         mbar_arrive(bar_opnd(0));                          // r*y1 -> G3
         // ---- GRU epilogue 3: tn = tanh(zn + nb1) --------------------------------------------------------------------------------------------
-        mbar_wait(bar_acc(0), par_accA);                   // G3
+        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // G3
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         tc_fence_before();
         mbar_arrive(bar_opnd(1));                          // tn -> G4
         // ---- GRU epilogue 4: h' = (1-u) (n + nb2) + u y1 ; masked ; state, operand, latent ---------------------------------------------------
-        mbar_wait(bar_acc(1), par_accB);                   // G4
+        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // G4
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -542,6 +557,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
 
   tc_fence_before();
   __syncthreads();
+#ifdef TRAJSDE_ENC_TIMELINE
+  if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_tl[0] += clock64() - tl_start;
+#endif
   if (warp == NUM_EPI_WARPS) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512);
@@ -583,3 +601,11 @@ int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s) {
 }
 
 }  // namespace trajsde
+
+#ifdef TRAJSDE_ENC_TIMELINE
+extern "C" int trajsde_debug_enc_timeline(long long* out4) {
+  long long zero[4] = {0};
+  if (cudaMemcpyFromSymbol(out4, trajsde::g_enc_tl, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::g_enc_tl, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
