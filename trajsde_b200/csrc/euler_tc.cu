@@ -38,24 +38,6 @@ constexpr int WARP_MMA0 = NUM_EPI_WARPS;                    // warps 16,17: MMA 
 constexpr int WARP_IO0 = NUM_EPI_WARPS + NUM_SLOTS;         // warps 18,19: IO (slot 0,1)
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2 * NUM_SLOTS) * 32;  // 640
 constexpr int EPI_REGS = 112, AUX_REGS = 32;              // setmaxnreg split: epilogue warpgroups grow, MMA/IO warpgroup shrinks
-// In-kernel-noise variant of the single-diffusion solve ("PROD"): a sixth warpgroup of four INCREMENT-PRODUCER warps (two per slot) draws
-// the Brownian increments of step k+1 into a double-buffered fp32 tile while the epilogue warps work on step k, so Philox + Box-Muller
-// (67 instructions per 4 increments, 2.5 k clk per slot-step when drawn inline: bench_micro/fwd_timeline.py) fill issue slots the
-// epilogue chain leaves idle instead of lengthening it.  The two tile buffers are the X staging buffer and the A1f|A1g region (free:
-// operands live in tensor memory) — which is why this variant writes ys / states / reads y0 with plain 128-byte-per-thread global
-// accesses from the epilogue threads instead of staging them for TMA.
-#ifndef TRAJSDE_FWD_PRODUCERS
-#define TRAJSDE_FWD_PRODUCERS 0
-#endif
-constexpr int WARP_PROD0 = NUM_EPI_WARPS + 2 * NUM_SLOTS;  // warps 20..23: increment producers (slot 0: 20, 21; slot 1: 22, 23)
-constexpr int NUM_THREADS_PROD = NUM_THREADS + 128;        // 768
-constexpr int PROD_THREADS_PER_SLOT = 64;
-constexpr int EPI_REGS_PROD = 96, PROD_REGS = 64;          // 512 x 96 + 128 x 32 + 128 x 64 = 768 x 80 (the launch allocation)
-template <bool HAS_DW, bool DUAL>
-struct FwdVariant {
-  static constexpr bool PROD = !HAS_DW && !DUAL && (TRAJSDE_FWD_PRODUCERS != 0);
-  static constexpr int THREADS = PROD ? NUM_THREADS_PROD : NUM_THREADS;
-};
 
 // ---- packed weight image (bytes) -----------------------------------------------------------------------------------------
 constexpr uint32_t IMG_B1 = 0;            // [192 rows][64] f16 SW128: W1y | V1y | V1y_alt
@@ -87,7 +69,7 @@ constexpr uint32_t RING_BYTES = 3 * RING_LD * 4;
 constexpr uint32_t SMEM_GPART = SMEM_RING + NUM_SLOTS * RING_BYTES;      // per slot: [2 halves][128 rows] fp32 partial g dots
 constexpr uint32_t GPART_BYTES = 2 * TILE_M * 4;
 constexpr uint32_t SMEM_BARS = SMEM_GPART + NUM_SLOTS * GPART_BYTES;
-constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 320;   // 1 + 2 x 10 mbarriers, TMEM base pointer, 2 x 4 producer barriers
+constexpr uint32_t SMEM_TOTAL = SMEM_BARS + 256;   // 1 + 2 x 10 mbarriers, TMEM base pointer
 constexpr uint32_t SMEM_ALLOC = SMEM_TOTAL + 1024;  // slack for manual 1024-B alignment
 static_assert(SMEM_ALLOC <= 232448, "exceeds 227 KB of shared memory per CTA");
 
@@ -244,27 +226,17 @@ struct Epi3Ctx {
   const float* out_w;
   float* ys_row;        // a.ys + grow * row_stride + hh*32
   int64_t ys_t_stride;
-  // DIRECT (producer variant): dW is read from the producers' tile (x_row points into the current buffer), results go straight to global
-  float* st_glob;       // states + (k * rows + grow) * 64 + hh*32 of this step, or unused
-  uint32_t bar_empty;   // mbarrier: this thread has read its dW chunks
 };
 
 // Epilogue 3: f = z3 + b3 ; y' = y + f h + g dW (dW already in this thread's X chunks) ; outputs in place ; Y, A0 <- y'.
 // Y_LOADED: the caller issued the tcgen05.ld of the state columns into `yv` before it waited for P3 (the read runs under that wait).
-template <bool MULTI, bool TMEM_A, bool Y_LOADED = false, bool BIAS_IN_MMA = TMEM_A, bool DIRECT = false>
+template <bool MULTI, bool TMEM_A, bool Y_LOADED = false, bool BIAS_IN_MMA = TMEM_A>
 __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]) {
   uint32_t fv[32];
   if (!Y_LOADED) tmem_ld_32x32b_x32(c.tm_y, yv);
   tmem_ld_32x32b_x32(c.tm_f, fv);
   tc_wait_ld();
-  if (DIRECT) {
-    if (c.save_states && c.valid) {  // Y[k] -> states[k] (this thread's 128 contiguous bytes)
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        st_cs_f4(c.st_glob + 4 * q, make_float4(__uint_as_float(yv[4 * q]), __uint_as_float(yv[4 * q + 1]), __uint_as_float(yv[4 * q + 2]),
-                                                __uint_as_float(yv[4 * q + 3])));
-    }
-  } else if (c.save_states) {  // Y[k] -> states staging (aliases A1f|A1g: both consumed by P2 already)
+  if (c.save_states) {  // Y[k] -> states staging (aliases A1f|A1g: both consumed by P2 already)
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<uint4*>(c.st_row + ((q ^ (c.row & 7u)) << 4)) = make_uint4(yv[4 * q], yv[4 * q + 1], yv[4 * q + 2], yv[4 * q + 3]);
@@ -284,14 +256,8 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
     const float n1 = fmaf(c.g, dw.y, fmaf(f1, c.h, y1));
     const float n2 = fmaf(c.g, dw.z, fmaf(f2, c.h, y2));
     const float n3 = fmaf(c.g, dw.w, fmaf(f3, c.h, y3));
-    if (c.has_out) {
-      const float4 o = make_float4(fmaf(c.w1, n0, c.w0 * y0), fmaf(c.w1, n1, c.w0 * y1), fmaf(c.w1, n2, c.w0 * y2), fmaf(c.w1, n3, c.w0 * y3));
-      if (DIRECT) {
-        if (c.valid) st_cs_f4(c.ys_row + (int64_t)(c.ob + 1) * c.ys_t_stride + 4 * q, o);
-      } else {
-        *xp = o;
-      }
-    }
+    if (c.has_out)
+      *xp = make_float4(fmaf(c.w1, n0, c.w0 * y0), fmaf(c.w1, n1, c.w0 * y1), fmaf(c.w1, n2, c.w0 * y2), fmaf(c.w1, n3, c.w0 * y3));
     if (MULTI) {  // rare: one step completes several outputs (zero-step intervals) -> direct global stores
       if (c.valid) {
         for (int o = 1; o < c.nout; ++o) {
@@ -304,7 +270,6 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
     yv[4 * q] = __float_as_uint(n0); yv[4 * q + 1] = __float_as_uint(n1);
     yv[4 * q + 2] = __float_as_uint(n2); yv[4 * q + 3] = __float_as_uint(n3);
   }
-  if (DIRECT) mbar_arrive(c.bar_empty);                        // the producers may overwrite this tile buffer
   tmem_st_32x32b_x32(c.tm_y, yv);
   if (TMEM_A) {
     uint32_t pk[16];
@@ -333,7 +298,7 @@ __device__ long long g_fwd_tl[8];
 #endif
 
 template <bool HAS_DW, bool DUAL>
-__global__ void __launch_bounds__((FwdVariant<HAS_DW, DUAL>::THREADS), 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_dw,
                     const __grid_constant__ CUtensorMap tm_ys, const __grid_constant__ CUtensorMap tm_st) {
   extern __shared__ uint8_t smem_raw[];
@@ -366,18 +331,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   auto bar_xfree = [&](int s) { return base + SMEM_BARS + 56u + 80u * s; };
   auto bar_ring = [&](int s, int i) { return base + SMEM_BARS + 64u + 80u * s + 8u * i; };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sm + SMEM_BARS + 192);
-  constexpr bool PROD = FwdVariant<HAS_DW, DUAL>::PROD;
-  auto bar_dwfull = [&](int s, int b) { return base + SMEM_BARS + 200u + 32u * s + 8u * b; };     // producers -> epilogue: tile b of slot s drawn
-  auto bar_dwempty = [&](int s, int b) { return base + SMEM_BARS + 216u + 32u * s + 8u * b; };    // epilogue -> producers: tile b read
 
   if (threadIdx.x == 0) {
     mbar_init(bar_w, 1);
-    if (PROD)
-      for (int s = 0; s < NUM_SLOTS; ++s)
-        for (int b = 0; b < 2; ++b) {
-          mbar_init(bar_dwfull(s, b), PROD_THREADS_PER_SLOT);
-          mbar_init(bar_dwempty(s, b), EPI_THREADS_PER_SLOT);
-        }
     for (int s = 0; s < NUM_SLOTS; ++s) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(bar_opnd(s, i), EPI_THREADS_PER_SLOT);
@@ -409,8 +365,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
   if (warp < NUM_EPI_WARPS) {
     // =============================================== EPILOGUE WARPS ===============================================
-    if (PROD) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS_PROD));
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));   // 16x32x112 + 4x32x32 = 640 x 96: inc only draws on what dec released
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));   // 16x32x112 + 4x32x32 = 640 x 96: inc only draws on what dec released
     const int slot = warp / EPI_WARPS_PER_SLOT;
     const int wq = warp % EPI_WARPS_PER_SLOT;
     const int quad = wq & 3;                               // TMEM lane quadrant (= warp index % 4)
@@ -471,27 +426,15 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
       c3.valid = valid;
       c3.ys_row = a.ys + grow * a.ys_row_stride + hh * 32;
 
-      // ---- tile prologue: y0 tile (TMA -> X; producer variant: this thread's 128 bytes straight from global) -> Y (TMEM) + A0 ----------
-      if (!PROD) {
-        mbar_wait(bar_tma(slot), par_tma);
-        par_tma ^= 1;
-      }
+      // ---- tile prologue: y0 tile (TMA -> X) -> Y (TMEM) + A0 ---------------------------------------------------------
+      mbar_wait(bar_tma(slot), par_tma);
+      par_tma ^= 1;
       {
         uint32_t yv[32];
-        if (PROD) {
-          const float* src = a.y0 + grow * a.y0_row_stride + hh * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 v = valid ? ld_nc_f4(src + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            yv[4 * q] = __float_as_uint(v.x); yv[4 * q + 1] = __float_as_uint(v.y); yv[4 * q + 2] = __float_as_uint(v.z); yv[4 * q + 3] = __float_as_uint(v.w);
-            if (valid) st_cs_f4(c3.ys_row + 4 * q, v);     // ys[0] = y0
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(x_row + ((q ^ (row & 7u)) << 4));
-            yv[4 * q] = v.x; yv[4 * q + 1] = v.y; yv[4 * q + 2] = v.z; yv[4 * q + 3] = v.w;
-          }
+        for (int q = 0; q < 8; ++q) {
+          const uint4 v = *reinterpret_cast<const uint4*>(x_row + ((q ^ (row & 7u)) << 4));
+          yv[4 * q] = v.x; yv[4 * q + 1] = v.y; yv[4 * q + 2] = v.z; yv[4 * q + 3] = v.w;
         }
         tmem_st_32x32b_x32(tm_lane + 192, yv);
         if (TMEM_A) {
@@ -573,7 +516,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             mbar_arrive(bar_opnd(slot, 0));                  // h1g ready -> P2g
 #endif
           }
-          if (!HAS_DW && !PROD) {
+          if (!HAS_DW) {
             mbar_wait(bar_xfree(slot), par_xfree);           // stores of the previous step have finished reading X / the states staging
             par_xfree ^= 1;
             draw(0, 3);
@@ -593,7 +536,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             else act32_to_tmem(v, b2, tm_oa);
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
-            if (!HAS_DW && !PROD) draw(3, 5);
+            if (!HAS_DW) draw(3, 5);
             mbar_wait(bar_acc(slot, 0), par_accA);
             par_accA ^= 1;
             tc_fence_after();
@@ -619,7 +562,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             par_xfree ^= 1;
             FWD_TL(2, mbar_wait(bar_tma(slot), par_tma));      // dW tile of this step has landed in X
             par_tma ^= 1;
-          } else if (!PROD) {
+          } else {
             draw(5, 8);
           }
           uint32_t yv[32];
@@ -644,14 +587,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           c3.ob = so.x;
           c3.nout = so.y;
           c3.has_out = so.y > 0;
-          if (PROD) {                                          // this step's increments: tile buffer gstep & 1, drawn by the producer warps
-            c3.x_row = slot_sm + ((gstep & 1u) ? OFF_A1F : OFF_X) + hh * 16384 + row * 128;
-            c3.bar_empty = bar_dwempty(slot, gstep & 1);
-            c3.st_glob = save_states ? a.states + ((int64_t)k * a.rows + grow) * 64 + hh * 32 : nullptr;
-            mbar_wait(bar_dwfull(slot, gstep & 1), (gstep >> 1) & 1);
-          }
-          if (so.y > 1) epi3_update<true, true, YPRE, BIAS_MMA, PROD>(c3, yv);
-          else epi3_update<false, true, YPRE, BIAS_MMA, PROD>(c3, yv);
+          if (so.y > 1) epi3_update<true, true, YPRE, BIAS_MMA>(c3, yv);
+          else epi3_update<false, true, YPRE, BIAS_MMA>(c3, yv);
           if (k == S - 1 && hh == 0 && a.g_last && valid) a.g_last[grow] = g;
           if (BIAS_MMA && k + 1 < S) {                         // bias operand slice of the next step (other parity: nobody reads it now)
             mbar_wait(bar_ring(slot, (gstep + 1) & 1), ((gstep + 1) >> 1) & 1);
@@ -868,47 +805,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         }
       }
     }
-  } else if (PROD && warp >= WARP_PROD0) {
-    // =============================================== INCREMENT PRODUCERS (producer variant) =================================
-    // Two warps per slot draw the increments of global step g into tile buffer g & 1 of the slot (same fp32 layout the TMA gives the
-    // supplied-dW tile: [32-channel half][128 rows][128 B], 16-byte chunks XOR-swizzled by row), up to two steps ahead of the epilogue.
-    // Keyed by (global row, step, channel / 4) like every other draw of the stream: the values are those of the inline draw.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PROD_REGS));
-    const int slot = (warp - WARP_PROD0) >> 1;
-    const uint32_t t = (uint32_t)((warp - WARP_PROD0) & 1) * 32u + (uint32_t)lane;         // 0..63
-    uint8_t* slot_sm = sm + SMEM_SLOTS + slot * SLOT_BYTES;
-    uint32_t g = 0;
-    for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
-      const uint64_t row0 = (uint64_t)tile * TILE_M + a.noise.row_offset;
-      for (int k = 0; k < S; ++k, ++g) {
-        const uint32_t b = g & 1u, n = g >> 1;
-        const float sqrt_h = sqrtf(__ldg(a.sched.step_tab + 4 * k + 1));
-        if (n > 0) mbar_wait(bar_dwempty(slot, b), (n - 1) & 1);                            // every epilogue thread has read the previous content
-        uint8_t* buf = slot_sm + (b ? OFF_A1F : OFF_X);
-        // (row, 4-channel chunk) items, 32 per thread, four at a time: the four Philox chains (10 dependent multiply rounds each) and
-        // Box-Muller MUFU chains are independent, which is what lets ONE warp per scheduler keep up with the step
-#pragma unroll 1
-        for (uint32_t it0 = t; it0 < 16u * TILE_M; it0 += 4u * PROD_THREADS_PER_SLOT) {
-          float4 v[4];
-#pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t item = it0 + j * PROD_THREADS_PER_SLOT;
-            v[j] = philox_dw4(noise_seed, row0 + (item & (TILE_M - 1)), a.noise.step_offset + (uint32_t)k, item >> 7, sqrt_h);
-          }
-#pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t item = it0 + j * PROD_THREADS_PER_SLOT;
-            const uint32_t r = item & (TILE_M - 1), chunk = item >> 7;                      // chunk 0..15 -> half chunk >> 3, 16-byte column chunk & 7
-            *reinterpret_cast<float4*>(buf + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7u) ^ (r & 7u)) << 4)) = v[j];
-          }
-        }
-        mbar_arrive(bar_dwfull(slot, b));
-      }
-    }
   } else {
     // =============================================== IO WARPS ===============================================================
-    // TMA in/out for the slot + staging of each step's layer-1 bias row and scalars into a 3-deep smem ring.  (Producer variant: the
-    // ring only — the epilogue threads read y0 and write ys / states themselves; bar_xfull still paces the ring.)
+    // TMA in/out for the slot + staging of each step's layer-1 bias row and scalars into a 3-deep smem ring.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AUX_REGS));
     const int slot = warp - WARP_IO0;
     const uint32_t slot_u32 = base + SMEM_SLOTS + slot * SLOT_BYTES;
@@ -969,9 +868,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     }
     for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) {
       const int row0 = tile * TILE_M;
-      if (lane == 0 && PROD) {
-        mbar_wait(bar_xfull(slot), par_xfull);             // pacing only
-      } else if (lane == 0) {
+      if (lane == 0) {
         mbar_arrive_expect_tx(bar_tma(slot), 32768);
         tma_load_3d(slot_u32 + OFF_X, &tm_y0, bar_tma(slot), 0, row0, 0);
         tma_load_3d(slot_u32 + OFF_X + 16384, &tm_y0, bar_tma(slot), 32, row0, 0);
@@ -994,9 +891,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           ent_fetch(gstep + 1, e);
           ent_publish(gstep + 1, e);
         }
-        if (lane == 0 && PROD) {
-          mbar_wait(bar_xfull(slot), par_xfull);           // pacing only: epilogue 3 of step k is done, ring entry k - 1 is free
-        } else if (lane == 0) {
+        if (lane == 0) {
           const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
           mbar_wait(bar_xfull(slot), par_xfull);           // epilogue 3 of step k finished writing X / states staging
           if (oe > ob) {
@@ -1116,14 +1011,13 @@ int launch_euler_fwd_tc(const TrajsdeEulerFwdArgs& a, cudaStream_t s) {
     tm_st = tm_y0;
   }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  const bool hd = a.noise.dw != nullptr, du = p.dual != 0;
-  const int threads = hd ? NUM_THREADS : du ? FwdVariant<false, true>::THREADS : FwdVariant<false, false>::THREADS;
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    kern<<<grid, threads, SMEM_ALLOC, s>>>(p, tm_y0, tm_dw, tm_ys, tm_st);
+    kern<<<grid, NUM_THREADS, SMEM_ALLOC, s>>>(p, tm_y0, tm_dw, tm_ys, tm_st);
     return cudaGetLastError();
   };
+  const bool hd = a.noise.dw != nullptr, du = p.dual != 0;
   TS_CUDA_CHECK(hd ? (du ? launch(euler_fwd_tc_kernel<true, true>) : launch(euler_fwd_tc_kernel<true, false>))
                    : (du ? launch(euler_fwd_tc_kernel<false, true>) : launch(euler_fwd_tc_kernel<false, false>)));
   return TRAJSDE_OK;
