@@ -210,6 +210,52 @@ def test_single_launch_sweep_matches_per_step_launches(rows, mixed, philox):
             assert e < 2e-5, (i, e)
 
 
+@pytest.mark.parametrize('rows', [200, 9000])
+def test_single_diffusion_recurrence_equals_dual_with_one_source(rows):
+    """The C ABI also serves a recurrence with ONE diffusion net (alt_mask == NULL: two roles / one SDE pass in the single-launch backward,
+    the <*, false> forward variants).  With every row on the first net the dual call must give the same latents, g and gradients of h0,
+    aa_out, f, g and the GRU — in both forms of the backward sweep."""
+    from trajsde_b200 import ops
+    from trajsde_b200.encoder import _enc_tables, _gru_params
+    from trajsde_b200.solver import _mlp_params
+    sde = init_like_reference(EncoderSDE(), seed=rows, bias_std=0.2).to(DEV)
+    gru = syn.init_reference_style(syn.GRUUnit(), rows + 1, bias_std=0.2).to(DEV)
+    g = torch.Generator().manual_seed(rows)
+    h0 = (torch.randn(rows, 64, generator=g) * 0.3).to(DEV)
+    aa = torch.randn(21, rows, 64, generator=g).to(DEV)
+    am = (torch.rand(rows, 21, generator=g) > 0.3).to(DEV)
+    cot = torch.randn(21, rows, 64, generator=g).to(DEV)
+    cot_g = torch.randn(21, rows, generator=g).to(DEV)
+    step_tab, slots = _enc_tables(2.0, 21, 0.1, torch.device(DEV))
+    p_f, p_g, p_a = _mlp_params(sde.f_func, 64, 'f_func'), _mlp_params(sde.g_nus, 1, 'g_nus'), _mlp_params(sde.g_argo, 1, 'g_argo')
+    gp = _gru_params(gru)
+    all_params = list(p_f) + list(p_g) + list(p_a) + list(gp)
+
+    def run(dual, per_step):
+        ops.ENC_BWD_PER_STEP = per_step
+        try:
+            for p_ in all_params:
+                p_.grad = None
+            h, a = h0.clone().requires_grad_(True), aa.clone().requires_grad_(True)
+            params = list(p_f) + list(p_g) + (list(p_a) if dual else [])
+            nm = torch.ones(rows, dtype=torch.bool, device=DEV) if dual else None
+            lat, gg = ops.enc_call(h, a, am, slots, params, list(gp), step_tab, None, nm, 77, 0, 0, True)
+            ((lat * cot).sum() + (gg * cot_g).sum()).backward()
+            torch.cuda.synchronize()
+            return lat.detach(), gg.detach(), [h.grad, a.grad] + [p_.grad.clone() for p_ in list(p_f) + list(p_g) + list(gp)]
+        finally:
+            ops.ENC_BWD_PER_STEP = False
+
+    lat_d, g_d, gr_d = run(True, False)
+    for per_step in (False, True):
+        lat_s, g_s, gr_s = run(False, per_step)
+        assert torch.equal(lat_s, lat_d) and torch.equal(g_s, g_d)
+        assert ops.backward_status(DEV) == 0
+        for i, (x, r) in enumerate(zip(gr_s, gr_d)):
+            e = float((x - r).abs().max() / r.abs().max())
+            assert e < 2e-5, (per_step, i, e)
+
+
 @pytest.mark.parametrize('rows', [1, 130, 700])
 def test_gru_jump_forward_and_gradients(rows):
     """Stand-alone fused GRU_Unit jump (trajsde_gru_fwd / trajsde_gru_bwd) against the oracle's gru_ref and fp64 autograd."""
