@@ -131,7 +131,15 @@ __global__ void bwd_row_activity_kernel(const float* __restrict__ x, int slabs, 
     }
     float m = 0.f;
     const float* px = x + r * row_stride + 4 * sub;
-    for (int t = 0; t < slabs; ++t) {
+    int t = 0;
+    for (; t + 8 <= slabs; t += 8) {                         // eight independent 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ld_nc_f4(px + (int64_t)(t + j) * slab_stride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m = fmaxf(m, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+    }
+    for (; t < slabs; ++t) {
       const float4 v = ld_nc_f4(px + (int64_t)t * slab_stride);
       m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
