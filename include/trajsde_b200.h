@@ -132,7 +132,7 @@ typedef struct {
  * are exact to 2^-11 (it grew by more than ~2^17 over max|incoming gradient|): gradients of this call may be clipped — rerun with
  * TRAJSDE_BWD_FLAG_EXACT_KERNELS or TRAJSDE_MODE_EXACT_F32. */
 #define TRAJSDE_STATUS_ADJOINT_RANGE 1
-/* trajsde_enc_bwd only: a CTA of the single-launch sweep waited ~2 s for a tile another CTA of the same launch had to hand over (the
+/* trajsde_enc_bwd only: a CTA of the single-launch sweep waited ~30 s for a tile another CTA of the same launch had to hand over (the
  * launch was not fully co-resident, e.g. the device is shared through MPS); the call's results are invalid — rerun with
  * TRAJSDE_BWD_FLAG_PER_STEP_LAUNCHES. */
 #define TRAJSDE_STATUS_SWEEP_TIMEOUT 2

@@ -101,7 +101,7 @@ __device__ __forceinline__ void load_rows_coalesced_cg(const float* slab, int64_
 // cumulative over the stores ordered before it by the barrier — the split-K semaphore pattern; a __threadfence() per thread in front of the
 // barrier cost 2.5 us per GRU tile).
 // Readers: every thread polls with ld.acquire.gpu and then reads the rows with ld.global.cg.  All CTAs of the launch are co-resident (grid
-// <= SM count, one CTA per SM), so the polls cannot starve the producers; a bounded spin (about 2 s) plus a launch-wide abort word turns a
+// <= SM count, one CTA per SM), so the polls cannot starve the producers; a bounded spin (about 30 s) plus a launch-wide abort word turns a
 // scheduling accident into a status bit instead of a hung GPU.
 struct SweepCtl {
   int S;                       // iterations of the recurrence (0: not a sweep)
@@ -138,7 +138,9 @@ __device__ __forceinline__ void sweep_wait_(const SweepCtl& sw, const int32_t* c
     __nanosleep(40);
     if ((++spins & 63u) == 0) {
       if (*reinterpret_cast<volatile int32_t*>(sw.abort_word) != 0) return;
-      if (clock64() - t0 > (1ll << 32)) {                      // ~2 s at 1.9 GHz: give up, flag the call
+      // ~36 s at 1.9 GHz: give up, flag the call.  Long on purpose: CTAs of this launch may legitimately sit behind another kernel of the
+      // process that holds a few SMs (an NCCL all-reduce on a side stream waiting for a straggler rank) and start late
+      if (clock64() - t0 > (1ll << 36)) {
         atomicExch(sw.abort_word, 1);
         if (sw.status) atomicOr(sw.status, TRAJSDE_STATUS_SWEEP_TIMEOUT);
         return;

@@ -80,7 +80,7 @@ class _StatusMonitor:
             self.word.zero_()
             self.seen = 0
             raise RuntimeError("trajsde_b200: trajsde_enc_bwd reported TRAJSDE_STATUS_SWEEP_TIMEOUT — the single-launch encoder backward was "
-                               "not fully co-resident on the device (shared GPU?) and gave up after ~2 s; the gradients of that step are "
+                               "not fully co-resident on the device (shared GPU?) and gave up after ~30 s; the gradients of that step are "
                                "invalid.  Set trajsde_b200.ops.ENC_BWD_PER_STEP = True and rerun the step.")
         if new_bits & _lib.STATUS_ADJOINT_RANGE:
             pol = _POLICY['adjoint_range']
