@@ -452,7 +452,7 @@ def main():
                    "agent_steps_per_s_fwd_bwd": world * twork / (ms * 1e-3), "scenes_per_s_fwd_bwd": world * scenes_per_gpu / (ms * 1e-3),
                    "allreduce_floats": (bk_dec.numel + bk_enc.numel) if world > 1 else 0, "gpu_launches_per_step": nl, "loss": loss_v}
             if not args.no_graph and (world == 1 or not args.no_graph_ddp):
-                # the same step captured ONCE into a CUDA graph (~75 launches + the Python between them become one replay): the Philox key
+                # the same step captured ONCE into a CUDA graph (~35 launches of this library, ~250 small aten launches and the Python between them become one replay): the Philox key
                 # lives in device memory (trajsde_b200.set_device_seed) and is bumped inside the graph, so every replay draws fresh noise
                 word = torch.zeros(1, dtype=torch.int64, device=dev)
                 tb.set_device_seed(word)
