@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TRAJSDE_ABI_VERSION 8
+#define TRAJSDE_ABI_VERSION 9
 #define TRAJSDE_DIM 64
 
 typedef enum {
@@ -174,6 +174,9 @@ typedef struct {
   TrajsdeMlpGrad grad_diffusion;
   TrajsdeMlpGrad grad_diffusion_alt; /* required iff alt_mask != NULL */
   int32_t* status;           /* device int32 or NULL: the TC kernels OR in TRAJSDE_STATUS_* bits (never cleared by the library) */
+  const float* grad_amax;    /* device float or NULL; only read together with row_flags: an estimate of max |grad_ys| over the flagged rows
+                                (within a few binades: it picks a power-of-two loss scale that has 2^17 of head-room) — the call then reads
+                                no gradient before the sweep itself.  trajsde_heads_bwd writes exactly this (TrajsdeHeadsBwdArgs.grad_amax) */
   const uint8_t* row_flags;  /* device [rows] or NULL.  With TRAJSDE_BWD_FLAG_SKIP_ZERO_ROWS: row_flags[r] == 0 PROMISES that every incoming
                                 gradient of row r is zero (its grad_ys entries are then never read and may be uninitialised), so the call
                                 skips its own activity scan — trajsde_heads_bwd produces exactly these flags */
@@ -388,6 +391,7 @@ typedef struct {
   int64_t gx_row_stride;
   int64_t gx_t_stride;
   TrajsdeHeadGrad grad_head[2];
+  float* grad_amax;          /* device float or NULL (row_flags mode): receives max |value written to grad_x| (0 when nothing was active) */
   uint8_t* row_flags;        /* device [rows] or NULL.  Non-NULL: grad_x may be UNINITIALISED on entry; the call writes row_flags[r] = "some
                                 point of row r carries a gradient", zero-fills the n_t entries of exactly those rows and accumulates into
                                 them — rows with flag 0 are left untouched (hand the flags to trajsde_euler_bwd, which then never reads them) */

@@ -255,7 +255,7 @@ def test_solve_and_heads_single_node_equals_the_composition():
 
     n0 = ops.LAUNCHES['n']
     loc_a, gy_a, gp_a = grads(lambda y0: hd.solve_and_heads(sde, loc_h, sc_h, y0, ts, 0.1, seed=77, row_offset=5))
-    assert ops.LAUNCHES['n'] - n0 == 4 + 4 + 5         # fwd: pack + solve + pack + heads; bwd: heads (flags, zero rows, main, reduce) + solver (5)
+    assert ops.LAUNCHES['n'] - n0 == 4 + 4 + 4         # fwd: pack + solve + pack + heads; bwd: heads (flags, zero rows, main, reduce) + solver (compaction, pack, sweep, reduce: flags and max|grad| come from the heads backward)
     loc_b, gy_b, gp_b = grads(lambda y0: hd.decoder_heads_from_solution(
         loc_h, sc_h, tb.sdeint(sde, y0, ts, dt=0.1, method='euler', seed=77, row_offset=5, rows_major=True)))
     assert torch.equal(loc_a, loc_b)

@@ -6,7 +6,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TRAJSDE_LIB_PATH') or os.path.join(_HERE, 'lib', 'libtrajsde_b200.so')   # override: instrumented debug builds
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MODE_EXACT_F32 = 0
 MODE_TC_F16 = 1
 MODES = {'exact': MODE_EXACT_F32, 'tc_f16': MODE_TC_F16}
@@ -55,8 +55,8 @@ class EulerBwdArgs(C.Structure):
                 ('flags', C.c_int32), ('sched', Schedule), ('drift', Mlp), ('diffusion', Mlp), ('diffusion_alt', Mlp),
                 ('alt_mask', _fp), ('noise', Noise), ('states', _fp), ('grad_ys', _fp), ('grad_ys_t_stride', C.c_int64),
                 ('grad_ys_row_stride', C.c_int64), ('grad_g_last', _fp), ('grad_y0', _fp), ('grad_drift', Mlp),
-                ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('status', _fp), ('row_flags', _fp), ('workspace', _fp),
-                ('workspace_bytes', C.c_int64)]
+                ('grad_diffusion', Mlp), ('grad_diffusion_alt', Mlp), ('status', _fp), ('grad_amax', _fp), ('row_flags', _fp),
+                ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 class Gru(C.Structure):
@@ -106,7 +106,7 @@ class HeadsBwdArgs(C.Structure):
                 ('flags', C.c_int32), ('n_t', C.c_int32), ('n_heads', C.c_int32), ('head', Head * 2), ('ln_eps', C.c_float),
                 ('min_scale', C.c_float), ('x', _fp), ('x_row_stride', C.c_int64), ('x_t_stride', C.c_int64), ('grad_out', _fp * 2),
                 ('grad_x', _fp), ('gx_row_stride', C.c_int64), ('gx_t_stride', C.c_int64), ('grad_head', Head * 2),
-                ('row_flags', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
+                ('grad_amax', _fp), ('row_flags', _fp), ('workspace', _fp), ('workspace_bytes', C.c_int64)]
 
 
 class AggrArgs(C.Structure):

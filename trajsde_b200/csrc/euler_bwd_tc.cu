@@ -348,14 +348,16 @@ int launch_euler_bwd_tc(const TrajsdeEulerBwdArgs& a, cudaStream_t s) {
       TS_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       uint32_t* counts = reinterpret_cast<uint32_t*>(n_active) + 2;        // {active, seen} sampled rows
       TS_CUDA_CHECK(cudaMemsetAsync(counts, 0, 8, s));
-      for (int sample = a.row_flags ? 0 : 1; sample >= 0; --sample) {          // caller's flags: no sampling pass, flagged rows only
+      const bool handed = a.row_flags && a.grad_amax && !a.grad_g_last;                          // flags AND the gradient's magnitude come from the caller:
+      if (handed) TS_CUDA_CHECK(cudaMemcpyAsync(amax, a.grad_amax, 4, cudaMemcpyDeviceToDevice, s));   // nothing to scan
+      for (int sample = a.row_flags ? 0 : 1; sample >= 0 && !handed; --sample) {   // caller's flags: no sampling pass, flagged rows only
         const int64_t want = ((sample ? ((a.rows + 255) / 256) * 32 : a.rows) + 15) / 16;
         bwd_row_activity_kernel<<<(int)(want < 8 * sms ? want : 8 * sms), 256, 0, s>>>(a.grad_ys, a.sched.n_outputs + 1, a.rows, a.grad_ys_t_stride,
                                                                                      a.grad_ys_row_stride, a.grad_g_last, amax, row_flags, counts, sample,
                                                                                      a.row_flags);
         TS_CUDA_CHECK(cudaGetLastError());
       }
-      bwd_compact_rows_kernel<<<1, 1024, 0, s>>>(row_flags, a.rows, row_map, n_active);
+      bwd_compact_rows_kernel<<<1, 1024, 0, s>>>(handed ? a.row_flags : row_flags, a.rows, row_map, n_active);
       TS_CUDA_CHECK(cudaGetLastError());
       TS_CUDA_CHECK(cudaMemsetAsync(a.grad_y0, 0, sizeof(float) * 64 * (size_t)a.rows, s));   // skipped rows: dL/dy0 = 0
     } else {

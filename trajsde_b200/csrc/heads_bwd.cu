@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
   float gw1[2][16];                    // dW1[j0 + 16 jj][k0 .. k0+3], j0 = tid / 16, k0 = 4 (tid % 16)      per head
   float gcol[2] = {0.f, 0.f};          // thread = (vector v = tid / 64, channel c = tid % 64): v = 0 db1, 1 dgamma, 2 dbeta, 3 dW2[0]
   float gcol2[2] = {0.f, 0.f};         // v == 3 threads also carry dW2[1][c]; v == 0 threads of c < 2 carry db2[c]
+  float gx_peak = 0.f;                 // largest |value| this thread has written to grad_x (-> a.grad_amax: the solver backward's loss scale)
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
           float4 o = *dst;                                               // a point may be active in both heads: accumulate
           o.x += acc[pp].x; o.y += acc[pp].y; o.z += acc[pp].z; o.w += acc[pp].w;
           *dst = o;
+          gx_peak = fmaxf(gx_peak, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
         }
       }
     }
@@ -352,6 +354,12 @@ __global__ void __launch_bounds__(HB_THREADS, 2) heads_bwd_kernel(const HeadsBwd
     if (n > 0) process(h, n);                                  // the remainder (< 64 points; the tile is padded with inert points)
   }
 
+  if (a.grad_amax) {                                           // non-negative floats order like their bit patterns
+    if (!(gx_peak <= 3.0e38f)) gx_peak = 3.0e38f;              // inf / nan: clamp (the result is garbage either way)
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) gx_peak = fmaxf(gx_peak, __shfl_xor_sync(0xffffffffu, gx_peak, off));
+    if (lane == 0 && gx_peak > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.grad_amax), __float_as_uint(gx_peak));
+  }
   // ---- this block's partial vector -----------------------------------------------------------------------------------------------------
   float* out = p.partial + (size_t)blockIdx.x * 2 * HG_PAD;
 #pragma unroll
@@ -453,6 +461,7 @@ int launch_heads_bwd(const TrajsdeHeadsBwdArgs& a, cudaStream_t s) {
   if (grid <= 0) return set_error(TRAJSDE_ERR_CUDA, "device attributes unavailable");
   const int64_t chunks = (p.n_points + HB_THREADS - 1) / HB_THREADS;
   if (chunks < grid) grid = (int)(chunks > 0 ? chunks : 1);
+  if (a.grad_amax) TS_CUDA_CHECK(cudaMemsetAsync(a.grad_amax, 0, 4, s));
   if (a.row_flags && a.rows > 0) {
     TS_CUDA_CHECK(cudaMemsetAsync(a.row_flags, 0, (size_t)a.rows, s));
     if (p.n_points > 0) {

@@ -87,7 +87,7 @@ def _(x, params, n_heads, ln_eps, cat4=None):
 
 def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, ln_eps: float, grad0: Optional[torch.Tensor],
                     grad1: Optional[torch.Tensor], grad_x: torch.Tensor, row_flags: Optional[torch.Tensor] = None,
-                    cat4: bool = False) -> List[torch.Tensor]:
+                    cat4: bool = False, grad_amax: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """Gradients of the 6 * n_heads head tensors; dL/dx is ACCUMULATED into the zero-filled ``grad_x`` (same shape as x, any row / t
     strides, unit channel stride) for the points that carry a non-zero dL/dout.  ``grad_h`` [rows, T, 2] or None per head.
     ``cat4``: ``grad0`` is dL/d out['loc'] [rows, T, 4] of the fused result (channels 2..3 pass through the ELU derivative)."""
@@ -118,6 +118,8 @@ def _heads_bwd_impl(x: torch.Tensor, params: List[torch.Tensor], n_heads: int, l
     a.grad_x, a.gx_row_stride, a.gx_t_stride = grad_x.data_ptr(), max(grad_x.stride(0), 64), max(grad_x.stride(1), 64)
     if row_flags is not None:      # grad_x may be uninitialised: the call flags the rows that carry a gradient and zero-fills only those
         a.row_flags = row_flags.data_ptr()
+    if grad_amax is not None:      # float32 [1]: receives max |value written to grad_x| (the solver backward's loss-scale input)
+        a.grad_amax = grad_amax.data_ptr()
     L = _lib.lib()
     need = _lib.check(L.trajsde_heads_bwd_workspace_bytes(_lib.MODE_TC_F16), "trajsde_heads_bwd_workspace_bytes")
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
@@ -185,13 +187,14 @@ class _SolveHeadsFn(torch.autograd.Function):
             gys = torch.empty_strided(ys.size(), ys.stride(), dtype=ys.dtype, device=ys.device)
             gys[0].zero_()                                  # dL/dys[0] = 0 (the heads read ys[1:]); 256 B per row
             flags = torch.empty((rows,), dtype=torch.uint8, device=ys.device)
+            amax = torch.empty((1,), dtype=torch.float32, device=ys.device)      # max |dL/dys|, written by the heads backward
         else:
             gys = torch.empty_strided(ys.size(), ys.stride(), dtype=ys.dtype, device=ys.device).zero_()
-            flags = None
+            flags = amax = None
         gps = _heads_bwd_impl(ys[1:].permute(1, 0, 2), head_params_, n_heads, ln_eps, g0, g1 if n_heads == 2 and not cat4 else None,
-                              gys[1:].permute(1, 0, 2), flags, cat4=cat4)
+                              gys[1:].permute(1, 0, 2), flags, cat4=cat4, grad_amax=amax)
         grads = ops._euler_bwd_impl(gys, None, states, sde_params, step_tab, out_begin, out_w, n_outputs, None, None, seed, row_offset, 0,
-                                    mode, flags)
+                                    mode, flags, amax)
         return (grads[0],) + (None,) * 11 + tuple(grads[1:]) + tuple(gps)
 
 

@@ -290,10 +290,12 @@ def _(y0, params, step_tab, out_begin, out_w, n_outputs, dw, alt_mask, seed, row
 def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tensor], states: torch.Tensor,
               params: List[torch.Tensor], step_tab: torch.Tensor, out_begin: torch.Tensor, out_w: torch.Tensor,
               n_outputs: int, dw: Optional[torch.Tensor], alt_mask: Optional[torch.Tensor], seed: int, row_offset: int,
-              step_offset: int, mode: int, row_flags: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+              step_offset: int, mode: int, row_flags: Optional[torch.Tensor] = None,
+              grad_amax: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """[grad_y0] + gradients of every tensor in ``params`` (same order/shapes).  ``row_flags`` (uint8 [rows], from
     ``trajsde_heads_bwd``): rows flagged 0 have no incoming gradient and their ``grad_ys`` entries may be uninitialised — honoured by
-    the tensor-core kernels of a single-diffusion solve only (the caller checks ``row_flags_supported``)."""
+    the tensor-core kernels of a single-diffusion solve only (the caller checks ``row_flags_supported``).  ``grad_amax`` (float32 [1],
+    also from ``trajsde_heads_bwd``): max |grad_ys| of the flagged rows — with it the call scans no gradient at all before the sweep."""
     dev = states.device
     _monitor(dev).poll()
     S, rows = states.shape[0], states.shape[1]
@@ -309,6 +311,8 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
             raise ValueError("row_flags need the tensor-core backward of a single-diffusion solve")
         skip_zero = True
         a.row_flags = row_flags.data_ptr()
+        if grad_amax is not None:
+            a.grad_amax = grad_amax.data_ptr()
     a.mode, a.rows, a.dim, a.flags = mode, rows, 64, (1 if BWD_EXACT_KERNELS else 0) | (2 if skip_zero else 0)
     a.sched.n_steps, a.sched.n_outputs = S, n_outputs
     a.sched.step_tab, a.sched.out_begin, a.sched.out_w = step_tab.data_ptr(), out_begin.data_ptr(), out_w.data_ptr()
@@ -349,7 +353,7 @@ def _euler_bwd_impl(grad_ys: Optional[torch.Tensor], grad_g: Optional[torch.Tens
         sampled = tc and grad_ys is not None and rows * grad_ys.shape[0] >= (1 << 16)   # sampled absmax + its conditional full scan
         if skip_zero:
             # row activity (sampled + full, or flagged rows only) + compaction + pack + fused dgrad/wgrad + reduce
-            LAUNCHES['n'] += 5 if row_flags is not None else 6
+            LAUNCHES['n'] += (4 if grad_amax is not None and grad_g is None else 5) if row_flags is not None else 6
         else:
             LAUNCHES['n'] += ((5 if dual else 4) + int(sampled)) if tc else (5 if dual else 3)
     return [grad_y0] + gparams
