@@ -52,6 +52,9 @@ constexpr uint32_t IMG_BYTES = 59392;     // 58 KB
 constexpr uint32_t SIMG_B1 = 0;           // [128 rows][64] f16 SW128: W1y | V1y
 constexpr uint32_t SIMG_BIAS = 16384;     // [128 rows][64] f16 SW128: slice 0 layer-1 bias + time columns, slice 1 b2 | c2, slice 2 b3
 constexpr uint32_t SIMG_W2 = 32768, SIMG_V2 = 40960, SIMG_W3 = 49152;
+#ifndef TRAJSDE_FWD_SEPARATE_DW
+#define TRAJSDE_FWD_SEPARATE_DW 1       // supplied-dW single-diffusion variant: dW tile in the A1f|A1g region instead of the output staging buffer (A/B)
+#endif
 #ifndef TRAJSDE_FWD_BIAS_MMA
 #define TRAJSDE_FWD_BIAS_MMA 1          // in-kernel-noise variants only (see BIAS_MMA); 0 adds the biases in the epilogues everywhere (A/B)
 #endif
@@ -212,7 +215,8 @@ __device__ __forceinline__ void ld_g(uint32_t tm_g_uniform, uint32_t tm_g_alt, b
 }
 
 struct Epi3Ctx {
-  uint8_t* x_row;
+  uint8_t* x_row;       // output staging row (and, unless dw_row points elsewhere, where the step's dW chunks are)
+  uint8_t* dw_row;      // this thread's dW chunks of the step
   uint8_t* a0_row;
   uint8_t* st_row;
   const float* b3;      // vec + VEC_B3 + hh*32
@@ -244,7 +248,7 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     float4* xp = reinterpret_cast<float4*>(c.x_row + ((q ^ (c.row & 7u)) << 4));
-    const float4 dw = *xp;
+    const float4 dw = *reinterpret_cast<const float4*>(c.dw_row + ((q ^ (c.row & 7u)) << 4));
     float f0 = __uint_as_float(fv[4 * q]), f1 = __uint_as_float(fv[4 * q + 1]), f2 = __uint_as_float(fv[4 * q + 2]), f3 = __uint_as_float(fv[4 * q + 3]);
     if (!BIAS_IN_MMA) {                                      // otherwise b3 came through the MMA (BIAS tile, slice 2)
       const float4 b3 = *reinterpret_cast<const float4*>(c.b3 + 4 * q);
@@ -389,7 +393,11 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     uint32_t par_accA = 0, par_accB = 0, par_tma = 0, par_xfree = 0;
     uint32_t gstep = 0;
     Epi3Ctx c3;
+    // Supplied dW, operands in tensor memory, no states to stage: the A1f|A1g region is free and takes the dW tile, so the IO warp can load
+    // the next step's tile as soon as epilogue 3 has read this one — without waiting for the output store to drain X
+    const bool sep_dw = HAS_DW && !DUAL && !save_states && (TRAJSDE_FWD_SEPARATE_DW != 0);
     c3.x_row = x_row;
+    c3.dw_row = sep_dw ? slot_sm + OFF_A1F + hh * 16384 + row * 128 : x_row;
     c3.a0_row = a0_row;
     c3.st_row = slot_sm + OFF_A1F + hh * 16384 + row * 128;
     c3.b3 = vec + VEC_B3 + hh * 32;
@@ -814,6 +822,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
     float* ring = reinterpret_cast<float*>(sm + SMEM_RING + slot * RING_BYTES);
     uint32_t par_xfull = 0;
     uint32_t gstep = 0;
+    const bool sep_dw = HAS_DW && !DUAL && !save_states && (TRAJSDE_FWD_SEPARATE_DW != 0);
+    const uint32_t dw_dst = slot_u32 + (sep_dw ? OFF_A1F : OFF_X);
     int my_tiles = 0;
     for (int tile = tile_lo + slot; tile < tile_hi; tile += NUM_SLOTS) ++my_tiles;
     const uint32_t total_steps = (uint32_t)my_tiles * (uint32_t)S;
@@ -880,8 +890,8 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         mbar_arrive(bar_xfree(slot));
         if (HAS_DW) {
           mbar_arrive_expect_tx(bar_tma(slot), 32768);
-          tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, 0);
-          tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, 0);
+          tma_load_3d(dw_dst, &tm_dw, bar_tma(slot), 0, row0, 0);
+          tma_load_3d(dw_dst + 16384, &tm_dw, bar_tma(slot), 32, row0, 0);
         }
       }
       par_xfull ^= 1;
@@ -894,6 +904,11 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         if (lane == 0) {
           const int ob = a.sched.out_begin[k], oe = a.sched.out_begin[k + 1];
           mbar_wait(bar_xfull(slot), par_xfull);           // epilogue 3 of step k finished writing X / states staging
+          if (HAS_DW && sep_dw && k + 1 < S) {               // ... and reading its dW tile: the next one goes out ahead of the stores
+            mbar_arrive_expect_tx(bar_tma(slot), 32768);
+            tma_load_3d(dw_dst, &tm_dw, bar_tma(slot), 0, row0, k + 1);
+            tma_load_3d(dw_dst + 16384, &tm_dw, bar_tma(slot), 32, row0, k + 1);
+          }
           if (oe > ob) {
             tma_store_3d(&tm_ys, slot_u32 + OFF_X, 0, row0, ob + 1);
             tma_store_3d(&tm_ys, slot_u32 + OFF_X + 16384, 32, row0, ob + 1);
@@ -906,7 +921,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
           tma_store_wait_read0();
           if (k + 1 < S) {
             mbar_arrive(bar_xfree(slot));
-            if (HAS_DW) {
+            if (HAS_DW && !sep_dw) {
               mbar_arrive_expect_tx(bar_tma(slot), 32768);
               tma_load_3d(slot_u32 + OFF_X, &tm_dw, bar_tma(slot), 0, row0, k + 1);
               tma_load_3d(slot_u32 + OFF_X + 16384, &tm_dw, bar_tma(slot), 32, row0, k + 1);
