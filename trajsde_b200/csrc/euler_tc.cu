@@ -296,9 +296,12 @@ __device__ __forceinline__ void epi3_update(const Epi3Ctx& c, uint32_t (&yv)[32]
 // debug build only (bench_micro/fwd_timeline.py): clocks of thread 0 of CTA 0 — [0] kernel, [1] waiting for X to be released (previous
 // step's output store), [2] waiting for the step's dW tile to land, [3] waiting for P3, [4] steps
 __device__ long long g_fwd_tl[8];
+__device__ long long g_fwd_seg[16];   // clocks between consecutive FWD_MARKs of a step (single-diffusion variants), thread 0 of CTA 0
 #define FWD_TL(i, expr) do { const long long _t0 = clock64(); expr; if (threadIdx.x == 0 && blockIdx.x == 0) g_fwd_tl[i] += clock64() - _t0; } while (0)
+#define FWD_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _t = clock64(); g_fwd_seg[i] += _t - seg_prev; seg_prev = _t; } } while (0)
 #else
 #define FWD_TL(i, expr) do { expr; } while (0)
+#define FWD_MARK(i) do { } while (0)
 #endif
 
 template <bool HAS_DW, bool DUAL>
@@ -315,6 +318,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
   const int S = a.sched.n_steps;
 #ifdef TRAJSDE_FWD_TIMELINE
   const long long tl_start = clock64();
+  long long seg_prev = tl_start;
 #endif
   // contiguous, balanced tile range of this CTA (sizes differ by at most one tile); its two slots take alternate tiles
   const int tiles_q = p.num_tiles / (int)gridDim.x, tiles_r = p.num_tiles % (int)gridDim.x;
@@ -476,6 +480,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
         if constexpr (TMEM_A) {
           // ===================== single-diffusion variants: operands in tensor memory, biases through the MMA =====================
           mbar_wait(bar_ring(slot, gstep & 1), (gstep >> 1) & 1);   // this step's scalars are in the ring
+          FWD_MARK(0);   // loop tail + ring wait
           const float* ent = ring + (gstep % 3u) * RING_LD;
           const float4 sc = *reinterpret_cast<const float4*>(ent + BIAS1_LD);      // h, sqrt(h), w0, w1
           const int2 so = *reinterpret_cast<const int2*>(ent + BIAS1_LD + 4);      // first output index, #outputs of this step
@@ -491,6 +496,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 
           // ---- epilogue 1: h1f = tanh(z1f) -> OA (P2f may start), h1g = tanh(z1g) -> OB (biases are in the accumulators) ----------
           mbar_wait(bar_acc(slot, 0), par_accA);
+          FWD_MARK(1);   // wait P1
           par_accA ^= 1;
           tc_fence_after();
           {
@@ -529,9 +535,11 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             par_xfree ^= 1;
             draw(0, 3);
           }
+          FWD_MARK(2);   // epilogue 1 (+ draw)
 
           // ---- epilogue 2: h2f = tanh(z2f) -> OA (P3 may start) ; partial of w3 . tanh(z2g) -----------------------------------------
           mbar_wait(bar_acc(slot, 1), par_accB);
+          FWD_MARK(3);   // wait P2f
           par_accB ^= 1;
           tc_fence_after();
           {
@@ -545,7 +553,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             tc_fence_before();
             mbar_arrive(bar_opnd(slot, 1));                  // h2f ready -> P3
             if (!HAS_DW) draw(3, 5);
+            FWD_MARK(4);   // epilogue 2a (+ draw)
             mbar_wait(bar_acc(slot, 0), par_accA);
+            FWD_MARK(5);   // wait P2g
             par_accA ^= 1;
             tc_fence_after();
             tmem_ld_32x32b_x32(tm_lane + 64, v);
@@ -563,6 +573,7 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
             }
             gpart[hh * TILE_M + row] = gd;
           }
+          FWD_MARK(6);   // epilogue 2b
 
           // ---- epilogue 3 ---------------------------------------------------------------------------------------------------------
           if (HAS_DW) {
@@ -580,7 +591,9 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
 #else
           constexpr bool YPRE = false;
 #endif
+          FWD_MARK(7);   // X free + dW landed (or draw)
           FWD_TL(3, mbar_wait(bar_acc(slot, 1), par_accB));
+          FWD_MARK(8);   // wait P3
 #ifdef TRAJSDE_FWD_TIMELINE
           if (threadIdx.x == 0 && blockIdx.x == 0) g_fwd_tl[4] += 1;
 #endif
@@ -604,10 +617,12 @@ euler_fwd_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tm_y0,
               *reinterpret_cast<uint4*>(a0_row + (((2u * ((gstep + 1) & 1u)) ^ (row & 7u)) << 4)) =
                   *reinterpret_cast<const uint4*>(ring + ((gstep + 1) % 3u) * RING_LD);
           }
+          FWD_MARK(9);   // epilogue 3
           fence_proxy_async();
           tc_fence_before();
           if (k + 1 < S) mbar_arrive(bar_opnd(slot, 0));     // y' (tensor memory) + bias slice ready -> P1 of step k+1
           mbar_arrive(bar_xfull(slot));                      // X (outputs) / states staging written -> IO warp stores them
+          FWD_MARK(10);  // fences + arrives
         } else {
           // ===================== dual-diffusion variants: operands through swizzled shared memory =====================================
           if (save_states && !TMEM_A) {                      // previous step's states store must have drained A1f|A1g before epilogue 1
@@ -1045,5 +1060,10 @@ extern "C" int trajsde_debug_fwd_timeline(long long* out8) {
   long long zero[8] = {0};
   if (cudaMemcpyFromSymbol(out8, trajsde::g_fwd_tl, sizeof(zero)) != cudaSuccess) return -1;
   return cudaMemcpyToSymbol(trajsde::g_fwd_tl, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int trajsde_debug_fwd_segments(long long* out16) {
+  long long zero[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, trajsde::g_fwd_seg, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::g_fwd_seg, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
 }
 #endif
