@@ -399,7 +399,7 @@ def main():
             pass
 
         dstage = syn.init_reference_style(DecStage(), 11).to(dev)
-        hidden = torch.nn.Parameter(torch.randn(64, device=dev) * 0.02)                 # enc…sep2.py:61-62
+        hidden = torch.nn.Parameter(torch.randn(64, generator=torch.Generator().manual_seed(5)).to(dev) * 0.02)     # enc…sep2.py:61-62; same on every rank
         dec_params = list(dstage.parameters())
         enc_params = list(enc_sde.parameters()) + list(gru.parameters()) + [hidden]
 
@@ -407,8 +407,9 @@ def main():
             tbatch = syn.make_train_batch(scenes_per_gpu, args.agents, seed=2000 + rank, device=dev)
             b = tbatch.base
             Et, Mt, Nt = b.enc_rows, b.dec_rows, scenes_per_gpu * args.agents
-            bk_dec, bk_enc = FlatGradBucket(dec_params), FlatGradBucket(enc_params)
-            opt = torch.optim.AdamW(dec_params + enc_params, lr=1e-3, weight_decay=7e-4)          # yml:2-3
+            bk_dec, bk_enc = FlatGradBucket(dec_params, pack=True), FlatGradBucket(enc_params, pack=True)
+            opt = torch.optim.AdamW(dec_params + enc_params, lr=1e-3, weight_decay=7e-4, fused=True)   # yml:2-3; fused: one launch per dtype/device group
+            # instead of ~150 foreach / per-tensor launches (the eager step is launch-bound at 128 scenes)
             eos = 20 - torch.argmax(b.bos_mask.float(), dim=1)                                # enc…sep2.py:187
             ar = torch.arange(Nt, device=dev)
             new_agent_index = torch.cat((tbatch.agent_index, torch.arange(Nt, Et, device=dev)))   # :101
@@ -446,17 +447,25 @@ def main():
             ms = timed(train_step, k_train) / k_train
             nl = (ops.LAUNCHES['n'] - n0) // k_train
             loss_v = float(train_step(99).detach())
+            in_sync = None
+            if world > 1:       # every rank started from the same weights: with the bucket all-reduces in place they stay bit-identical
+                chk = torch.stack([p_.detach().double().sum() for p_ in dec_params + enc_params]).sum().reshape(1)
+                hi, lo = chk.clone(), chk.clone()
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                in_sync = bool((hi == lo).item())
             twork = Et * ENC_STEPS + Mt * DEC_STEPS
             gs = global_scenes or world * scenes_per_gpu
             out = {"scenes_per_gpu": scenes_per_gpu, "global_scenes": gs, "ms_per_step": ms, "steps": k_train,
                    "agent_steps_per_s_fwd_bwd": world * twork / (ms * 1e-3), "scenes_per_s_fwd_bwd": world * scenes_per_gpu / (ms * 1e-3),
-                   "allreduce_floats": (bk_dec.numel + bk_enc.numel) if world > 1 else 0, "gpu_launches_per_step": nl, "loss": loss_v}
+                   "allreduce_floats": (bk_dec.numel + bk_enc.numel) if world > 1 else 0, "gpu_launches_per_step": nl, "loss": loss_v,
+                   "params_in_sync_across_ranks": in_sync}
             if not args.no_graph and (world == 1 or not args.no_graph_ddp):
                 # the same step captured ONCE into a CUDA graph (~35 launches of this library, ~250 small aten launches and the Python between them become one replay): the Philox key
                 # lives in device memory (trajsde_b200.set_device_seed) and is bumped inside the graph, so every replay draws fresh noise
                 word = torch.zeros(1, dtype=torch.int64, device=dev)
                 tb.set_device_seed(word)
-                opt_eager, opt = opt, torch.optim.AdamW(dec_params + enc_params, lr=1e-3, weight_decay=7e-4, capturable=True)
+                opt_eager, opt = opt, torch.optim.AdamW(dec_params + enc_params, lr=1e-3, weight_decay=7e-4, fused=True, capturable=True)
 
                 def graph_body():
                     l_ = train_step(0)

@@ -31,12 +31,12 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, pack=False):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(66, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1))
-    bucket = FlatGradBucket(net.parameters())
+    bucket = FlatGradBucket(net.parameters(), pack=pack)
     assert bucket.numel == 66 * 64 + 64 + 64 + 1
     # scene-sharded batch: each rank sees its own rows of one global batch
     g = torch.Generator().manual_seed(123)
@@ -44,7 +44,10 @@ def _worker(rank, world, port, out):
     s, e = shard_scenes(40, world, rank)
     bucket.zero_()
     net(x_all[s:e]).sum().div(e - s).backward()
-    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())   # grads accumulated into the bucket
+    if pack:                                                        # autograd handed over its own tensors: nothing in the bucket yet
+        assert all(p.grad is not None and p.grad.data_ptr() != v.data_ptr() for p, v in zip(bucket.params, bucket._views))
+    else:
+        assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())   # grads accumulated into the bucket
     if rank == 0:
         bucket.all_reduce_mean()
     else:
@@ -57,6 +60,7 @@ def _worker(rank, world, port, out):
     loss.backward()
     flat_ref = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
     ok = torch.allclose(bucket.flat, flat_ref, atol=1e-6, rtol=1e-5)
+    ok = ok and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket._views))   # the optimizer reads the reduced values
     t = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -64,11 +68,12 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_gloo_world2():
+@pytest.mark.parametrize('pack', [False, True])
+def test_flat_bucket_allreduce_gloo_world2(pack):
     ctx = mp.get_context('spawn')
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, pack)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
