@@ -64,7 +64,34 @@ def timeline(rows):
         print(f"rows={rows} role {role}: kernel {tot / 1e3:.1f} kclk  in wait {wt / 1e3:.1f} kclk  in publish {pb / 1e3:.1f} kclk  blocked waits {nb:.1f}  (per CTA, thread 0, mean of {G} CTAs)")
 
 
+def gru_timeline(rows):
+    """needs a -DTRAJSDE_GRU_TIMELINE build: clocks per GRU tile of CTA 0 of the single-launch sweep, by segment"""
+    import ctypes as C
+    from trajsde_b200 import _lib
+    L = _lib.lib()
+    buf = (C.c_longlong * 24)()
+    run(rows, False, reps=2)
+    L.trajsde_debug_gru_segments(buf)
+    run(rows, False, reps=1)        # 4 calls
+    L.trajsde_debug_gru_segments(buf)
+    tiles = (rows + 127) // 128
+    Gg = min(tiles, 148 - 2 * (148 // 4))
+    n_tiles = 4 * 21 * (tiles // Gg + (1 if 0 < tiles % Gg else 0))        # CTA 0 gets the larger share
+    names = ['loop / flush tail', 'tile start (role waits, loads, transposes)'] + [f'{ph}: {what}' for ph in ('F1', 'F2', 'F3', 'F4', 'B1', 'B2', 'B3', 'B4')
+                                                                                    for what in ('work before wait', 'wait MMA')]
+    names += ['B4 epilogue + stores + publish', 'wait weight-gradient MMAs', 'dU1|dR1 flush']
+    tot = 0
+    for i, nm in enumerate(names):
+        print(f"  {nm:44s} {buf[i] / n_tiles:8.0f} clk per tile")
+        tot += buf[i] / n_tiles
+    print(f"  total {tot:.0f} clk per GRU tile (rows={rows}, {n_tiles // 4} tiles per call on CTA 0)")
+
+
 if __name__ == '__main__':
+    if '--gru-timeline' in sys.argv:
+        for rows in (2688, 21504):
+            gru_timeline(rows)
+        sys.exit(0)
     if '--timeline' in sys.argv:
         for rows in (2688, 21504, 86016):
             timeline(rows)

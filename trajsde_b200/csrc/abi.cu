@@ -19,6 +19,7 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }   // tensors the kernels touch with 256-bit accesses
 
 static int check_mlp(const TrajsdeMlp& m, const char* name) {
   if (!m.w1 || !m.b1 || !m.w2 || !m.b2 || !m.w3 || !m.b3)
@@ -132,6 +133,7 @@ int trajsde_euler_bwd(const TrajsdeEulerBwdArgs* a, void* cuda_stream) {
                       !a->grad_diffusion_alt.b2 || !a->grad_diffusion_alt.w3 || !a->grad_diffusion_alt.b3))
     return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "null grad_diffusion_alt pointer with alt_mask set");
   if (a->rows > 0 && (!a->states || !a->grad_y0)) return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "states/grad_y0 null");
+  if (a->grad_y0 && !aligned32(a->grad_y0)) return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_y0 must be 32-byte aligned");
   if (a->grad_ys && ((a->grad_ys_row_stride & 3) || (a->grad_ys_t_stride & 3) || !aligned16(a->grad_ys)))
     return set_error(TRAJSDE_ERR_UNSUPPORTED, "grad_ys must be 16-byte aligned with strides multiple of 4 elements");
   if (a->mode != TRAJSDE_MODE_EXACT_F32 && a->mode != TRAJSDE_MODE_TC_F16) return set_error(TRAJSDE_ERR_UNSUPPORTED, "unknown mode %d", a->mode);
@@ -169,9 +171,9 @@ int trajsde_enc_fwd(const TrajsdeEncFwdArgs* a, void* cuda_stream) {
   if (a->rows == 0) return TRAJSDE_OK;
   if (!a->h0 || !a->aa_out || !a->slot || !a->obs_mask || !a->latent || !a->g_out)
     return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h0/aa_out/slot/obs_mask/latent/g_out null");
-  if (!aligned16(a->h0) || (a->h0_row_stride & 3) || !aligned16(a->aa_out) || !aligned16(a->latent) ||
-      (a->noise.dw && !aligned16(a->noise.dw)))
-    return set_error(TRAJSDE_ERR_UNSUPPORTED, "h0/aa_out/latent/dw must be 16-byte aligned (row stride multiple of 4 elements)");
+  if (!aligned16(a->h0) || (a->h0_row_stride & 3) || !aligned32(a->aa_out) || !aligned32(a->latent) ||
+      (a->noise.dw && !aligned32(a->noise.dw)) || (a->y1_out && !aligned32(a->y1_out)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "h0 must be 16-byte aligned (row stride multiple of 4 elements), aa_out/latent/dw/y1_out 32-byte aligned");
   int64_t need = enc_fwd_tc_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
   if (a->workspace_bytes < need || !a->workspace)
     return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);
@@ -235,10 +237,10 @@ int trajsde_enc_bwd(const TrajsdeEncBwdArgs* a, void* cuda_stream) {
   }
   if (!a->h0 || !a->aa_out || !a->slot || !a->obs_mask || !a->latent || !a->y1 || !a->grad_h0)
     return set_error(TRAJSDE_ERR_INVALID_ARGUMENT, "h0/aa_out/slot/obs_mask/latent/y1/grad_h0 null");
-  if (!aligned16(a->h0) || !aligned16(a->aa_out) || !aligned16(a->latent) || !aligned16(a->y1) || !aligned16(a->grad_h0) ||
+  if (!aligned16(a->h0) || !aligned16(a->aa_out) || !aligned16(a->latent) || !aligned16(a->y1) || !aligned32(a->grad_h0) ||
       (a->grad_latent && !aligned16(a->grad_latent)) || (a->noise.dw && !aligned16(a->noise.dw)) ||
-      (a->grad_aa_out && !aligned16(a->grad_aa_out)))
-    return set_error(TRAJSDE_ERR_UNSUPPORTED, "tensors must be 16-byte aligned");
+      (a->grad_aa_out && !aligned32(a->grad_aa_out)))
+    return set_error(TRAJSDE_ERR_UNSUPPORTED, "tensors must be 16-byte aligned (grad_h0, grad_aa_out: 32-byte)");
   int64_t need = enc_bwd_workspace_bytes(a->rows, a->sched.n_steps, a->alt_mask != nullptr);
   if (a->workspace_bytes < need || !a->workspace)
     return set_error(TRAJSDE_ERR_WORKSPACE, "workspace %lld < required %lld bytes", (long long)a->workspace_bytes, (long long)need);

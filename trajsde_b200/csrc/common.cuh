@@ -106,6 +106,21 @@ __device__ __forceinline__ float4 ld_nc_f4(const float* p) {
   return v;
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256, 32-byte aligned): a thread that owns 128 contiguous bytes of a row moves them as four
+// whole 32-byte sectors instead of eight half-used ones (a warp's 16-byte stores to 32 different rows touch 32 sectors for 512 bytes)
+__device__ __forceinline__ void st_f8(float* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z),
+               "f"(b.w) : "memory");
+}
+__device__ __forceinline__ void st_cs_f8(float* p, float4 a, float4 b) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y),
+               "f"(b.z), "f"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_nc_f8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ void st_cs_f4(float* p, float4 v) {
   asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

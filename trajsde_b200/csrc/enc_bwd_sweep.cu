@@ -145,3 +145,12 @@ extern "C" int trajsde_debug_sweep_timeline(long long* out640) {
   return cudaMemcpyToSymbol(trajsde::bwdtc::g_sweep_tl, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
 }
 #endif
+
+#ifdef TRAJSDE_GRU_TIMELINE
+extern "C" int trajsde_debug_gru_segments(long long* out24) {
+  static long long zero[24];
+  if (cudaMemcpyFromSymbol(out24, trajsde::grutc::g_gru_seg, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::grutc::g_gru_seg, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
+#endif
+

@@ -259,10 +259,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         // iteration) and store it once G3 has read the old one, so epilogue 1 never waits for a global load.
         const int slot0 = __shfl_sync(0xffffffffu, lane_slot, 0);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) v = ld_nc_f4(a.aa_out + ((int64_t)slot0 * a.rows + grow) * 64 + hh * 32 + 4 * q);
+        for (int q = 0; q < 8; q += 2) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = v;
+          if (valid) ld_nc_f8(a.aa_out + ((int64_t)slot0 * a.rows + grow) * 64 + hh * 32 + 4 * q, v, w);
           t[4 * q] = v.x; t[4 * q + 1] = v.y; t[4 * q + 2] = v.z; t[4 * q + 3] = v.w;
+          t[4 * q + 4] = w.x; t[4 * q + 5] = w.y; t[4 * q + 6] = w.z; t[4 * q + 7] = w.w;
         }
         st_operand32(o_ax, t);
         tc_wait_st();
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           if (HAS_DW) {
             const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dwv[q] = ld_nc_f4(ds + 4 * q);
+            for (int q = 0; q < 8; q += 2) ld_nc_f8(ds + 4 * q, dwv[q], dwv[q + 1]);
           }
         }
 
@@ -383,7 +384,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           if (a.y1_out && valid) {                         // pre-GRU state, saved for the backward call
             float* dst = a.y1_out + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+            for (int q = 0; q < 4; ++q)
+              st_cs_f8(dst + 8 * q, make_float4(t[8 * q], t[8 * q + 1], t[8 * q + 2], t[8 * q + 3]), make_float4(t[8 * q + 4], t[8 * q + 5], t[8 * q + 6], t[8 * q + 7]));
           }
           tc_wait_st();
         }
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         if (valid && it + 1 < S) {
           const float* xs = a.aa_out + ((int64_t)slot_next * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) xn[q] = ld_nc_f4(xs + 4 * q);
+          for (int q = 0; q < 8; q += 2) ld_nc_f8(xs + 4 * q, xn[q], xn[q + 1]);
         }
         // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
         ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // G1
@@ -479,7 +481,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           if (valid) {
             float* dst = a.latent + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) st_cs_f4(dst + 4 * q, make_float4(t[4 * q], t[4 * q + 1], t[4 * q + 2], t[4 * q + 3]));
+            for (int q = 0; q < 4; ++q)
+              st_cs_f8(dst + 8 * q, make_float4(t[8 * q], t[8 * q + 1], t[8 * q + 2], t[8 * q + 3]), make_float4(t[8 * q + 4], t[8 * q + 5], t[8 * q + 6], t[8 * q + 7]));
           }
           tc_wait_st();
         }

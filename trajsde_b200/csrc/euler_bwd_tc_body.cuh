@@ -510,13 +510,17 @@ __device__ __forceinline__ void euler_bwd_tc_body(const BwdTcParams& p, const Sw
       if (valid) {
         float* dst = gy0_p + grow * 64 + hh * 32;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 o = make_float4(adj[4 * q] * inv_sigma, adj[4 * q + 1] * inv_sigma, adj[4 * q + 2] * inv_sigma, adj[4 * q + 3] * inv_sigma);
-          if (a.grad_ys) {
-            const float4 g = ld_nc_f4(a.grad_ys + grow * a.grad_ys_row_stride + hh * 32 + 4 * q);
-            o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+        for (int q = 0; q < 8; q += 2) {
+          float4 o[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            o[e] = make_float4(adj[4 * (q + e)] * inv_sigma, adj[4 * (q + e) + 1] * inv_sigma, adj[4 * (q + e) + 2] * inv_sigma, adj[4 * (q + e) + 3] * inv_sigma);
+            if (a.grad_ys) {
+              const float4 g = ld_nc_f4(a.grad_ys + grow * a.grad_ys_row_stride + hh * 32 + 4 * (q + e));
+              o[e].x += g.x; o[e].y += g.y; o[e].z += g.z; o[e].w += g.w;
+            }
           }
-          *reinterpret_cast<float4*>(dst + 4 * q) = o;
+          st_f8(dst + 4 * q, o[0], o[1]);                       // 32-byte sectors (grad_y0 / the carry buffer are 256-byte aligned rows)
         }
       }
       if (SWEEP) sweep_publish(sw.sde_done[pass] + tile, sw.S - it, 6, NUM_EPI_THREADS, threadIdx.x == 0);   // carried adjoint of the tile is out

@@ -70,6 +70,14 @@ struct GruTcParams {
   float* h_out;                // [rows,64], fwd_only
 };
 
+#ifdef TRAJSDE_GRU_TIMELINE
+// debug build only (bench_micro/enc_bwd_ab.py --gru-timeline): clocks of thread 0 of CTA 0 between consecutive marks of a GRU tile
+static __device__ long long g_gru_seg[24];
+#define GRU_MARK(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long _t = clock64(); g_gru_seg[i] += _t - seg_prev; seg_prev = _t; } } while (0)
+#else
+#define GRU_MARK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, ts_tanh_approx(0.5f * x), 0.5f); }
 
 // SWEEP: the GRU role of the single-launch encoder sweep — every iteration i = S-1 .. 0 of the recurrence over this CTA's tiles, pointers
@@ -132,6 +140,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
         inv_sigma = ldexpf(1.f, -e);
       }
     }
+#ifdef TRAJSDE_GRU_TIMELINE
+    long long seg_prev = clock64();
+#endif
     float bs_n2 = 0.f, bs_n1 = 0.f, bs_u2 = 0.f, bs_r2 = 0.f, bs_u1 = 0.f, bs_r1 = 0.f;   // column (hh*32 + lane) sums over this warp's rows
     uint32_t hs = 0, ntile = 0;
     mbar_wait(bar_w, 0);
@@ -144,6 +155,7 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       const float* y1p = SWEEP ? p.y1 + (int64_t)it * p.x_slab : p.y1;
       const float* carry = SWEEP ? (it == it_hi ? nullptr : p.carry) : p.carry;
       const float* glat = SWEEP && p.grad_latent ? p.grad_latent + (int64_t)it * p.x_slab : p.grad_latent;
+      GRU_MARK(0);   // previous tile's flush tail / loop
       const int64_t row0 = (int64_t)tile * TILE_M + quad * 32;
       const int64_t grow = (int64_t)tile * TILE_M + row;
       const bool valid = grow < p.rows;
@@ -187,11 +199,14 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // y1, x -> F1
+      GRU_MARK(1);   // tile start: waits for the other roles, row loads, transposes, operand stores
 
       uint32_t v[32];
       float t[32];
       // ---- F1: tu, tr ------------------------------------------------------------------------------------------------------------------
+      GRU_MARK(2);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(3);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -208,7 +223,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       mbar_arrive(bar_opnd);                                       // tu, tr -> F2
       // ---- F2: u, r ; r*y1 ---------------------------------------------------------------------------------------------------------------
       float u[32], r[32];
+      GRU_MARK(4);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(5);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -226,7 +243,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // r*y1 -> F3
       // ---- F3: tn ------------------------------------------------------------------------------------------------------------------------
+      GRU_MARK(6);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(7);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -238,7 +257,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       mbar_arrive(bar_opnd);                                       // tn -> F4
       // ---- F4: n ; d_n = a (1-u) ; d_u' = a (y1 - n) u (1-u) ; d_y1 = a u   (a = 0 on unobserved rows, which pass dL/dh' straight on) ------
       float dy1[32], dup[32];
+      GRU_MARK(8);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(9);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -274,7 +295,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // d_n -> B1
       // ---- B1: dz_n = d_tn (1 - tn^2) -------------------------------------------------------------------------------------------------------
+      GRU_MARK(10);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(11);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       ld_row32(trow(T_TN), row, hh, t);
@@ -288,7 +311,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       mbar_arrive(bar_opnd);                                       // dz_n -> dN1, dN2 products, then B2
       // ---- B2: d_x (part), d(r y1) -> d_r', d_y1 ; d_u', d_r' tiles ---------------------------------------------------------------------------
       float dx[32];
+      GRU_MARK(12);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(13);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -310,7 +335,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // d_u', d_r' -> B3
       // ---- B3: dz_u = d_tu (1 - tu^2), dz_r = d_tr (1 - tr^2) ------------------------------------------------------------------------------------
+      GRU_MARK(14);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(15);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       ld_row32(trow(T_TU), row, hh, t);
@@ -330,7 +357,9 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // dz_u, dz_r -> B4
       // ---- B4: d_y1, d_x complete -> global ----------------------------------------------------------------------------------------------------
+      GRU_MARK(16);
       mbar_wait(bar_acc, hs & 1); ++hs;
+      GRU_MARK(17);
       tc_fence_after();
       tmem_ld_32x32b_x32(tm + TM_W, v);
       tc_wait_ld();
@@ -343,18 +372,24 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
       tc_fence_before();
       mbar_arrive(bar_opnd);                                       // working columns read -> dU2|dR2, dU1|dR1 products
       if (valid) {
-        float* d1 = p.grad_y1 + grow * 64 + hh * 32;
+        float* d1 = p.grad_y1 + grow * 64 + hh * 32;               // 256-bit stores: whole 32-byte sectors (see st_f8)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(d1 + 4 * q) = make_float4(dy1[4 * q], dy1[4 * q + 1], dy1[4 * q + 2], dy1[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          st_f8(d1 + 8 * q, make_float4(dy1[8 * q], dy1[8 * q + 1], dy1[8 * q + 2], dy1[8 * q + 3]),
+                make_float4(dy1[8 * q + 4], dy1[8 * q + 5], dy1[8 * q + 6], dy1[8 * q + 7]));
         if (gx) {
           float* d2 = gx + grow * 64 + hh * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(d2 + 4 * q) = make_float4(dx[4 * q], dx[4 * q + 1], dx[4 * q + 2], dx[4 * q + 3]);
+          for (int q = 0; q < 4; ++q)
+            st_f8(d2 + 8 * q, make_float4(dx[8 * q], dx[8 * q + 1], dx[8 * q + 2], dx[8 * q + 3]),
+                  make_float4(dx[8 * q + 4], dx[8 * q + 5], dx[8 * q + 6], dx[8 * q + 7]));
         }
       }
       if (SWEEP) sweep_publish(sw.gru_done + tile, sw.S - it, 6, NUM_EPI_THREADS, threadIdx.x == 0);   // dL/dy1 of the tile is out
       // ---- dU1 | dR1 live in the working columns: flush them for this tile before the next F1 overwrites them -------------------------------------
+      GRU_MARK(18);  // B4 epilogue: stores + publish
       mbar_wait(bar_wg, ntile & 1);
+      GRU_MARK(19);  // wait for the weight-gradient products
       tc_fence_after();
       {
         float* out = p.partial + (size_t)cta * GRU_G_PAD;
@@ -369,6 +404,7 @@ __device__ __forceinline__ void gru_bwd_tc_body(const GruTcParams& p, const Swee
         flush_row32(d + 64 + hh * 32, v, inv_sigma, true);
       }
       tc_fence_before();
+      GRU_MARK(20);  // per-tile dU1 | dR1 flush
     }
 
     // ================= remaining weight-gradient accumulators + bias sums of this CTA -> partial =================================================
