@@ -15,6 +15,8 @@ enc_sde = syn.init_reference_style(syn.EncoderSDEFunc(), 1).to(dev)
 gru = syn.init_reference_style(syn.GRUUnit(), 3).to(dev)
 L = _lib.lib()
 buf = (C.c_longlong * 4)()
+seg = (C.c_longlong * 20)()
+PH = ['P1', 'P2f', 'P2g', 'P3', 'G1', 'G2', 'G3', 'G4']
 for scenes in (128, 1024):
     b = syn.make_batch(scenes, 20, seed=5, mixed_sources=True)
     tr = {k: getattr(b, k).to(dev) for k in ('enc_h0', 'aa_out', 'actors_mask', 'nus_mask')}
@@ -25,11 +27,15 @@ for scenes in (128, 1024):
                 enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], tr['aa_out'], tr['actors_mask'], tr['nus_mask'], **kw)
             torch.cuda.synchronize()
             L.trajsde_debug_enc_timeline(buf)
+            L.trajsde_debug_enc_segments(seg)
             n = 4
             for _ in range(n):
                 enc_mod.encoder_recurrence(enc_sde, gru, tr['enc_h0'], tr['aa_out'], tr['actors_mask'], tr['nus_mask'], **kw)
             torch.cuda.synchronize()
             L.trajsde_debug_enc_timeline(buf)
+        L.trajsde_debug_enc_segments(seg)
         its = max(buf[2] / n, 1)
         print(f"scenes={scenes} {name}: kernel {buf[0] / n / 1e3:.0f} kclk, {its:.0f} iterations on CTA 0 -> {buf[0] / n / its:.0f} clk per iteration, "
               f"{buf[1] / n / its:.0f} of them waiting for the tensor core (8 hand-shakes)")
+        print('    ' + ' | '.join(f"{PH[k]}: {seg[2 * k] / n / its:.0f} + wait {seg[2 * k + 1] / n / its:.0f}" for k in range(8)) + f" | tail {seg[16] / n / its:.0f}")
+

@@ -163,15 +163,18 @@ __device__ __forceinline__ void ld_g32(uint32_t tm_uniform, uint32_t tm_alt, boo
 // debug build only (bench_micro/enc_fwd_timeline.py): thread 0 of CTA 0: [0] kernel clocks, [1] clocks waiting for the tensor core (all eight
 // accumulator barriers of an iteration), [2] iterations
 __device__ long long g_enc_tl[4];
-#define ENC_TL_WAIT(expr) do { const long long _t0 = clock64(); expr; if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_tl[1] += clock64() - _t0; } while (0)
+__device__ long long g_enc_seg[20];   // [2k] work before hand-shake k, [2k+1] the wait itself (k = P1, P2f, P2g, P3, G1, G2, G3, G4), [16] iteration tail
+#define ENC_TL_WAIT(k, expr) do { const long long _t0 = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_seg[2 * (k)] += _t0 - seg_prev; expr; \
+    seg_prev = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) { g_enc_tl[1] += seg_prev - _t0; g_enc_seg[2 * (k) + 1] += seg_prev - _t0; } } while (0)
 #else
-#define ENC_TL_WAIT(expr) do { expr; } while (0)
+#define ENC_TL_WAIT(k, expr) do { expr; } while (0)
 #endif
 
 template <bool HAS_DW, bool DUAL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncParams p) {
 #ifdef TRAJSDE_ENC_TIMELINE
   const long long tl_start = clock64();
+  long long seg_prev = tl_start;
 #endif
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int64_t grow = (int64_t)tile * TILE_M + row;
       const bool valid = grow < a.rows;
+      const int64_t lrow = valid ? grow : a.rows - 1;        // row the unconditional loads of this thread read
       const bool use_alt = DUAL && valid && (a.alt_mask[grow] == 0);
       const int gcol = use_alt ? 128 : 64;
       const bool w_all_alt = DUAL && __all_sync(0xffffffffu, use_alt);
@@ -290,20 +294,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         const int slot_next = __shfl_sync(0xffffffffu, lane_slot, (it + 1) & 31);
         const float* b1row = bias1_tab + it * 192;
         // ---- early global loads of this iteration: Brownian increments ------------------------------------------------------
+        // Supplied increments of this iteration.  Unconditional loads from a clamped row — rows past the end read the last row and are
+        // never stored; a predicated load into zero-initialised registers makes the compiler merge the two values right behind the load.
+        // (Issuing them one iteration ahead changes nothing: what the kernel pays for its per-thread row accesses is L1 tag throughput —
+        // every 256-bit access of a warp touches 32 different lines — and that ~2 k clk per iteration shows up at whichever global
+        // access comes first, bench_micro/enc_fwd_timeline.py.)
         float4 dwv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dwv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         const bool observed = (obs_bits >> it) & 1u;
-        if (valid) {
-          if (HAS_DW) {
-            const float* ds = a.noise.dw + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
+        if (HAS_DW) {
+          const float* ds = a.noise.dw + ((int64_t)it * a.rows + lrow) * 64 + hh * 32;
 #pragma unroll
-            for (int q = 0; q < 8; q += 2) ld_nc_f8(ds + 4 * q, dwv[q], dwv[q + 1]);
-          }
+          for (int q = 0; q < 8; q += 2) ld_nc_f8(ds + 4 * q, dwv[q], dwv[q + 1]);
         }
 
         // ---- epilogue 1 ------------------------------------------------------------------------------------------------------
-        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // P1
+        ENC_TL_WAIT(0, mbar_wait(bar_acc(0), par_accA));                   // P1
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           mbar_arrive(bar_opnd(0));                        // h1g -> P2g
         }
         // ---- epilogue 2 ------------------------------------------------------------------------------------------------------
-        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // P2f
+        ENC_TL_WAIT(1, mbar_wait(bar_acc(1), par_accB));                   // P2f
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(bar_opnd(1));                        // h2f -> P3
-          ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                 // P2g
+          ENC_TL_WAIT(2, mbar_wait(bar_acc(0), par_accA));                 // P2g
           par_accA ^= 1;
           tc_fence_after();
           ld_g32<DUAL>(tm + ucol, tm + 128, w_mixed, use_alt, v);
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
                                 (uint32_t)(hh * 8 + q), sqrt_h);
           }
         }
-        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // P3
+        ENC_TL_WAIT(3, mbar_wait(bar_acc(1), par_accB));                   // P3
         par_accB ^= 1;
         tc_fence_after();
         named_bar_sync(pair_bar, 64);                      // both partial diffusion dots of every row are in smem
@@ -380,6 +385,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           for (int j = 0; j < 32; ++j) yv[j] = __float_as_uint(t[j]);
           tmem_st_32x32b_x32(tm + TM_Y, yv);               // Y <- y1
           st_operand32(o_ah, t);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_opnd(0));                        // y1 -> G1 (x is in AX since the previous iteration / the tile prologue)
+          // the global stores go out behind the hand-over: G1 runs while they drain
           if (hh == 0 && valid) a.g_out[(int64_t)it * a.rows + grow] = g;
           if (a.y1_out && valid) {                         // pre-GRU state, saved for the backward call
             float* dst = a.y1_out + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
@@ -387,21 +396,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
             for (int q = 0; q < 4; ++q)
               st_cs_f8(dst + 8 * q, make_float4(t[8 * q], t[8 * q + 1], t[8 * q + 2], t[8 * q + 3]), make_float4(t[8 * q + 4], t[8 * q + 5], t[8 * q + 6], t[8 * q + 7]));
           }
-          tc_wait_st();
         }
-        tc_fence_before();
-        mbar_arrive(bar_opnd(0));                          // y1 -> G1 (x is in AX since the previous iteration / the tile prologue)
         // next iteration's GRU input: in flight during G1..G3, stored to AX after G3 (its last reader this iteration)
         float4 xn[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) xn[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && it + 1 < S) {
-          const float* xs = a.aa_out + ((int64_t)slot_next * a.rows + grow) * 64 + hh * 32;
+        {                                                    // (slot_next of the last iteration wraps to a valid slot; its x is never used)
+          const float* xs = a.aa_out + ((int64_t)slot_next * a.rows + lrow) * 64 + hh * 32;
 #pragma unroll
           for (int q = 0; q < 8; q += 2) ld_nc_f8(xs + 4 * q, xn[q], xn[q + 1]);
         }
         // ---- GRU epilogue 1: tu = tanh(zu + ub1), tr = tanh(zr + rb1) -----------------------------------------------------------------
-        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // G1
+        ENC_TL_WAIT(4, mbar_wait(bar_acc(0), par_accA));                   // G1
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         mbar_arrive(bar_opnd(1));                          // tu, tr -> G2
         // ---- GRU epilogue 2: u = sigmoid(u' + ub2) (kept), r = sigmoid(r' + rb2), r * y1 -> AH ---------------------------------------------
         float u[32];
-        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // G2
+        ENC_TL_WAIT(5, mbar_wait(bar_acc(1), par_accB));                   // G2
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         tc_fence_before();
         mbar_arrive(bar_opnd(0));                          // r*y1 -> G3
         // ---- GRU epilogue 3: tn = tanh(zn + nb1) --------------------------------------------------------------------------------------------
-        ENC_TL_WAIT(mbar_wait(bar_acc(0), par_accA));                   // G3
+        ENC_TL_WAIT(6, mbar_wait(bar_acc(0), par_accA));                   // G3
         par_accA ^= 1;
         tc_fence_after();
         {
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
         tc_fence_before();
         mbar_arrive(bar_opnd(1));                          // tn -> G4
         // ---- GRU epilogue 4: h' = (1-u) (n + nb2) + u y1 ; masked ; state, operand, latent ---------------------------------------------------
-        ENC_TL_WAIT(mbar_wait(bar_acc(1), par_accB));                   // G4
+        ENC_TL_WAIT(7, mbar_wait(bar_acc(1), par_accB));                   // G4
         par_accB ^= 1;
         tc_fence_after();
         {
@@ -478,16 +482,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) enc_fwd_tc_kernel(const EncPar
           }
           tmem_st_32x32b_x32(tm + TM_Y, yv);
           st_operand32(o_ah, t);                           // AH (r*y1) was consumed by G3
-          if (valid) {
+          tc_wait_st();
+          tc_fence_before();
+          if (it + 1 < S) mbar_arrive(bar_opnd(0));        // h' -> P1 of the next iteration
+          if (valid) {                                     // the latent store goes out behind the hand-over
             float* dst = a.latent + ((int64_t)it * a.rows + grow) * 64 + hh * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               st_cs_f8(dst + 8 * q, make_float4(t[8 * q], t[8 * q + 1], t[8 * q + 2], t[8 * q + 3]), make_float4(t[8 * q + 4], t[8 * q + 5], t[8 * q + 6], t[8 * q + 7]));
           }
-          tc_wait_st();
         }
-        tc_fence_before();
-        if (it + 1 < S) mbar_arrive(bar_opnd(0));          // h' -> P1 of the next iteration
+#ifdef TRAJSDE_ENC_TIMELINE
+        { const long long _t = clock64(); if (threadIdx.x == 0 && blockIdx.x == 0) g_enc_seg[16] += _t - seg_prev; seg_prev = _t; }
+#endif
       }
     }
   } else {
@@ -606,6 +613,11 @@ int launch_enc_fwd_tc(const TrajsdeEncFwdArgs& a, cudaStream_t s) {
 }  // namespace trajsde
 
 #ifdef TRAJSDE_ENC_TIMELINE
+extern "C" int trajsde_debug_enc_segments(long long* out20) {
+  long long zero[20] = {0};
+  if (cudaMemcpyFromSymbol(out20, trajsde::g_enc_seg, sizeof(zero)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(trajsde::g_enc_seg, zero, sizeof(zero)) == cudaSuccess ? 0 : -1;
+}
 extern "C" int trajsde_debug_enc_timeline(long long* out4) {
   long long zero[4] = {0};
   if (cudaMemcpyFromSymbol(out4, trajsde::g_enc_tl, sizeof(zero)) != cudaSuccess) return -1;
